@@ -1,0 +1,132 @@
+/*
+ * w2l_b200.h — C ABI of libw2l_b200.so: the B200-native (sm_100a) implementation of
+ * wav2letter's training hot path.  Every entry point below replaces one piece of the
+ * un-vendored flashlight-0.3 backend that the reference's Train.cpp loop reaches through
+ * fl::pkg::speech::SequenceCriterion / fl::Module.  The binding a
+ * maintainer adds on the reference side is shown in INTEGRATION.md; include/fl_compat/
+ * holds the C++ classes with the reference's own names (ASGLoss, CTCLoss, ...) on top.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant
+ *     across streams, and keep no hidden state: scratch memory is a caller-owned workspace
+ *     whose size the matching *_workspace_size() call returns (SURVEY.md §8b "Threading");
+ *   - return value: W2L_OK or an error code; w2l_last_error() gives the thread-local text.
+ *     The fl_compat C++ layer turns codes into std::invalid_argument / std::runtime_error
+ *     like the reference (cpc/SequentialBuilder.cpp:107-109);
+ *   - numerical failure is signalled in-band (NaN / Inf in the loss), which the caller
+ *     checks exactly as Train.cpp:1686-1698 does.
+ *
+ * Layouts (ArrayFire column-major dims -> row-major C):
+ *   emissions  af [N,T,B]  -> float  emis[B][T][N]
+ *   targets    af [L,B]    -> int32  target[B][L], padded with negative values
+ *                             (kTargetPadValue = -1, recipes/slimIPL/src/Train.cpp:318-322)
+ *   transitions af [N,N]   -> float  trans[N][N], trans[i*N+j] = score of moving FROM j TO i
+ *                             (criterion->param(0), tools/StreamingTDSModelConverter.cpp:310-321)
+ *   losses     af [B]      -> float  loss[B]           (per sample, not reduced; Train.cpp:1743)
+ *   paths      af [T,B]    -> int32  path[B][T]
+ */
+#ifndef W2L_B200_H_
+#define W2L_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2L_API __attribute__((visibility("default")))
+
+/* status codes */
+enum {
+  W2L_OK = 0,
+  W2L_ERR_INVALID_ARGUMENT = 1, /* bad shape / null pointer  (-> std::invalid_argument) */
+  W2L_ERR_WORKSPACE = 2,        /* workspace too small        (-> std::invalid_argument) */
+  W2L_ERR_CUDA = 3,             /* a CUDA runtime call failed (-> std::runtime_error)    */
+  W2L_ERR_UNSUPPORTED = 4       /* size outside what the kernels cover                   */
+};
+
+/* flashlight/lib/sequence/criterion/Defines.h CriterionScaleMode, selected by
+ * getCriterionScaleMode(FLAGS_onorm, FLAGS_sqnorm) at Train.cpp:389 */
+enum {
+  W2L_SCALE_NONE = 0,
+  W2L_SCALE_INPUT_SZ = 1,
+  W2L_SCALE_INPUT_SZ_SQRT = 2,
+  W2L_SCALE_TARGET_SZ = 3,
+  W2L_SCALE_TARGET_SZ_SQRT = 4
+};
+
+/* which terms of the ASG criterion a call evaluates */
+enum {
+  W2L_TERM_FCC = 1, /* FullConnectionCriterion: loss = +FCC                       */
+  W2L_TERM_FAC = 2, /* ForceAlignmentCriterion: loss = +FAC (LinSeg uses this)    */
+  W2L_TERM_ASG = 3  /* AutoSegmentationCriterion: loss = FCC - FAC                */
+};
+
+W2L_API int w2l_version(void);
+W2L_API const char* w2l_last_error(void);
+/* number of kernels this library launched on the calling thread since the last reset
+ * (bench.py's "gpu_launches" claim) */
+W2L_API long long w2l_launch_count(void);
+W2L_API void w2l_reset_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------
+ * ASG = FullConnectionCriterion - ForceAlignmentCriterion, fused forward + backward.
+ * Replaces AutoSegmentationCriterion::forward + its gradFunc (constructed at
+ * recipes/slimIPL/src/Train.cpp:408-410, called :1675, backward :1720).
+ *
+ *   loss[b]   = scale_b * (FCC_b - FAC_b)                         (terms selects the parts)
+ *   d_emis    = dloss[b] * d loss[b] / d emis     [B][T][N]
+ *   d_trans   = sum_b dloss[b] * d loss[b] / d trans   [N][N]
+ * dloss == NULL means ones (what loss.backward() seeds).  d_emis and d_trans may be NULL
+ * together for a forward-only call (criterion->forward in eval mode, Train.cpp:977).
+ * L is the padded target width; the per-sample size is the index of the last non-negative
+ * entry + 1, clamped to T (upstream getTargetSizeArray).  Samples whose target is empty or
+ * holds a label outside [0,N) get loss = NaN and zero gradient.
+ * Supported: N <= 32 (token sets of the ASG recipes are ~30: conv_glu/.../train.cfg),
+ * L such that the per-CTA shared-memory rows fit (L <= ~6000).
+ * ---------------------------------------------------------------------------------------- */
+W2L_API size_t w2l_asg_workspace_size(int B, int T, int N, int L);
+W2L_API int w2l_asg_forward_backward(void* stream, int terms, int B, int T, int N, int L, int scale_mode,
+                                     const float* emis, const int32_t* target, const float* trans,
+                                     const float* dloss, float* loss, float* d_emis, float* d_trans,
+                                     void* workspace, size_t workspace_bytes);
+
+/* ----------------------------------------------------------------------------------------
+ * Viterbi decoding.  w2l_fcc_viterbi replaces ASGLoss::viterbiPath (Train.cpp:838, :1375):
+ * max-plus FCC + backtrace, fp32 add/compare in ascending-j order, first maximum wins —
+ * bit-exact with upstream ViterbiPath.  w2l_fac_viterbi is the forced alignment
+ * (upstream ForceAlignmentCriterion::viterbiPath / fl_asr_align): path = label per frame,
+ * path_idx (nullable) = position in the target per frame.
+ * ---------------------------------------------------------------------------------------- */
+W2L_API size_t w2l_fcc_viterbi_workspace_size(int B, int T, int N);
+W2L_API int w2l_fcc_viterbi(void* stream, int B, int T, int N, const float* emis, const float* trans,
+                            int32_t* path, void* workspace, size_t workspace_bytes);
+W2L_API size_t w2l_fac_viterbi_workspace_size(int B, int T, int N, int L);
+W2L_API int w2l_fac_viterbi(void* stream, int B, int T, int N, int L, const float* emis, const int32_t* target,
+                            const float* trans, int32_t* path, int32_t* path_idx, void* workspace,
+                            size_t workspace_bytes);
+
+/* ----------------------------------------------------------------------------------------
+ * CTC, fused forward + backward on RAW activations (internal log-softmax over N, blank =
+ * N-1 appended last: Train.cpp:248-251).  Replaces ConnectionistTemporalClassification
+ * Criterion::forward (CTCLoss, Train.cpp:406-407; CUDA backend upstream = warp-ctc).
+ * Every sample runs over the full padded T (the loop passes no input sizes to CTC/ASG:
+ * Train.cpp:1473-1477).  d_emis may be NULL (forward only).
+ * w2l_argmax_path = CTCLoss::viterbiPath (per-frame argmax, first maximum wins).
+ * ---------------------------------------------------------------------------------------- */
+W2L_API size_t w2l_ctc_workspace_size(int B, int T, int N, int L);
+W2L_API int w2l_ctc_forward_backward(void* stream, int B, int T, int N, int L, int scale_mode, const float* emis,
+                                     const int32_t* target, const float* dloss, float* loss, float* d_emis,
+                                     void* workspace, size_t workspace_bytes);
+W2L_API int w2l_argmax_path(void* stream, int B, int T, int N, const float* emis, int32_t* path);
+
+/* LinearSegmentationCriterion's target stretch (Train.cpp:589-617, --linseg): out[b][t] =
+ * target[b][floor(t * L_b / T)]; feed it to w2l_asg_forward_backward(W2L_TERM_FAC, L = T). */
+W2L_API int w2l_linseg_target(void* stream, int B, int T, int L, const int32_t* target, int32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2L_B200_H_ */

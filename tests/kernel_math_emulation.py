@@ -1,0 +1,189 @@
+"""numpy emulation of the arithmetic formulation the CUDA ASG kernels use (fp32 where the
+kernels use fp32).  This is NOT the product and NOT the oracle: it exists so that the kernel
+math (scaling bookkeeping, meet-in-the-middle junction, gradient identities) can be checked
+against the oracle on the CPU-only dev box before a GPU round trip.  See DESIGN.md §kernels.
+"""
+import numpy as np
+
+F = np.float32
+
+
+def pow2_scale(mx):
+    """2^-exponent(mx) built from the exponent bits (exact), clamp like the kernel."""
+    bits = np.float32(mx).view(np.int32)
+    k = int((bits >> 23) & 0xFF) - 127
+    k = max(-126, min(126, k))
+    return F(2.0) ** F(-k), k
+
+
+def fcc_emulate(e, tr):
+    """Linear-domain FCC alpha/beta with lagged power-of-two rescaling.
+    returns logZ, gamma[T,N], xi_sum[N,N]"""
+    T, N = e.shape
+    tmax = tr.max()
+    M = np.exp((tr - tmax).astype(F)).astype(F)  # M[i][j]
+    m = e.max(axis=1)
+    X = np.exp((e - m[:, None]).astype(F)).astype(F)
+    A = np.zeros((T, N), F)
+    sA = np.ones(T, F)
+    a = X[0].copy()
+    A[0] = a
+    ksum = 0
+    s = F(1.0)
+    for t in range(1, T):
+        v = a  # a_{t-1}
+        acc = (M @ v).astype(F)
+        mx = v.max()
+        a = (X[t] * s) * acc
+        A[t] = a
+        sA[t] = s
+        ksum += -int(np.log2(s))
+        s, _ = pow2_scale(mx)  # applied at the NEXT step: normalises by a_{t-1}'s magnitude
+    logZ = float(m.astype(np.float64).sum()) + (T - 1) * float(tmax) + np.log(2.0) * ksum + np.log(
+        float(a.astype(np.float64).sum()))
+    Bh = np.zeros((T, N), F)
+    bh = np.ones(N, F)
+    Bh[T - 1] = bh
+    s = F(1.0)
+    for t in range(T - 2, -1, -1):
+        u = bh * (X[t + 1] * s)
+        mx = u.max()
+        bh = (M.T @ u).astype(F)
+        Bh[t] = bh
+        s, _ = pow2_scale(mx)
+    g = A * Bh
+    gs = g.sum(axis=1)
+    gamma = g / gs[:, None]
+    xi = np.zeros((N, N), F)
+    for t in range(1, T):
+        w = X[t] * Bh[t] * (sA[t] / gs[t])
+        xi += np.outer(w, A[t - 1])
+    xi *= M
+    return logZ, gamma, xi
+
+
+def lse2(a, b):
+    m = np.maximum(a, b)
+    n = np.minimum(a, b)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r = m + np.log1p(np.exp((n - m).astype(F))).astype(F)
+    return np.where(n == -np.inf, m, r).astype(F)
+
+
+def fac_emulate(e, y, tr):
+    """log-domain FAC, alpha from t=0 and beta from t=T-1 meeting at h=T//2, per-step
+    re-centring by the band max, gamma = xi_stay + xi_adv, renormalised per frame.  returns logZ, G[T,N], dtrans[N,N]"""
+    T, N = e.shape
+    L = len(y)
+    NI = F(-np.inf)
+    s1 = tr[y, y].astype(F)
+    s2 = np.concatenate([[NI], tr[y[1:], y[:-1]]]).astype(F)
+    G = np.zeros((T, N), np.float64)
+    dtr = np.zeros((N, N), np.float64)
+    if T == 1:
+        G[0, y[0]] = 1.0
+        return float(e[0, y[0]]), G, dtr
+    h = T // 2
+
+    def band(t):
+        return max(0, L - (T - t)), min(t, L - 1)
+
+    def mask(row, t):
+        lo, hi = band(t)
+        out = np.full(L, NI, F)
+        out[lo:hi + 1] = row[lo:hi + 1]
+        return out
+
+    alpha = np.full((T, L), NI, F)
+    cA = np.zeros(T, np.float64)
+    row = np.full(L, NI, F)
+    row[0] = e[0, y[0]]
+    alpha[0] = row
+    C = 0.0
+
+    def alpha_step(prev, t, C):
+        d = prev.max()
+        C += float(d)
+        stay = prev + (s1 - d)
+        adv = np.concatenate([[NI], prev[:-1]]) + (s2 - d)
+        new = mask(e[t, y] + lse2(stay, adv), t)
+        return new.astype(F), C
+
+    for t in range(1, h):
+        row, C = alpha_step(row, t, C)
+        alpha[t] = row
+        cA[t] = C
+    beta = np.full((T, L), NI, F)
+    cB = np.zeros(T, np.float64)
+    rb = np.full(L, NI, F)
+    rb[L - 1] = e[T - 1, y[L - 1]]
+    beta[T - 1] = rb
+    Cb = 0.0
+
+    def beta_step(nxt, t, Cb):
+        d = nxt.max()
+        Cb += float(d)
+        stay = nxt + (s1 - d)
+        adv = np.concatenate([nxt[1:], [NI]]) + (np.concatenate([s2[1:], [NI]]) - d)
+        new = mask(e[t, y] + lse2(stay, adv), t)
+        return new.astype(F), Cb
+
+    for t in range(T - 2, h - 1, -1):
+        rb, Cb = beta_step(rb, t, Cb)
+        beta[t] = rb
+        cB[t] = Cb
+    # junction at t = h
+    prevA = row
+    CA_prev = C
+    row, C = alpha_step(row, h, C)
+    alpha[h] = row
+    cA[h] = C
+    q = row + beta[h] - e[h, y]
+    qm = q.max()
+    tot = np.exp((q - qm).astype(F)).astype(F).sum(dtype=np.float64)
+    logZ = cA[h] + cB[h] + float(qm) + np.log(tot)
+    gam = np.exp((q - qm).astype(F)) / F(tot)
+    np.add.at(G[h], y, gam)
+    ds1 = np.zeros(L, np.float64)
+    ds2 = np.zeros(L, np.float64)
+    rn = {}  # per-frame normalisers 1/sum_l gamma_t[l]; the kernel applies them with a lag of two steps
+
+    # group A: t = h+1 .. T-1
+    for t in range(h + 1, T):
+        prev = row
+        Cp = C
+        row, C = alpha_step(row, t, C)
+        K = F(Cp + cB[t] - logZ)
+        with np.errstate(invalid="ignore"):
+            xs = np.exp((prev + s1 + beta[t] + K).astype(F))
+            xa = np.exp((np.concatenate([[NI], prev[:-1]]) + s2 + beta[t] + K).astype(F))
+        xs = np.nan_to_num(xs, nan=0.0)
+        xa = np.nan_to_num(xa, nan=0.0)
+        lag = rn.get(t - 2, 1.0) if t - 2 > h else 1.0
+        ds1 += xs * lag
+        ds2 += xa * lag
+        tot = float((xs + xa).sum(dtype=np.float64))
+        rn[t] = 1.0 / tot if tot > 0 else 0.0
+        np.add.at(G[t], y, (xs + xa) * rn[t])
+    rn = {}
+    # group B: t = h-1 .. 0 (transitions t -> t+1)
+    for t in range(h - 1, -1, -1):
+        nxt = rb
+        Cn = Cb
+        rb, Cb = beta_step(rb, t, Cb)
+        K = F(cA[t] + Cn - logZ)
+        at = alpha[t]
+        with np.errstate(invalid="ignore"):
+            xs = np.exp((at + s1 + nxt + K).astype(F))
+            xa = np.exp((at + np.concatenate([s2[1:], [NI]]) + np.concatenate([nxt[1:], [NI]]) + K).astype(F))
+        xs = np.nan_to_num(xs, nan=0.0)
+        xa = np.nan_to_num(xa, nan=0.0)
+        lag = rn.get(t + 2, 1.0)
+        ds1 += xs * lag
+        ds2[1:] += xa[:-1] * lag
+        tot = float((xs + xa).sum(dtype=np.float64))
+        rn[t] = 1.0 / tot if tot > 0 else 0.0
+        np.add.at(G[t], y, (xs + xa) * rn[t])
+    np.add.at(dtr, (y, y), ds1)
+    np.add.at(dtr, (y[1:], y[:-1]), ds2[1:])
+    return logZ, G, dtr

@@ -1,0 +1,192 @@
+"""ctypes binding of include/w2l_b200.h for the Python harness (tests, bench, smoke).
+
+Every function takes CUDA torch tensors, checks dtype/contiguity, and passes raw device
+pointers and the current CUDA stream to the C ABI.  Workspaces are torch byte tensors owned
+by the caller side (cached per size here), exactly as the C ABI demands.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libw2l_b200.so")
+
+SCALE_MODES = {"none": 0, "input_sz": 1, "input_sz_sqrt": 2, "target_sz": 3, "target_sz_sqrt": 4}
+TERM_FCC, TERM_FAC, TERM_ASG = 1, 2, 3
+
+# every entry point include/w2l_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count",
+    "w2l_asg_workspace_size", "w2l_asg_forward_backward",
+    "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
+    "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
+    "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
+]
+
+
+class W2LError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"w2l error {code}: {msg}")
+        self.code = code
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.w2l_last_error.restype = ctypes.c_char_p
+    lib.w2l_launch_count.restype = ctypes.c_longlong
+    lib.w2l_asg_workspace_size.restype = sz
+    lib.w2l_asg_workspace_size.argtypes = [i, i, i, i]
+    lib.w2l_asg_forward_backward.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, sz]
+    lib.w2l_fcc_viterbi_workspace_size.restype = sz
+    lib.w2l_fcc_viterbi_workspace_size.argtypes = [i, i, i]
+    lib.w2l_fcc_viterbi.argtypes = [vp, i, i, i, vp, vp, vp, vp, sz]
+    lib.w2l_fac_viterbi_workspace_size.restype = sz
+    lib.w2l_fac_viterbi_workspace_size.argtypes = [i, i, i, i]
+    lib.w2l_fac_viterbi.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, sz]
+    lib.w2l_ctc_workspace_size.restype = sz
+    lib.w2l_ctc_workspace_size.argtypes = [i, i, i, i]
+    lib.w2l_ctc_forward_backward.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, sz]
+    lib.w2l_argmax_path.argtypes = [vp, i, i, i, vp, vp]
+    lib.w2l_linseg_target.argtypes = [vp, i, i, i, vp, vp]
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise W2LError(rc, lib.w2l_last_error().decode())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise TypeError(f"{name}: expected a contiguous CUDA tensor of {dtype}")
+    return t
+
+
+_ws_cache: dict = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    key = (str(device), "ws")
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+def _mode(m) -> int:
+    return SCALE_MODES[m] if isinstance(m, str) else int(m)
+
+
+def launch_count() -> int:
+    return int(lib.w2l_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib.w2l_reset_launch_count()
+
+
+def asg_forward_backward(emis, target, trans, scale_mode="none", dloss=None, terms=TERM_ASG, need_grad=True,
+                         out=None, ws=None):
+    """Fused ASG (FCC - FAC) forward+backward.  emis [B,T,N] f32, target [B,L] i32 (-1 padded),
+    trans [N,N] f32.  Returns (loss[B], d_emis[B,T,N] | None, d_trans[N,N] | None)."""
+    emis = _req(emis, torch.float32, "emis")
+    trans = _req(trans, torch.float32, "trans")
+    target = _req(target, torch.int32, "target")
+    dloss = _req(dloss, torch.float32, "dloss")
+    B, T, N = emis.shape
+    L = 0 if target is None else target.shape[1]
+    if out is None:
+        loss = torch.empty(B, dtype=torch.float32, device=emis.device)
+        d_emis = torch.empty_like(emis) if need_grad else None
+        d_trans = torch.empty_like(trans) if need_grad else None
+    else:
+        loss, d_emis, d_trans = out
+    need = lib.w2l_asg_workspace_size(B, T, N, L)
+    if ws is None:
+        ws = workspace(need, emis.device)
+    _check(lib.w2l_asg_forward_backward(_stream(), terms, B, T, N, L, _mode(scale_mode), _ptr(emis), _ptr(target),
+                                        _ptr(trans), _ptr(dloss), _ptr(loss), _ptr(d_emis), _ptr(d_trans),
+                                        _ptr(ws), ws.numel()))
+    return loss, d_emis, d_trans
+
+
+def fcc_viterbi(emis, trans):
+    emis = _req(emis, torch.float32, "emis")
+    trans = _req(trans, torch.float32, "trans")
+    B, T, N = emis.shape
+    path = torch.empty((B, T), dtype=torch.int32, device=emis.device)
+    ws = workspace(lib.w2l_fcc_viterbi_workspace_size(B, T, N), emis.device)
+    _check(lib.w2l_fcc_viterbi(_stream(), B, T, N, _ptr(emis), _ptr(trans), _ptr(path), _ptr(ws), ws.numel()))
+    return path
+
+
+def fac_viterbi(emis, target, trans, return_index=False):
+    emis = _req(emis, torch.float32, "emis")
+    trans = _req(trans, torch.float32, "trans")
+    target = _req(target, torch.int32, "target")
+    B, T, N = emis.shape
+    L = target.shape[1]
+    path = torch.empty((B, T), dtype=torch.int32, device=emis.device)
+    idx = torch.empty((B, T), dtype=torch.int32, device=emis.device) if return_index else None
+    ws = workspace(lib.w2l_fac_viterbi_workspace_size(B, T, N, L), emis.device)
+    _check(lib.w2l_fac_viterbi(_stream(), B, T, N, L, _ptr(emis), _ptr(target), _ptr(trans), _ptr(path), _ptr(idx),
+                               _ptr(ws), ws.numel()))
+    return (path, idx) if return_index else path
+
+
+def ctc_forward_backward(emis, target, scale_mode="none", dloss=None, need_grad=True, out=None, ws=None):
+    """CTC on raw activations (blank = N-1).  Returns (loss[B], d_emis | None)."""
+    emis = _req(emis, torch.float32, "emis")
+    target = _req(target, torch.int32, "target")
+    dloss = _req(dloss, torch.float32, "dloss")
+    B, T, N = emis.shape
+    L = 0 if target is None else target.shape[1]
+    if out is None:
+        loss = torch.empty(B, dtype=torch.float32, device=emis.device)
+        d_emis = torch.empty_like(emis) if need_grad else None
+    else:
+        loss, d_emis = out
+    need = lib.w2l_ctc_workspace_size(B, T, N, L)
+    if ws is None:
+        ws = workspace(need, emis.device)
+    _check(lib.w2l_ctc_forward_backward(_stream(), B, T, N, L, _mode(scale_mode), _ptr(emis), _ptr(target),
+                                        _ptr(dloss), _ptr(loss), _ptr(d_emis), _ptr(ws), ws.numel()))
+    return loss, d_emis
+
+
+def argmax_path(emis):
+    emis = _req(emis, torch.float32, "emis")
+    B, T, N = emis.shape
+    path = torch.empty((B, T), dtype=torch.int32, device=emis.device)
+    _check(lib.w2l_argmax_path(_stream(), B, T, N, _ptr(emis), _ptr(path)))
+    return path
+
+
+def linseg_target(target, T: int):
+    target = _req(target, torch.int32, "target")
+    B, L = target.shape
+    out = torch.empty((B, int(T)), dtype=torch.int32, device=target.device)
+    _check(lib.w2l_linseg_target(_stream(), B, int(T), L, _ptr(target), _ptr(out)))
+    return out
