@@ -70,6 +70,11 @@ W2L_API const char* w2l_last_error(void);
  * (bench.py's "gpu_launches" claim) */
 W2L_API long long w2l_launch_count(void);
 W2L_API void w2l_reset_launch_count(void);
+/* Measurement hook (bench.py's roofline leg): while set (non-NULL cudaEvent_t handles), every
+ * call on this thread records `start` right before and `stop` right after its DOMINANT kernel
+ * (asg_chains_kernel, ctc_chains_kernel, the GEMM of a dense op) on the call's stream, so that
+ * kernel can be timed live inside a timed region.  Pass NULL, NULL to clear. */
+W2L_API void w2l_set_profile_events(void* start_event, void* stop_event);
 
 /* ----------------------------------------------------------------------------------------
  * ASG = FullConnectionCriterion - ForceAlignmentCriterion, fused forward + backward.

@@ -8,15 +8,15 @@ import numpy as np
 F = np.float32
 
 
-def pow2_scale(mx):
-    """2^-exponent(mx) built from the exponent bits (exact), clamp like the kernel."""
+def pow2_scale(mx, damp=0):
+    """2^-(exponent(mx) >> damp) built from the exponent bits (exact), clamp like the kernel."""
     bits = np.float32(mx).view(np.int32)
     k = int((bits >> 23) & 0xFF) - 127
-    k = max(-126, min(126, k))
+    k = max(-126, min(126, k)) >> damp
     return F(2.0) ** F(-k), k
 
 
-def fcc_emulate(e, tr):
+def fcc_emulate(e, tr, alpha_damp=1, return_exponents=False):
     """Linear-domain FCC alpha/beta with lagged power-of-two rescaling.
     returns logZ, gamma[T,N], xi_sum[N,N]"""
     T, N = e.shape
@@ -34,11 +34,15 @@ def fcc_emulate(e, tr):
         v = a  # a_{t-1}
         acc = (M @ v).astype(F)
         mx = v.max()
-        a = (X[t] * s) * acc
+        with np.errstate(over="ignore", under="ignore"):
+            a = (X[t] * s) * acc
         A[t] = a
         sA[t] = s
         ksum += -int(np.log2(s))
-        s, _ = pow2_scale(mx)  # applied at the NEXT step: normalises by a_{t-1}'s magnitude
+        s, _ = pow2_scale(mx, alpha_damp)  # applied at the NEXT step from |a_{t-1}|: lag two, damped
+    if return_exponents:
+        with np.errstate(divide="ignore"):
+            return np.log2(A.max(axis=1))
     logZ = float(m.astype(np.float64).sum()) + (T - 1) * float(tmax) + np.log(2.0) * ksum + np.log(
         float(a.astype(np.float64).sum()))
     Bh = np.zeros((T, N), F)

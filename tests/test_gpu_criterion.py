@@ -20,10 +20,12 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def rel(a, b):
+def rel(a, b, floor=2e-3):
+    """max abs error over max abs reference; `floor` = scale of the cancelling components when the
+    reference itself is ~0 (N = 1: gamma_fcc - gamma_fac = 1 - 1, d_trans = (T-1) - (T-1))."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
-    return float(np.abs(a - b).max() / max(1e-20, np.abs(b).max()))
+    return float(np.abs(a - b).max() / max(floor, np.abs(b).max()))
 
 
 def make_asg(B, T, N, L, seed, escale=3.0, ragged=True):
@@ -55,7 +57,8 @@ def check_asg(e, tr, y, mode="none", dloss=None, terms=None, tol=TOL):
     assert np.array_equal(np.isnan(gl), np.isnan(ol))
     assert rel(gde, ode) <= tol, f"d_emis rel err {rel(gde, ode)}"
     if e.shape[1] > 1:
-        assert rel(gdt, odt) <= tol, f"d_trans rel err {rel(gdt, odt)}"
+        floor = 1e-2 * e.shape[0] * e.shape[1]  # each of FCC / FAC contributes ~B*(T-1) mass
+        assert rel(gdt, odt, floor if e.shape[2] == 1 else 2e-3) <= tol, f"d_trans rel err {rel(gdt, odt)}"
     # forward-only entry gives the same loss
     fl, _, _ = w.asg_forward_backward(dev(e), dev(y), dev(tr), mode, None, terms, need_grad=False)
     np.testing.assert_allclose(fl.cpu().numpy(), ol, rtol=tol, atol=tol)

@@ -39,3 +39,20 @@ def test_fac_meet_in_the_middle_formulation(T, N, L, scale, seed):
     assert rel(G, de[0]) < tol
     if T > 1:
         assert rel(dtr, dt) < tol
+
+
+@pytest.mark.parametrize("scale", [3, 60])
+def test_fcc_rescale_controller_is_stable(scale):
+    """The alpha walk's lag-two rescale must be damped: undamped it leaves fp32 range (this bug
+    was seen on the GPU as NaN transition gradients at T=1500)."""
+    worst_damped, worst_undamped = 0.0, 0.0
+    for seed in range(6):
+        rng = np.random.default_rng(900 + seed)
+        e = (rng.normal(0, 1, (1500, 30)) * scale).astype(np.float32)
+        tr = (4 * np.eye(30) + rng.normal(0, 0.1, (30, 30))).astype(np.float32)
+        worst_damped = max(worst_damped, float(np.abs(fcc_emulate(e, tr, 1, True)).max()))
+        ex = fcc_emulate(e, tr, 0, True)
+        worst_undamped = max(worst_undamped, float(np.abs(ex[np.isfinite(ex)]).max()))
+    assert worst_damped < 40
+    if scale == 3:
+        assert worst_undamped > 60  # documents why the damping is there

@@ -19,7 +19,7 @@ TERM_FCC, TERM_FAC, TERM_ASG = 1, 2, 3
 
 # every entry point include/w2l_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count",
+    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count", "w2l_set_profile_events",
     "w2l_asg_workspace_size", "w2l_asg_forward_backward",
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
@@ -42,6 +42,7 @@ def _load() -> ctypes.CDLL:
     vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
     lib.w2l_last_error.restype = ctypes.c_char_p
     lib.w2l_launch_count.restype = ctypes.c_longlong
+    lib.w2l_set_profile_events.argtypes = [vp, vp]
     lib.w2l_asg_workspace_size.restype = sz
     lib.w2l_asg_workspace_size.argtypes = [i, i, i, i]
     lib.w2l_asg_forward_backward.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, sz]
@@ -105,6 +106,16 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib.w2l_reset_launch_count()
+
+
+def set_profile_events(start=None, stop=None) -> None:
+    """torch.cuda.Event(enable_timing=True) pair recorded around each call's dominant kernel."""
+    if start is None:
+        lib.w2l_set_profile_events(None, None)
+    else:
+        start.record()  # make sure the lazily created handles exist
+        stop.record()
+        lib.w2l_set_profile_events(ctypes.c_void_p(start.cuda_event), ctypes.c_void_p(stop.cuda_event))
 
 
 def asg_forward_backward(emis, target, trans, scale_mode="none", dloss=None, terms=TERM_ASG, need_grad=True,

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 namespace w2l {
+void set_profile_events(cudaEvent_t a, cudaEvent_t b);
 static thread_local std::string g_err;
 static thread_local long long g_launches = 0;
 
@@ -13,6 +14,17 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 void count_launch(int n) { g_launches += n; }
+static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+void profile_start(cudaStream_t s) {
+  if (g_ev_start) cudaEventRecord(g_ev_start, s);
+}
+void profile_stop(cudaStream_t s) {
+  if (g_ev_stop) cudaEventRecord(g_ev_stop, s);
+}
+void set_profile_events(cudaEvent_t a, cudaEvent_t b) {
+  g_ev_start = a;
+  g_ev_stop = b;
+}
 }  // namespace w2l
 
 extern "C" {
@@ -20,4 +32,7 @@ int w2l_version(void) { return 100; }
 const char* w2l_last_error(void) { return w2l::g_err.c_str(); }
 long long w2l_launch_count(void) { return w2l::g_launches; }
 void w2l_reset_launch_count(void) { w2l::g_launches = 0; }
+void w2l_set_profile_events(void* a, void* b) {
+  w2l::set_profile_events(static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b));
+}
 }

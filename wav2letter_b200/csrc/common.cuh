@@ -15,6 +15,9 @@ namespace w2l {
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
+// bench hook: events recorded around a call's dominant kernel (nullptr when unset)
+void profile_start(cudaStream_t s);
+void profile_stop(cudaStream_t s);
 
 #define W2L_CUDA_CHECK(expr)                                                                      \
   do {                                                                                            \

@@ -3,7 +3,7 @@
 // {FullConnectionCriterion,ForceAlignmentCriterion}.cu as reached from
 // recipes/slimIPL/src/Train.cpp:408-410 (construction), :1675 (forward), :1720 (backward).
 //
-// Pipeline (3 launches + 1 memset, all on the caller's stream):
+// Pipeline (4 launches, all on the caller's stream):
 //   1. asg_prep_kernel    HBM-bound, parallel over frames: m_t = max_i e_t[i],
 //                         X_t[i] = exp(e_t[i]-m_t) (padded to 32 lanes); per-sample target
 //                         size, validity, scale*dloss.
@@ -12,16 +12,21 @@
 //                 time, in the LINEAR domain: a_t = X_t .* (M' a_{t-1}) * 2^-k with M' =
 //                 exp(trans - max trans) held in registers (row i in lane i), the vector
 //                 exchanged through shared memory (1 STS + 8 broadcast LDS.128), 16 FFMA2 per
-//                 step, and a power-of-two rescale taken from the exponent bits of
-//                 max(a_{t-2}) (lagged, so no reduction sits on the dependent chain; exact).
+//                 step, X streamed into a shared-memory ring by cp.async 16 frames ahead, and a
+//                 power-of-two rescale taken from the exponent bits of a lagged maximum (no
+//                 reduction on the dependent chain; exact; damped — see pow2_rescale).
 //        FAC CTA: 128 threads walk alpha from t=0 and 128 walk beta from t=T-1 in the LOG
 //                 domain (the left-to-right band has unbounded dynamic range, a linear-domain
 //                 form is not safe there), re-centred every step by the band maximum; they
 //                 meet at h = T/2, the partition function is taken at the junction, and each
 //                 group finishes its walk reading the other group's stored half lattice to
 //                 emit occupancies (gamma = xi_stay + xi_adv) and transition statistics.
+//                 Every global read of the walk (emission frames, stored rows, offsets) is
+//                 issued 8 steps ahead with cp.async into shared-memory rings.
 //   3. asg_grad_kernel    parallel over (sample, frame chunk): gamma_fcc = a.*b / sum,
-//                         d_emis = coef*(gamma_fcc - gamma_fac), d_trans += M' .* sum_t w_t a_{t-1}^T.
+//                         d_emis = coef*(gamma_fcc - gamma_fac), per-CTA partial of
+//                         d_trans = M' .* sum_t w_t a_{t-1}^T.
+//   4. asg_dtrans_reduce_kernel  deterministic sum of the d_trans partials (no atomics).
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -30,14 +35,18 @@ namespace w2l {
 namespace {
 
 constexpr int kW = 32;            // padded FCC state width (one lane per state)
-constexpr int kChainThreads = 256;
+constexpr int kChainThreads = 320;    // FAC: 4 + 4 compute warps + 2 flush warps; FCC uses warps 0-2
 constexpr int kGroup = 128;       // threads per FAC direction
-constexpr int kGroupWarps = kGroup / 32;
-constexpr int kPrefetch = 8;      // frames of X prefetched ahead of the FCC chains
+constexpr int kXDepth = 16;       // frames of X in flight ahead of the FCC walks
+constexpr int kXRing = 32;        // ring slots (power of two > kXDepth)
+constexpr int kFDepth = 8;        // steps in flight ahead of the FAC walks
+constexpr int kFRing = 16;        // ring slots (power of two > kFDepth)
+constexpr int kGradWarps = 8;     // warps per CTA in the grad kernel
 constexpr int kGradChunk = 32;    // frames per warp in the grad kernel
+constexpr float kFix = 268435456.0f;  // 2^28 fixed point for the integer REDUX frame sums
 
 struct AsgParams {
-  int B, T, N, L, Lp, scale_mode, terms, h, need_grad;
+  int B, T, N, L, Lp, scale_mode, terms, h, need_grad, oring, n_grad_parts;
   const float* emis;
   const int32_t* target;
   const float* trans;
@@ -51,18 +60,33 @@ struct AsgParams {
   float* A;       // [B][T][32] FCC alpha-hat
   float* Bh;      // [B][T][32] FCC beta-hat
   float* sA;      // [B][T] power-of-two scale applied at step t of the alpha walk
-  float* G;       // [B][T][32] FAC occupancy per label
+  float* G;       // [B][T][32] FAC occupancy per label (unnormalised; the grad kernel normalises)
   float* facA;    // [B][h][Lp]    stored alpha-tilde rows, t < h
   float* facB;    // [B][T-h][Lp]  stored beta-tilde rows,  t >= h
   double* cA;     // [B][T] re-centring offsets of the FAC alpha walk
   double* cB;     // [B][T]
   double* fccLogZ;  // [B]
   double* facLogZ;  // [B]
+  float* parts;   // [n_grad_parts + B][32*32] d_trans partial sums
   int* tsz;       // [B]
   int* valid;     // [B]
   float* scale;   // [B]
   float* coef;    // [B] scale * dloss
 };
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // 1. prep
@@ -107,15 +131,23 @@ __global__ void __launch_bounds__(256) asg_prep_kernel(AsgParams p, int frame_bl
 // ------------------------------------------------------------------------------------------
 // 2a. FCC chains (linear domain)
 // ------------------------------------------------------------------------------------------
-// acc = sum_j M[j] * v[j] over the 32 shared-memory entries (broadcast LDS.128), mx = max_j v[j]
+// acc = sum_j M[j] * v[j] over the 32 shared-memory entries (broadcast LDS.128), mx = max_j v[j].
+// The eight loads are issued back to back through volatile asm: left to itself ptxas reuses one
+// register quad for successive loads, which serialises them into dependent ~30-cycle rounds
+// (41% short-scoreboard stalls in profiles/asg_chains_r1.md).
 __device__ __forceinline__ void matvec32(const float (&M)[kW], const float* vsm, float& acc, float& mx) {
-  const float4* v4 = reinterpret_cast<const float4*>(vsm);
+  const unsigned base = (unsigned)__cvta_generic_to_shared(vsm);
+  float4 v[kW / 4];
+#pragma unroll
+  for (int q = 0; q < kW / 4; ++q)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
+                 : "r"(base + 16u * q));
   float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
   float m0 = 0.f, m1 = 0.f;
 #pragma unroll
   for (int q = 0; q < kW / 4; ++q) {
-    float4 v = v4[q];
-    float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+    float2 lo = make_float2(v[q].x, v[q].y), hi = make_float2(v[q].z, v[q].w);
     float2 mlo = make_float2(M[4 * q], M[4 * q + 1]), mhi = make_float2(M[4 * q + 2], M[4 * q + 3]);
     if (q & 1) {
       a2 = __ffma2_rn(mlo, lo, a2);
@@ -124,18 +156,29 @@ __device__ __forceinline__ void matvec32(const float (&M)[kW], const float* vsm,
       a0 = __ffma2_rn(mlo, lo, a0);
       a1 = __ffma2_rn(mhi, hi, a1);
     }
-    m0 = fmaxf(fmaxf(m0, v.x), v.y);
-    m1 = fmaxf(fmaxf(m1, v.z), v.w);
+    m0 = fmaxf(fmaxf(m0, v[q].x), v[q].y);
+    m1 = fmaxf(fmaxf(m1, v[q].z), v[q].w);
   }
   float2 s = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
   acc = s.x + s.y;
   mx = fmaxf(m0, m1);
 }
 
-// 2^-k with k = unbiased exponent of mx (clamped); returns k through kout.  Exact.
+// 2^-k with k = (unbiased exponent of mx) >> kDamp; returns k through kout.  Exact.
+// kDamp = 1 for the alpha walk: its rescale acts with a lag of two steps (A_t = A_{t-1} + rho_t
+// - k(A_{t-2})), and the undamped feedback has its characteristic roots ON the unit circle, so the
+// exponent random-walks out of fp32 range within ~1000 frames; halving the correction puts the
+// roots at |lambda| = 0.71 (exponent stays within ~[-14, +3]; tests/test_kernel_math.py).  The
+// beta walk's rescale has lag one (dead-beat) and uses kDamp = 0.  mx >= 0, so the exponent
+// field is the top bits; for kDamp = 1, k lies in [-64, 64] and 127 - k is always a valid
+// exponent field; kDamp = 0 clamps.
+template <int kDamp>
 __device__ __forceinline__ float pow2_rescale(float mx, int& kout) {
-  int k = ((__float_as_int(mx) >> 23) & 0xff) - 127;
-  k = max(-126, min(126, k));
+  int k = (__float_as_int(mx) >> 23) - 127;
+  if (kDamp == 0)
+    k = max(-126, min(126, k));
+  else
+    k >>= kDamp;
   kout = k;
   return __int_as_float((127 - k) << 23);
 }
@@ -144,6 +187,7 @@ template <bool kGrad>
 __device__ void fcc_role(const AsgParams& p, int b) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ __align__(16) float vec[2][2][kW];
+  __shared__ float xring[2][kXRing][kW];
   __shared__ double msum_s;
   const int T = p.T, N = p.N;
   if (warp == 2) {  // sum of the per-frame maxima, off the chains
@@ -171,44 +215,41 @@ __device__ void fcc_role(const AsgParams& p, int b) {
     if (lane < N && j < N) v = __expf(__ldg(p.trans + (warp == 0 ? lane * N + j : j * N + lane)) - tmax);
     M[j] = v;
   }
-  const float* Xb = p.X + (size_t)b * T * kW;
-  float xq[kPrefetch];
+  const float* Xl = p.X + (size_t)b * T * kW + lane;  // this lane's column of X
+  float* xr = &xring[warp][0][lane];
 
   if (warp == 0) {
     // ---- alpha walk: a_t = (X_t * s_t) .* (M' a_{t-1}) ----------------------------------------
-    float* Ab = p.A + (size_t)b * T * kW;
+    float* Al = p.A + (size_t)b * T * kW + lane;
     float* sAb = p.sA + (size_t)b * T;
-    float a = Xb[lane];
+    float a = __ldg(Xl);
     if (kGrad) {
-      Ab[lane] = a;
+      Al[0] = a;
       if (lane == 0) sAb[0] = 1.0f;
     }
-#pragma unroll
-    for (int q = 0; q < kPrefetch; ++q) xq[q] = (1 + q < T) ? Xb[(size_t)(1 + q) * kW + lane] : 0.f;
+    for (int q = 1; q <= kXDepth; ++q) {  // group g (0-based) carries frame g + 1
+      if (q < T) cp_async4(xr + (q & (kXRing - 1)) * kW, Xl + (size_t)q * kW);
+      cp_async_commit();
+    }
     float s = 1.0f;
     int ksum = 0, kcur = 0;
-    int buf = 0;
-    for (int t0 = 1; t0 < T; t0 += kPrefetch) {
-#pragma unroll
-      for (int q = 0; q < kPrefetch; ++q) {
-        const int t = t0 + q;
-        if (t < T) {
-          vec[0][buf][lane] = a;
-          __syncwarp();
-          float acc, mx;
-          matvec32(M, vec[0][buf], acc, mx);
-          const float xs = xq[q] * s;
-          a = xs * acc;
-          ksum += kcur;
-          if (kGrad) {
-            Ab[(size_t)t * kW + lane] = a;
-            if (lane == 0) sAb[t] = s;
-          }
-          s = pow2_rescale(mx, kcur);  // applied at t+1; normalises by |a_{t-1}|
-          xq[q] = (t + kPrefetch < T) ? Xb[(size_t)(t + kPrefetch) * kW + lane] : 0.f;
-          buf ^= 1;
-        }
+    for (int t = 1; t < T; ++t) {
+      float* vb = vec[0][t & 1];
+      vb[lane] = a;
+      if (t + kXDepth < T) cp_async4(xr + ((t + kXDepth) & (kXRing - 1)) * kW, Xl + (size_t)(t + kXDepth) * kW);
+      cp_async_commit();
+      cp_async_wait<kXDepth>();  // the group carrying frame t has landed (own lane's element)
+      const float xs = xr[(t & (kXRing - 1)) * kW] * s;
+      __syncwarp();
+      float acc, mx;
+      matvec32(M, vb, acc, mx);
+      a = xs * acc;
+      ksum += kcur;
+      if (kGrad) {
+        Al[(size_t)t * kW] = a;
+        if (lane == 0) sAb[t] = s;
       }
+      s = pow2_rescale<1>(mx, kcur);  // applied at t+1 from |a_{t-1}| (lag two): damped
     }
     const float tot = warp_sum(a);
     asm volatile("bar.sync 1, 64;" ::: "memory");
@@ -218,404 +259,500 @@ __device__ void fcc_role(const AsgParams& p, int b) {
     }
   } else {
     // ---- beta walk: b_t = M'^T (X_{t+1} .* b_{t+1} * s) -----------------------------------------
-    float* Bb = p.Bh + (size_t)b * T * kW;
+    float* Bl = p.Bh + (size_t)b * T * kW + lane;
     float bh = lane < N ? 1.0f : 0.0f;
-    Bb[(size_t)(T - 1) * kW + lane] = bh;
-#pragma unroll
-    for (int q = 0; q < kPrefetch; ++q) xq[q] = (T - 1 - q >= 1) ? Xb[(size_t)(T - 1 - q) * kW + lane] : 0.f;
+    Bl[(size_t)(T - 1) * kW] = bh;
+    // step t (T-2 .. 0) consumes X_{t+1}; group g (0-based) carries frame T-1-g
+    for (int q = 0; q < kXDepth; ++q) {
+      const int f = T - 1 - q;
+      if (f >= 1) cp_async4(xr + (f & (kXRing - 1)) * kW, Xl + (size_t)f * kW);
+      cp_async_commit();
+    }
     float s = 1.0f;
     int kdummy;
-    int buf = 0;
-    for (int t0 = T - 2; t0 >= 0; t0 -= kPrefetch) {
-#pragma unroll
-      for (int q = 0; q < kPrefetch; ++q) {
-        const int t = t0 - q;
-        if (t >= 0) {
-          const float u = bh * (xq[q] * s);  // uses X_{t+1}
-          vec[1][buf][lane] = u;
-          __syncwarp();
-          float acc, mx;
-          matvec32(M, vec[1][buf], acc, mx);
-          bh = acc;
-          Bb[(size_t)t * kW + lane] = bh;
-          s = pow2_rescale(mx, kdummy);
-          xq[q] = (t + 1 - kPrefetch >= 1) ? Xb[(size_t)(t + 1 - kPrefetch) * kW + lane] : 0.f;
-          buf ^= 1;
-        }
-      }
+    for (int t = T - 2; t >= 0; --t) {
+      float* vb = vec[1][t & 1];
+      const int f = t + 1 - kXDepth;  // frame needed kXDepth steps from now
+      if (f >= 1) cp_async4(xr + (f & (kXRing - 1)) * kW, Xl + (size_t)f * kW);
+      cp_async_commit();
+      cp_async_wait<kXDepth>();
+      const float u = bh * (xr[((t + 1) & (kXRing - 1)) * kW] * s);  // uses X_{t+1}
+      vb[lane] = u;
+      __syncwarp();
+      float acc, mx;
+      matvec32(M, vb, acc, mx);
+      bh = acc;
+      Bl[(size_t)t * kW] = bh;
+      s = pow2_rescale<0>(mx, kdummy);
     }
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------
 // 2b. FAC chains (log domain, meet in the middle)
+//
+// CTA = 10 warps: warps 0-3 walk alpha (group 0), warps 4-7 walk beta (group 1), warp 8 / 9 are
+// the groups' FLUSH warps.  A compute thread owns target positions l = gt + 128 k (k < KMAX) and
+// keeps their label, transition scores and transition-gradient accumulators in registers; the
+// rows live in shared memory (neighbour exchange) and every global read is prefetched kFDepth
+// steps ahead with cp.async.  In phase 2 a compute thread writes its state occupancy to a
+// shared-memory row; the flush warp sums it per label through a label-sorted index (no atomics:
+// shared-memory fp32 atomics are CAS spin loops on sm_100) while the compute warps already run
+// the next step, and publishes the frame's normaliser (integer REDUX on a 2^28 fixed-point
+// image) that rescales the transition statistics two steps later.
 // ------------------------------------------------------------------------------------------
-struct FacSmem {
-  int32_t* y;
-  float* s1;
-  float* s2;
-  float* rowA[2];  // index l in [-1, Lp]
-  float* rowB[2];
-  float* ds1[2];  // [group]
-  float* ds2[2];
-  float* bins;   // [2 groups][2 bufs][32]
-  float* wmax;   // [2 groups][2 bufs][4]
-  float* ring;   // [2 groups][4][32]
-  float* rnorm;  // [2 groups][2]
-  float* red;    // [16]
-  double* dred;  // [4]
+struct FacLayout {  // offsets in 4-byte words from the start of dynamic shared memory
+  int cring, red, wmax, rnorm, ering, dtr, y, order, start, rows, gam, oring, total;
 };
-
-// floats: red 16, bins 128, wmax 16, ring 256, rnorm 4, y/s1/s2 3*(Lp+4), rows 4*(Lp+4), ds 4*Lp; + 4 doubles
-__host__ __device__ inline size_t fac_smem_bytes(int Lp) {
-  return (size_t)(16 + 128 + 16 + 256 + 4 + 3 * (Lp + 4) + 4 * (Lp + 4) + 4 * Lp) * 4 + 4 * 8;
+__host__ __device__ inline FacLayout fac_layout(int Lp, int oring) {
+  FacLayout f;
+  int o = 0;
+  f.cring = o;  o += 2 * (2 * kFRing + 4);       // doubles: [2][kFRing] (+4 spare)
+  f.red = o;    o += 16;
+  f.wmax = o;   o += 16;                         // [2 groups][2 bufs][4 warps]
+  f.rnorm = o;  o += 16;                         // [2 groups][2]
+  f.ering = o;  o += 2 * kFRing * 32;            // [2 groups][kFRing][32]
+  f.dtr = o;    o += kW * kW;
+  f.y = o;      o += Lp + 4;
+  f.order = o;  o += Lp;
+  f.start = o;  o += 36;
+  f.rows = o;   o += 4 * (Lp + 4);               // rowA[2], rowB[2], each with 2 pad slots on both sides
+  f.gam = o;    o += 4 * Lp;                     // [2 groups][2 bufs][Lp]
+  f.oring = o;  o += oring ? 2 * kFRing * Lp : 0;
+  f.total = o;
+  return f;
 }
-
-__device__ inline FacSmem fac_carve(unsigned char* raw, int Lp) {
-  FacSmem s;
-  double* d = reinterpret_cast<double*>(raw);
-  s.dred = d;
-  float* f = reinterpret_cast<float*>(d + 4);
-  s.red = f;
-  f += 16;
-  s.bins = f;
-  f += 2 * 2 * 32;
-  s.wmax = f;
-  f += 2 * 2 * 4;
-  s.ring = f;
-  f += 2 * 4 * 32;
-  s.rnorm = f;
-  f += 4;
-  s.y = reinterpret_cast<int32_t*>(f);
-  f += Lp + 4;
-  s.s1 = f;
-  f += Lp + 4;
-  s.s2 = f;
-  f += Lp + 4;
-  for (int k = 0; k < 2; ++k) {
-    s.rowA[k] = f + 2;
-    f += Lp + 4;
-  }
-  for (int k = 0; k < 2; ++k) {
-    s.rowB[k] = f + 2;
-    f += Lp + 4;
-  }
-  for (int k = 0; k < 2; ++k) {
-    s.ds1[k] = f;
-    f += Lp;
-    s.ds2[k] = f;
-    f += Lp;
-  }
-  return s;
-}
+__host__ __device__ inline size_t fac_smem_bytes(int Lp, int oring) { return (size_t)fac_layout(Lp, oring).total * 4; }
 
 __device__ __forceinline__ float max4_guard(const float* w) {
   float d = fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3]));
   return (d > -1e30f) ? d : 0.0f;
 }
 
-template <bool kGrad>
-__device__ void fac_role(const AsgParams& p, int b, unsigned char* smem_raw) {
+// State of one group's walk; every method is force-inlined so the fields live in registers.
+template <int KMAX>
+struct FacWalk {
+  const AsgParams& p;
+  int b, grp, gt, gw, lane, T, N, L, Lp, dir, p2_lo, p2_hi, cur;
+  bool use_oring, p2_open;
+  const float* eb;
+  float *rowbase, *wmax, *ering, *oring, *gam, *rnorm;
+  double* cring;
+  const float* other_base;
+  const double* other_c;
+  double C;
+  int yk[KMAX];
+  float s1k[KMAX], s2k[KMAX], ds1k[KMAX], ds2k[KMAX];
+
+  __device__ __forceinline__ explicit FacWalk(const AsgParams& p_) : p(p_) {}
+  __device__ __forceinline__ const float* other_row(int t) const {
+    return other_base + (size_t)(grp == 0 ? t - p.h : t) * Lp;
+  }
+  __device__ __forceinline__ float* row(int k) const { return rowbase + k * (Lp + 4); }
+  __device__ __forceinline__ void issue_other(int t) {
+    if (t >= p2_lo && t <= p2_hi) {
+      if (use_oring) {
+        const float* src = other_row(t);
+        float* dst = oring + (size_t)(t & (kFRing - 1)) * Lp;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = gt + k * kGroup;
+          if (l < L) cp_async4(dst + l, src + l);
+        }
+      }
+      if (gt == 0) cp_async8(cring + (t & (kFRing - 1)), other_c + t);
+    }
+  }
+  // issue (one commit group) the asynchronous copies that step `t` of this walk will consume
+  __device__ __forceinline__ void issue(int t) {
+    if (t >= 0 && t < T) {
+      if (gt < N) cp_async4(ering + (t & (kFRing - 1)) * 32 + gt, eb + (size_t)t * N + gt);
+      if (p2_open) issue_other(t);
+    }
+    cp_async_commit();
+  }
+  // One step of this group's walk at frame t: computes row[cur^1] from row[cur] (re-centred by
+  // the previous row's maximum).  kMode 0: plain; 1: also store the row to the half lattice;
+  // 2: phase 2 — also emit occupancies / transition statistics from the other group's row.
+  template <int kMode>
+  __device__ __forceinline__ void step(int t, double logZ) {
+    const float delta = max4_guard(wmax + cur * 4);
+    issue(t + dir * kFDepth);
+    const int lo = max(0, L - (T - t)), hi = min(t, L - 1);
+    const float* rp = row(cur);
+    float* rn = row(cur ^ 1);
+    const float* fr = ering + (t & (kFRing - 1)) * 32;
+    float Kd = 0.f, rn_lag = 1.f;
+    const float* orow = nullptr;
+    float* gm = nullptr;
+    float* srow = nullptr;
+    if (kMode == 1)
+      srow = grp == 0 ? p.facA + ((size_t)b * p.h + t) * Lp : p.facB + ((size_t)b * (T - p.h) + (t - p.h)) * Lp;
+    if (kMode == 2) {
+      // K = C_prev + C_other(t) - logZ ; xi = exp(a + o + K + delta) with a already re-centred
+      Kd = (float)(C + cring[t & (kFRing - 1)] - logZ) + delta;
+      orow = use_oring ? oring + (size_t)(t & (kFRing - 1)) * Lp : other_row(t);
+      gm = gam + (t & 1) * Lp;
+      rn_lag = rnorm[t & 1];  // normaliser of two steps ago (written by the flush warp)
+    }
+    C += (double)delta;
+    float lmax = kNegInf;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int l = gt + k * kGroup;
+      if (l < L) {
+        const float a0 = rp[l] + (s1k[k] - delta);
+        const float a1 = rp[l - dir] + (s2k[k] - delta);  // pads and missing transitions are -inf
+        float val = kNegInf;
+        if (l >= lo && l <= hi) val = fr[yk[k]] + lse2f(a0, a1);
+        rn[l] = val;
+        lmax = fmaxf(lmax, val);
+        if (kMode == 1) srow[l] = val;
+        if (kMode == 2) {
+          const float o = orow[l] + Kd;
+          const float xs = __expf(a0 + o);
+          const float xa = __expf(a1 + o);
+          ds1k[k] = fmaf(xs, rn_lag, ds1k[k]);
+          ds2k[k] = fmaf(xa, rn_lag, ds2k[k]);
+          gm[l] = xs + xa;
+        }
+      }
+    }
+    const float wm = warp_max(lmax);
+    if (lane == 0) wmax[(cur ^ 1) * 4 + gw] = wm;
+    if (kMode == 1 && gt == 0) (grp == 0 ? p.cA : p.cB)[(size_t)b * T + t] = C;
+    cur ^= 1;
+    cp_async_wait<kFDepth - 1>();  // everything the next step needs has landed (this thread's copies)
+    if (kMode == 2)
+      named_barrier_sync(4 + grp, kGroup + 32);  // compute warps + flush warp
+    else
+      named_barrier_sync(2 + grp, kGroup);
+  }
+};
+
+// flush warp: occupancy of frame t per label from the group's gamma row, through the label-sorted index
+__device__ __forceinline__ void fac_flush(const float* gm, const int* order, const int* start, int lane, float* Grow,
+                                          float* rnorm_slot) {
+  float s = 0.f;
+  const int i0 = start[lane], i1 = start[lane + 1];
+  for (int i = i0; i < i1; ++i) s += gm[order[i]];
+  const int tot_i = __reduce_add_sync(0xffffffffu, __float2int_rn(s * kFix));
+  Grow[lane] = s;
+  if (lane == 0) *rnorm_slot = tot_i > 0 ? __fdividef(kFix, (float)tot_i) : 0.f;
+}
+
+template <bool kGrad, int KMAX>
+__device__ void fac_role(const AsgParams& p, int b, float* smem) {
   const int tid = threadIdx.x;
-  const int grp = tid / kGroup;       // 0: alpha walk, 1: beta walk
-  const int gt = tid % kGroup;        // thread within group
-  const int gw = gt >> 5, lane = tid & 31;
   const int T = p.T, N = p.N, Lp = p.Lp;
   const int L = p.tsz[b];
-  FacSmem sm = fac_carve(smem_raw, Lp);
+  const FacLayout lay = fac_layout(Lp, p.oring);
+  int* y_s = reinterpret_cast<int*>(smem + lay.y);
+  int* order_s = reinterpret_cast<int*>(smem + lay.order);
+  int* start_s = reinterpret_cast<int*>(smem + lay.start);
+  float* dtr_s = smem + lay.dtr;
+  float* red_s = smem + lay.red;
+  const bool is_flush = tid >= 2 * kGroup;
+  const int grp = is_flush ? (tid - 2 * kGroup) >> 5 : tid / kGroup;  // 0: alpha walk, 1: beta walk
+  const int gt = is_flush ? 0 : tid % kGroup;
+  const int gw = gt >> 5, lane = tid & 31;
   const float* eb = p.emis + (size_t)b * T * N;
   float* Gb = p.G + (size_t)b * T * kW;
+  float* part = p.parts ? p.parts + (size_t)(p.n_grad_parts + b) * (kW * kW) : nullptr;
 
   if (!p.valid[b]) {
     if (tid == 0) p.facLogZ[b] = (double)NAN;
+    if (kGrad && part)
+      for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = 0.f;
     return;  // whole CTA (uniform)
   }
   const int32_t* yg = p.target + (size_t)b * p.L;
-  for (int l = tid; l < Lp; l += kChainThreads) {
-    int yl = l < L ? yg[l] : 0;
-    sm.y[l] = yl;
-    sm.s1[l] = l < L ? __ldg(p.trans + yl * N + yl) : 0.f;
-    sm.s2[l] = (l < L && l > 0) ? __ldg(p.trans + yl * N + yg[l - 1]) : kNegInf;
-    if (kGrad) {
-      sm.ds1[0][l] = sm.ds1[1][l] = 0.f;
-      sm.ds2[0][l] = sm.ds2[1][l] = 0.f;
-    }
-  }
-  for (int l = tid; l < Lp + 4; l += kChainThreads) {
-    sm.rowA[0][l - 2] = sm.rowA[1][l - 2] = kNegInf;
-    sm.rowB[0][l - 2] = sm.rowB[1][l - 2] = kNegInf;
-  }
-  if (tid < 2 * 2 * 32) sm.bins[tid] = 0.f;
-  if (tid < 4) sm.rnorm[tid] = 1.0f;
-  __syncthreads();
+  for (int l = tid; l < Lp + 4; l += kChainThreads) y_s[l] = l < L ? yg[l] : 0;
+  for (int l = tid; l < 4 * (Lp + 4); l += kChainThreads) smem[lay.rows + l] = kNegInf;
+  if (kGrad)
+    for (int k = tid; k < kW * kW; k += kChainThreads) dtr_s[k] = 0.f;
+  if (tid < 16) smem[lay.rnorm + tid] = 1.0f;
+  __syncthreads();  // S1
 
   if (T == 1) {  // single frame: the only alignment is (0,0); L was clamped to 1
-    if (tid == 0) p.facLogZ[b] = (double)eb[sm.y[0]];
-    if (kGrad && tid < kW) Gb[tid] = (tid == sm.y[0]) ? 1.0f : 0.0f;
+    if (tid == 0) p.facLogZ[b] = (double)eb[y_s[0]];
+    if (kGrad && tid < kW) Gb[tid] = (tid == y_s[0]) ? 1.0f : 0.0f;
+    if (kGrad && part)
+      for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = 0.f;
     return;
   }
-  const int h = kGrad ? p.h : T;  // forward only: the alpha group walks the whole sequence
-  float* row[2] = {grp == 0 ? sm.rowA[0] : sm.rowB[0], grp == 0 ? sm.rowA[1] : sm.rowB[1]};
-  float* wmax = sm.wmax + grp * 8;
-  float* ring = sm.ring + grp * 4 * 32;
-  float* bins = sm.bins + grp * 64;
-  float* rnorm = sm.rnorm + grp * 2;
-  float* ds1 = sm.ds1[grp];
-  float* ds2 = sm.ds2[grp];
-  const int bar_id = 2 + grp;
-  const int dir = grp == 0 ? 1 : -1;
-  double C = 0.0;  // re-centring offset of the current row (uniform across the group)
-  int cur = 0;
-
-  // ring[t & 3][i] = e_t[i]; preload the first three frames of this group's walk
-  const int t_first = grp == 0 ? 0 : T - 1;
-  if (gt < N) {
-    for (int q = 0; q < 3; ++q) {
-      int t = t_first + dir * q;
-      if (t >= 0 && t < T) ring[(t & 3) * 32 + gt] = __ldg(eb + (size_t)t * N + gt);
+  if (kGrad) {
+    // label-sorted index of the target positions (stable, deterministic): lane k lists y_l == k
+    if (tid < 32) {
+      int cnt = 0;
+      for (int l = 0; l < L; ++l) cnt += (y_s[l] == tid);
+      int pre = cnt;  // inclusive scan over the 32 labels
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (tid >= o) pre += v;
+      }
+      int w0 = pre - cnt;
+      start_s[tid] = w0;
+      if (tid == 31) start_s[32] = pre;
+      for (int l = 0; l < L; ++l)
+        if (y_s[l] == tid) order_s[w0++] = l;
     }
+    __syncthreads();  // S1b
+  } else if (is_flush || grp == 1) {
+    return;  // forward only: the alpha group walks the whole sequence alone
   }
-  named_barrier_sync(bar_id, kGroup);
+
+  const int h = kGrad ? p.h : T;
+  float* ering_g = smem + lay.ering + grp * kFRing * 32;
+  float* gam_g = smem + lay.gam + grp * 2 * Lp;
+  float* rnorm_g = smem + lay.rnorm + grp * 2;
+
+  if (is_flush) {
+    // ---- flush warp: sleeps on the phase-2 barrier of its group, one frame per release ----------
+    __syncthreads();  // S2 (mid-point)
+    __syncthreads();  // S3
+    __syncthreads();  // S4 (phase 2 open)
+    if (grp == 0) {
+      for (int t = h; t < T; ++t) {
+        named_barrier_sync(4, kGroup + 32);
+        fac_flush(gam_g + (t & 1) * Lp, order_s, start_s, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
+      }
+    } else {
+      for (int t = h - 1; t >= 0; --t) {
+        named_barrier_sync(5, kGroup + 32);
+        fac_flush(gam_g + (t & 1) * Lp, order_s, start_s, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
+      }
+    }
+    __syncthreads();  // S5
+    __syncthreads();  // S6
+    if (part != nullptr)
+      for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = dtr_s[k];
+    return;
+  }
+
+  // ---- compute warps ------------------------------------------------------------------------------
+  FacWalk<KMAX> w(p);
+  w.b = b;
+  w.grp = grp;
+  w.gt = gt;
+  w.gw = gw;
+  w.lane = lane;
+  w.T = T;
+  w.N = N;
+  w.L = L;
+  w.Lp = Lp;
+  w.eb = eb;
+  w.rowbase = smem + lay.rows + grp * 2 * (Lp + 4) + 2;
+  w.wmax = smem + lay.wmax + grp * 8;
+  w.ering = ering_g;
+  w.cring = reinterpret_cast<double*>(smem + lay.cring) + grp * kFRing;
+  w.oring = smem + lay.oring + (size_t)grp * kFRing * Lp;
+  w.gam = gam_g;
+  w.rnorm = rnorm_g;
+  w.dir = grp == 0 ? 1 : -1;
+  w.use_oring = p.oring != 0;
+  // phase-2 sources: the OTHER group's stored half lattice and offsets
+  w.other_base = grp == 0 ? p.facB + (size_t)b * (T - p.h) * Lp : p.facA + (size_t)b * p.h * Lp;
+  w.other_c = (grp == 0 ? p.cB : p.cA) + (size_t)b * T;
+  w.p2_lo = grp == 0 ? p.h + 1 : 0;
+  w.p2_hi = grp == 0 ? T - 1 : p.h - 1;
+  w.p2_open = false;  // the other group's rows exist only after the mid-point barrier
+  w.C = 0.0;          // re-centring offset of the current row (uniform across the group)
+  w.cur = 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int l = gt + k * kGroup;
+    const int yl = l < L ? y_s[l] : 0;
+    w.yk[k] = yl;
+    w.s1k[k] = l < L ? __ldg(p.trans + yl * N + yl) : 0.f;
+    float s2 = kNegInf;
+    if (grp == 0) {
+      if (l < L && l > 0) s2 = __ldg(p.trans + yl * N + y_s[l - 1]);  // transition l-1 -> l
+    } else {
+      if (l + 1 < L) s2 = __ldg(p.trans + y_s[l + 1] * N + yl);       // transition l -> l+1
+    }
+    w.s2k[k] = s2;
+    w.ds1k[k] = 0.f;
+    w.ds2k[k] = 0.f;
+  }
+  const int bar_c = 2 + grp, dir = w.dir;
+  const int t_first = grp == 0 ? 0 : T - 1;
+  // group g (0-based) carries the frame at walk offset g; offsets 0..kFDepth are issued here,
+  // step at offset q issues offset q + kFDepth and, before its barrier, waits until at most
+  // kFDepth-1 groups are pending, i.e. offset q+1 has landed.
+  for (int q = 0; q <= kFDepth; ++q) w.issue(t_first + dir * q);
+  cp_async_wait<kFDepth - 1>();
+  named_barrier_sync(bar_c, kGroup);
 
   // ---- initial row ------------------------------------------------------------------------
   {
     float lmax = kNegInf;
+    float* r0 = w.row(0);
     if (grp == 0) {
+      const float v = ering_g[(0 & (kFRing - 1)) * 32 + y_s[0]];
       if (gt == 0) {
-        float v = ring[(0 & 3) * 32 + sm.y[0]];
-        row[0][0] = v;
+        r0[0] = v;
         lmax = v;
-        if (kGrad) p.facA[((size_t)b * p.h + 0) * Lp + 0] = v;
+        if (kGrad) p.cA[(size_t)b * T] = 0.0;
       }
       if (kGrad)
-        for (int l = gt + (gt == 0 ? kGroup : 0); l < L; l += kGroup) p.facA[((size_t)b * p.h + 0) * Lp + l] = kNegInf;
-      if (kGrad && gt == 0) p.cA[(size_t)b * T] = 0.0;
+        for (int l = gt; l < L; l += kGroup) p.facA[((size_t)b * p.h + 0) * Lp + l] = (l == 0) ? v : kNegInf;
     } else {
+      const float v = ering_g[((T - 1) & (kFRing - 1)) * 32 + y_s[L - 1]];
       if (gt == 0) {
-        float v = ring[((T - 1) & 3) * 32 + sm.y[L - 1]];
-        row[0][L - 1] = v;
+        r0[L - 1] = v;
         lmax = v;
+        p.cB[(size_t)b * T + T - 1] = 0.0;
       }
       for (int l = gt; l < L; l += kGroup)
-        p.facB[((size_t)b * (T - p.h) + (T - 1 - p.h)) * Lp + l] = (l == L - 1) ? ring[((T - 1) & 3) * 32 + sm.y[L - 1]] : kNegInf;
-      if (gt == 0) p.cB[(size_t)b * T + T - 1] = 0.0;
+        p.facB[((size_t)b * (T - p.h) + (T - 1 - p.h)) * Lp + l] = (l == L - 1) ? v : kNegInf;
     }
     float wm = warp_max(lmax);
-    if (lane == 0) wmax[0 * 4 + gw] = wm;
-    named_barrier_sync(bar_id, kGroup);
+    if (lane == 0) w.wmax[0 * 4 + gw] = wm;
+    named_barrier_sync(bar_c, kGroup);
   }
-
-  // one step of this group's walk: computes row[cur^1] at frame t from row[cur]; optionally
-  // stores the new row to the half lattice.  Returns nothing; state in smem.
-  auto step = [&](int t, bool store) {
-    const int prev = cur, nxt = cur ^ 1;
-    const float delta = max4_guard(wmax + prev * 4);
-    C += (double)delta;
-    // stage the frame two steps ahead into the ring
-    const int tp = t + 2 * dir;
-    float pf = 0.f;
-    const bool do_pf = gt < N && tp >= 0 && tp < T;
-    if (do_pf) pf = __ldg(eb + (size_t)tp * N + gt);
-    const int lo = max(0, L - (T - t)), hi = min(t, L - 1);
-    const float* rp = row[prev];
-    float* rn = row[nxt];
-    const float* fr = ring + (t & 3) * 32;
-    float lmax = kNegInf;
-    for (int l = gt; l < L; l += kGroup) {
-      float val = kNegInf;
-      if (l >= lo && l <= hi) {
-        float a0, a1;
-        if (grp == 0) {
-          a0 = rp[l] + (sm.s1[l] - delta);
-          a1 = rp[l - 1] + (sm.s2[l] - delta);
-        } else {
-          a0 = rp[l] + (sm.s1[l] - delta);
-          a1 = (l + 1 < L) ? rp[l + 1] + (sm.s2[l + 1] - delta) : kNegInf;
-        }
-        val = fr[sm.y[l]] + lse2f(a0, a1);
-      }
-      rn[l] = val;
-      lmax = fmaxf(lmax, val);
-      if (store) {
-        if (grp == 0)
-          p.facA[((size_t)b * p.h + t) * Lp + l] = val;
-        else
-          p.facB[((size_t)b * (T - p.h) + (t - p.h)) * Lp + l] = val;
-      }
-    }
-    float wm = warp_max(lmax);
-    if (lane == 0) wmax[nxt * 4 + gw] = wm;
-    if (store && gt == 0) (grp == 0 ? p.cA : p.cB)[(size_t)b * T + t] = C;
-    if (do_pf) ring[(tp & 3) * 32 + gt] = pf;
-    cur = nxt;
-  };
 
   // ---- phase 1: walk to the middle, storing the half lattices ---------------------------------
   if (grp == 0) {
-    for (int t = 1; t < h; ++t) {
-      step(t, kGrad);
-      named_barrier_sync(bar_id, kGroup);
+    if (kGrad) {
+      for (int t = 1; t < h; ++t) w.template step<1>(t, 0.0);
+    } else {
+      for (int t = 1; t < h; ++t) w.template step<0>(t, 0.0);
     }
-  } else if (kGrad) {
-    for (int t = T - 2; t >= h; --t) {
-      step(t, true);
-      named_barrier_sync(bar_id, kGroup);
-    }
+  } else {
+    for (int t = T - 2; t >= h; --t) w.template step<1>(t, 0.0);
   }
   if (!kGrad) {
-    if (grp == 0 && gt == 0) p.facLogZ[b] = (double)row[cur][L - 1] + C;
+    if (gt == 0) p.facLogZ[b] = (double)w.row(w.cur)[L - 1] + w.C;
+    cp_async_wait<0>();
     return;
   }
-  __syncthreads();
+  __syncthreads();  // S2
 
   // ---- junction at t = h: alpha group computes alpha_h; partition function from alpha_h + beta_h
-  // beta group's current row (frame h) lives in sm.rowB[curB]; both groups ran the same number of
-  // steps when T is even, one apart when odd -> publish the buffer index.
   __shared__ int curB_s;
   __shared__ double CB_h_s, logZ_s;
   if (grp == 1 && gt == 0) {
-    curB_s = cur;
-    CB_h_s = C;
+    curB_s = w.cur;
+    CB_h_s = w.C;
   }
-  __syncthreads();
+  __syncthreads();  // S3
   if (grp == 0) {
-    const float* rb = sm.rowB[curB_s];
-    const double C_prev = C;
-    (void)C_prev;
-    step(h, false);  // row[cur] = alpha-tilde_h, offset C
-    // the ring slot of frame h was loaded by this group (alpha ring holds frames h-1.. h+2)
-    named_barrier_sync(bar_id, kGroup);
-    const float* ra = row[cur];
-    const float* fr = ring + (h & 3) * 32;
+    const float* rb = smem + lay.rows + (2 + curB_s) * (Lp + 4) + 2;
+    w.template step<0>(h, 0.0);  // row[cur] = alpha-tilde_h, offset C
+    const float* ra = w.row(w.cur);
+    const float* fr = ering_g + (h & (kFRing - 1)) * 32;
+    float qk[KMAX];
     float qmax = kNegInf;
-    for (int l = gt; l < L; l += kGroup) qmax = fmaxf(qmax, ra[l] + rb[l] - fr[sm.y[l]]);
-    qmax = warp_max(qmax);
-    if (lane == 0) sm.red[gw] = qmax;
-    named_barrier_sync(bar_id, kGroup);
-    qmax = fmaxf(fmaxf(sm.red[0], sm.red[1]), fmaxf(sm.red[2], sm.red[3]));
-    float part = 0.f;
-    for (int l = gt; l < L; l += kGroup) {
-      float q = ra[l] + rb[l] - fr[sm.y[l]];
-      part += (q == kNegInf) ? 0.f : __expf(q - qmax);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int l = gt + k * kGroup;
+      qk[k] = l < L ? ra[l] + rb[l] - fr[w.yk[k]] : kNegInf;
+      qmax = fmaxf(qmax, qk[k]);
     }
-    part = warp_sum(part);
-    if (lane == 0) sm.red[4 + gw] = part;
-    named_barrier_sync(bar_id, kGroup);
-    const float tot = sm.red[4] + sm.red[5] + sm.red[6] + sm.red[7];
+    qmax = warp_max(qmax);
+    if (lane == 0) red_s[gw] = qmax;
+    named_barrier_sync(bar_c, kGroup);
+    qmax = fmaxf(fmaxf(red_s[0], red_s[1]), fmaxf(red_s[2], red_s[3]));
+    float part_sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      qk[k] = (qk[k] == kNegInf) ? 0.f : __expf(qk[k] - qmax);
+      part_sum += qk[k];
+    }
+    part_sum = warp_sum(part_sum);
+    if (lane == 0) red_s[4 + gw] = part_sum;
+    named_barrier_sync(bar_c, kGroup);
+    const float tot = red_s[4] + red_s[5] + red_s[6] + red_s[7];
     if (gt == 0) {
-      double lz = C + CB_h_s + (double)qmax + log((double)tot);
+      double lz = w.C + CB_h_s + (double)qmax + log((double)tot);
       logZ_s = lz;
       p.facLogZ[b] = lz;
     }
-    // occupancy of frame h
-    float* bn = bins + (h & 1) * 32;
+    // occupancy of frame h -> gamma row; the flush warp takes it at the first phase-2 barrier
+    float* gm = gam_g + (h & 1) * Lp;
     const float inv = 1.0f / tot;
-    for (int l = gt; l < L; l += kGroup) {
-      float q = ra[l] + rb[l] - fr[sm.y[l]];
-      float g = (q == kNegInf) ? 0.f : __expf(q - qmax) * inv;
-      if (g > 0.f) atomicAdd(&bn[sm.y[l]], g);
-    }
-    named_barrier_sync(bar_id, kGroup);
-    if (gt < kW) {
-      Gb[(size_t)h * kW + gt] = bn[gt];
-      bn[gt] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int l = gt + k * kGroup;
+      if (l < L) gm[l] = qk[k] * inv;
     }
   }
-  __syncthreads();
+  // Open phase 2: the half lattices are complete (barrier above); catch up on the other group's
+  // rows for the first kFDepth steps (their frame copies are already in flight), one extra
+  // commit group, drained before the walks resume.
+  {
+    w.p2_open = true;
+    const int t_next = grp == 0 ? h + 1 : h - 1;
+    for (int q = 0; q < kFDepth; ++q) w.issue_other(t_next + dir * q);
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  __syncthreads();  // S4
   const double logZ = logZ_s;
 
   // ---- phase 2: finish the walks, emitting occupancies and transition statistics --------------
   // alpha group: t = h+1 .. T-1, transitions (t-1 -> t), reads stored beta-tilde_t
   // beta  group: t = h-1 .. 0,   transitions (t -> t+1), reads stored alpha-tilde_t
-  auto phase2_step = [&](int t) {
-    const int prev = cur;  // row[prev]: alpha_{t-1} (grp 0) or beta_{t+1} (grp 1), offset C
-    const double C_prev = C;
-    const float* rp = row[prev];
-    float K;
-    const float* other;
-    if (grp == 0) {
-      K = (float)(C_prev + p.cB[(size_t)b * T + t] - logZ);
-      other = p.facB + ((size_t)b * (T - p.h) + (t - p.h)) * Lp;
-    } else {
-      K = (float)(p.cA[(size_t)b * T + t] + C_prev - logZ);
-      other = p.facA + ((size_t)b * p.h + t) * Lp;
-    }
-    float* bn = bins + (t & 1) * 32;
-    const float rn_lag = rnorm[t & 1];  // normaliser of two steps ago (see flush below)
-    for (int l = gt; l < L; l += kGroup) {
-      const float o = other[l];  // written by the other group in phase 1: plain (coherent) load
-      float xs, xa;
-      if (grp == 0) {
-        xs = __expf(rp[l] + sm.s1[l] + o + K);
-        xa = __expf(rp[l - 1] + sm.s2[l] + o + K);
-        ds1[l] += xs * rn_lag;
-        ds2[l] += xa * rn_lag;
-      } else {
-        xs = __expf(o + sm.s1[l] + rp[l] + K);
-        xa = (l + 1 < L) ? __expf(o + sm.s2[l + 1] + rp[l + 1] + K) : 0.f;
-        ds1[l] += xs * rn_lag;
-        if (l + 1 < L) ds2[l + 1] += xa * rn_lag;
-      }
-      const float g = xs + xa;
-      if (g > 0.f) atomicAdd(&bn[sm.y[l]], g);
-    }
-    step(t, false);
-    named_barrier_sync(bar_id, kGroup);
-    // flush this frame's occupancy, renormalised so that it sums to one (removes the common-mode
-    // rounding error of the fp32 log-domain walk); the normaliser is reused two steps later for the
-    // transition statistics.
-    if (gw == 0) {
-      float v = bn[lane];
-      float tot = warp_sum(v);
-      float inv = tot > 0.f ? 1.0f / tot : 0.f;
-      Gb[(size_t)t * kW + lane] = v * inv;
-      bn[lane] = 0.f;
-      if (lane == 0) rnorm[t & 1] = inv;
-    }
-  };
   if (grp == 0) {
-    for (int t = h + 1; t < T; ++t) phase2_step(t);
+    named_barrier_sync(4, kGroup + 32);  // releases the flush of frame h
+    for (int t = h + 1; t < T; ++t) w.template step<2>(t, logZ);
   } else {
-    for (int t = h - 1; t >= 0; --t) phase2_step(t);
+    for (int t = h - 1; t >= 0; --t) w.template step<2>(t, logZ);
   }
-  __syncthreads();
-  // transition-gradient scatter: FAC enters ASG with a minus sign
-  if (p.d_trans != nullptr) {
+  cp_async_wait<0>();
+  __syncthreads();  // S5
+  // transition-gradient partial of this CTA: FAC enters ASG with a minus sign
+  if (part != nullptr) {
     const float sgn = (p.terms & W2L_TERM_FCC) ? -1.0f : 1.0f;
     const float c = sgn * p.coef[b];
-    for (int l = tid; l < L; l += kChainThreads) {
-      const int yl = sm.y[l];
-      float v1 = sm.ds1[0][l] + sm.ds1[1][l];
-      if (v1 != 0.f) atomicAdd(p.d_trans + yl * N + yl, c * v1);
-      if (l > 0) {
-        float v2 = sm.ds2[0][l] + sm.ds2[1][l];
-        if (v2 != 0.f) atomicAdd(p.d_trans + yl * N + sm.y[l - 1], c * v2);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int l = gt + k * kGroup;
+      if (l < L) {
+        const int yl = w.yk[k];
+        if (w.ds1k[k] != 0.f) atomicAdd(&dtr_s[yl * kW + yl], c * w.ds1k[k]);
+        if (w.ds2k[k] != 0.f) {
+          if (grp == 0) {
+            if (l > 0) atomicAdd(&dtr_s[yl * kW + y_s[l - 1]], c * w.ds2k[k]);
+          } else {
+            if (l + 1 < L) atomicAdd(&dtr_s[y_s[l + 1] * kW + yl], c * w.ds2k[k]);
+          }
+        }
       }
     }
   }
+  __syncthreads();  // S6
+  if (part != nullptr)
+    for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = dtr_s[k];
 }
 
-template <bool kGrad>
+template <bool kGrad, int KMAX>
 __global__ void __launch_bounds__(kChainThreads) asg_chains_kernel(AsgParams p, int n_fac) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) float smem_dyn[];
   if ((int)blockIdx.x < n_fac) {
-    fac_role<kGrad>(p, blockIdx.x, smem_raw);
+    fac_role<kGrad, KMAX>(p, blockIdx.x, smem_dyn);
   } else {
     fcc_role<kGrad>(p, blockIdx.x - n_fac);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// 3. gradient assembly (parallel)
+// 3. gradient assembly (parallel) — one CTA = kGradWarps warps x kGradChunk frames of one sample
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) asg_grad_kernel(AsgParams p) {
+__global__ void __launch_bounds__(kGradWarps * 32) asg_grad_kernel(AsgParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int chunk = blockIdx.x * 4 + warp;
+  const int chunk = blockIdx.x * kGradWarps + warp;
   const int T = p.T, N = p.N;
   const int t0 = chunk * kGradChunk, t1 = min(T, t0 + kGradChunk);
   const bool has_fcc = p.terms & W2L_TERM_FCC, has_fac = p.terms & W2L_TERM_FAC;
+  const bool want_dtr = has_fcc && p.parts != nullptr;
   const int ok = p.valid[b];
+  __shared__ __align__(16) float aprev_s[kGradWarps][kW];
+  __shared__ float acc_s[kGradWarps][kW][kW + 1];
   if (chunk == 0 && lane == 0) {
     float l = NAN;
     if (ok) {
@@ -626,64 +763,91 @@ __global__ void __launch_bounds__(128) asg_grad_kernel(AsgParams p) {
     }
     p.loss[b] = l;
   }
-  if (t0 >= T || p.d_emis == nullptr) return;
-  float* de = p.d_emis + (size_t)b * T * N;
-  if (!ok) {
-    for (int t = t0; t < t1; ++t)
-      if (lane < N) de[(size_t)t * N + lane] = 0.f;
-    return;
-  }
-  __shared__ __align__(16) float aprev_s[4][kW];
-  const float coef = p.coef[b];
-  const float sG = has_fac ? (has_fcc ? -1.f : 1.f) : 0.f;
-  const float* Ab = p.A + (size_t)b * T * kW;
-  const float* Bb = p.Bh + (size_t)b * T * kW;
-  const float* Xb = p.X + (size_t)b * T * kW;
-  const float* Gb = p.G + (size_t)b * T * kW;
   float acc[kW];
 #pragma unroll
   for (int j = 0; j < kW; ++j) acc[j] = 0.f;
-  for (int t = t0; t < t1; ++t) {
-    float gam = 0.f;
-    if (has_fcc) {
-      const float a = Ab[(size_t)t * kW + lane];
-      const float bh = Bb[(size_t)t * kW + lane];
-      const float g = a * bh;
-      const float gs = warp_sum(g);
-      gam = g / gs;
-      if (t >= 1 && p.d_trans != nullptr) {
-        const float w = Xb[(size_t)t * kW + lane] * bh * (p.sA[(size_t)b * T + t] / gs);
-        aprev_s[warp][lane] = Ab[(size_t)(t - 1) * kW + lane];
-        __syncwarp();
-        const float4* v4 = reinterpret_cast<const float4*>(aprev_s[warp]);
+  if (t0 < T && p.d_emis != nullptr) {
+    float* de = p.d_emis + (size_t)b * T * N;
+    if (!ok) {
+      for (int t = t0; t < t1; ++t)
+        if (lane < N) de[(size_t)t * N + lane] = 0.f;
+    } else {
+      const float coef = p.coef[b];
+      const float sG = has_fac ? (has_fcc ? -1.f : 1.f) : 0.f;
+      const float* Ab = p.A + (size_t)b * T * kW;
+      const float* Bb = p.Bh + (size_t)b * T * kW;
+      const float* Xb = p.X + (size_t)b * T * kW;
+      const float* Gb = p.G + (size_t)b * T * kW;
+      for (int t = t0; t < t1; ++t) {
+        float gam = 0.f;
+        if (has_fcc) {
+          const float a = Ab[(size_t)t * kW + lane];
+          const float bh = Bb[(size_t)t * kW + lane];
+          const float g = a * bh;
+          const float gs = warp_sum(g);
+          gam = g / gs;
+          if (t >= 1 && want_dtr) {
+            const float w = Xb[(size_t)t * kW + lane] * bh * (p.sA[(size_t)b * T + t] / gs);
+            aprev_s[warp][lane] = Ab[(size_t)(t - 1) * kW + lane];
+            __syncwarp();
+            const float4* v4 = reinterpret_cast<const float4*>(aprev_s[warp]);
 #pragma unroll
-        for (int q = 0; q < kW / 4; ++q) {
-          float4 v = v4[q];
-          acc[4 * q + 0] = fmaf(w, v.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(w, v.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(w, v.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(w, v.w, acc[4 * q + 3]);
+            for (int q = 0; q < kW / 4; ++q) {
+              float4 v = v4[q];
+              acc[4 * q + 0] = fmaf(w, v.x, acc[4 * q + 0]);
+              acc[4 * q + 1] = fmaf(w, v.y, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(w, v.z, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(w, v.w, acc[4 * q + 3]);
+            }
+            __syncwarp();
+          }
         }
-        __syncwarp();
+        float gf = 0.f;
+        if (has_fac) {
+          gf = Gb[(size_t)t * kW + lane];
+          const float tot = warp_sum(gf);  // FAC occupancies are stored unnormalised
+          gf = tot > 0.f ? gf / tot : 0.f;
+        }
+        if (lane < N) de[(size_t)t * N + lane] = coef * (gam + sG * gf);
       }
     }
-    const float gf = has_fac ? Gb[(size_t)t * kW + lane] : 0.f;
-    if (lane < N) de[(size_t)t * N + lane] = coef * (gam + sG * gf);
   }
-  float tmax = kNegInf;
-  if (has_fcc && p.d_trans != nullptr) {
-    for (int k = lane; k < N * N; k += 32) tmax = fmaxf(tmax, __ldg(p.trans + k));
-    tmax = warp_max(tmax);
-  }
-  if (has_fcc && p.d_trans != nullptr && lane < N) {
+  if (!want_dtr) return;
+  // CTA partial of the FCC transition gradient: sum the warps' accumulators, apply coef * M'
 #pragma unroll
-    for (int j = 0; j < kW; ++j) {
-      if (j < N) {
-        const float v = coef * acc[j] * __expf(__ldg(p.trans + lane * N + j) - tmax);
-        if (v != 0.f) atomicAdd(p.d_trans + lane * N + j, v);
-      }
-    }
+  for (int j = 0; j < kW; ++j) acc_s[warp][lane][j] = acc[j];
+  __syncthreads();
+  float tmax = kNegInf;
+  for (int k = lane; k < N * N; k += 32) tmax = fmaxf(tmax, __ldg(p.trans + k));
+  tmax = warp_max(tmax);
+  const float coef = ok ? p.coef[b] : 0.f;
+  float* part = p.parts + ((size_t)b * gridDim.x + blockIdx.x) * (kW * kW);
+  for (int k = threadIdx.x; k < kW * kW; k += kGradWarps * 32) {
+    const int i = k / kW, j = k % kW;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kGradWarps; ++w) s += acc_s[w][i][j];
+    const float m = (i < N && j < N) ? __expf(__ldg(p.trans + i * N + j) - tmax) : 0.f;
+    part[k] = coef * s * m;
   }
+}
+
+// 4. d_trans[i][j] = sum over partials (FCC grad CTAs, then FAC CTAs) — fixed order, no atomics
+__global__ void __launch_bounds__(256) asg_dtrans_reduce_kernel(AsgParams p, int n_parts) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kW * kW) return;
+  const int i = k / kW, j = k % kW;
+  if (i >= p.N || j >= p.N) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int q = 0;
+  for (; q + 3 < n_parts; q += 4) {
+    s0 += p.parts[(size_t)q * (kW * kW) + k];
+    s1 += p.parts[(size_t)(q + 1) * (kW * kW) + k];
+    s2 += p.parts[(size_t)(q + 2) * (kW * kW) + k];
+    s3 += p.parts[(size_t)(q + 3) * (kW * kW) + k];
+  }
+  for (; q < n_parts; ++q) s0 += p.parts[(size_t)q * (kW * kW) + k];
+  p.d_trans[i * p.N + j] = (s0 + s1) + (s2 + s3);
 }
 
 __global__ void asg_loss_only_kernel(AsgParams p) {
@@ -698,6 +862,8 @@ __global__ void asg_loss_only_kernel(AsgParams p) {
   }
   p.loss[b] = l;
 }
+
+int grad_ctas_per_sample(int T) { return (T + kGradChunk * kGradWarps - 1) / (kGradChunk * kGradWarps); }
 
 void carve(AsgParams& p, void* ws, size_t& total) {
   Carver c(ws);
@@ -714,6 +880,7 @@ void carve(AsgParams& p, void* ws, size_t& total) {
   p.cB = c.take<double>(BT);
   p.fccLogZ = c.take<double>(p.B);
   p.facLogZ = c.take<double>(p.B);
+  p.parts = c.take<float>((size_t)(grad_ctas_per_sample(p.T) + 1) * p.B * kW * kW);
   p.tsz = c.take<int>(p.B);
   p.valid = c.take<int>(p.B);
   p.scale = c.take<float>(p.B);
@@ -779,30 +946,54 @@ extern "C" int w2l_asg_forward_backward(void* stream_, int terms, int B, int T, 
   carve(p, workspace, need);
   if (!workspace || workspace_bytes < need)
     return fail(W2L_ERR_WORKSPACE, "asg: workspace too small (need " + std::to_string(need) + " bytes)");
-  const size_t smem = (terms & W2L_TERM_FAC) ? fac_smem_bytes(p.Lp) : 0;
-  if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "asg: target too long for the shared-memory rows");
+  size_t smem = 0;
+  if (terms & W2L_TERM_FAC) {
+    p.oring = fac_smem_bytes(p.Lp, 1) <= 200 * 1024;
+    smem = fac_smem_bytes(p.Lp, p.oring);
+    if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "asg: target too long for the shared-memory rows");
+  }
+  const int n_fac = (terms & W2L_TERM_FAC) ? B : 0;
+  const int n_fcc = (terms & W2L_TERM_FCC) ? B : 0;
+  const int gpc = grad_ctas_per_sample(T);
+  p.n_grad_parts = (terms & W2L_TERM_FCC) ? gpc * B : 0;
+  if (!p.need_grad) p.parts = nullptr;
 
-  if (p.need_grad) W2L_CUDA_CHECK(cudaMemsetAsync(d_trans, 0, sizeof(float) * N * N, stream));
   const long long nframes = (long long)B * T;
   int frame_blocks = (int)std::min<long long>((nframes + 7) / 8, 148 * 8);
   int meta_blocks = (B + 255) / 256;
   asg_prep_kernel<<<frame_blocks + meta_blocks, 256, 0, stream>>>(p, frame_blocks);
   W2L_LAUNCH_CHECK("asg_prep_kernel");
 
-  const int n_fac = (terms & W2L_TERM_FAC) ? B : 0;
-  const int n_fcc = (terms & W2L_TERM_FCC) ? B : 0;
+  const int kmax = p.Lp <= 2 * kGroup ? 2 : p.Lp <= 4 * kGroup ? 4 : p.Lp <= 8 * kGroup ? 8 : 32;
+  if ((terms & W2L_TERM_FAC) && p.Lp > 32 * kGroup)
+    return fail(W2L_ERR_UNSUPPORTED, "asg: target longer than 4096 is not covered");
+#define W2L_LAUNCH_CHAINS(GRAD, K)                                                                            \
+  do {                                                                                                        \
+    if (smem > 48 * 1024)                                                                                     \
+      W2L_CUDA_CHECK(cudaFuncSetAttribute(asg_chains_kernel<GRAD, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem));                                                        \
+    profile_start(stream);                                                                                    \
+    asg_chains_kernel<GRAD, K><<<n_fac + n_fcc, kChainThreads, smem, stream>>>(p, n_fac);                      \
+    profile_stop(stream);                                                                                     \
+  } while (0)
+#define W2L_DISPATCH_CHAINS(GRAD)              \
+  do {                                         \
+    if (kmax == 2) W2L_LAUNCH_CHAINS(GRAD, 2); \
+    else if (kmax == 4) W2L_LAUNCH_CHAINS(GRAD, 4); \
+    else if (kmax == 8) W2L_LAUNCH_CHAINS(GRAD, 8); \
+    else W2L_LAUNCH_CHAINS(GRAD, 32);          \
+  } while (0)
   if (p.need_grad) {
-    if (smem > 48 * 1024)
-      W2L_CUDA_CHECK(cudaFuncSetAttribute(asg_chains_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    asg_chains_kernel<true><<<n_fac + n_fcc, kChainThreads, smem, stream>>>(p, n_fac);
+    W2L_DISPATCH_CHAINS(true);
     W2L_LAUNCH_CHECK("asg_chains_kernel<grad>");
-    dim3 grid((T + kGradChunk * 4 - 1) / (kGradChunk * 4), B);
-    asg_grad_kernel<<<grid, 128, 0, stream>>>(p);
+    dim3 grid(gpc, B);
+    asg_grad_kernel<<<grid, kGradWarps * 32, 0, stream>>>(p);
     W2L_LAUNCH_CHECK("asg_grad_kernel");
+    // partial rows: [0, n_grad_parts) from the FCC grad CTAs, then n_fac rows from the FAC CTAs
+    asg_dtrans_reduce_kernel<<<(kW * kW + 255) / 256, 256, 0, stream>>>(p, p.n_grad_parts + n_fac);
+    W2L_LAUNCH_CHECK("asg_dtrans_reduce_kernel");
   } else {
-    if (smem > 48 * 1024)
-      W2L_CUDA_CHECK(cudaFuncSetAttribute(asg_chains_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    asg_chains_kernel<false><<<n_fac + n_fcc, kChainThreads, smem, stream>>>(p, n_fac);
+    W2L_DISPATCH_CHAINS(false);
     W2L_LAUNCH_CHECK("asg_chains_kernel<fwd>");
     asg_loss_only_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p);
     W2L_LAUNCH_CHECK("asg_loss_only_kernel");

@@ -396,7 +396,9 @@ extern "C" int w2l_ctc_forward_backward(void* stream_, int B, int T, int N, int 
   if (p.need_grad) {
     if (smem > 48 * 1024)
       W2L_CUDA_CHECK(cudaFuncSetAttribute(ctc_chains_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    profile_start(stream);
     ctc_chains_kernel<true><<<B, kCtcThreads, smem, stream>>>(p);
+    profile_stop(stream);
     W2L_LAUNCH_CHECK("ctc_chains_kernel<grad>");
     ctc_grad_kernel<<<(unsigned)nframes, 256, 0, stream>>>(p);
     W2L_LAUNCH_CHECK("ctc_grad_kernel");
