@@ -131,6 +131,18 @@ W2L_API int w2l_argmax_path(void* stream, int B, int T, int N, const float* emis
  * target[b][floor(t * L_b / T)]; feed it to w2l_asg_forward_backward(W2L_TERM_FAC, L = T). */
 W2L_API int w2l_linseg_target(void* stream, int B, int T, int L, const int32_t* target, int32_t* out);
 
+/* ----------------------------------------------------------------------------------------
+ * Dense contraction of the acoustic model (replaces fl::Linear's af::matmul -> cuBLAS and the
+ * GEMM inside cuDNN's convolutions; forward at Train.cpp:1470, backward at :1720).
+ *   C[m][n] = act( sum_k A(m,k) * B(n,k) + bias[n] ),  fp32 storage, TF32 tcgen05 math, fp32
+ *   accumulation.  a_mn_major = 0: A stored [M][K] (lda), 1: A stored [K][M];  b_mn_major = 0:
+ *   B stored [N][K] (ldb), 1: B stored [K][N].  forward Y = X W^T : (0,0); dgrad dX = dY W :
+ *   (0,1) with B = W; wgrad dW = dY^T X : (1,1) with A = dY, B = X.  bias nullable; act 0 none,
+ *   1 ReLU.  lda/ldb must be multiples of 4 floats and A/B 16-byte aligned (TMA).
+ * ---------------------------------------------------------------------------------------- */
+W2L_API int w2l_gemm_tf32(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                          const float* B, int ldb, float* C, int ldc, const float* bias, int act);
+
 #ifdef __cplusplus
 }
 #endif

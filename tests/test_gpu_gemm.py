@@ -1,0 +1,53 @@
+"""GPU parity of the tcgen05/TMA GEMM (TF32 math, fp32 accumulate) against a float64 reference of
+the same op.  Tolerance: TF32 keeps 10 mantissa bits per operand (TMA rounds on load), so each
+product carries <= 2^-10 relative error: |C - ref| <= 1.5e-3 * (|A| |B|^T) element-wise."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def run(M, N, K, a_mn, b_mn, bias, act, seed=0):
+    import wav2letter_b200 as w
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g)
+    B = torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g)
+    bv = torch.randn(N, device="cuda", generator=g) if bias else None
+    C = w.capi.gemm_tf32(A, B, bv, act, a_mn, b_mn)
+    torch.cuda.synchronize()
+    A64 = (A.t() if a_mn else A).double()
+    B64 = (B.t() if b_mn else B).double()
+    ref = A64 @ B64.t()
+    bound = 1.5e-3 * (A64.abs() @ B64.abs().t()) + 1e-5
+    if bias:
+        ref = ref + bv.double()
+    if act:
+        ref = ref.clamp_min(0)
+    err = (C.double() - ref).abs()
+    ratio = float((err / bound).max())
+    assert ratio <= 1.0, f"M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn}: err/bound {ratio}, max err {float(err.max())}"
+    # and it must be a real TF32-accurate product, not garbage that happens to be small
+    assert float(err.max()) < 0.05 * float(ref.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 384, 64), (200, 136, 100), (76, 52, 36),
+                                   (4000, 800, 800), (1000, 2000, 1440)])
+def test_gemm_majors_and_tails(M, N, K, a_mn, b_mn):
+    run(M, N, K, a_mn, b_mn, bias=False, act=0, seed=M + N + K)
+
+
+def test_gemm_bias_relu_epilogue():
+    run(300, 1120, 1120, False, False, bias=True, act=1)
+    run(130, 100, 64, False, False, bias=True, act=0)
+
+
+def test_gemm_rejects_unaligned():
+    import wav2letter_b200 as w
+
+    A = torch.randn(8, 30, device="cuda")
+    B = torch.randn(8, 30, device="cuda")
+    with pytest.raises(w.W2LError):
+        w.capi.gemm_tf32(A, B)

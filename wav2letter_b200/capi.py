@@ -24,6 +24,7 @@ EXPORTS = [
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
     "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
+    "w2l_gemm_tf32",
 ]
 
 
@@ -57,6 +58,7 @@ def _load() -> ctypes.CDLL:
     lib.w2l_ctc_forward_backward.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, sz]
     lib.w2l_argmax_path.argtypes = [vp, i, i, i, vp, vp]
     lib.w2l_linseg_target.argtypes = [vp, i, i, i, vp, vp]
+    lib.w2l_gemm_tf32.argtypes = [vp, i, i, i, i, i, vp, i, vp, i, vp, i, vp, i]
     return lib
 
 
@@ -200,4 +202,18 @@ def linseg_target(target, T: int):
     B, L = target.shape
     out = torch.empty((B, int(T)), dtype=torch.int32, device=target.device)
     _check(lib.w2l_linseg_target(_stream(), B, int(T), L, _ptr(target), _ptr(out)))
+    return out
+
+
+def gemm_tf32(A, B, bias=None, act=0, a_mn=False, b_mn=False, out=None):
+    """C[m][n] = act(sum_k A(m,k) B(n,k) + bias[n]).  A: [M,K] (or [K,M] if a_mn), B: [N,K] (or [K,N] if b_mn)."""
+    A = _req(A, torch.float32, "A")
+    B = _req(B, torch.float32, "B")
+    bias = _req(bias, torch.float32, "bias")
+    M, K = (A.shape[1], A.shape[0]) if a_mn else A.shape
+    N = B.shape[1] if b_mn else B.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    _check(lib.w2l_gemm_tf32(_stream(), int(a_mn), int(b_mn), M, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0),
+                             _ptr(out), out.stride(0), _ptr(bias), int(act)))
     return out

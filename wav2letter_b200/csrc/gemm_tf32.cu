@@ -1,0 +1,325 @@
+// gemm_tf32.cu — hand-written sm_100a GEMM for the dense contractions of the acoustic model
+// (TDS fully-connected layers, output Linear; reference: fl::Linear / af::matmul through cuBLAS,
+// reached from recipes/slimIPL/src/Train.cpp:1470 (forward) and :1720 (backward)).
+//
+//   C[m][n] = act( sum_k A(m,k) * B(n,k) + bias[n] )        fp32 in HBM, TF32 tensor-core math,
+//                                                            fp32 accumulation in TMEM
+// Operand storage ("major"):
+//   A K-major : A stored [M][K] (row stride lda)      A MN-major : A stored [K][M]
+//   B K-major : B stored [N][K] (row stride ldb)      B MN-major : B stored [K][N]
+// so one kernel family covers  forward  Y = X W^T            (A = X  K-major,  B = W  K-major)
+//                              dgrad    dX = dY W            (A = dY K-major,  B = W  MN-major)
+//                              wgrad    dW = dY^T X          (A = dY MN-major, B = X  MN-major)
+// without any transposition pass.
+//
+// Structure (one CTA per 128 x 128 output tile, 192 threads):
+//   warp 4        TMA producer: cp.async.bulk.tensor 2D boxes (128B inner extent, SWIZZLE_128B, TF32
+//                 rounding on load) into a 6-stage shared-memory ring, mbarrier expect_tx
+//   warp 5        TMEM allocation (128 columns) + single-thread tcgen05.mma.cta_group::1.kind::tf32
+//                 issue (UMMA 128x128x8, 4 per 32-wide k block), tcgen05.commit onto the stage's
+//                 empty barrier, final commit onto the accumulator-full barrier
+//   warps 0..3    epilogue: tcgen05.ld 32x32b (thread = accumulator row), bias + ReLU, 128-bit
+//                 global stores
+// Shared-memory operand layouts are the canonical UMMA ones (cute/atom/mma_traits_sm100.hpp):
+//   K-major  SW128: rows of 128 B (32 fp32 along k), 8-row groups 1024 B apart (SBO), LBO = 1
+//   MN-major SW128_BASE32B (the only MN-major layout valid for 32-bit operands; TMA swizzle
+//                   128B_ATOM_32B): boxes of [32 k-rows][128 B = 32 elements along m/n]; LBO = box
+//                   size (4096 B), SBO = 512 B (4 k-rows); one UMMA (k = 8) advances the start by 1024 B.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace w2l {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;  // tile; BK fp32 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;                   // tf32
+constexpr int kStages = 6;
+constexpr int kTileBytes = BM * BK * 4;     // 16 KB per operand per stage
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout the
+// tensor core accepts for MN-major 32-bit operands: Swizzle<2,5,2>, atoms of 4 k-rows x 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor: D = f32, A = B = tf32, M x N, operand majors
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct GemmParams {
+  int M, N, K, ldc, act;
+  float* C;
+  const float* bias;
+};
+
+template <bool kAMn, bool kBMn>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + kStages * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStages * kTileBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], 2 * kTileBytes);
+        unsigned char* sa = smem_a + s * kTileBytes;
+        unsigned char* sb = smem_b + s * kTileBytes;
+        const int k0 = kb * BK;
+        if (!kAMn) {
+          tma_load_2d(&map_a, &full[s], sa, k0, m0);  // box {32 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(&map_a, &full[s], sa + j * (BK * 128), m0 + 32 * j, k0);  // box {32 m, 32 k}
+        }
+        if (!kBMn) {
+          tma_load_2d(&map_b, &full[s], sb, k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&map_b, &full[s], sb + j * (BK * 128), n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (one elected thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, kAMn, kBMn);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem_a + s * kTileBytes);
+        const uint32_t sb = smem_u32(smem_b + s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: +32 B per UMMA_K inside the 128 B swizzle row; MN-major: +8 k-rows = 1024 B
+          // MN-major (BASE32B): LBO = one [32 k][128 B] box, SBO = 4 k-rows = 512 B
+          const uint64_t da = kAMn ? make_smem_desc(sa + k * 1024, BK * 128, 512, 1) : make_smem_desc(sa + k * 32, 16, 1024, 2);
+          const uint64_t db = kBMn ? make_smem_desc(sb + k * 1024, BK * 128, 512, 1) : make_smem_desc(sb + k * 32, 16, 1024, 2);
+          umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty[s]);  // frees the stage when the MMAs above have read it
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ===== epilogue warps 0..3: TMEM lanes 32*warp .. +31 =====
+    mbar_wait(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + warp * 32 + lane;
+    float* crow = p.C + (size_t)row * p.ldc;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int nb = n0 + c * 32;
+      if (row < p.M && nb < p.N) {
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (p.bias != nullptr && nb + j < p.N) x += __ldg(p.bias + nb + j);
+          if (p.act == 1) x = fmaxf(x, 0.f);
+          o[j] = x;
+        }
+        if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + nb + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) crow[nb + j] = o[j];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2D map over a row-major fp32 matrix [rows][cols] (row stride ld floats); box {32 cols, box_rows}
+int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols, long long ld, int box_rows, bool mn_major) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(W2L_ERR_CUDA, "gemm: cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(W2L_ERR_CUDA, "gemm: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return W2L_OK;
+}
+
+template <bool kAMn, bool kBMn>
+int launch(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  const size_t smem = 2 * kStages * kTileBytes + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+  profile_start(stream);
+  gemm_tf32_kernel<kAMn, kBMn><<<grid, kGemmThreads, smem, stream>>>(ma, mb, p);
+  profile_stop(stream);
+  W2L_LAUNCH_CHECK("gemm_tf32_kernel");
+  return W2L_OK;
+}
+
+}  // namespace
+}  // namespace w2l
+
+using namespace w2l;
+
+extern "C" int w2l_gemm_tf32(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                             const float* B, int ldb, float* C, int ldc, const float* bias, int act) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: M, N, K must be positive");
+  if (!A || !B || !C) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: null pointer");
+  if (act < 0 || act > 1) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: act must be 0 (none) or 1 (relu)");
+  if ((lda % 4) || (ldb % 4) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: operand rows must be 16-byte aligned (ld % 4 == 0)");
+  if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N)
+    return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: leading dimension smaller than the row length");
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a_mn_major)
+    rc = make_map(&ma, A, M, K, lda, BM, false);   // [M][K]: box {32 k, 128 m}
+  else
+    rc = make_map(&ma, A, K, M, lda, BK, true);   // [K][M]: box {32 m, 32 k}
+  if (rc) return rc;
+  if (!b_mn_major)
+    rc = make_map(&mb, B, N, K, ldb, BN, false);
+  else
+    rc = make_map(&mb, B, K, N, ldb, BK, true);
+  if (rc) return rc;
+  GemmParams p{M, N, K, ldc, act, C, bias};
+  if (!a_mn_major && !b_mn_major) return launch<false, false>(stream, ma, mb, p);
+  if (!a_mn_major && b_mn_major) return launch<false, true>(stream, ma, mb, p);
+  if (a_mn_major && b_mn_major) return launch<true, true>(stream, ma, mb, p);
+  return launch<true, false>(stream, ma, mb, p);
+}
