@@ -143,6 +143,55 @@ W2L_API int w2l_linseg_target(void* stream, int B, int T, int L, const int32_t* 
 W2L_API int w2l_gemm_tf32(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
                           const float* B, int ldb, float* C, int ldc, const float* bias, int act);
 
+/* Extended epilogue: after bias/act, (a) forward dropout with keep-scale 1/(1-p) (Philox4x32-10 keyed by
+ * (seed, element index)), (b) backward activation mask read back from a stored activation tensor
+ * aux[M][ld_aux]: aux_mode 1 multiplies by (aux > 0) * aux_scale (fused ReLU+dropout backward),
+ * 2 by (aux != 0) * aux_scale (dropout backward), (c) accumulate != 0: C += result. */
+W2L_API int w2l_gemm_tf32_ex(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                             const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
+                             const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
+                             unsigned long long seed);
+
+/* ----------------------------------------------------------------------------------------
+ * Time convolution of the acoustic models: fl::Conv2D with a kw x 1 kernel (TDSBlock's conv,
+ * the strided `C2` front-ends; arch parser cpc/SequentialBuilder.cpp:254-301).  Activations are
+ * float [B][T][C][W] (W <= 80 innermost), weights float wt[Cout][Cin][K] (= fl's [kw,1,cin,cout]
+ * column-major), out frame `to` reads input frames to*stride + dk - pad_left.
+ *   fwd   : y = dropout(act(conv(x) + bias)) (+ add)          act 0 none / 1 ReLU
+ *   dgrad : dx = conv^T(dy) (+ add)
+ *   wgrad : dwt += ..., dbias += ...  (deterministic two-stage reduction)
+ * The workspace size call covers all three.
+ * ---------------------------------------------------------------------------------------- */
+W2L_API size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K);
+W2L_API int w2l_conv_time_fwd(void* stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                              int pad_left, const float* x, const float* wt, const float* bias, const float* add, float* y,
+                              int act, float dropout_p, unsigned long long seed, void* ws, size_t ws_bytes);
+W2L_API int w2l_conv_time_dgrad(void* stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                                int pad_left, const float* dy, const float* wt, const float* add, float* dx, void* ws,
+                                size_t ws_bytes);
+W2L_API int w2l_conv_time_wgrad(void* stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                                int pad_left, const float* x, const float* dy, float* dwt, float* dbias, void* ws,
+                                size_t ws_bytes);
+
+/* fl::LayerNorm over a whole sample (R = T*C*W elements; `LN 0 1 2` / TDSBlock with lnIncludeTime)
+ * with scalar gain/bias (device scalars, nullable = 1/0) and a fused residual: y = LN(a + r).
+ * mean_rstd [B][2] is saved for the backward pass; scratch = 2*B doubles.
+ * Backward: d_res = ds, d_branch = ds * mask(a) where the mask undoes the fused ReLU/dropout of the
+ * branch that produced `a` (branch_mode 0 none, 1 (a>0)*scale, 2 (a!=0)*scale); dgain/dbias accumulate. */
+W2L_API int w2l_layernorm_fwd(void* stream, int B, long long R, float eps, const float* a, const float* r,
+                              const float* gain, const float* bias, float* y, float* mean_rstd, double* scratch);
+W2L_API int w2l_layernorm_bwd(void* stream, int B, long long R, const float* a, const float* r, const float* dy,
+                              const float* gain, const float* mean_rstd, float* d_branch, float* d_res, int branch_mode,
+                              float branch_scale, float* dgain, float* dbias, double* scratch);
+
+/* out[n] += sum_m X[m][n]  (bias gradient of fl::Linear) */
+W2L_API int w2l_colsum_accumulate(void* stream, int M, int N, const float* X, int ld, float* out);
+/* fl::clipGradNorm + fl::SGDOptimizer::step + the loop's gradient scaling (Train.cpp:1743-1803) on a
+ * flat parameter arena: out += sum g^2 ;  g' = g*grad_scale*clip ; g' += wd*p ; v = mom*v + g' ; p -= lr*v */
+W2L_API int w2l_sq_norm_accumulate(void* stream, long long n, const float* g, double* out);
+W2L_API int w2l_sgd_step(void* stream, long long n, float* params, const float* grads, float* velocity, float lr,
+                         float momentum, float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,9 @@ EXPORTS = [
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
     "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
-    "w2l_gemm_tf32",
+    "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
+    "w2l_conv_time_wgrad", "w2l_layernorm_fwd", "w2l_layernorm_bwd", "w2l_colsum_accumulate", "w2l_sq_norm_accumulate",
+    "w2l_sgd_step",
 ]
 
 
@@ -59,6 +61,18 @@ def _load() -> ctypes.CDLL:
     lib.w2l_argmax_path.argtypes = [vp, i, i, i, vp, vp]
     lib.w2l_linseg_target.argtypes = [vp, i, i, i, vp, vp]
     lib.w2l_gemm_tf32.argtypes = [vp, i, i, i, i, i, vp, i, vp, i, vp, i, vp, i]
+    f32, u64, ll = ctypes.c_float, ctypes.c_ulonglong, ctypes.c_longlong
+    lib.w2l_gemm_tf32_ex.argtypes = [vp, i, i, i, i, i, vp, i, vp, i, vp, i, vp, i, i, vp, i, i, f32, f32, u64]
+    lib.w2l_conv_time_workspace_size.restype = sz
+    lib.w2l_conv_time_workspace_size.argtypes = [i, i, i, i, i]
+    lib.w2l_conv_time_fwd.argtypes = [vp, i, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, i, f32, u64, vp, sz]
+    lib.w2l_conv_time_dgrad.argtypes = [vp, i, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, sz]
+    lib.w2l_conv_time_wgrad.argtypes = [vp, i, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, sz]
+    lib.w2l_layernorm_fwd.argtypes = [vp, i, ll, f32, vp, vp, vp, vp, vp, vp, vp]
+    lib.w2l_layernorm_bwd.argtypes = [vp, i, ll, vp, vp, vp, vp, vp, vp, vp, i, f32, vp, vp, vp]
+    lib.w2l_colsum_accumulate.argtypes = [vp, i, i, vp, i, vp]
+    lib.w2l_sq_norm_accumulate.argtypes = [vp, ll, vp, vp]
+    lib.w2l_sgd_step.argtypes = [vp, ll, vp, vp, vp, f32, f32, f32, f32, f32, vp]
     return lib
 
 
@@ -217,3 +231,76 @@ def gemm_tf32(A, B, bias=None, act=0, a_mn=False, b_mn=False, out=None):
     _check(lib.w2l_gemm_tf32(_stream(), int(a_mn), int(b_mn), M, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0),
                              _ptr(out), out.stride(0), _ptr(bias), int(act)))
     return out
+
+
+def gemm_tf32_ex(A, B, out, bias=None, act=0, a_mn=False, b_mn=False, accumulate=False, aux=None, aux_mode=0,
+                 aux_scale=1.0, dropout_p=0.0, seed=0):
+    M, K = (A.shape[1], A.shape[0]) if a_mn else A.shape
+    N = B.shape[1] if b_mn else B.shape[0]
+    _check(lib.w2l_gemm_tf32_ex(_stream(), int(a_mn), int(b_mn), M, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0),
+                                _ptr(out), out.stride(0), _ptr(bias), int(act), int(accumulate), _ptr(aux),
+                                0 if aux is None else aux.stride(0), int(aux_mode), float(aux_scale), float(dropout_p),
+                                int(seed)))
+    return out
+
+
+def conv_time_ws(B, Tout, Cin, Cout, K, device):
+    return workspace(lib.w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K), device)
+
+
+def conv_time_fwd(x, wt, bias, Tout, stride, pad_left, act=0, dropout_p=0.0, seed=0, add=None):
+    """x [B,T,Cin,W], wt [Cout,Cin,K] -> y [B,Tout,Cout,W]"""
+    B, T, Cin, W = x.shape
+    Cout, _, K = wt.shape
+    y = torch.empty((B, Tout, Cout, W), dtype=torch.float32, device=x.device)
+    ws = conv_time_ws(B, Tout, Cin, Cout, K, x.device)
+    _check(lib.w2l_conv_time_fwd(_stream(), B, T, Tout, W, Cin, Cout, K, stride, pad_left, _ptr(x), _ptr(wt), _ptr(bias),
+                                 _ptr(add), _ptr(y), act, float(dropout_p), int(seed), _ptr(ws), ws.numel()))
+    return y
+
+
+def conv_time_dgrad(dy, wt, T, stride, pad_left, add=None):
+    B, Tout, Cout, W = dy.shape
+    _, Cin, K = wt.shape
+    dx = torch.empty((B, T, Cin, W), dtype=torch.float32, device=dy.device)
+    ws = conv_time_ws(B, Tout, Cin, Cout, K, dy.device)
+    _check(lib.w2l_conv_time_dgrad(_stream(), B, T, Tout, W, Cin, Cout, K, stride, pad_left, _ptr(dy), _ptr(wt), _ptr(add),
+                                   _ptr(dx), _ptr(ws), ws.numel()))
+    return dx
+
+
+def conv_time_wgrad(x, dy, K, stride, pad_left, dwt=None, dbias=None):
+    B, T, Cin, W = x.shape
+    _, Tout, Cout, _ = dy.shape
+    if dwt is None:
+        dwt = torch.zeros((Cout, Cin, K), dtype=torch.float32, device=x.device)
+        dbias = torch.zeros(Cout, dtype=torch.float32, device=x.device)
+    ws = conv_time_ws(B, Tout, Cin, Cout, K, x.device)
+    _check(lib.w2l_conv_time_wgrad(_stream(), B, T, Tout, W, Cin, Cout, K, stride, pad_left, _ptr(x), _ptr(dy), _ptr(dwt),
+                                   _ptr(dbias), _ptr(ws), ws.numel()))
+    return dwt, dbias
+
+
+def layernorm_fwd(a, r, gain, bias, eps=1e-5):
+    B = a.shape[0]
+    R = a[0].numel()
+    y = torch.empty_like(a)
+    mr = torch.empty((B, 2), dtype=torch.float32, device=a.device)
+    scratch = torch.empty(2 * B, dtype=torch.float64, device=a.device)
+    _check(lib.w2l_layernorm_fwd(_stream(), B, R, float(eps), _ptr(a), _ptr(r), _ptr(gain), _ptr(bias), _ptr(y), _ptr(mr),
+                                 _ptr(scratch)))
+    return y, mr
+
+
+def layernorm_bwd(a, r, dy, gain, mr, branch_mode=0, branch_scale=1.0):
+    B = a.shape[0]
+    R = a[0].numel()
+    d_branch = torch.empty_like(a)
+    d_res = torch.empty_like(a)
+    dgain = torch.zeros(1, dtype=torch.float32, device=a.device)
+    dbias = torch.zeros(1, dtype=torch.float32, device=a.device)
+    scratch = torch.empty(2 * B, dtype=torch.float64, device=a.device)
+    _check(lib.w2l_layernorm_bwd(_stream(), B, R, _ptr(a), _ptr(r), _ptr(dy), _ptr(gain), _ptr(mr), _ptr(d_branch),
+                                 _ptr(d_res), int(branch_mode), float(branch_scale), _ptr(dgain), _ptr(dbias),
+                                 _ptr(scratch)))
+    return d_branch, d_res, dgain, dbias

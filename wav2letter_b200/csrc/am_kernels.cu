@@ -1,0 +1,673 @@
+// am_kernels.cu — non-GEMM kernels of the acoustic-model forward/backward (sm_100a).
+//
+// Activations are fp32 [B][T][C][W] (W = 80 filterbank channels innermost, feature index
+// f = c*W + w — the order flashlight's `V 0 1440 1 0` view produces from [T,W,C,B], so Linear
+// weights keep upstream's layout).  Reference modules (built by the arch parser,
+// recipes/joint_training_vox_populi/cpc/SequentialBuilder.cpp:203-313,358-394,423-428):
+//   fl::Conv2D (kw x 1, stride sx, SAME / explicit padding) -> w2l_conv_time_{fwd,dgrad,wgrad}
+//   fl::LayerNorm over (T,W,C) per sample with scalar affine (TDSBlock, `LN 0 1 2`,
+//     tools/StreamingTDSModelConverter.cpp:49-53)            -> w2l_layernorm_{fwd,bwd}
+//   fl::ReLU / fl::Dropout                                    -> fused into the producers' epilogues
+//     and into the LayerNorm backward (the mask is read back from the stored activation sign)
+//   fl::SGDOptimizer / fl::clipGradNorm (Train.cpp:1791-1803) -> w2l_sq_norm / w2l_sgd_step on a flat arena
+// These passes are HBM-bound (the k x 1 convolution has only 10-27 channels: SURVEY.md §7.4-3);
+// the dense contractions live in gemm_tf32.cu.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace w2l {
+
+// ---- Philox4x32-10 (counter-based; the backward pass regenerates nothing — masks are read from
+// the stored activations — but forward passes must be reproducible per (seed, offset)) ----------
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask scale for element `idx`: 1/(1-p) with probability 1-p, else 0
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
+  const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t lane = (uint32_t)idx & 3u;
+  const uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+  return ((float)(v >> 8) * (1.0f / 16777216.0f)) >= p ? inv_keep : 0.f;
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// time convolution, forward (also used for the stride-1 data gradient with flipped weights)
+//   y[b][to][co][w] = act( bias[co] + sum_{ci,dk} x[b][to*s + dk - pl][ci][w] * wt[ci][dk][co] ) (+ add)
+// weights arrive pre-arranged as wt_s[ci][dk][CO] (CO = Cout padded to a multiple of 4)
+// ------------------------------------------------------------------------------------------
+constexpr int kConvTo = 8;  // output frames per CTA (2 per thread row)
+
+template <int CO>
+__global__ void __launch_bounds__(96 * (kConvTo / 2)) conv_time_fwd_kernel(
+    int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left, const float* __restrict__ x,
+    const float* __restrict__ wt_arranged, const float* __restrict__ bias, const float* __restrict__ add,
+    float* __restrict__ y, int act, float drop_p, unsigned long long seed) {
+  extern __shared__ __align__(16) float wsm[];  // [Cin][K][CO]
+  const int b = blockIdx.y;
+  const int w = threadIdx.x;                   // 0..95, active < W
+  const int to0 = blockIdx.x * kConvTo + threadIdx.y * 2;
+  const int nw = Cin * K * CO;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < nw; i += blockDim.x * blockDim.y) wsm[i] = wt_arranged[i];
+  __syncthreads();
+  if (w >= W || to0 >= Tout) return;
+  const bool has1 = to0 + 1 < Tout;
+  float acc0[CO], acc1[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    const float bv = (bias != nullptr && c < Cout) ? __ldg(bias + c) : 0.f;
+    acc0[c] = bv;
+    acc1[c] = bv;
+  }
+  const float* xb = x + (size_t)b * T * Cin * W + w;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float* xc = xb + (size_t)ci * W;
+    const float* wrow = wsm + (size_t)ci * K * CO;
+    for (int dk = 0; dk < K; ++dk) {
+      const int t0 = to0 * stride + dk - pad_left;
+      const int t1 = t0 + stride;
+      const float x0 = (t0 >= 0 && t0 < T) ? __ldg(xc + (size_t)t0 * Cin * W) : 0.f;
+      const float x1 = (has1 && t1 >= 0 && t1 < T) ? __ldg(xc + (size_t)t1 * Cin * W) : 0.f;
+      const float4* w4 = reinterpret_cast<const float4*>(wrow + dk * CO);
+#pragma unroll
+      for (int q = 0; q < CO / 4; ++q) {
+        const float4 wv = w4[q];
+        acc0[4 * q + 0] = fmaf(x0, wv.x, acc0[4 * q + 0]);
+        acc0[4 * q + 1] = fmaf(x0, wv.y, acc0[4 * q + 1]);
+        acc0[4 * q + 2] = fmaf(x0, wv.z, acc0[4 * q + 2]);
+        acc0[4 * q + 3] = fmaf(x0, wv.w, acc0[4 * q + 3]);
+        acc1[4 * q + 0] = fmaf(x1, wv.x, acc1[4 * q + 0]);
+        acc1[4 * q + 1] = fmaf(x1, wv.y, acc1[4 * q + 1]);
+        acc1[4 * q + 2] = fmaf(x1, wv.z, acc1[4 * q + 2]);
+        acc1[4 * q + 3] = fmaf(x1, wv.w, acc1[4 * q + 3]);
+      }
+    }
+  }
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    if (c < Cout) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !has1) continue;
+        const size_t idx = (((size_t)b * Tout + to0 + h) * Cout + c) * W + w;
+        float v = h ? acc1[c] : acc0[c];
+        if (act == 1) v = fmaxf(v, 0.f);
+        if (drop_p > 0.f) v *= dropout_scale(seed, idx, drop_p, inv_keep);
+        if (add != nullptr) v += __ldg(add + idx);
+        y[idx] = v;
+      }
+    }
+  }
+}
+
+// wt [Cout][Cin][K] -> arranged [Cin][K][CO] (forward) or, for the stride-1 data gradient,
+// arranged'[Cout][K][CI] with the taps flipped: arranged'[co][dk'][ci] = wt[co][ci][K-1-dk']
+__global__ void conv_arrange_weights_kernel(int Cin, int Cout, int K, int CO, const float* __restrict__ wt,
+                                            float* __restrict__ out, int flip_for_dgrad) {
+  const int n_out = (flip_for_dgrad ? Cout : Cin) * K * CO;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
+    const int c_inner = i % CO, dk = (i / CO) % K, c_outer = i / (CO * K);
+    float v = 0.f;
+    if (!flip_for_dgrad) {
+      if (c_inner < Cout) v = wt[((size_t)c_inner * Cin + c_outer) * K + dk];  // outer = ci, inner = co
+    } else {
+      if (c_inner < Cin) v = wt[((size_t)c_outer * Cin + c_inner) * K + (K - 1 - dk)];  // outer = co, inner = ci
+    }
+    out[i] = v;
+  }
+}
+
+// strided data gradient (front-end C2 layers): dx[b][t][ci][w] = sum_{co,dk: (t+pl-dk) % s == 0}
+//   dy[b][(t+pl-dk)/s][co][w] * wt[co][ci][dk]        (+ add)
+template <int CI>
+__global__ void __launch_bounds__(96 * 4) conv_time_dgrad_strided_kernel(int T, int Tout, int W, int Cin, int Cout, int K,
+                                                                        int stride, int pad_left,
+                                                                        const float* __restrict__ dy,
+                                                                        const float* __restrict__ wt,
+                                                                        const float* __restrict__ add,
+                                                                        float* __restrict__ dx) {
+  extern __shared__ __align__(16) float wsm[];  // [K][Cout][CI]
+  const int b = blockIdx.y, w = threadIdx.x, t = blockIdx.x * 4 + threadIdx.y;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < K * Cout * CI; i += blockDim.x * blockDim.y) {
+    const int ci = i % CI, co = (i / CI) % Cout, dk = i / (CI * Cout);
+    wsm[i] = ci < Cin ? wt[((size_t)co * Cin + ci) * K + dk] : 0.f;
+  }
+  __syncthreads();
+  if (w >= W || t >= T) return;
+  float acc[CI];
+#pragma unroll
+  for (int c = 0; c < CI; ++c) acc[c] = 0.f;
+  for (int dk = 0; dk < K; ++dk) {
+    const int num = t + pad_left - dk;
+    if (num < 0 || num % stride != 0) continue;
+    const int to = num / stride;
+    if (to >= Tout) continue;
+    const float* dyr = dy + (((size_t)b * Tout + to) * Cout) * W + w;
+    for (int co = 0; co < Cout; ++co) {
+      const float g = __ldg(dyr + (size_t)co * W);
+      const float4* w4 = reinterpret_cast<const float4*>(wsm + ((size_t)dk * Cout + co) * CI);
+#pragma unroll
+      for (int q = 0; q < CI / 4; ++q) {
+        const float4 wv = w4[q];
+        acc[4 * q + 0] = fmaf(g, wv.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(g, wv.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(g, wv.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(g, wv.w, acc[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CI; ++c)
+    if (c < Cin) {
+      const size_t idx = (((size_t)b * T + t) * Cin + c) * W + w;
+      dx[idx] = acc[c] + (add ? __ldg(add + idx) : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient: dwt[co][ci][dk] += sum_{b,to,w} dy[b][to][co][w] * x[b][to*s+dk-pl][ci][w]
+// One CTA walks a chunk of output frames of one sample; the K input rows a frame needs are kept
+// in a shared-memory ring (one new row per frame for stride 1).  A thread owns register tiles of
+// 2 output channels x 4 (ci,dk) taps and reduces over w with 128-bit shared-memory reads.
+// CTA partials go to a workspace; conv_wgrad_reduce_kernel sums them (deterministic).
+// ------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 256;
+constexpr int kWgMaxTiles = 6;
+
+__global__ void __launch_bounds__(kWgThreads) conv_time_wgrad_kernel(int T, int Tout, int W, int Cin, int Cout, int K,
+                                                                     int stride, int pad_left, int chunk,
+                                                                     const float* __restrict__ x,
+                                                                     const float* __restrict__ dy,
+                                                                     float* __restrict__ partial /*[ctas][Cout*Cin*K + Cout]*/) {
+  extern __shared__ __align__(16) float sm[];
+  const int Wp = 80;  // W <= 80 (filterbank width); rows padded to 80 floats
+  float* ring = sm;                         // [K][Cin][Wp]
+  float* dys = ring + (size_t)K * Cin * Wp;  // [Cout][Wp]
+  const int b = blockIdx.y;
+  const int to_begin = blockIdx.x * chunk, to_end = min(Tout, to_begin + chunk);
+  const int tid = threadIdx.x;
+  const int copairs = (Cout + 1) / 2, taps = Cin * K, tapgroups = (taps + 3) / 4;
+  const int ntiles = copairs * tapgroups;
+  float acc[kWgMaxTiles][8];
+#pragma unroll
+  for (int i = 0; i < kWgMaxTiles; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float bias_acc = 0.f;  // thread co < Cout accumulates sum_w dy
+  // ring slot of input frame tin: tin mod K (computed incrementally)
+  auto load_row = [&](int tin) {
+    const int slot = ((tin % K) + K) % K;
+    float* dst = ring + (size_t)slot * Cin * Wp;
+    const bool ok = tin >= 0 && tin < T;
+    const float* src = x + ((size_t)b * T + (ok ? tin : 0)) * Cin * W;
+    for (int i = tid; i < Cin * Wp; i += kWgThreads) {
+      const int ci = i / Wp, w = i % Wp;
+      dst[i] = (ok && w < W) ? __ldg(src + (size_t)ci * W + w) : 0.f;
+    }
+  };
+  // prime the ring with the first frame's window minus its last `stride` rows
+  {
+    const int tin0 = to_begin * stride - pad_left;
+    for (int r = 0; r < K - stride; ++r) load_row(tin0 + r);
+  }
+  for (int to = to_begin; to < to_end; ++to) {
+    __syncthreads();  // previous frame's reads are done
+    const int tin0 = to * stride - pad_left;
+    for (int r = max(0, K - stride); r < K; ++r) load_row(tin0 + r);
+    if (K < stride) {}  // (not used by any arch)
+    {
+      const float* src = dy + ((size_t)b * Tout + to) * Cout * W;
+      for (int i = tid; i < Cout * Wp; i += kWgThreads) {
+        const int co = i / Wp, w = i % Wp;
+        dys[i] = w < W ? __ldg(src + (size_t)co * W + w) : 0.f;
+      }
+    }
+    __syncthreads();
+    const int base = ((tin0 % K) + K) % K;  // ring slot of tap dk = 0
+#pragma unroll
+    for (int i = 0; i < kWgMaxTiles; ++i) {
+      const int tile = tid + i * kWgThreads;
+      if (tile < ntiles) {
+        const int cp = tile % copairs, g = tile / copairs;
+        const int co0 = 2 * cp, co1 = min(co0 + 1, Cout - 1);
+        const float4* d0 = reinterpret_cast<const float4*>(dys + (size_t)co0 * Wp);
+        const float4* d1 = reinterpret_cast<const float4*>(dys + (size_t)co1 * Wp);
+        const float4* xr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tap = min(4 * g + q, taps - 1);
+          const int ci = tap / K, dk = tap % K;
+          int slot = base + dk;
+          if (slot >= K) slot -= K;
+          xr[q] = reinterpret_cast<const float4*>(ring + ((size_t)slot * Cin + ci) * Wp);
+        }
+#pragma unroll 4
+        for (int w4 = 0; w4 < Wp / 4; ++w4) {
+          const float4 a = d0[w4], c = d1[w4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = xr[q][w4];
+            acc[i][q] += a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
+            acc[i][4 + q] += c.x * v.x + c.y * v.y + c.z * v.z + c.w * v.w;
+          }
+        }
+      }
+    }
+    if (tid < Cout) {
+      float s = 0.f;
+      for (int w = 0; w < W; ++w) s += dys[(size_t)tid * Wp + w];
+      bias_acc += s;
+    }
+  }
+  // write the CTA partial
+  float* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)Cout * Cin * K + Cout);
+#pragma unroll
+  for (int i = 0; i < kWgMaxTiles; ++i) {
+    const int tile = tid + i * kWgThreads;
+    if (tile < ntiles) {
+      const int cp = tile % copairs, g = tile / copairs;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int tap = 4 * g + q;
+        if (tap < taps) {
+          const int ci = tap / K, dk = tap % K;
+          out[((size_t)(2 * cp) * Cin + ci) * K + dk] = acc[i][q];
+          if (2 * cp + 1 < Cout) out[((size_t)(2 * cp + 1) * Cin + ci) * K + dk] = acc[i][4 + q];
+        }
+      }
+    }
+  }
+  if (tid < Cout) out[(size_t)Cout * Cin * K + tid] = bias_acc;
+}
+
+__global__ void conv_wgrad_reduce_kernel(int n_parts, int n_w, int n_b, const float* __restrict__ partial,
+                                         float* __restrict__ dwt, float* __restrict__ dbias) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_w + n_b) return;
+  float s = 0.f;
+  for (int q = 0; q < n_parts; ++q) s += partial[(size_t)q * (n_w + n_b) + k];
+  if (k < n_w)
+    dwt[k] += s;
+  else if (dbias != nullptr)
+    dbias[k - n_w] += s;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over a whole sample (R = T*C*W elements) with scalar gain/bias, fused residual:
+//   s = a + r ; y = (s - mean) * rstd * gain + bias
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_stats_kernel(long long R, const float* __restrict__ a, const float* __restrict__ r,
+                                                       double* __restrict__ stats /*[B][2] sum, sumsq*/) {
+  const int b = blockIdx.y;
+  const float* ab = a + (size_t)b * R;
+  const float* rb = r ? r + (size_t)b * R : nullptr;
+  double s = 0.0, q = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
+    const float v = ab[i] + (rb ? rb[i] : 0.f);
+    s += v;
+    q += (double)v * v;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  __shared__ double ss[8], qq[8];
+  if ((threadIdx.x & 31) == 0) {
+    ss[threadIdx.x >> 5] = s;
+    qq[threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0, Q = 0;
+    for (int w = 0; w < 8; ++w) {
+      S += ss[w];
+      Q += qq[w];
+    }
+    atomicAdd(stats + 2 * b, S);
+    atomicAdd(stats + 2 * b + 1, Q);
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_apply_kernel(long long R, float eps, const float* __restrict__ a,
+                                                       const float* __restrict__ r, const float* __restrict__ gain,
+                                                       const float* __restrict__ bias, const double* __restrict__ stats,
+                                                       float* __restrict__ y, float* __restrict__ mean_rstd /*[B][2]*/) {
+  const int b = blockIdx.y;
+  const double mean = stats[2 * b] / (double)R;
+  const double var = fmax(stats[2 * b + 1] / (double)R - mean * mean, 0.0);
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float mu = (float)mean, g = gain ? *gain : 1.f, bi = bias ? *bias : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    mean_rstd[2 * b] = mu;
+    mean_rstd[2 * b + 1] = rstd;
+  }
+  const float* ab = a + (size_t)b * R;
+  const float* rb = r ? r + (size_t)b * R : nullptr;
+  float* yb = y + (size_t)b * R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
+    const float v = ab[i] + (rb ? rb[i] : 0.f);
+    yb[i] = (v - mu) * rstd * g + bi;
+  }
+}
+
+// backward pass 1: per-sample sums of dy and dy * xhat
+__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(long long R, const float* __restrict__ a,
+                                                           const float* __restrict__ r, const float* __restrict__ dy,
+                                                           const float* __restrict__ mean_rstd,
+                                                           double* __restrict__ sums /*[B][2]*/) {
+  const int b = blockIdx.y;
+  const float mu = mean_rstd[2 * b], rstd = mean_rstd[2 * b + 1];
+  const float* ab = a + (size_t)b * R;
+  const float* rb = r ? r + (size_t)b * R : nullptr;
+  const float* db = dy + (size_t)b * R;
+  double s = 0.0, q = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
+    const float xh = (ab[i] + (rb ? rb[i] : 0.f) - mu) * rstd;
+    const float d = db[i];
+    s += d;
+    q += (double)d * xh;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  __shared__ double ss[8], qq[8];
+  if ((threadIdx.x & 31) == 0) {
+    ss[threadIdx.x >> 5] = s;
+    qq[threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0, Q = 0;
+    for (int w = 0; w < 8; ++w) {
+      S += ss[w];
+      Q += qq[w];
+    }
+    atomicAdd(sums + 2 * b, S);
+    atomicAdd(sums + 2 * b + 1, Q);
+  }
+}
+
+// backward pass 2: ds = rstd * gain * (dy - mean(dy) - xhat * mean(dy*xhat));
+//   d_res = ds ; d_branch = ds * mask(a) where mask undoes the branch's fused ReLU / dropout:
+//   branch_mode 0: 1 ; 1: (a > 0) * scale ; 2: (a != 0) * scale
+__global__ void __launch_bounds__(256) ln_bwd_apply_kernel(long long R, const float* __restrict__ a,
+                                                           const float* __restrict__ r, const float* __restrict__ dy,
+                                                           const float* __restrict__ gain, const float* __restrict__ mean_rstd,
+                                                           const double* __restrict__ sums, float* __restrict__ d_branch,
+                                                           float* __restrict__ d_res, int branch_mode, float branch_scale,
+                                                           float* __restrict__ dgain, float* __restrict__ dbias) {
+  const int b = blockIdx.y;
+  const float mu = mean_rstd[2 * b], rstd = mean_rstd[2 * b + 1], g = gain ? *gain : 1.f;
+  const float m1 = (float)(sums[2 * b] / (double)R), m2 = (float)(sums[2 * b + 1] / (double)R);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (dbias) atomicAdd(dbias, (float)sums[2 * b]);
+    if (dgain) atomicAdd(dgain, (float)sums[2 * b + 1]);
+  }
+  const float* ab = a + (size_t)b * R;
+  const float* rb = r ? r + (size_t)b * R : nullptr;
+  const float* db = dy + (size_t)b * R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
+    const float av = ab[i];
+    const float xh = (av + (rb ? rb[i] : 0.f) - mu) * rstd;
+    const float ds = rstd * g * (db[i] - m1 - xh * m2);
+    if (d_res) d_res[(size_t)b * R + i] = ds;
+    float m = 1.f;
+    if (branch_mode == 1) m = av > 0.f ? branch_scale : 0.f;
+    if (branch_mode == 2) m = av != 0.f ? branch_scale : 0.f;
+    d_branch[(size_t)b * R + i] = ds * m;
+  }
+}
+
+// out[n] += sum_m X[m][n]   (bias gradients of Linear)
+__global__ void __launch_bounds__(256) colsum_kernel(int M, int N, const float* __restrict__ X, int ld, int rows_per_cta,
+                                                     float* __restrict__ out) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  float s = 0.f;
+  if (n < N)
+    for (int m = m0 + (threadIdx.x >> 5); m < m1; m += 8) s += X[(size_t)m * ld + n];
+  __shared__ float red[8][33];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (threadIdx.x < 32 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + n, t);
+  }
+}
+
+// ---- optimizer on a flat parameter arena -------------------------------------------------------
+__global__ void __launch_bounds__(256) sq_norm_kernel(long long n, const float* __restrict__ g, double* __restrict__ out) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = g[i];
+    s += (double)v * v;
+  }
+  s = warp_sum(s);
+  __shared__ double ss[8];
+  if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0;
+    for (int w = 0; w < 8; ++w) S += ss[w];
+    atomicAdd(out, S);
+  }
+}
+
+// fl::SGDOptimizer::step with the loop's gradient scaling and fl::clipGradNorm folded in:
+//   g = grad * grad_scale * min(1, max_norm / (sqrt(sq_norm) * grad_scale))   (max_norm <= 0: no clip)
+//   g += wd * p ; v = momentum * v + g ; p -= lr * v      (momentum == 0: p -= lr * g)
+__global__ void __launch_bounds__(256) sgd_step_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ v, float lr, float momentum, float wd,
+                                                       float grad_scale, float max_norm, const double* __restrict__ sq_norm) {
+  float scale = grad_scale;
+  if (max_norm > 0.f && sq_norm != nullptr) {
+    const float nrm = sqrtf((float)*sq_norm) * grad_scale;
+    if (nrm > max_norm) scale *= max_norm / (nrm + 1e-6f);
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * scale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    if (momentum != 0.f) {
+      const float vi = fmaf(momentum, v[i], gi);
+      v[i] = vi;
+      gi = vi;
+    }
+    p[i] = pi - lr * gi;
+  }
+}
+
+int blocks_for(long long n, int per_block = 256 * 8) { return (int)std::min<long long>((n + per_block - 1) / per_block, 148 * 8); }
+
+}  // namespace
+}  // namespace w2l
+
+using namespace w2l;
+
+static int co_pad(int c) { return (c + 3) / 4 * 4; }
+
+extern "C" size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K) {
+  const int chunk = 16;
+  const size_t ctas = (size_t)B * ((Tout + chunk - 1) / chunk);
+  const size_t part = ctas * ((size_t)Cout * Cin * K + Cout) * sizeof(float);
+  const size_t arranged = (size_t)std::max(Cin, Cout) * K * co_pad(std::max(Cin, Cout)) * sizeof(float);
+  return align_up(part, 256) + align_up(arranged, 256);
+}
+
+#define W2L_CONV_DISPATCH(CO_VAL, ...)                   \
+  switch (CO_VAL) {                                              \
+    case 4: { constexpr int CO = 4; __VA_ARGS__; } break;        \
+    case 8: { constexpr int CO = 8; __VA_ARGS__; } break;        \
+    case 12: { constexpr int CO = 12; __VA_ARGS__; } break;      \
+    case 16: { constexpr int CO = 16; __VA_ARGS__; } break;      \
+    case 20: { constexpr int CO = 20; __VA_ARGS__; } break;      \
+    case 24: { constexpr int CO = 24; __VA_ARGS__; } break;      \
+    case 28: { constexpr int CO = 28; __VA_ARGS__; } break;      \
+    case 32: { constexpr int CO = 32; __VA_ARGS__; } break;      \
+    default: return fail(W2L_ERR_UNSUPPORTED, "conv_time: more than 32 channels is not covered"); \
+  }
+
+static int conv_check(int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride) {
+  if (B <= 0 || T <= 0 || Tout <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || K <= 0 || stride <= 0)
+    return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time: non-positive dimension");
+  if (W > 80) return fail(W2L_ERR_UNSUPPORTED, "conv_time: W > 80 is not covered");
+  if (Cin > 32 || Cout > 32) return fail(W2L_ERR_UNSUPPORTED, "conv_time: more than 32 channels is not covered");
+  return W2L_OK;
+}
+
+extern "C" int w2l_conv_time_fwd(void* stream_, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                                 int pad_left, const float* x, const float* wt, const float* bias, const float* add,
+                                 float* y, int act, float dropout_p, unsigned long long seed, void* ws, size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = conv_check(B, T, Tout, W, Cin, Cout, K, stride)) return rc;
+  if (!x || !wt || !y || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_fwd: null pointer");
+  if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_fwd: workspace too small");
+  const int CO = co_pad(Cout);
+  float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * ((Tout + 15) / 16) * ((size_t)Cout * Cin * K + Cout) * 4, 256));
+  conv_arrange_weights_kernel<<<8, 256, 0, stream>>>(Cin, Cout, K, CO, wt, arranged, 0);
+  W2L_LAUNCH_CHECK("conv_arrange_weights_kernel");
+  const size_t smem = (size_t)Cin * K * CO * sizeof(float);
+  dim3 grid((Tout + kConvTo - 1) / kConvTo, B), block(96, kConvTo / 2);
+  W2L_CONV_DISPATCH(CO, {
+    if (smem > 48 * 1024)
+      W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_fwd_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_time_fwd_kernel<CO><<<grid, block, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, x, arranged, bias, add, y,
+                                                            act, dropout_p, seed);
+  });
+  W2L_LAUNCH_CHECK("conv_time_fwd_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_conv_time_dgrad(void* stream_, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                                   int pad_left, const float* dy, const float* wt, const float* add, float* dx, void* ws,
+                                   size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = conv_check(B, T, Tout, W, Cin, Cout, K, stride)) return rc;
+  if (!dy || !wt || !dx || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_dgrad: null pointer");
+  if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_dgrad: workspace too small");
+  if (stride == 1 && Tout == T) {
+    // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped
+    const int CI = co_pad(Cin);
+    float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * ((Tout + 15) / 16) * ((size_t)Cout * Cin * K + Cout) * 4, 256));
+    conv_arrange_weights_kernel<<<8, 256, 0, stream>>>(Cin, Cout, K, CI, wt, arranged, 1);
+    W2L_LAUNCH_CHECK("conv_arrange_weights_kernel");
+    const size_t smem = (size_t)Cout * K * CI * sizeof(float);
+    dim3 grid((T + kConvTo - 1) / kConvTo, B), block(96, kConvTo / 2);
+    W2L_CONV_DISPATCH(CI, {
+      if (smem > 48 * 1024)
+        W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_fwd_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv_time_fwd_kernel<CO><<<grid, block, smem, stream>>>(Tout, T, W, Cout, Cin, K, 1, K - 1 - pad_left, dy, arranged, nullptr,
+                                                              add, dx, 0, 0.f, 0ull);
+    });
+    W2L_LAUNCH_CHECK("conv_time_fwd_kernel(dgrad)");
+    return W2L_OK;
+  }
+  const int CI = co_pad(Cin);
+  const size_t smem = (size_t)K * Cout * CI * sizeof(float);
+  dim3 grid((T + 3) / 4, B), block(96, 4);
+  W2L_CONV_DISPATCH(CI, {
+    if (smem > 48 * 1024)
+      W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_dgrad_strided_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_time_dgrad_strided_kernel<CO><<<grid, block, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, dy, wt, add, dx);
+  });
+  W2L_LAUNCH_CHECK("conv_time_dgrad_strided_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_conv_time_wgrad(void* stream_, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                                   int pad_left, const float* x, const float* dy, float* dwt, float* dbias, void* ws,
+                                   size_t ws_bytes) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = conv_check(B, T, Tout, W, Cin, Cout, K, stride)) return rc;
+  if (!x || !dy || !dwt || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_wgrad: null pointer");
+  if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_wgrad: workspace too small");
+  if (stride > K) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: stride > kernel width");
+  const int ntiles = ((Cout + 1) / 2) * ((Cin * K + 3) / 4);
+  if (ntiles > kWgMaxTiles * kWgThreads) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: filter too large for the register tiles");
+  const int chunk = 16;
+  dim3 grid((Tout + chunk - 1) / chunk, B);
+  const size_t smem = ((size_t)K * Cin * 80 + (size_t)Cout * 80) * sizeof(float);
+  if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: input window does not fit in shared memory");
+  if (smem > 48 * 1024)
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  float* partial = static_cast<float*>(ws);
+  conv_time_wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, chunk, x, dy, partial);
+  W2L_LAUNCH_CHECK("conv_time_wgrad_kernel");
+  const int n_w = Cout * Cin * K;
+  conv_wgrad_reduce_kernel<<<(n_w + Cout + 255) / 256, 256, 0, stream>>>((int)(grid.x * grid.y), n_w, Cout, partial, dwt, dbias);
+  W2L_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_layernorm_fwd(void* stream_, int B, long long R, float eps, const float* a, const float* r,
+                                 const float* gain, const float* bias, float* y, float* mean_rstd, double* scratch) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (B <= 0 || R <= 0 || !a || !y || !mean_rstd || !scratch) return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_fwd: bad arguments");
+  W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
+  dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
+  ln_stats_kernel<<<grid, 256, 0, stream>>>(R, a, r, scratch);
+  W2L_LAUNCH_CHECK("ln_stats_kernel");
+  ln_apply_kernel<<<grid, 256, 0, stream>>>(R, eps, a, r, gain, bias, scratch, y, mean_rstd);
+  W2L_LAUNCH_CHECK("ln_apply_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_layernorm_bwd(void* stream_, int B, long long R, const float* a, const float* r, const float* dy,
+                                 const float* gain, const float* mean_rstd, float* d_branch, float* d_res, int branch_mode,
+                                 float branch_scale, float* dgain, float* dbias, double* scratch) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (B <= 0 || R <= 0 || !a || !dy || !mean_rstd || !d_branch || !scratch)
+    return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_bwd: bad arguments");
+  if (branch_mode < 0 || branch_mode > 2) return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_bwd: bad branch mode");
+  W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
+  dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
+  ln_bwd_stats_kernel<<<grid, 256, 0, stream>>>(R, a, r, dy, mean_rstd, scratch);
+  W2L_LAUNCH_CHECK("ln_bwd_stats_kernel");
+  ln_bwd_apply_kernel<<<grid, 256, 0, stream>>>(R, a, r, dy, gain, mean_rstd, scratch, d_branch, d_res, branch_mode, branch_scale,
+                                                dgain, dbias);
+  W2L_LAUNCH_CHECK("ln_bwd_apply_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_colsum_accumulate(void* stream_, int M, int N, const float* X, int ld, float* out) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || !X || !out) return fail(W2L_ERR_INVALID_ARGUMENT, "colsum: bad arguments");
+  const int rows_per_cta = 256;
+  dim3 grid((N + 31) / 32, (M + rows_per_cta - 1) / rows_per_cta);
+  colsum_kernel<<<grid, 256, 0, stream>>>(M, N, X, ld, rows_per_cta, out);
+  W2L_LAUNCH_CHECK("colsum_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_sq_norm_accumulate(void* stream_, long long n, const float* g, double* out) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || !g || !out) return fail(W2L_ERR_INVALID_ARGUMENT, "sq_norm: bad arguments");
+  sq_norm_kernel<<<blocks_for(n), 256, 0, stream>>>(n, g, out);
+  W2L_LAUNCH_CHECK("sq_norm_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_sgd_step(void* stream_, long long n, float* params, const float* grads, float* velocity, float lr,
+                            float momentum, float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || !params || !grads || (momentum != 0.f && !velocity)) return fail(W2L_ERR_INVALID_ARGUMENT, "sgd_step: bad arguments");
+  sgd_step_kernel<<<blocks_for(n), 256, 0, stream>>>(n, params, grads, velocity, lr, momentum, weight_decay, grad_scale,
+                                                     max_grad_norm, sq_norm);
+  W2L_LAUNCH_CHECK("sgd_step_kernel");
+  return W2L_OK;
+}

@@ -103,7 +103,29 @@ struct GemmParams {
   int M, N, K, ldc, act;
   float* C;
   const float* bias;
+  // epilogue extensions: forward dropout, backward mask read from a stored activation, C += acc
+  int accumulate, aux_mode, ld_aux;  // aux_mode 0: none, 1: (aux > 0) * aux_scale, 2: (aux != 0) * aux_scale
+  const float* aux;
+  float aux_scale, drop_p;
+  unsigned long long seed;
 };
+
+__device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
 
 template <bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -214,12 +236,49 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int nb = n0 + c * 32;
       if (row < p.M && nb < p.N) {
         float o[32];
+        const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]);
           if (p.bias != nullptr && nb + j < p.N) x += __ldg(p.bias + nb + j);
           if (p.act == 1) x = fmaxf(x, 0.f);
           o[j] = x;
+        }
+        if (p.drop_p > 0.f) {
+          // element index row * N + n; one Philox call covers 4 consecutive columns (nb % 4 == 0)
+          const unsigned long long base_idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const unsigned long long idx = base_idx + j;
+            const uint4 r = philox4x32_g((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // lane of element idx+e inside its Philox block is (idx+e) & 3
+              const unsigned long long ie = idx + e;
+              uint32_t rv = rr[(int)(ie & 3ull)];
+              if ((ie >> 2) != (idx >> 2)) {
+                const uint4 r2 = philox4x32_g((uint32_t)(ie >> 2), (uint32_t)(ie >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                const uint32_t rr2[4] = {r2.x, r2.y, r2.z, r2.w};
+                rv = rr2[(int)(ie & 3ull)];
+              }
+              o[j + e] *= ((float)(rv >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+            }
+          }
+        }
+        if (p.aux_mode != 0) {
+          const float* arow = p.aux + (size_t)row * p.ld_aux + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) {
+              const float a = __ldg(arow + j);
+              o[j] *= (p.aux_mode == 1 ? a > 0.f : a != 0.f) ? p.aux_scale : 0.f;
+            }
+        }
+        if (p.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) o[j] += crow[nb + j];
         }
         if (vec_ok && nb + 32 <= p.N) {
 #pragma unroll
@@ -295,12 +354,27 @@ int launch(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, co
 
 using namespace w2l;
 
+extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                                const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
+                                const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
+                                unsigned long long seed);
+
 extern "C" int w2l_gemm_tf32(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
                              const float* B, int ldb, float* C, int ldc, const float* bias, int act) {
+  return w2l_gemm_tf32_ex(stream_, a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, bias, act, 0, nullptr, 0, 0, 1.f, 0.f, 0ull);
+}
+
+extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                                const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
+                                const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
+                                unsigned long long seed) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: M, N, K must be positive");
   if (!A || !B || !C) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: null pointer");
   if (act < 0 || act > 1) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: act must be 0 (none) or 1 (relu)");
+  if (aux_mode < 0 || aux_mode > 2 || (aux_mode != 0 && (!aux || ld_aux < N)))
+    return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: bad aux mask arguments");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: dropout_p must be in [0, 1)");
   if ((lda % 4) || (ldb % 4) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: operand rows must be 16-byte aligned (ld % 4 == 0)");
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N)
@@ -317,7 +391,7 @@ extern "C" int w2l_gemm_tf32(void* stream_, int a_mn_major, int b_mn_major, int 
   else
     rc = make_map(&mb, B, K, N, ldb, BK, true);
   if (rc) return rc;
-  GemmParams p{M, N, K, ldc, act, C, bias};
+  GemmParams p{M, N, K, ldc, act, C, bias, accumulate, aux_mode, ld_aux, aux, aux_scale, dropout_p, seed};
   if (!a_mn_major && !b_mn_major) return launch<false, false>(stream, ma, mb, p);
   if (!a_mn_major && b_mn_major) return launch<false, true>(stream, ma, mb, p);
   if (a_mn_major && b_mn_major) return launch<true, true>(stream, ma, mb, p);
