@@ -75,6 +75,10 @@ W2L_API void w2l_reset_launch_count(void);
  * (asg_chains_kernel, ctc_chains_kernel, the GEMM of a dense op) on the call's stream, so that
  * kernel can be timed live inside a timed region.  Pass NULL, NULL to clear. */
 W2L_API void w2l_set_profile_events(void* start_event, void* stop_event);
+/* list mode: the k-th dominant-kernel launch of `kind` (0 any, 1 GEMM, 2 criterion chains) records pair k of the
+ * caller-owned arrays (n pairs); w2l_profile_events_used() tells how many were consumed.  NULL clears. */
+W2L_API int w2l_set_profile_event_list(int kind, void** start_events, void** stop_events, int n);
+W2L_API int w2l_profile_events_used(void);
 
 /* ----------------------------------------------------------------------------------------
  * ASG = FullConnectionCriterion - ForceAlignmentCriterion, fused forward + backward.
@@ -191,6 +195,40 @@ W2L_API int w2l_colsum_accumulate(void* stream, int M, int N, const float* X, in
 W2L_API int w2l_sq_norm_accumulate(void* stream, long long n, const float* g, double* out);
 W2L_API int w2l_sgd_step(void* stream, long long n, float* params, const float* grads, float* velocity, float lr,
                          float momentum, float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm);
+
+/* small element-wise helpers of the host layer: network input [T,F,1,B] (ArrayFire, T fastest) -> internal
+ * [B][T][1][F]; y += a*x; y = v; standalone ReLU/Dropout forward and their backward mask. */
+W2L_API int w2l_transpose_input(void* stream, int B, int F, int T, const float* in, float* out);
+W2L_API int w2l_axpy(void* stream, long long n, float a, const float* x, float* y);
+W2L_API int w2l_fill(void* stream, long long n, float v, float* y);
+W2L_API int w2l_act_fwd(void* stream, long long n, const float* x, int relu, float dropout_p, unsigned long long seed, float* y);
+W2L_API int w2l_mask_mul(void* stream, long long n, const float* g, const float* ref, int mode, float scale, float* out);
+
+/* ----------------------------------------------------------------------------------------
+ * Training-step driver: the body of the reference loop (recipes/slimIPL/src/Train.cpp:1454-1803) written
+ * in C++ against include/fl_compat/fl_compat.h — network forward, criterion, loss.backward(), NCCL
+ * all-reduce of every gradient, division by the global batch size, clipGradNorm over net U criterion,
+ * criterion + network SGD steps.  `arch_text` is a wav2letter arch file (opcodes V RO PD C2 R DO LN TDS L
+ * SAUG), `criterion` "ctc" or "asg".  All pointers below are DEVICE pointers:
+ * features [T,F,1,B] (ArrayFire layout, T fastest), target [L,B] int32 (-1 padded), loss_out [B].
+ * Returns NULL / a status code; w2l_last_error() has the text.
+ * ---------------------------------------------------------------------------------------- */
+W2L_API void* w2l_trainer_create(void* stream, const char* arch_text, int n_feat, int n_label, const char* criterion,
+                                 int scale_mode, float transdiag, float lr, float lrcrit, float momentum, float maxgradnorm);
+W2L_API void w2l_trainer_destroy(void* trainer);
+W2L_API int w2l_trainer_step(void* trainer, void* stream, int B, int T, const float* features, int L, const int32_t* target,
+                             float* loss_out, int train, float total_batch);
+W2L_API int w2l_trainer_forward(void* trainer, void* stream, int B, int T, const float* features, float* emissions_out,
+                                long long capacity, int* t_out);
+W2L_API long long w2l_trainer_num_params(void* trainer, int which /*0 network, 1 criterion*/);
+W2L_API int w2l_trainer_param_layout(void* trainer, int which, int max_params, long long* elements, long long* dims4);
+W2L_API int w2l_trainer_get_flat(void* trainer, void* stream, int which, int what /*0 values, 1 gradients*/, float* out);
+W2L_API int w2l_trainer_set_flat(void* trainer, void* stream, int which, const float* in);
+W2L_API int w2l_trainer_sync_parameters(void* trainer, void* stream);   /* fl::allReduceParameters, Train.cpp:1078-1079 */
+W2L_API const char* w2l_trainer_describe(void* trainer);
+/* data-parallel rendezvous: rank 0 creates the 128-byte NCCL id, the launcher ships it to every rank */
+W2L_API int w2l_nccl_unique_id(void* out128);
+W2L_API int w2l_init_distributed(int rank, int world, const void* id128);
 
 #ifdef __cplusplus
 }

@@ -19,14 +19,17 @@ TERM_FCC, TERM_FAC, TERM_ASG = 1, 2, 3
 
 # every entry point include/w2l_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count", "w2l_set_profile_events",
+    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count", "w2l_set_profile_events", "w2l_set_profile_event_list", "w2l_profile_events_used",
     "w2l_asg_workspace_size", "w2l_asg_forward_backward",
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
     "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
     "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
     "w2l_conv_time_wgrad", "w2l_layernorm_fwd", "w2l_layernorm_bwd", "w2l_colsum_accumulate", "w2l_sq_norm_accumulate",
-    "w2l_sgd_step",
+    "w2l_sgd_step", "w2l_transpose_input", "w2l_axpy", "w2l_fill", "w2l_act_fwd", "w2l_mask_mul",
+    "w2l_trainer_create", "w2l_trainer_destroy", "w2l_trainer_step", "w2l_trainer_forward", "w2l_trainer_num_params",
+    "w2l_trainer_param_layout", "w2l_trainer_get_flat", "w2l_trainer_set_flat", "w2l_trainer_sync_parameters",
+    "w2l_trainer_describe", "w2l_nccl_unique_id", "w2l_init_distributed",
 ]
 
 
@@ -46,6 +49,7 @@ def _load() -> ctypes.CDLL:
     lib.w2l_last_error.restype = ctypes.c_char_p
     lib.w2l_launch_count.restype = ctypes.c_longlong
     lib.w2l_set_profile_events.argtypes = [vp, vp]
+    lib.w2l_set_profile_event_list.argtypes = [i, vp, vp, i]
     lib.w2l_asg_workspace_size.restype = sz
     lib.w2l_asg_workspace_size.argtypes = [i, i, i, i]
     lib.w2l_asg_forward_backward.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, sz]
@@ -73,6 +77,22 @@ def _load() -> ctypes.CDLL:
     lib.w2l_colsum_accumulate.argtypes = [vp, i, i, vp, i, vp]
     lib.w2l_sq_norm_accumulate.argtypes = [vp, ll, vp, vp]
     lib.w2l_sgd_step.argtypes = [vp, ll, vp, vp, vp, f32, f32, f32, f32, f32, vp]
+    lib.w2l_trainer_create.restype = vp
+    lib.w2l_trainer_create.argtypes = [vp, ctypes.c_char_p, i, i, ctypes.c_char_p, i, f32, f32, f32, f32, f32]
+    lib.w2l_trainer_destroy.argtypes = [vp]
+    lib.w2l_trainer_destroy.restype = None
+    lib.w2l_trainer_step.argtypes = [vp, vp, i, i, vp, i, vp, vp, i, f32]
+    lib.w2l_trainer_forward.argtypes = [vp, vp, i, i, vp, vp, ll, vp]
+    lib.w2l_trainer_num_params.restype = ll
+    lib.w2l_trainer_num_params.argtypes = [vp, i]
+    lib.w2l_trainer_param_layout.argtypes = [vp, i, i, vp, vp]
+    lib.w2l_trainer_get_flat.argtypes = [vp, vp, i, i, vp]
+    lib.w2l_trainer_set_flat.argtypes = [vp, vp, i, vp]
+    lib.w2l_trainer_sync_parameters.argtypes = [vp, vp]
+    lib.w2l_trainer_describe.restype = ctypes.c_char_p
+    lib.w2l_trainer_describe.argtypes = [vp]
+    lib.w2l_nccl_unique_id.argtypes = [vp]
+    lib.w2l_init_distributed.argtypes = [i, i, vp]
     return lib
 
 
@@ -217,6 +237,30 @@ def linseg_target(target, T: int):
     out = torch.empty((B, int(T)), dtype=torch.int32, device=target.device)
     _check(lib.w2l_linseg_target(_stream(), B, int(T), L, _ptr(target), _ptr(out)))
     return out
+
+
+class ProfileList:
+    """n CUDA event pairs recorded around the dominant-kernel launches of `kind` (1 GEMM, 2 criterion chains)."""
+
+    def __init__(self, kind: int, n: int):
+        self.starts = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        self.stops = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        for e in self.starts + self.stops:
+            e.record()
+        self._a = (ctypes.c_void_p * n)(*[e.cuda_event for e in self.starts])
+        self._b = (ctypes.c_void_p * n)(*[e.cuda_event for e in self.stops])
+        self.kind, self.n = kind, n
+
+    def arm(self):
+        lib.w2l_set_profile_event_list(self.kind, self._a, self._b, self.n)
+
+    def disarm(self) -> int:
+        used = int(lib.w2l_profile_events_used())
+        lib.w2l_set_profile_event_list(0, None, None, 0)
+        return used
+
+    def times_ms(self, used: int):
+        return [self.starts[k].elapsed_time(self.stops[k]) for k in range(used)]
 
 
 def gemm_tf32(A, B, bias=None, act=0, a_mn=False, b_mn=False, out=None):

@@ -492,6 +492,50 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(long long n, float* __res
   }
 }
 
+// features arrive as ArrayFire [T,F,1,B] (T fastest): in[b][f][t] -> internal [B][T][1][W=F]: out[b][t][f]
+__global__ void transpose_bft_kernel(int F, int T, const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const float* ib = in + (size_t)b * F * T;
+  float* ob = out + (size_t)b * T * F;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int f = f0 + j, t = t0 + threadIdx.x;
+    tile[j][threadIdx.x] = (f < F && t < T) ? ib[(size_t)f * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, f = f0 + threadIdx.x;
+    if (t < T && f < F) ob[(size_t)t * F + f] = tile[threadIdx.x][j];
+  }
+}
+__global__ void axpy_kernel(long long n, float a, const float* __restrict__ x, float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+__global__ void fill_kernel(long long n, float v, float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = v;
+}
+// out[i] = act_mask(ref[i]) * scale * g[i]   (standalone ReLU / Dropout backward); mode 1: ref > 0, 2: ref != 0
+__global__ void mask_mul_kernel(long long n, const float* __restrict__ g, const float* __restrict__ ref, int mode, float scale,
+                                float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float r = ref[i];
+    out[i] = ((mode == 1 ? r > 0.f : r != 0.f) ? scale : 0.f) * g[i];
+  }
+}
+// standalone ReLU / Dropout forward: y = dropout(relu?(x))
+__global__ void act_fwd_kernel(long long n, const float* __restrict__ x, int relu, float drop_p, unsigned long long seed,
+                               float* __restrict__ y) {
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (relu) v = fmaxf(v, 0.f);
+    if (drop_p > 0.f) v *= dropout_scale(seed, (unsigned long long)i, drop_p, inv_keep);
+    y[i] = v;
+  }
+}
+
 int blocks_for(long long n, int per_block = 256 * 8) { return (int)std::min<long long>((n + per_block - 1) / per_block, 148 * 8); }
 
 }  // namespace
@@ -669,5 +713,42 @@ extern "C" int w2l_sgd_step(void* stream_, long long n, float* params, const flo
   sgd_step_kernel<<<blocks_for(n), 256, 0, stream>>>(n, params, grads, velocity, lr, momentum, weight_decay, grad_scale,
                                                      max_grad_norm, sq_norm);
   W2L_LAUNCH_CHECK("sgd_step_kernel");
+  return W2L_OK;
+}
+
+extern "C" int w2l_transpose_input(void* stream_, int B, int F, int T, const float* in, float* out) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (B <= 0 || F <= 0 || T <= 0 || !in || !out) return fail(W2L_ERR_INVALID_ARGUMENT, "transpose_input: bad arguments");
+  dim3 grid((T + 31) / 32, (F + 31) / 32, B), block(32, 8);
+  transpose_bft_kernel<<<grid, block, 0, stream>>>(F, T, in, out);
+  W2L_LAUNCH_CHECK("transpose_bft_kernel");
+  return W2L_OK;
+}
+extern "C" int w2l_axpy(void* stream_, long long n, float a, const float* x, float* y) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || !x || !y) return fail(W2L_ERR_INVALID_ARGUMENT, "axpy: bad arguments");
+  axpy_kernel<<<blocks_for(n), 256, 0, stream>>>(n, a, x, y);
+  W2L_LAUNCH_CHECK("axpy_kernel");
+  return W2L_OK;
+}
+extern "C" int w2l_fill(void* stream_, long long n, float v, float* y) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || !y) return fail(W2L_ERR_INVALID_ARGUMENT, "fill: bad arguments");
+  fill_kernel<<<blocks_for(n), 256, 0, stream>>>(n, v, y);
+  W2L_LAUNCH_CHECK("fill_kernel");
+  return W2L_OK;
+}
+extern "C" int w2l_mask_mul(void* stream_, long long n, const float* g, const float* ref, int mode, float scale, float* out) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || !g || !ref || !out || mode < 1 || mode > 2) return fail(W2L_ERR_INVALID_ARGUMENT, "mask_mul: bad arguments");
+  mask_mul_kernel<<<blocks_for(n), 256, 0, stream>>>(n, g, ref, mode, scale, out);
+  W2L_LAUNCH_CHECK("mask_mul_kernel");
+  return W2L_OK;
+}
+extern "C" int w2l_act_fwd(void* stream_, long long n, const float* x, int relu, float dropout_p, unsigned long long seed, float* y) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0 || !x || !y) return fail(W2L_ERR_INVALID_ARGUMENT, "act_fwd: bad arguments");
+  act_fwd_kernel<<<blocks_for(n), 256, 0, stream>>>(n, x, relu, dropout_p, seed, y);
+  W2L_LAUNCH_CHECK("act_fwd_kernel");
   return W2L_OK;
 }

@@ -16,6 +16,7 @@ void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
 // bench hook: events recorded around a call's dominant kernel (nullptr when unset)
+void profile_kind(int kind);  // 1 = GEMM, 2 = criterion chains (set right before profile_start)
 void profile_start(cudaStream_t s);
 void profile_stop(cudaStream_t s);
 

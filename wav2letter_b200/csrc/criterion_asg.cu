@@ -972,6 +972,7 @@ extern "C" int w2l_asg_forward_backward(void* stream_, int terms, int B, int T, 
     if (smem > 48 * 1024)                                                                                     \
       W2L_CUDA_CHECK(cudaFuncSetAttribute(asg_chains_kernel<GRAD, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)smem));                                                        \
+    profile_kind(2);                                                                                          \
     profile_start(stream);                                                                                    \
     asg_chains_kernel<GRAD, K><<<n_fac + n_fcc, kChainThreads, smem, stream>>>(p, n_fac);                      \
     profile_stop(stream);                                                                                     \

@@ -396,6 +396,7 @@ extern "C" int w2l_ctc_forward_backward(void* stream_, int B, int T, int N, int 
   if (p.need_grad) {
     if (smem > 48 * 1024)
       W2L_CUDA_CHECK(cudaFuncSetAttribute(ctc_chains_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    profile_kind(2);
     profile_start(stream);
     ctc_chains_kernel<true><<<B, kCtcThreads, smem, stream>>>(p);
     profile_stop(stream);

@@ -1,0 +1,1053 @@
+// fl_compat.cpp — implementation of include/fl_compat/fl_compat.h on top of the C ABI (include/w2l_b200.h).
+// Host code only: every arithmetic operation is a call into libw2l_b200's sm_100a kernels.
+#include "fl_compat/fl_compat.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <unordered_set>
+
+#include "w2l_b200.h"
+
+namespace w2l {
+
+namespace {
+thread_local cudaStream_t g_stream = nullptr;
+void cudaCheck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+}  // namespace
+
+void check(int rc) {  // C ABI status -> the reference's exception style
+  if (rc == W2L_OK) return;
+  const std::string msg = w2l_last_error();
+  if (rc == W2L_ERR_CUDA) throw std::runtime_error(msg);
+  throw std::invalid_argument(msg);
+}
+
+void* currentStream() { return g_stream; }
+void setCurrentStream(void* s) { g_stream = static_cast<cudaStream_t>(s); }
+void sync() { cudaCheck(cudaStreamSynchronize(g_stream), "af::sync"); }
+
+size_t dtypeSize(DType t) {
+  switch (t) {
+    case DType::f32:
+    case DType::i32:
+      return 4;
+    case DType::f64:
+      return 8;
+    default:
+      return 1;
+  }
+}
+
+std::string Dims::str() const {
+  std::ostringstream o;
+  o << "[" << d[0] << " " << d[1] << " " << d[2] << " " << d[3] << "]";
+  return o.str();
+}
+
+struct Storage {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaStream_t stream = nullptr;
+  bool owner = true;
+  ~Storage() {
+    if (ptr && owner) cudaFreeAsync(ptr, stream);
+  }
+};
+
+namespace {
+// Stream-ordered allocation comes from the device's default pool.  By default that pool returns its memory
+// to the driver at every synchronisation (release threshold 0), which turns every step into a burst of
+// cudaMalloc calls; keep it resident instead (flashlight's CachingMemoryManager plays the same role).
+void configurePoolOnce() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  done = true;
+}
+}  // namespace
+
+Tensor Tensor::empty(const Dims& dims, DType t) {
+  configurePoolOnce();
+  Tensor r;
+  r.dims_ = dims;
+  r.type_ = t;
+  r.st_ = std::make_shared<Storage>();
+  r.st_->bytes = std::max<size_t>(r.bytes(), 16);
+  r.st_->stream = g_stream;
+  cudaCheck(cudaMallocAsync(&r.st_->ptr, r.st_->bytes, g_stream), "cudaMallocAsync");
+  return r;
+}
+Tensor Tensor::zeros(const Dims& dims, DType t) {
+  Tensor r = empty(dims, t);
+  r.zero();
+  return r;
+}
+Tensor Tensor::fromHost(const void* host, const Dims& dims, DType t) {
+  Tensor r = empty(dims, t);
+  cudaCheck(cudaMemcpyAsync(r.ptr(), host, r.bytes(), cudaMemcpyHostToDevice, g_stream), "cudaMemcpyAsync H2D");
+  return r;
+}
+Tensor Tensor::view(const Tensor& base, size_t byte_offset, const Dims& dims, DType t) {
+  Tensor r;
+  r.st_ = base.st_;
+  r.off_ = base.off_ + byte_offset;
+  r.dims_ = dims;
+  r.type_ = t;
+  if (r.off_ + r.bytes() > base.st_->bytes) throw std::invalid_argument("Tensor::view: window outside the storage");
+  return r;
+}
+Tensor Tensor::wrap(void* device_ptr, const Dims& dims, DType t) {
+  Tensor r;
+  r.dims_ = dims;
+  r.type_ = t;
+  r.st_ = std::make_shared<Storage>();
+  r.st_->ptr = device_ptr;
+  r.st_->bytes = r.bytes();
+  r.st_->owner = false;
+  return r;
+}
+void* Tensor::ptr() const { return st_ ? static_cast<char*>(st_->ptr) + off_ : nullptr; }
+Tensor Tensor::reshaped(const Dims& dims) const {
+  if (dims.elements() != elements()) throw std::invalid_argument("moddims: element count mismatch " + dims_.str() + " -> " + dims.str());
+  Tensor r = *this;
+  r.dims_ = dims;
+  return r;
+}
+void Tensor::copyToHost(void* host) const {
+  cudaCheck(cudaMemcpyAsync(host, ptr(), bytes(), cudaMemcpyDeviceToHost, g_stream), "cudaMemcpyAsync D2H");
+  sync();
+}
+void Tensor::zero() const { cudaCheck(cudaMemsetAsync(ptr(), 0, bytes(), g_stream), "cudaMemsetAsync"); }
+void Tensor::fill(float v) const {
+  if (type_ != DType::f32) throw std::invalid_argument("fill: f32 only");
+  check(w2l_fill(g_stream, elements(), v, f32()));
+}
+void Tensor::copyFrom(const Tensor& src) const {
+  if (src.bytes() != bytes()) throw std::invalid_argument("copyFrom: size mismatch");
+  cudaCheck(cudaMemcpyAsync(ptr(), src.ptr(), bytes(), cudaMemcpyDeviceToDevice, g_stream), "cudaMemcpyAsync D2D");
+}
+
+}  // namespace w2l
+
+namespace fl {
+
+using w2l::check;
+using w2l::currentStream;
+using w2l::DType;
+
+// ================================================================================================
+// Variable / autograd
+// ================================================================================================
+struct Variable::Impl {
+  af::array data;
+  bool calcGrad = false;
+  std::vector<Variable> inputs;
+  GradFunc gradFunc;
+  std::shared_ptr<Variable> grad;
+  af::array boundGrad;  // pre-bound accumulation buffer (gradient arena)
+  bool gradLive = false;  // boundGrad holds a valid (accumulated) gradient
+  bool onesSeed = false;
+};
+
+Variable::Variable(const af::array& data, bool calcGrad) : impl_(std::make_shared<Impl>()) {
+  impl_->data = data;
+  impl_->calcGrad = calcGrad;
+}
+Variable::Variable(const af::array& data, std::vector<Variable> inputs, GradFunc gradFunc) : impl_(std::make_shared<Impl>()) {
+  impl_->data = data;
+  bool any = false;
+  for (auto& in : inputs) any = any || in.isCalcGrad();
+  impl_->calcGrad = any;
+  if (any) {
+    impl_->inputs = std::move(inputs);
+    impl_->gradFunc = std::move(gradFunc);
+  }
+}
+af::array& Variable::array() const {
+  if (!impl_) throw std::logic_error("Variable: empty");
+  return impl_->data;
+}
+bool Variable::isCalcGrad() const { return impl_ && impl_->calcGrad; }
+bool Variable::isGradAvailable() const { return impl_ && impl_->calcGrad && (impl_->grad != nullptr); }
+Variable& Variable::grad() const {
+  if (!isGradAvailable()) throw std::logic_error("Variable::grad: gradient not available");
+  return *impl_->grad;
+}
+bool Variable::isOnesSeed() const { return impl_ && impl_->onesSeed; }
+void Variable::setGradStorage(const af::array& buf) {
+  if (buf.elements() != array().elements()) throw std::invalid_argument("setGradStorage: size mismatch");
+  impl_->boundGrad = buf.reshaped(array().dims());
+  impl_->gradLive = false;
+  impl_->grad.reset();
+}
+void Variable::addGrad(const Variable& g) {
+  if (!impl_ || !impl_->calcGrad) return;
+  if (g.elements() != elements()) throw std::invalid_argument("addGrad: size mismatch");
+  if (!impl_->boundGrad.isEmpty()) {
+    // parameter with a slot in the gradient arena: the arena is zeroed by zeroGrad(), so accumulate
+    if (g.array().ptr() != impl_->boundGrad.ptr())
+      check(w2l_axpy(currentStream(), elements(), 1.0f, g.array().f32(), impl_->boundGrad.f32()));
+    if (!impl_->grad) impl_->grad = std::make_shared<Variable>(impl_->boundGrad, false);
+    return;
+  }
+  if (!impl_->grad) {
+    impl_->grad = std::make_shared<Variable>(g.array(), false);
+    impl_->grad->impl_->onesSeed = g.isOnesSeed();
+  } else {
+    // second consumer: out-of-place sum (keeps the first producer's buffer intact)
+    af::array sum = af::array::empty(array().dims());
+    sum.copyFrom(impl_->grad->array());
+    check(w2l_axpy(currentStream(), elements(), 1.0f, g.array().f32(), sum.f32()));
+    impl_->grad = std::make_shared<Variable>(sum, false);
+  }
+}
+void Variable::zeroGrad(bool zeroStorage) {
+  if (!impl_) return;
+  impl_->grad.reset();
+  impl_->gradLive = false;
+  if (zeroStorage && !impl_->boundGrad.isEmpty()) impl_->boundGrad.zero();
+}
+void Variable::backward(bool retainGraph) {
+  af::array ones = af::array::empty(array().dims());
+  ones.fill(1.0f);
+  Variable seed(ones, false);
+  seed.impl_->onesSeed = true;
+  backward(seed, retainGraph);
+}
+void Variable::backward(const Variable& g, bool retainGraph) {
+  addGrad(g);
+  // topological order (post-order DFS), then reverse
+  std::vector<Variable> order;
+  std::unordered_set<const void*> seen;
+  std::function<void(const Variable&)> dfs = [&](const Variable& v) {
+    if (!v.impl_ || seen.count(v.id())) return;
+    seen.insert(v.id());
+    for (auto& in : v.impl_->inputs) dfs(in);
+    order.push_back(v);
+  };
+  dfs(*this);
+  for (auto it = order.rbegin(); it != order.rend(); ++it) {
+    Variable& v = *it;
+    if (v.impl_->gradFunc && v.isGradAvailable()) v.impl_->gradFunc(v.impl_->inputs, v.grad());
+    if (!retainGraph && v.impl_->gradFunc) {
+      v.impl_->gradFunc = nullptr;
+      v.impl_->inputs.clear();
+      v.impl_->grad.reset();  // activation gradients are not needed after use
+    }
+  }
+}
+Variable constant(double v, const af::dim4& dims, DType t, bool calcGrad) {
+  af::array a = af::array::empty(dims, t);
+  if (t == DType::f32)
+    a.fill((float)v);
+  else
+    a.zero();
+  return Variable(a, calcGrad);
+}
+
+// ================================================================================================
+// Module plumbing
+// ================================================================================================
+Variable Module::param(int i) const {
+  auto p = params();
+  if (i < 0 || i >= (int)p.size()) throw std::out_of_range("Module::param: index out of range");
+  return p[i];
+}
+void Module::setParams(const Variable& v, int i) {
+  if (i < 0 || i >= (int)params_.size()) throw std::out_of_range("Module::setParams: index out of range");
+  params_[i] = v;
+}
+void Module::zeroGrad() {
+  for (auto& p : params()) p.zeroGrad();
+}
+std::vector<Variable> UnaryModule::forward(const std::vector<Variable>& inputs) {
+  if (inputs.empty()) throw std::invalid_argument("UnaryModule: expects at least one input");
+  return {forward(inputs[0])};
+}
+void Sequential::add(std::shared_ptr<Module> m) { modules_.push_back(std::move(m)); }
+std::vector<Variable> Sequential::forward(const std::vector<Variable>& inputs) {
+  std::vector<Variable> cur = inputs;
+  for (auto& m : modules_) cur = m->forward(cur);
+  return cur;
+}
+std::vector<Variable> Sequential::params() const {
+  std::vector<Variable> all;
+  for (auto& m : modules_) {
+    auto p = m->params();
+    all.insert(all.end(), p.begin(), p.end());
+  }
+  return all;
+}
+void Sequential::setParams(const Variable& v, int i) {
+  for (auto& m : modules_) {
+    const int n = (int)m->params().size();
+    if (i < n) {
+      m->setParams(v, i);
+      return;
+    }
+    i -= n;
+  }
+  throw std::out_of_range("Sequential::setParams: index out of range");
+}
+void Sequential::train() {
+  train_ = true;
+  for (auto& m : modules_) m->train();
+}
+void Sequential::eval() {
+  train_ = false;
+  for (auto& m : modules_) m->eval();
+}
+std::string Sequential::prettyString() const {
+  std::ostringstream o;
+  o << "Sequential [input";
+  for (size_t i = 0; i < modules_.size(); ++i) o << " -> (" << i << ")";
+  o << " -> output]";
+  for (size_t i = 0; i < modules_.size(); ++i) o << "\n\t(" << i << "): " << modules_[i]->prettyString();
+  return o.str();
+}
+
+namespace {
+std::atomic<unsigned long long> g_seed_counter{0x5eed0000ull};
+unsigned long long nextSeed() { return g_seed_counter.fetch_add(0x9E3779B97F4A7C15ull); }
+
+// weights ~ U(-b, b), b = sqrt(1/fan_in) * gain-ish (flashlight's default Conv2D/Linear init family);
+// generated on the host (deterministic per process) and uploaded once
+af::array uniformInit(const af::dim4& dims, double bound, unsigned long long seed) {
+  std::mt19937_64 gen(seed);
+  std::uniform_real_distribution<float> dist((float)-bound, (float)bound);
+  std::vector<float> h((size_t)dims.elements());
+  for (auto& v : h) v = dist(gen);
+  return af::array::fromHost(h.data(), dims);
+}
+
+// internal activation layout: dims [W, C, T, B] (memory [B][T][C][W])
+void requireInternal(const Variable& v, const char* who) {
+  if (v.type() != DType::f32) throw std::invalid_argument(std::string(who) + ": expects f32 activations");
+}
+af::array workspaceFor(af::array& cache, size_t bytes) {
+  if (cache.isEmpty() || cache.bytes() < bytes) cache = af::array::empty(af::dim4((long long)std::max<size_t>(bytes, 256)), DType::u8);
+  return cache;
+}
+thread_local af::array g_conv_ws;
+}  // namespace
+
+// ================================================================================================
+// View (network head): [T,F,1,B] ArrayFire -> internal [W=F, C=1, T, B]; other views are relabellings
+// ================================================================================================
+Variable View::forward(const Variable& in) {
+  // head of a TDS arch: `V -1 NFEAT 1 0` applied to the loader's [T,F,1,B] tensor
+  if (dims_[2] == 1 && dims_[0] == -1 && in.dims(2) == 1 && in.dims(1) == dims_[1]) {
+    const long long T = in.dims(0), F = in.dims(1), B = in.dims(3);
+    af::array out = af::array::empty(af::dim4(F, 1, T, B));
+    check(w2l_transpose_input(currentStream(), (int)B, (int)F, (int)T, in.array().f32(), out.f32()));
+    return Variable(out, in.isCalcGrad());
+  }
+  return in;  // [T,W,C,B] <-> [C*W,T,B] <-> [N,T,B] are the same memory in the internal layout
+}
+std::string View::prettyString() const { return "View (" + dims_.str() + ")"; }
+std::string Reorder::prettyString() const {
+  std::ostringstream o;
+  o << "Reorder (" << perm_[0] << "," << perm_[1] << "," << perm_[2] << "," << perm_[3] << ")";
+  return o.str();
+}
+
+// ================================================================================================
+// Conv2D (kw x 1 over time)
+// ================================================================================================
+Conv2D::Conv2D(int nIn_, int nOut_, int wx, int wy, int sx, int sy, int px, int py, int dx, int dy, bool bias, int groups)
+    : nIn(nIn_), nOut(nOut_), kw(wx), stride(sx), pad(px), hasBias_(bias) {
+  if (wy != 1 || sy != 1 || dx != 1 || dy != 1 || groups != 1 || (py != 0 && py != -1))
+    throw std::invalid_argument("Conv2D: only kw x 1 kernels over time (wy = sy = 1, no dilation/groups) are covered");
+  if (nIn <= 0 || nOut <= 0 || kw <= 0 || sx <= 0) throw std::invalid_argument("Conv2D: non-positive size");
+  // flashlight's default conv init: uniform with std-dev sqrt(1 / fan_in)
+  const double bound = std::sqrt(3.0 / (double)(nIn * kw));
+  params_.push_back(Variable(uniformInit(af::dim4(kw, 1, nIn, nOut), bound, nextSeed()), true));  // [kw,1,cin,cout] == [cout][cin][kw]
+  if (bias) params_.push_back(Variable(uniformInit(af::dim4(1, 1, nOut, 1), bound, nextSeed()), true));
+}
+std::string Conv2D::prettyString() const {
+  std::ostringstream o;
+  o << "Conv2D (" << nIn << "->" << nOut << ", " << kw << "x1, " << stride << ",1, " << (pad == -1 ? std::string("SAME") : std::to_string(pad))
+    << ",0, 1, 1)" << (hasBias_ ? " (with bias)" : " (without bias)") << (relu_ ? " +ReLU" : "") << (dropP_ > 0 ? " +Dropout" : "");
+  return o.str();
+}
+Variable Conv2D::forwardMasked(const Variable& in, bool maskByConsumer) {
+  requireInternal(in, "Conv2D");
+  const int W = (int)in.dims(0), Cin = (int)in.dims(1), T = (int)in.dims(2), B = (int)in.dims(3);
+  if (Cin != nIn) throw std::invalid_argument("Conv2D: input has " + std::to_string(Cin) + " channels, expected " + std::to_string(nIn));
+  int pl, pr;
+  if (explicitPad_) {
+    pl = padL_;
+    pr = padR_;
+  } else if (pad == (int)PaddingMode::SAME) {  // flashlight derivePadding: symmetric
+    const int rem = T % stride;
+    int tot = (kw - 1) - (rem == 0 ? stride : rem) + 1;
+    pl = pr = std::max((tot + 1) / 2, 0);
+  } else {
+    pl = pr = pad;
+  }
+  const int Tout = (T + pl + pr - kw) / stride + 1;
+  if (Tout <= 0) throw std::invalid_argument("Conv2D: input shorter than the kernel");
+  af::array y = af::array::empty(af::dim4(W, nOut, Tout, B));
+  const size_t wsb = w2l_conv_time_workspace_size(B, Tout, nIn, nOut, kw);
+  af::array ws = workspaceFor(g_conv_ws, wsb);
+  const float dp = (train_ && dropP_ > 0) ? dropP_ : 0.f;
+  const unsigned long long seed = nextSeed();
+  Variable wv = params_[0];
+  Variable bv = hasBias_ ? params_[1] : Variable();
+  check(w2l_conv_time_fwd(currentStream(), B, T, Tout, W, nIn, nOut, kw, stride, pl, in.array().f32(), wv.array().f32(),
+                          hasBias_ ? bv.array().f32() : nullptr, nullptr, y.f32(), relu_ ? 1 : 0, dp, seed, ws.ptr(), ws.bytes()));
+  const bool relu = relu_;
+  const int k = kw, s = stride, cin = nIn, cout = nOut;
+  const bool hasBias = hasBias_;
+  std::vector<Variable> inputs{in, wv};
+  if (hasBias) inputs.push_back(bv);
+  return Variable(y, inputs, [=](std::vector<Variable>& ins, const Variable& gout) {
+    af::array dy = gout.array();
+    if (!maskByConsumer && (relu || dp > 0.f)) {  // undo the fused activation from the stored output
+      af::array m = af::array::empty(y.dims());
+      check(w2l_mask_mul(currentStream(), y.elements(), dy.f32(), y.f32(), relu ? 1 : 2, dp > 0.f ? 1.0f / (1.0f - dp) : 1.0f, m.f32()));
+      dy = m;
+    }
+    af::array ws2 = workspaceFor(g_conv_ws, w2l_conv_time_workspace_size(B, Tout, cin, cout, k));
+    if (ins[1].isCalcGrad()) {
+      af::array dw = af::array::zeros(ins[1].dims());
+      af::array db = hasBias ? af::array::zeros(ins[2].dims()) : af::array();
+      check(w2l_conv_time_wgrad(currentStream(), B, T, Tout, W, cin, cout, k, s, pl, ins[0].array().f32(), dy.f32(), dw.f32(),
+                                hasBias ? db.f32() : nullptr, ws2.ptr(), ws2.bytes()));
+      ins[1].addGrad(Variable(dw, false));
+      if (hasBias) ins[2].addGrad(Variable(db, false));
+    }
+    if (ins[0].isCalcGrad()) {
+      af::array dx = af::array::empty(ins[0].dims());
+      check(w2l_conv_time_dgrad(currentStream(), B, T, Tout, W, cin, cout, k, s, pl, dy.f32(), ins[1].array().f32(), nullptr, dx.f32(),
+                                ws2.ptr(), ws2.bytes()));
+      ins[0].addGrad(Variable(dx, false));
+    }
+  });
+}
+
+// ================================================================================================
+// ReLU / Dropout (standalone; the arch builder fuses them into the preceding Conv2D when it can)
+// ================================================================================================
+Variable ReLU::forward(const Variable& in) {
+  af::array y = af::array::empty(in.dims());
+  check(w2l_act_fwd(currentStream(), in.elements(), in.array().f32(), 1, 0.f, 0ull, y.f32()));
+  return Variable(y, {in}, [y](std::vector<Variable>& ins, const Variable& g) {
+    af::array d = af::array::empty(y.dims());
+    check(w2l_mask_mul(currentStream(), y.elements(), g.array().f32(), y.f32(), 1, 1.0f, d.f32()));
+    ins[0].addGrad(Variable(d, false));
+  });
+}
+Variable Dropout::forward(const Variable& in) {
+  if (!train_ || p_ <= 0) return in;
+  af::array y = af::array::empty(in.dims());
+  const float p = (float)p_;
+  check(w2l_act_fwd(currentStream(), in.elements(), in.array().f32(), 0, p, nextSeed(), y.f32()));
+  return Variable(y, {in}, [y, p](std::vector<Variable>& ins, const Variable& g) {
+    af::array d = af::array::empty(y.dims());
+    check(w2l_mask_mul(currentStream(), y.elements(), g.array().f32(), y.f32(), 2, 1.0f / (1.0f - p), d.f32()));
+    ins[0].addGrad(Variable(d, false));
+  });
+}
+std::string Dropout::prettyString() const { return "Dropout (" + std::to_string(p_) + ")"; }
+
+// ================================================================================================
+// LayerNorm over the whole sample, scalar affine
+// ================================================================================================
+LayerNorm::LayerNorm(const std::vector<int>& axes, double eps, bool affine) : axes_(axes), eps_(eps) {
+  std::vector<int> s = axes;
+  std::sort(s.begin(), s.end());
+  // `LN 0 1 2`, and the legacy `LN 3` (= feature axis 3 -> normalise over 0,1,2) of seq2seq_tds/librispeech/network.arch
+  const bool whole = (s == std::vector<int>{0, 1, 2}) || (s == std::vector<int>{3});
+  if (!whole) throw std::invalid_argument("LayerNorm: only normalisation over the whole sample (axes 0 1 2) is covered");
+  if (affine) {
+    params_.push_back(Variable(af::array::zeros(af::dim4(1)), true));
+    params_[0].array().fill(1.0f);
+    params_.push_back(Variable(af::array::zeros(af::dim4(1)), true));
+  }
+}
+std::string LayerNorm::prettyString() const { return "LayerNorm ( axis : { 0 1 2 } , size : -1)"; }
+Variable LayerNorm::forward(const Variable& in) { return forwardResidual(in, Variable(), 0, 1.0f); }
+Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int branchMode, float keepScale) {
+  requireInternal(a, "LayerNorm");
+  const int B = (int)a.dims(3);
+  const long long R = a.elements() / B;
+  const bool hasRes = !r.isEmpty();
+  if (hasRes && r.elements() != a.elements()) throw std::invalid_argument("LayerNorm: residual size mismatch");
+  af::array y = af::array::empty(a.dims());
+  af::array mr = af::array::empty(af::dim4(2, B));
+  af::array scratch = af::array::empty(af::dim4(2 * B), DType::f64);
+  const bool affine = !params_.empty();
+  check(w2l_layernorm_fwd(currentStream(), B, R, (float)eps_, a.array().f32(), hasRes ? r.array().f32() : nullptr,
+                          affine ? params_[0].array().f32() : nullptr, affine ? params_[1].array().f32() : nullptr, y.f32(), mr.f32(),
+                          scratch.f64()));
+  std::vector<Variable> inputs{a};
+  if (hasRes) inputs.push_back(r);
+  if (affine) {
+    inputs.push_back(params_[0]);
+    inputs.push_back(params_[1]);
+  }
+  return Variable(y, inputs, [=](std::vector<Variable>& ins, const Variable& g) {
+    const int gi = hasRes ? 2 : 1;
+    af::array d_branch = af::array::empty(ins[0].dims());
+    af::array d_res = hasRes ? af::array::empty(ins[0].dims()) : af::array();
+    af::array dg = affine ? af::array::zeros(af::dim4(1)) : af::array();
+    af::array db = affine ? af::array::zeros(af::dim4(1)) : af::array();
+    af::array sc = af::array::empty(af::dim4(2 * B), DType::f64);
+    check(w2l_layernorm_bwd(currentStream(), B, R, ins[0].array().f32(), hasRes ? ins[1].array().f32() : nullptr, g.array().f32(),
+                            affine ? ins[gi].array().f32() : nullptr, mr.f32(), d_branch.f32(), hasRes ? d_res.f32() : nullptr,
+                            branchMode, keepScale, affine ? dg.f32() : nullptr, affine ? db.f32() : nullptr, sc.f64()));
+    ins[0].addGrad(Variable(d_branch, false));
+    if (hasRes) ins[1].addGrad(Variable(d_res, false));
+    if (affine) {
+      ins[gi].addGrad(Variable(dg, false));
+      ins[gi + 1].addGrad(Variable(db, false));
+    }
+  });
+}
+
+// ================================================================================================
+// Linear (tcgen05 GEMM)
+// ================================================================================================
+Linear::Linear(int nIn_, int nOut_, bool bias) : nIn(nIn_), nOut(nOut_), hasBias_(bias) {
+  if (nIn <= 0 || nOut <= 0) throw std::invalid_argument("Linear: non-positive size");
+  if (nIn % 4 || nOut % 4)
+    throw std::invalid_argument("Linear: in/out sizes must be multiples of 4 (16-byte rows for the TMA loads)");
+  const double bound = std::sqrt(1.0 / (double)nIn);
+  // memory [nOut][nIn] (nIn fastest) == column-major dims [nIn, nOut]: the K-major B operand of the forward
+  // GEMM.  Upstream stores the transpose ([out, in] column-major); INTEGRATION.md lists the conversion.
+  params_.push_back(Variable(uniformInit(af::dim4(nIn, nOut), bound, nextSeed()), true));
+  if (bias) params_.push_back(Variable(uniformInit(af::dim4(nOut), bound, nextSeed()), true));
+}
+std::string Linear::prettyString() const {
+  return "Linear (" + std::to_string(nIn) + "->" + std::to_string(nOut) + ")" + (hasBias_ ? " (with bias)" : " (without bias)");
+}
+Variable Linear::forward(const Variable& in) { return forwardFused(in, false, 0.f); }
+Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool maskByConsumer, int inMaskMode, float inMaskScale) {
+  requireInternal(in, "Linear");
+  long long T, B;
+  if (in.dims(0) == nIn) {  // flattened [K, T, B]
+    T = in.dims(1);
+    B = in.dims(2) * in.dims(3);
+  } else if (in.dims(0) * in.dims(1) == nIn) {  // activation [W, C, T, B]
+    T = in.dims(2);
+    B = in.dims(3);
+  } else {
+    throw std::invalid_argument("Linear: input " + in.dims().str() + " does not have " + std::to_string(nIn) + " features");
+  }
+  const int M = (int)(T * B);
+  af::array y = af::array::empty(af::dim4(nOut, T, B));
+  Variable wv = params_[0];
+  Variable bv = hasBias_ ? params_[1] : Variable();
+  const float dp = (train_ && dropP > 0) ? dropP : 0.f;
+  // NOTE: the weight is stored [nOut][nIn] row-major (K-major B operand)
+  check(w2l_gemm_tf32_ex(currentStream(), 0, 0, M, nOut, nIn, in.array().f32(), nIn, wv.array().f32(), nIn, y.f32(), nOut,
+                         hasBias_ ? bv.array().f32() : nullptr, relu ? 1 : 0, 0, nullptr, 0, 0, 1.f, dp, nextSeed()));
+  const int nin = nIn, nout = nOut;
+  const bool hasBias = hasBias_;
+  std::vector<Variable> inputs{in, wv};
+  if (hasBias) inputs.push_back(bv);
+  return Variable(y, inputs, [=](std::vector<Variable>& ins, const Variable& gout) {
+    af::array dy = gout.array();
+    if (!maskByConsumer && (relu || dp > 0.f)) {
+      af::array m = af::array::empty(y.dims());
+      check(w2l_mask_mul(currentStream(), y.elements(), dy.f32(), y.f32(), relu ? 1 : 2, dp > 0.f ? 1.0f / (1.0f - dp) : 1.0f, m.f32()));
+      dy = m;
+    }
+    if (ins[1].isCalcGrad()) {  // dW[nout][nin] = dy^T x  (both operands MN-major, no transposition pass)
+      af::array dw = af::array::empty(ins[1].dims());
+      check(w2l_gemm_tf32_ex(currentStream(), 1, 1, nout, nin, M, dy.f32(), nout, ins[0].array().f32(), nin, dw.f32(), nin, nullptr, 0, 0,
+                             nullptr, 0, 0, 1.f, 0.f, 0ull));
+      ins[1].addGrad(Variable(dw, false));
+      if (hasBias) {
+        af::array db = af::array::zeros(ins[2].dims());
+        check(w2l_colsum_accumulate(currentStream(), M, nout, dy.f32(), nout, db.f32()));
+        ins[2].addGrad(Variable(db, false));
+      }
+    }
+    if (ins[0].isCalcGrad()) {  // dx[M][nin] = dy W  (B = W MN-major)
+      af::array dx = af::array::empty(ins[0].dims());
+      check(w2l_gemm_tf32_ex(currentStream(), 0, 1, M, nin, nout, dy.f32(), nout, ins[1].array().f32(), nin, dx.f32(), nin, nullptr, 0, 0,
+                             inMaskMode ? ins[0].array().f32() : nullptr, nin, inMaskMode, inMaskScale, 0.f, 0ull));
+      ins[0].addGrad(Variable(dx, false));
+    }
+  });
+}
+
+// ================================================================================================
+// TDSBlock — one autograd node: forward and backward run the fused kernel sequence of DESIGN.md §4
+// ================================================================================================
+TDSBlock::TDSBlock(int channels, int kernelSize, int width, double dropout, int innerLinearDim, int rightPadding, bool lNormIncludeTime)
+    : c_(channels), k_(kernelSize), w_(width), inner_(innerLinearDim > 0 ? innerLinearDim : channels * width), dropout_(dropout) {
+  if (!lNormIncludeTime) throw std::invalid_argument("TDSBlock: lNormIncludeTime = false (per-frame LayerNorm) is not covered yet");
+  conv_ = std::make_shared<Conv2D>(c_, c_, k_, 1, 1, 1, (int)PaddingMode::SAME, 0);
+  if (rightPadding >= 0) {
+    if (rightPadding > k_ - 1) throw std::invalid_argument("TDSBlock: rightPadding exceeds kernel - 1");
+    conv_->setAsymmetricPad(k_ - 1 - rightPadding, rightPadding);
+  }
+  conv_->fuseRelu();
+  conv_->fuseDropout((float)dropout);
+  ln1_ = std::make_shared<LayerNorm>(std::vector<int>{0, 1, 2});
+  ln2_ = std::make_shared<LayerNorm>(std::vector<int>{0, 1, 2});
+  lin1_ = std::make_shared<Linear>(c_ * w_, inner_);
+  lin2_ = std::make_shared<Linear>(inner_, c_ * w_);
+}
+std::vector<Variable> TDSBlock::params() const {
+  std::vector<Variable> p;
+  for (const Module* m : {(const Module*)conv_.get(), (const Module*)ln1_.get(), (const Module*)lin1_.get(), (const Module*)lin2_.get(),
+                          (const Module*)ln2_.get()}) {
+    auto q = m->params();
+    p.insert(p.end(), q.begin(), q.end());
+  }
+  return p;  // conv w,b; LN1 g,b; lin1 W,b; lin2 W,b; LN2 g,b (StreamingTDSModelConverter.cpp:110-135)
+}
+void TDSBlock::setParams(const Variable& v, int i) {
+  Module* mods[5] = {conv_.get(), ln1_.get(), lin1_.get(), lin2_.get(), ln2_.get()};
+  for (Module* m : mods) {
+    const int n = (int)m->params().size();
+    if (i < n) {
+      m->setParams(v, i);
+      return;
+    }
+    i -= n;
+  }
+  throw std::out_of_range("TDSBlock::setParams: index out of range");
+}
+void TDSBlock::train() {
+  train_ = true;
+  for (Module* m : {(Module*)conv_.get(), (Module*)ln1_.get(), (Module*)lin1_.get(), (Module*)lin2_.get(), (Module*)ln2_.get()}) m->train();
+}
+void TDSBlock::eval() {
+  train_ = false;
+  for (Module* m : {(Module*)conv_.get(), (Module*)ln1_.get(), (Module*)lin1_.get(), (Module*)lin2_.get(), (Module*)ln2_.get()}) m->eval();
+}
+std::string TDSBlock::prettyString() const {
+  std::ostringstream o;
+  o << "TDSBlock (c=" << c_ << ", k=" << k_ << ", w=" << w_ << ", dropout=" << dropout_ << ", inner=" << inner_ << ")\n\t\t" << conv_->prettyString()
+    << "\n\t\t" << lin1_->prettyString() << "\n\t\t" << lin2_->prettyString();
+  return o.str();
+}
+Variable TDSBlock::forward(const Variable& in) {
+  if (in.dims(0) != w_ || in.dims(1) != c_) throw std::invalid_argument("TDSBlock: expects [W=" + std::to_string(w_) + ", C=" + std::to_string(c_) + ", T, B] input, got " + in.dims().str());
+  const float dp = train_ ? (float)dropout_ : 0.f;
+  const float keep = dp > 0 ? 1.0f / (1.0f - dp) : 1.0f;
+  // conv branch (+ReLU+dropout fused) -> LN(x + branch); LN's backward undoes the conv's fused activation
+  Variable y1 = conv_->forwardMasked(in, true);
+  Variable z = ln1_->forwardResidual(y1, in, 1, keep);
+  // fc branch: Linear+ReLU+dropout -> Linear+dropout -> LN(z + branch).  lin1's activation mask is applied in
+  // lin2's data-gradient GEMM epilogue, lin2's dropout mask in LN2's backward.
+  Variable h = lin1_->forwardFused(z, true, dp, /*maskByConsumer=*/true);
+  Variable u = lin2_->forwardFused(h, false, dp, /*maskByConsumer=*/true, /*inMaskMode=*/1, keep);
+  Variable ur(u.array().reshaped(z.dims()), {u}, [](std::vector<Variable>& ins, const Variable& g) {
+    ins[0].addGrad(Variable(g.array().reshaped(ins[0].dims()), false));
+  });
+  return ln2_->forwardResidual(ur, z, dp > 0.f ? 2 : 0, keep);
+}
+
+// ================================================================================================
+// Optimizers
+// ================================================================================================
+void FirstOrderOptimizer::zeroGrad() {
+  for (auto& p : parameters_) p.zeroGrad();
+}
+SGDOptimizer::SGDOptimizer(const std::vector<Variable>& params, double lr, double momentum, double weightDecay, bool useNesterov)
+    : FirstOrderOptimizer(params, lr), mu_(momentum), wd_(weightDecay) {
+  if (useNesterov) throw std::invalid_argument("SGDOptimizer: Nesterov momentum is not covered");
+  if (mu_ != 0)
+    for (auto& p : parameters_) velocities_.push_back(af::array::zeros(p.dims()));
+}
+void SGDOptimizer::step() {
+  for (size_t i = 0; i < parameters_.size(); ++i) {
+    auto& p = parameters_[i];
+    if (!p.isGradAvailable()) continue;
+    check(w2l_sgd_step(currentStream(), p.elements(), p.array().f32(), p.grad().array().f32(), mu_ != 0 ? velocities_[i].f32() : nullptr,
+                       (float)lr_, (float)mu_, (float)wd_, 1.0f, 0.f, nullptr));
+  }
+}
+std::string SGDOptimizer::prettyString() const {
+  std::ostringstream o;
+  o << "SGD" << (mu_ != 0 ? " (momentum=" + std::to_string(mu_) + ")" : "") << (wd_ != 0 ? " (weight decay=" + std::to_string(wd_) + ")" : "");
+  return o.str();
+}
+double clipGradNorm(const std::vector<Variable>& params, double maxNorm) {
+  af::array sq = af::array::zeros(af::dim4(1), DType::f64);
+  for (auto& p : params)
+    if (p.isGradAvailable()) check(w2l_sq_norm_accumulate(currentStream(), p.elements(), p.grad().array().f32(), sq.f64()));
+  const double norm = std::sqrt(sq.scalar<double>());
+  const double scale = maxNorm / (norm + 1e-6);
+  if (scale < 1.0)
+    for (auto& p : params)
+      if (p.isGradAvailable()) {
+        af::array g = p.grad().array();
+        af::array tmp = af::array::zeros(g.dims());
+        check(w2l_axpy(currentStream(), g.elements(), (float)scale, g.f32(), tmp.f32()));
+        g.copyFrom(tmp);
+      }
+  return norm;
+}
+ParameterArena flattenParameters(const std::vector<std::shared_ptr<Module>>& modules) {
+  ParameterArena a;
+  std::vector<std::pair<Module*, int>> slots;
+  long long total = 0;
+  for (auto& m : modules) {
+    auto ps = m->params();
+    for (int i = 0; i < (int)ps.size(); ++i) {
+      slots.emplace_back(m.get(), i);
+      total += (ps[i].elements() + 3) / 4 * 4;  // 16-byte aligned slots (TMA operands)
+    }
+  }
+  a.elements = total;
+  a.values = af::array::zeros(af::dim4(total));
+  a.grads = af::array::zeros(af::dim4(total));
+  a.velocity = af::array::zeros(af::dim4(total));
+  long long off = 0;
+  for (auto& s : slots) {
+    Variable p = s.first->param(s.second);
+    af::array slot = af::array::view(a.values, (size_t)off * 4, p.dims(), DType::f32);
+    slot.copyFrom(p.array());
+    Variable np(slot, true);
+    np.setGradStorage(af::array::view(a.grads, (size_t)off * 4, p.dims(), DType::f32));
+    s.first->setParams(np, s.second);
+    off += (p.elements() + 3) / 4 * 4;
+  }
+  return a;
+}
+
+// ================================================================================================
+// Distributed (NCCL over NVLink; one process per GPU)
+// ================================================================================================
+namespace {
+ncclComm_t g_comm = nullptr;
+int g_rank = 0, g_world = 1;
+void ncclCheck(ncclResult_t r, const char* what) {
+  if (r != ncclSuccess) throw std::runtime_error(std::string(what) + ": " + ncclGetErrorString(r));
+}
+}  // namespace
+int getWorldRank() { return g_rank; }
+int getWorldSize() { return g_world; }
+bool isDistributedInit() { return g_comm != nullptr; }
+void allReduce(af::array& arr, double scale) {
+  if (g_comm) {
+    const ncclDataType_t t = arr.type() == DType::f64 ? ncclDouble : (arr.type() == DType::i32 ? ncclInt32 : ncclFloat32);
+    ncclCheck(ncclAllReduce(arr.ptr(), arr.ptr(), (size_t)arr.elements(), t, ncclSum, g_comm, static_cast<cudaStream_t>(currentStream())),
+              "ncclAllReduce");
+  }
+  if (scale != 1.0 && arr.type() == DType::f32) {
+    af::array tmp = af::array::zeros(arr.dims());
+    check(w2l_axpy(currentStream(), arr.elements(), (float)scale, arr.f32(), tmp.f32()));
+    arr.copyFrom(tmp);
+  }
+}
+void allReduceParameters(const std::shared_ptr<const Module>& module) {
+  if (!g_comm) return;
+  for (auto& p : module->params()) allReduce(p.array(), 1.0 / g_world);
+}
+CoalescingReducer::CoalescingReducer(double scale, bool, bool) : scale_(scale) {}
+void CoalescingReducer::add(Variable& var) { pending_.push_back(var.array()); }
+void CoalescingReducer::finalize() {
+  // gradients bound to a flat arena are contiguous: neighbours coalesce into one NCCL call
+  size_t i = 0;
+  while (i < pending_.size()) {
+    char* begin = static_cast<char*>(pending_[i].ptr());
+    char* end = begin + pending_[i].bytes();
+    size_t j = i + 1;
+    while (j < pending_.size() && static_cast<char*>(pending_[j].ptr()) >= end &&
+           static_cast<char*>(pending_[j].ptr()) - end < 16 && pending_[j].type() == DType::f32) {
+      end = static_cast<char*>(pending_[j].ptr()) + pending_[j].bytes();
+      ++j;
+    }
+    if (g_comm)
+      ncclCheck(ncclAllReduce(begin, begin, (size_t)(end - begin) / 4, ncclFloat32, ncclSum, g_comm, static_cast<cudaStream_t>(currentStream())),
+                "ncclAllReduce");
+    i = j;
+  }
+  if (scale_ != 1.0)
+    for (auto& a : pending_) {
+      af::array tmp = af::array::zeros(a.dims());
+      check(w2l_axpy(currentStream(), a.elements(), (float)scale_, a.f32(), tmp.f32()));
+      a.copyFrom(tmp);
+    }
+  pending_.clear();
+}
+namespace pkg {
+namespace runtime {
+void createUniqueId(void* id128) {
+  ncclUniqueId id;
+  ncclCheck(ncclGetUniqueId(&id), "ncclGetUniqueId");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id128, &id, 128);
+}
+void initDistributed(int worldRank, int worldSize, const void* id128) {
+  if (g_comm) return;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclCheck(ncclCommInitRank(&g_comm, worldSize, id, worldRank), "ncclCommInitRank");
+  g_rank = worldRank;
+  g_world = worldSize;
+}
+
+// ---- arch DSL (cpc/SequentialBuilder.cpp:29-57 for the file walk, :92-626 for the opcodes) ------------
+namespace {
+std::vector<std::string> splitWs(const std::string& line) {
+  std::istringstream is(line);
+  std::vector<std::string> out;
+  std::string tok;
+  while (is >> tok) out.push_back(tok);
+  return out;
+}
+std::string replaceAll(std::string s, const std::string& from, const std::string& to) {
+  size_t pos = 0;
+  while ((pos = s.find(from, pos)) != std::string::npos) {
+    s.replace(pos, from.size(), to);
+    pos += to.size();
+  }
+  return s;
+}
+}  // namespace
+
+std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, int64_t nFeatures, int64_t nClasses) {
+  auto net = std::make_shared<Sequential>();
+  std::istringstream in(archText);
+  std::string line;
+  std::shared_ptr<Conv2D> lastConv;  // candidate for ReLU / Dropout fusion
+  int pendingPadL = -1, pendingPadR = -1;
+  int lineNo = 0;
+  while (std::getline(in, line)) {
+    ++lineNo;
+    const auto hash = line.find('#');
+    if (hash != std::string::npos) line = line.substr(0, hash);
+    line = replaceAll(line, "NFEAT", std::to_string(nFeatures));
+    line = replaceAll(line, "NLABEL", std::to_string(nClasses));
+    auto p = splitWs(line);
+    if (p.empty()) continue;
+    auto bad = [&](const std::string& why) { return std::invalid_argument("arch line " + std::to_string(lineNo) + " '" + line + "': " + why); };
+    auto num = [&](size_t i) -> int {
+      if (i >= p.size()) throw bad("missing argument");
+      return std::stoi(p[i]);
+    };
+    const std::string& op = p[0];
+    if (op == "V") {
+      if (p.size() != 5) throw bad("V expects 4 dims");
+      net->add(std::make_shared<View>(af::dim4(num(1), num(2), num(3), num(4))));
+      lastConv.reset();
+    } else if (op == "RO") {
+      if (p.size() != 5) throw bad("RO expects 4 dims");
+      net->add(std::make_shared<Reorder>(num(1), num(2), num(3), num(4)));
+      lastConv.reset();
+    } else if (op == "PD") {
+      // `PD val l0 r0 [l1 r1 ...]`: the archs pad time (dim 0) only, before a C2 (streaming TDS)
+      if (p.size() < 4 || std::stod(p[1]) != 0.0) throw bad("only zero padding of the time axis is covered");
+      for (size_t i = 4; i < p.size(); ++i)
+        if (num(i) != 0) throw bad("only the time axis may be padded");
+      pendingPadL = num(2);
+      pendingPadR = num(3);
+    } else if (op == "C2") {
+      if (p.size() < 7) throw bad("C2 expects cin cout kw kh sx sy [px py dx dy]");
+      const int px = p.size() > 7 ? num(7) : 0, py = p.size() > 8 ? num(8) : 0;
+      auto conv = std::make_shared<Conv2D>(num(1), num(2), num(3), num(4), num(5), num(6), px, py, p.size() > 9 ? num(9) : 1,
+                                           p.size() > 10 ? num(10) : 1);
+      if (pendingPadL >= 0) {
+        if (px != 0) throw bad("PD followed by a padded convolution");
+        conv->setAsymmetricPad(pendingPadL, pendingPadR);
+        pendingPadL = pendingPadR = -1;
+      }
+      net->add(conv);
+      lastConv = conv;
+    } else if (op == "R") {
+      if (lastConv)
+        lastConv->fuseRelu();  // fused into the convolution's epilogue
+      else
+        net->add(std::make_shared<ReLU>());
+    } else if (op == "DO") {
+      if (p.size() != 2) throw bad("DO expects a probability");
+      if (lastConv)
+        lastConv->fuseDropout(std::stof(p[1]));
+      else
+        net->add(std::make_shared<Dropout>(std::stod(p[1])));
+      lastConv.reset();
+    } else if (op == "LN") {
+      std::vector<int> axes;
+      for (size_t i = 1; i < p.size(); ++i) axes.push_back(num(i));
+      if (axes.empty()) throw bad("LN expects axes");
+      net->add(std::make_shared<LayerNorm>(axes));
+      lastConv.reset();
+    } else if (op == "TDS") {
+      if (p.size() < 4) throw bad("TDS expects c kw w [dropout] [inner] [rPad] [lnIncludeTime]");
+      net->add(std::make_shared<TDSBlock>(num(1), num(2), num(3), p.size() > 4 ? std::stod(p[4]) : 0.0, p.size() > 5 ? num(5) : 0,
+                                          p.size() > 6 ? num(6) : -1, p.size() > 7 ? num(7) != 0 : true));
+      lastConv.reset();
+    } else if (op == "L") {
+      if (p.size() < 3) throw bad("L expects in out [bias]");
+      net->add(std::make_shared<Linear>(num(1), num(2), p.size() > 3 ? num(3) != 0 : true));
+      lastConv.reset();
+    } else if (op == "SAUG") {
+      // SpecAugment is data augmentation ahead of the hot path: identity here
+      lastConv.reset();
+    } else {
+      throw bad("opcode '" + op + "' is outside the hot-path subset (V RO PD C2 R DO LN TDS L SAUG)");
+    }
+  }
+  return net;
+}
+std::shared_ptr<Sequential> buildSequentialModuleFromFile(const std::string& path, int64_t nFeatures, int64_t nClasses) {
+  std::ifstream f(path);
+  if (!f) throw std::invalid_argument("arch file not found: " + path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return buildSequentialModule(ss.str(), nFeatures, nClasses);
+}
+}  // namespace runtime
+
+// ================================================================================================
+// Sequence criteria
+// ================================================================================================
+namespace speech {
+CriterionScaleMode getCriterionScaleMode(const std::string& onorm, bool sqnorm) {
+  if (onorm == "none") return CriterionScaleMode::NONE;
+  if (onorm == "input") return sqnorm ? CriterionScaleMode::INPUT_SZ_SQRT : CriterionScaleMode::INPUT_SZ;
+  if (onorm == "target") return sqnorm ? CriterionScaleMode::TARGET_SZ_SQRT : CriterionScaleMode::TARGET_SZ;
+  throw std::invalid_argument("invalid onorm option: " + onorm);
+}
+namespace {
+void checkCriterionInputs(const std::vector<Variable>& inputs, const char* who) {
+  if (inputs.size() != 2) throw std::invalid_argument(std::string(who) + ": expects {emissions, target}");
+  if (inputs[0].type() != DType::f32) throw std::invalid_argument(std::string(who) + ": emissions must be f32");
+  if (inputs[1].type() != DType::i32) throw std::invalid_argument(std::string(who) + ": target must be s32");
+  if (inputs[0].dims(2) != inputs[1].dims(1)) throw std::invalid_argument(std::string(who) + ": batch size mismatch between emissions and target");
+}
+}  // namespace
+
+AutoSegmentationCriterion::AutoSegmentationCriterion(int N, CriterionScaleMode scalemode, double transdiag) : N_(N), scaleMode_(scalemode) {
+  if (N <= 0) throw std::invalid_argument("ASG: N must be positive");
+  std::vector<float> tr((size_t)N * N, 0.f);
+  for (int i = 0; i < N; ++i) tr[(size_t)i * N + i] = (float)transdiag;
+  params_.push_back(Variable(af::array::fromHost(tr.data(), af::dim4(N, N)), true));
+}
+std::string AutoSegmentationCriterion::prettyString() const { return "AutoSegmentationCriterion"; }
+
+namespace {
+// shared by ASG (terms = FCC|FAC) and LinSeg (terms = FAC on the stretched target)
+std::vector<Variable> asgForward(int terms, int N, CriterionScaleMode mode, bool train, Variable trans, af::array& wsCache,
+                                 const Variable& emis, const af::array& target) {
+  const int T = (int)emis.dims(1), B = (int)emis.dims(2), L = (int)target.dims(0);
+  if (emis.dims(0) != N) throw std::invalid_argument("ASG: emissions have " + std::to_string(emis.dims(0)) + " classes, expected " + std::to_string(N));
+  const size_t wsb = w2l_asg_workspace_size(B, T, N, L);
+  af::array ws = workspaceFor(wsCache, wsb);
+  af::array loss = af::array::empty(af::dim4(B));
+  const bool needGrad = train && (emis.isCalcGrad() || trans.isCalcGrad());
+  if (!needGrad) {
+    check(w2l_asg_forward_backward(currentStream(), terms, B, T, N, L, (int)mode, emis.array().f32(), target.i32(), trans.array().f32(), nullptr,
+                                   loss.f32(), nullptr, nullptr, ws.ptr(), ws.bytes()));
+    return {Variable(loss, false)};
+  }
+  // fused forward+backward with dloss = 1 (what loss.backward() seeds, Train.cpp:1720)
+  af::array dEmis = af::array::empty(emis.dims());
+  af::array dTrans = af::array::empty(trans.dims());
+  check(w2l_asg_forward_backward(currentStream(), terms, B, T, N, L, (int)mode, emis.array().f32(), target.i32(), trans.array().f32(), nullptr,
+                                 loss.f32(), dEmis.f32(), dTrans.f32(), ws.ptr(), ws.bytes()));
+  return {Variable(loss, {emis, trans}, [=](std::vector<Variable>& ins, const Variable& g) mutable {
+    af::array de = dEmis, dt = dTrans;
+    if (!g.isOnesSeed()) {  // arbitrary upstream gradient: re-run the fused call with it (rare path)
+      af::array ws2 = af::array::empty(af::dim4((long long)wsb), DType::u8);
+      af::array l2 = af::array::empty(af::dim4(B));
+      de = af::array::empty(ins[0].dims());
+      dt = af::array::empty(ins[1].dims());
+      check(w2l_asg_forward_backward(currentStream(), terms, B, T, N, L, (int)mode, ins[0].array().f32(), target.i32(), ins[1].array().f32(),
+                                     g.array().f32(), l2.f32(), de.f32(), dt.f32(), ws2.ptr(), ws2.bytes()));
+    }
+    ins[0].addGrad(Variable(de, false));
+    ins[1].addGrad(Variable(dt, false));
+  })};
+}
+}  // namespace
+
+std::vector<Variable> AutoSegmentationCriterion::forward(const std::vector<Variable>& inputs) {
+  checkCriterionInputs(inputs, "AutoSegmentationCriterion");
+  return asgForward(W2L_TERM_ASG, N_, scaleMode_, train_, params_[0], ws_, inputs[0], inputs[1].array());
+}
+af::array AutoSegmentationCriterion::viterbiPath(const af::array& input, const af::array&) {
+  const int N = (int)input.dims(0), T = (int)input.dims(1), B = (int)input.dims(2);
+  if (N != N_) throw std::invalid_argument("ASG viterbiPath: class count mismatch");
+  af::array path = af::array::empty(af::dim4(T, B), DType::i32);
+  af::array ws = af::array::empty(af::dim4((long long)std::max<size_t>(w2l_fcc_viterbi_workspace_size(B, T, N), 256)), DType::u8);
+  check(w2l_fcc_viterbi(currentStream(), B, T, N, input.f32(), params_[0].array().f32(), path.i32(), ws.ptr(), ws.bytes()));
+  return path;
+}
+
+ConnectionistTemporalClassificationCriterion::ConnectionistTemporalClassificationCriterion(CriterionScaleMode scalemode) : scaleMode_(scalemode) {}
+std::string ConnectionistTemporalClassificationCriterion::prettyString() const { return "ConnectionistTemporalClassificationCriterion"; }
+std::vector<Variable> ConnectionistTemporalClassificationCriterion::forward(const std::vector<Variable>& inputs) {
+  checkCriterionInputs(inputs, "ConnectionistTemporalClassificationCriterion");
+  const Variable& emis = inputs[0];
+  const af::array target = inputs[1].array();
+  const int N = (int)emis.dims(0), T = (int)emis.dims(1), B = (int)emis.dims(2), L = (int)target.dims(0);
+  const size_t wsb = w2l_ctc_workspace_size(B, T, N, L);
+  af::array ws = workspaceFor(ws_, wsb);
+  af::array loss = af::array::empty(af::dim4(B));
+  const CriterionScaleMode mode = scaleMode_;
+  if (!(train_ && emis.isCalcGrad())) {
+    check(w2l_ctc_forward_backward(currentStream(), B, T, N, L, (int)mode, emis.array().f32(), target.i32(), nullptr, loss.f32(), nullptr, ws.ptr(),
+                                   ws.bytes()));
+    return {Variable(loss, false)};
+  }
+  af::array dEmis = af::array::empty(emis.dims());
+  check(w2l_ctc_forward_backward(currentStream(), B, T, N, L, (int)mode, emis.array().f32(), target.i32(), nullptr, loss.f32(), dEmis.f32(), ws.ptr(),
+                                 ws.bytes()));
+  return {Variable(loss, {emis}, [=](std::vector<Variable>& ins, const Variable& g) mutable {
+    af::array de = dEmis;
+    if (!g.isOnesSeed()) {
+      af::array ws2 = af::array::empty(af::dim4((long long)wsb), DType::u8);
+      af::array l2 = af::array::empty(af::dim4(B));
+      de = af::array::empty(ins[0].dims());
+      check(w2l_ctc_forward_backward(currentStream(), B, T, N, L, (int)mode, ins[0].array().f32(), target.i32(), g.array().f32(), l2.f32(), de.f32(),
+                                     ws2.ptr(), ws2.bytes()));
+    }
+    ins[0].addGrad(Variable(de, false));
+  })};
+}
+af::array ConnectionistTemporalClassificationCriterion::viterbiPath(const af::array& input, const af::array&) {
+  const int N = (int)input.dims(0), T = (int)input.dims(1), B = (int)input.dims(2);
+  af::array path = af::array::empty(af::dim4(T, B), DType::i32);
+  check(w2l_argmax_path(currentStream(), B, T, N, input.f32(), path.i32()));
+  return path;
+}
+
+LinearSegmentationCriterion::LinearSegmentationCriterion(int N, CriterionScaleMode scalemode) : N_(N), scaleMode_(scalemode) {
+  params_.push_back(Variable(af::array::zeros(af::dim4(N, N)), true));
+}
+std::string LinearSegmentationCriterion::prettyString() const { return "LinearSegmentationCriterion"; }
+std::vector<Variable> LinearSegmentationCriterion::forward(const std::vector<Variable>& inputs) {
+  checkCriterionInputs(inputs, "LinearSegmentationCriterion");
+  const int T = (int)inputs[0].dims(1), B = (int)inputs[0].dims(2), L = (int)inputs[1].dims(0);
+  af::array stretched = af::array::empty(af::dim4(T, B), DType::i32);
+  check(w2l_linseg_target(currentStream(), B, T, L, inputs[1].array().i32(), stretched.i32()));
+  return asgForward(W2L_TERM_FAC, N_, scaleMode_, train_, params_[0], ws_, inputs[0], stretched);
+}
+af::array LinearSegmentationCriterion::viterbiPath(const af::array& input, const af::array&) {
+  const int N = (int)input.dims(0), T = (int)input.dims(1), B = (int)input.dims(2);
+  af::array path = af::array::empty(af::dim4(T, B), DType::i32);
+  af::array ws = af::array::empty(af::dim4((long long)std::max<size_t>(w2l_fcc_viterbi_workspace_size(B, T, N), 256)), DType::u8);
+  check(w2l_fcc_viterbi(currentStream(), B, T, N, input.f32(), params_[0].array().f32(), path.i32(), ws.ptr(), ws.bytes()));
+  return path;
+}
+
+}  // namespace speech
+}  // namespace pkg
+}  // namespace fl

@@ -1,0 +1,125 @@
+"""Python handle on the C++ training-step driver (w2l_trainer_* in include/w2l_b200.h).
+
+The harness owns device memory (torch tensors) and the launch (torchrun); every arithmetic step of the
+training loop runs inside libw2l_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import _check, _ptr, _stream, lib
+
+
+class Trainer:
+    def __init__(self, arch_text: str, n_feat: int, n_label: int, criterion: str = "ctc", scale_mode="none",
+                 transdiag: float = 0.0, lr: float = 0.05, lrcrit: float = 0.0, momentum: float = 0.0,
+                 maxgradnorm: float = 0.0):
+        mode = capi.SCALE_MODES[scale_mode] if isinstance(scale_mode, str) else int(scale_mode)
+        self.h = lib.w2l_trainer_create(_stream(), arch_text.encode(), n_feat, n_label, criterion.encode(), mode,
+                                        transdiag, lr, lrcrit, momentum, maxgradnorm)
+        if not self.h:
+            raise capi.W2LError(1, lib.w2l_last_error().decode())
+        self.h = ctypes.c_void_p(self.h)
+        self.n_feat, self.n_label, self.criterion = n_feat, n_label, criterion
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.w2l_trainer_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def describe(self) -> str:
+        return lib.w2l_trainer_describe(self.h).decode()
+
+    def num_params(self, which: int = 0) -> int:
+        return int(lib.w2l_trainer_num_params(self.h, which))
+
+    def layout(self, which: int = 0):
+        """[(offset, elements, dims)] of every parameter inside the flat arena (16-byte aligned slots)."""
+        n = 4096
+        el = (ctypes.c_longlong * n)()
+        dims = (ctypes.c_longlong * (4 * n))()
+        cnt = lib.w2l_trainer_param_layout(self.h, which, n, el, dims)
+        out, off = [], 0
+        for i in range(cnt):
+            out.append((off, int(el[i]), tuple(int(dims[4 * i + d]) for d in range(4))))
+            off += (int(el[i]) + 3) // 4 * 4
+        return out
+
+    def get_flat(self, which: int = 0, what: int = 0) -> torch.Tensor:
+        n = self.num_params(which)
+        out = torch.empty(max(n, 1), dtype=torch.float32, device="cuda")
+        _check(lib.w2l_trainer_get_flat(self.h, _stream(), which, what, _ptr(out)))
+        return out[:n]
+
+    def set_flat(self, flat: torch.Tensor, which: int = 0):
+        _check(lib.w2l_trainer_set_flat(self.h, _stream(), which, _ptr(flat.contiguous())))
+
+    def step(self, features: torch.Tensor, target: torch.Tensor, train: bool = True, total_batch: float | None = None,
+             loss_out: torch.Tensor | None = None) -> torch.Tensor:
+        """features: CUDA float [B,1,F,T] contiguous (== ArrayFire [T,F,1,B]); target CUDA int32 [B,L]."""
+        B, _, F, T = features.shape
+        L = target.shape[1]
+        if loss_out is None:
+            loss_out = torch.empty(B, dtype=torch.float32, device=features.device)
+        _check(lib.w2l_trainer_step(self.h, _stream(), B, T, _ptr(features), L, _ptr(target), _ptr(loss_out), int(train),
+                                    float(total_batch if total_batch is not None else B)))
+        return loss_out
+
+    def forward(self, features: torch.Tensor) -> torch.Tensor:
+        B, _, F, T = features.shape
+        cap = B * T * self.n_label
+        out = torch.empty(cap, dtype=torch.float32, device=features.device)
+        tout = ctypes.c_int(0)
+        _check(lib.w2l_trainer_forward(self.h, _stream(), B, T, _ptr(features), _ptr(out), cap, ctypes.byref(tout)))
+        return out[: B * tout.value * self.n_label].view(B, tout.value, self.n_label)
+
+    def sync_parameters(self):
+        _check(lib.w2l_trainer_sync_parameters(self.h, _stream()))
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check(lib.w2l_nccl_unique_id(buf))
+    return buf.raw
+
+
+def init_distributed(rank: int, world: int, uid: bytes):
+    _check(lib.w2l_init_distributed(rank, world, ctypes.c_char_p(uid)))
+
+
+SEQ2SEQ_TDS_CTC_ARCH = """# recipes/seq2seq_tds/librispeech/network.arch with the CTC head BASELINE.json configs[1] asks for
+# (last line `L 1440 NLABEL` instead of the seq2seq encoder's `L 1440 1024`)
+V -1 NFEAT 1 0
+C2 1 10 21 1 2 1 -1 -1
+R
+DO 0.2
+LN 3
+TDS 10 21 80 0.2
+TDS 10 21 80 0.2
+C2 10 14 21 1 2 1 -1 -1
+R
+DO 0.2
+LN 3
+TDS 14 21 80 0.2
+TDS 14 21 80 0.2
+TDS 14 21 80 0.2
+C2 14 18 21 1 2 1 -1 -1
+R
+DO 0.2
+LN 3
+TDS 18 21 80 0.2
+TDS 18 21 80 0.2
+TDS 18 21 80 0.2
+TDS 18 21 80 0.2
+TDS 18 21 80 0.2
+TDS 18 21 80 0.2
+V 0 1440 1 0
+RO 1 0 3 2
+L 1440 NLABEL
+"""
