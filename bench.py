@@ -415,7 +415,7 @@ def run_tds(args, rank, world, local_rank):
     gemm_ms_per_step = sum(kern) / prof_steps
     achieved = gemm_flops / (gemm_ms_per_step * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    cpu_fps, cpu_s, cpu_threads = cpu_tds(2, 2, 1)
+    cpu_fps, cpu_s, cpu_threads = cpu_tds(2, 2, 1) if world == 1 else (None, 0.0, 0)  # CPU baseline: rank 0 at N=1 only
     traffic = None
     tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tp):
@@ -442,8 +442,9 @@ def run_tds(args, rank, world, local_rank):
                      "peak_source": src + " bf16_tflops_sustained; tf32 math has half the bf16 hardware ceiling",
                      "gemm_ms_per_step": gemm_ms_per_step, "gemm_launches_per_step": len(kern) / prof_steps,
                      "algorithmic_flops_per_step": gemm_flops, "gemm_share_of_step": gemm_ms_per_step / (ms / args.steps)},
-        "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
-                         "sample": f"2 train steps of B=2,T={T} on torch-CPU/oneDNN + C-oracle CTC ({cpu_s:.1f} s/step)"},
+        "cpu_baseline": ({"value": cpu_fps, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
+                          "sample": f"2 train steps of B=2,T={T} on torch-CPU/oneDNN + C-oracle CTC ({cpu_s:.1f} s/step)"}
+                         if cpu_fps is not None else None),
     }
     if asg is not None:
         alg = asg_algorithmic_bytes(ASG_CFG["B"], ASG_CFG["T"], ASG_CFG["N"], ASG_CFG["L"])
