@@ -126,6 +126,7 @@ class Variable {
   Variable& grad() const;  // throws std::logic_error if absent, like flashlight
   void addGrad(const Variable& g);
   void setGradStorage(const af::array& buf);  // pre-bound accumulation buffer (flat gradient arena)
+  af::array gradStorage() const;              // that buffer (empty if none): kernels accumulate into it directly
   void zeroGrad(bool zeroStorage = true);  // zeroStorage = false: the caller cleared the gradient arena itself
   void backward(bool retainGraph = false);                       // seeds ones (loss.backward(), Train.cpp:1720)
   void backward(const Variable& grad, bool retainGraph = false);

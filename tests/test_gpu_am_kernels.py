@@ -31,7 +31,7 @@ def ref_conv(x, wt, bias, stride, pad_left, Tout):
 
 @pytest.mark.parametrize("B,T,Cin,Cout,K,stride,W", [
     (2, 37, 10, 10, 21, 1, 80), (3, 50, 1, 10, 21, 2, 80), (2, 41, 10, 14, 21, 2, 80), (2, 33, 18, 18, 21, 1, 80),
-    (1, 20, 27, 27, 11, 1, 80), (2, 9, 3, 5, 3, 1, 7),
+    (1, 20, 27, 27, 11, 1, 80), (2, 9, 3, 5, 3, 1, 7), (2, 30, 15, 19, 10, 2, 80), (1, 3, 10, 10, 21, 1, 80),
 ])
 def test_conv_time_fwd_dgrad_wgrad(B, T, Cin, Cout, K, stride, W):
     from wav2letter_b200 import capi
@@ -52,15 +52,18 @@ def test_conv_time_fwd_dgrad_wgrad(B, T, Cin, Cout, K, stride, W):
     b64 = bias.double().requires_grad_(True)
     pre = ref_conv(x64, w64, b64, stride, pl, Tout)
     yr = pre.clamp_min(0) + add.double()
-    assert rel(y, yr) < 1e-5
+    # W % 8 == 0 routes to the tensor-core path (mma.sync TF32 operands, fp32 accumulate): TF32 tolerance;
+    # other widths use the fp32 SIMT kernels
+    tol = 3e-3 if W % 8 == 0 else 1e-5
+    assert rel(y, yr) < tol
     dy = torch.randn((B, Tout, Cout, W), device="cuda", generator=g)
     pre.backward(dy.double())
     addx = torch.randn((B, T, Cin, W), device="cuda", generator=g)
     dx = capi.conv_time_dgrad(dy, wt, T, stride, pl, add=addx)
-    assert rel(dx, x64.grad + addx.double()) < 1e-5
+    assert rel(dx, x64.grad + addx.double()) < tol
     dwt, dbias = capi.conv_time_wgrad(x, dy, K, stride, pl)
-    assert rel(dwt, w64.grad) < 1e-5
-    assert rel(dbias, b64.grad) < 1e-5
+    assert rel(dwt, w64.grad) < tol
+    assert rel(dbias, b64.grad) < tol
 
 
 def test_conv1d_reference_golden():

@@ -17,32 +17,17 @@
 #include "common.cuh"
 
 namespace w2l {
+// tensor-core path (conv_mma.cu)
+bool conv_mma_supported(int W, int Cin, int Cout, int K, int stride);
+size_t conv_mma_arranged_floats(int Cin, int Cout, int K);
+int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
+                 const float* x, const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y,
+                 int act, float drop_p, unsigned long long seed, float* arranged);
+size_t conv_mma_wgrad_parts(int B, int Tout, int Cin, int Cout, int K, int stride, int* tc_out);
+int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
+                   const float* x, const float* dy, float* dwt, float* dbias, float* partial);
 
-// ---- Philox4x32-10 (counter-based; the backward pass regenerates nothing — masks are read from
-// the stored activations — but forward passes must be reproducible per (seed, offset)) ----------
-__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
-  uint32_t c2 = 0, c3 = 0;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0;
-    c1 = lo1;
-    c2 = n2;
-    c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-// keep-mask scale for element `idx`: 1/(1-p) with probability 1-p, else 0
-__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
-  const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint32_t lane = (uint32_t)idx & 3u;
-  const uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
-  return ((float)(v >> 8) * (1.0f / 16777216.0f)) >= p ? inv_keep : 0.f;
-}
+// (Philox4x32-10 and dropout_scale live in common.cuh)
 
 namespace {
 
@@ -51,62 +36,66 @@ namespace {
 //   y[b][to][co][w] = act( bias[co] + sum_{ci,dk} x[b][to*s + dk - pl][ci][w] * wt[ci][dk][co] ) (+ add)
 // weights arrive pre-arranged as wt_s[ci][dk][CO] (CO = Cout padded to a multiple of 4)
 // ------------------------------------------------------------------------------------------
-constexpr int kConvTo = 8;  // output frames per CTA (2 per thread row)
+constexpr int kConvRows = 4;  // thread rows per CTA; a thread computes TT consecutive output frames x CO channels
 
-template <int CO>
-__global__ void __launch_bounds__(96 * (kConvTo / 2)) conv_time_fwd_kernel(
+// Register tile: TT output frames x CO channels per thread (acc <= 96 registers).  Per (ci, dk) a thread
+// issues TT coalesced global loads (L1-resident: neighbouring taps re-read the same rows) and CO/4
+// broadcast LDS.128 for TT*CO FMAs (~9 FMAs per load instruction).
+template <int CO, int TT>
+__global__ void __launch_bounds__(96 * kConvRows) conv_time_fwd_kernel(
     int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left, const float* __restrict__ x,
     const float* __restrict__ wt_arranged, const float* __restrict__ bias, const float* __restrict__ add,
     float* __restrict__ y, int act, float drop_p, unsigned long long seed) {
   extern __shared__ __align__(16) float wsm[];  // [Cin][K][CO]
   const int b = blockIdx.y;
   const int w = threadIdx.x;                   // 0..95, active < W
-  const int to0 = blockIdx.x * kConvTo + threadIdx.y * 2;
+  const int to0 = (blockIdx.x * kConvRows + threadIdx.y) * TT;
   const int nw = Cin * K * CO;
   for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < nw; i += blockDim.x * blockDim.y) wsm[i] = wt_arranged[i];
   __syncthreads();
   if (w >= W || to0 >= Tout) return;
-  const bool has1 = to0 + 1 < Tout;
-  float acc0[CO], acc1[CO];
+  float acc[TT][CO];
 #pragma unroll
   for (int c = 0; c < CO; ++c) {
     const float bv = (bias != nullptr && c < Cout) ? __ldg(bias + c) : 0.f;
-    acc0[c] = bv;
-    acc1[c] = bv;
+#pragma unroll
+    for (int h = 0; h < TT; ++h) acc[h][c] = bv;
   }
   const float* xb = x + (size_t)b * T * Cin * W + w;
+  const size_t tstride = (size_t)Cin * W;
   for (int ci = 0; ci < Cin; ++ci) {
     const float* xc = xb + (size_t)ci * W;
     const float* wrow = wsm + (size_t)ci * K * CO;
     for (int dk = 0; dk < K; ++dk) {
-      const int t0 = to0 * stride + dk - pad_left;
-      const int t1 = t0 + stride;
-      const float x0 = (t0 >= 0 && t0 < T) ? __ldg(xc + (size_t)t0 * Cin * W) : 0.f;
-      const float x1 = (has1 && t1 >= 0 && t1 < T) ? __ldg(xc + (size_t)t1 * Cin * W) : 0.f;
+      float xv[TT];
+#pragma unroll
+      for (int h = 0; h < TT; ++h) {
+        const int tin = (to0 + h) * stride + dk - pad_left;
+        xv[h] = (tin >= 0 && tin < T) ? __ldg(xc + (size_t)tin * tstride) : 0.f;
+      }
       const float4* w4 = reinterpret_cast<const float4*>(wrow + dk * CO);
 #pragma unroll
       for (int q = 0; q < CO / 4; ++q) {
         const float4 wv = w4[q];
-        acc0[4 * q + 0] = fmaf(x0, wv.x, acc0[4 * q + 0]);
-        acc0[4 * q + 1] = fmaf(x0, wv.y, acc0[4 * q + 1]);
-        acc0[4 * q + 2] = fmaf(x0, wv.z, acc0[4 * q + 2]);
-        acc0[4 * q + 3] = fmaf(x0, wv.w, acc0[4 * q + 3]);
-        acc1[4 * q + 0] = fmaf(x1, wv.x, acc1[4 * q + 0]);
-        acc1[4 * q + 1] = fmaf(x1, wv.y, acc1[4 * q + 1]);
-        acc1[4 * q + 2] = fmaf(x1, wv.z, acc1[4 * q + 2]);
-        acc1[4 * q + 3] = fmaf(x1, wv.w, acc1[4 * q + 3]);
+#pragma unroll
+        for (int h = 0; h < TT; ++h) {
+          acc[h][4 * q + 0] = fmaf(xv[h], wv.x, acc[h][4 * q + 0]);
+          acc[h][4 * q + 1] = fmaf(xv[h], wv.y, acc[h][4 * q + 1]);
+          acc[h][4 * q + 2] = fmaf(xv[h], wv.z, acc[h][4 * q + 2]);
+          acc[h][4 * q + 3] = fmaf(xv[h], wv.w, acc[h][4 * q + 3]);
+        }
       }
     }
   }
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
 #pragma unroll
-  for (int c = 0; c < CO; ++c) {
-    if (c < Cout) {
+  for (int h = 0; h < TT; ++h) {
+    if (to0 + h >= Tout) continue;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !has1) continue;
+    for (int c = 0; c < CO; ++c) {
+      if (c < Cout) {
         const size_t idx = (((size_t)b * Tout + to0 + h) * Cout + c) * W + w;
-        float v = h ? acc1[c] : acc0[c];
+        float v = acc[h][c];
         if (act == 1) v = fmaxf(v, 0.f);
         if (drop_p > 0.f) v *= dropout_scale(seed, idx, drop_p, inv_keep);
         if (add != nullptr) v += __ldg(add + idx);
@@ -196,7 +185,8 @@ __global__ void __launch_bounds__(kWgThreads) conv_time_wgrad_kernel(int T, int 
                                                                      const float* __restrict__ dy,
                                                                      float* __restrict__ partial /*[ctas][Cout*Cin*K + Cout]*/) {
   extern __shared__ __align__(16) float sm[];
-  const int Wp = 80;  // W <= 80 (filterbank width); rows padded to 80 floats
+  const int Wp = 84;  // W <= 80; rows padded to 84 floats: 84 = 20 (mod 32) spreads 8 rows over all 32 banks, so the
+                      // 128-bit reads of 32 different rows cost the minimum 4 wavefronts (80-float rows: 16-way conflicts)
   float* ring = sm;                         // [K][Cin][Wp]
   float* dys = ring + (size_t)K * Cin * Wp;  // [Cout][Wp]
   const int b = blockIdx.y;
@@ -545,24 +535,28 @@ using namespace w2l;
 
 static int co_pad(int c) { return (c + 3) / 4 * 4; }
 
+// workspace = [CTA partials of the weight gradient][re-arranged weights]; sized for both the tensor-core and the SIMT path
+static size_t conv_ws_partial_bytes(int B, int Tout, int Cin, int Cout, int K) {
+  const size_t per = ((size_t)Cout * Cin * K + Cout) * sizeof(float);
+  const size_t simt = (size_t)B * ((Tout + 15) / 16);
+  const size_t mma = conv_mma_wgrad_parts(B, Tout, Cin, Cout, K, 1, nullptr);  // stride 1 gives the smallest TC -> most parts
+  return align_up(std::max(simt, std::max(mma, (size_t)B * (size_t)Tout)) * per, 256);
+}
 extern "C" size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K) {
-  const int chunk = 16;
-  const size_t ctas = (size_t)B * ((Tout + chunk - 1) / chunk);
-  const size_t part = ctas * ((size_t)Cout * Cin * K + Cout) * sizeof(float);
-  const size_t arranged = (size_t)std::max(Cin, Cout) * K * co_pad(std::max(Cin, Cout)) * sizeof(float);
-  return align_up(part, 256) + align_up(arranged, 256);
+  const size_t arranged = std::max((size_t)std::max(Cin, Cout) * K * co_pad(std::max(Cin, Cout)), conv_mma_arranged_floats(Cin, Cout, K)) * sizeof(float);
+  return conv_ws_partial_bytes(B, Tout, Cin, Cout, K) + align_up(arranged, 256);
 }
 
 #define W2L_CONV_DISPATCH(CO_VAL, ...)                   \
   switch (CO_VAL) {                                              \
-    case 4: { constexpr int CO = 4; __VA_ARGS__; } break;        \
-    case 8: { constexpr int CO = 8; __VA_ARGS__; } break;        \
-    case 12: { constexpr int CO = 12; __VA_ARGS__; } break;      \
-    case 16: { constexpr int CO = 16; __VA_ARGS__; } break;      \
-    case 20: { constexpr int CO = 20; __VA_ARGS__; } break;      \
-    case 24: { constexpr int CO = 24; __VA_ARGS__; } break;      \
-    case 28: { constexpr int CO = 28; __VA_ARGS__; } break;      \
-    case 32: { constexpr int CO = 32; __VA_ARGS__; } break;      \
+    case 4: { constexpr int CO = 4; constexpr int TT = 8; (void)TT; __VA_ARGS__; } break;        \
+    case 8: { constexpr int CO = 8; constexpr int TT = 8; (void)TT; __VA_ARGS__; } break;        \
+    case 12: { constexpr int CO = 12; constexpr int TT = 8; (void)TT; __VA_ARGS__; } break;      \
+    case 16: { constexpr int CO = 16; constexpr int TT = 6; (void)TT; __VA_ARGS__; } break;      \
+    case 20: { constexpr int CO = 20; constexpr int TT = 4; (void)TT; __VA_ARGS__; } break;      \
+    case 24: { constexpr int CO = 24; constexpr int TT = 4; (void)TT; __VA_ARGS__; } break;      \
+    case 28: { constexpr int CO = 28; constexpr int TT = 3; (void)TT; __VA_ARGS__; } break;      \
+    case 32: { constexpr int CO = 32; constexpr int TT = 3; (void)TT; __VA_ARGS__; } break;      \
     default: return fail(W2L_ERR_UNSUPPORTED, "conv_time: more than 32 channels is not covered"); \
   }
 
@@ -582,16 +576,20 @@ extern "C" int w2l_conv_time_fwd(void* stream_, int B, int T, int Tout, int W, i
   if (!x || !wt || !y || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_fwd: null pointer");
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_fwd: workspace too small");
   const int CO = co_pad(Cout);
-  float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * ((Tout + 15) / 16) * ((size_t)Cout * Cin * K + Cout) * 4, 256));
+  float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
+  if (conv_mma_supported(W, Cin, Cout, K, stride))
+    return conv_mma_fwd(stream, B, T, Tout, W, Cin, Cout, K, stride, pad_left, x, wt, Cin, Cout, 0, bias, add, y, act, dropout_p, seed,
+                        arranged);
   conv_arrange_weights_kernel<<<8, 256, 0, stream>>>(Cin, Cout, K, CO, wt, arranged, 0);
   W2L_LAUNCH_CHECK("conv_arrange_weights_kernel");
   const size_t smem = (size_t)Cin * K * CO * sizeof(float);
-  dim3 grid((Tout + kConvTo - 1) / kConvTo, B), block(96, kConvTo / 2);
+  dim3 block(96, kConvRows);
   W2L_CONV_DISPATCH(CO, {
     if (smem > 48 * 1024)
-      W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_fwd_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_time_fwd_kernel<CO><<<grid, block, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, x, arranged, bias, add, y,
-                                                            act, dropout_p, seed);
+      W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_fwd_kernel<CO, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((Tout + kConvRows * TT - 1) / (kConvRows * TT), B);
+    conv_time_fwd_kernel<CO, TT><<<grid, block, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, x, arranged, bias, add,
+                                                                y, act, dropout_p, seed);
   });
   W2L_LAUNCH_CHECK("conv_time_fwd_kernel");
   return W2L_OK;
@@ -604,19 +602,26 @@ extern "C" int w2l_conv_time_dgrad(void* stream_, int B, int T, int Tout, int W,
   if (int rc = conv_check(B, T, Tout, W, Cin, Cout, K, stride)) return rc;
   if (!dy || !wt || !dx || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_dgrad: null pointer");
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_dgrad: workspace too small");
+  if (stride == 1 && conv_mma_supported(W, Cout, Cin, K, 1)) {
+    // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped — on the tensor-core path
+    float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
+    return conv_mma_fwd(stream, B, Tout, T, W, Cout, Cin, K, 1, K - 1 - pad_left, dy, wt, Cin, Cout, 1, nullptr, add, dx, 0, 0.f, 0ull,
+                        arranged);
+  }
   if (stride == 1 && Tout == T) {
     // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped
     const int CI = co_pad(Cin);
-    float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * ((Tout + 15) / 16) * ((size_t)Cout * Cin * K + Cout) * 4, 256));
+    float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
     conv_arrange_weights_kernel<<<8, 256, 0, stream>>>(Cin, Cout, K, CI, wt, arranged, 1);
     W2L_LAUNCH_CHECK("conv_arrange_weights_kernel");
     const size_t smem = (size_t)Cout * K * CI * sizeof(float);
-    dim3 grid((T + kConvTo - 1) / kConvTo, B), block(96, kConvTo / 2);
+    dim3 block(96, kConvRows);
     W2L_CONV_DISPATCH(CI, {
       if (smem > 48 * 1024)
-        W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_fwd_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv_time_fwd_kernel<CO><<<grid, block, smem, stream>>>(Tout, T, W, Cout, Cin, K, 1, K - 1 - pad_left, dy, arranged, nullptr,
-                                                              add, dx, 0, 0.f, 0ull);
+        W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_fwd_kernel<CO, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((T + kConvRows * TT - 1) / (kConvRows * TT), B);
+      conv_time_fwd_kernel<CO, TT><<<grid, block, smem, stream>>>(Tout, T, W, Cout, Cin, K, 1, K - 1 - pad_left, dy, arranged, nullptr,
+                                                                  add, dx, 0, 0.f, 0ull);
     });
     W2L_LAUNCH_CHECK("conv_time_fwd_kernel(dgrad)");
     return W2L_OK;
@@ -641,11 +646,13 @@ extern "C" int w2l_conv_time_wgrad(void* stream_, int B, int T, int Tout, int W,
   if (!x || !dy || !dwt || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_wgrad: null pointer");
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_wgrad: workspace too small");
   if (stride > K) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: stride > kernel width");
+  if (conv_mma_supported(W, Cin, Cout, K, stride))
+    return conv_mma_wgrad(stream, B, T, Tout, W, Cin, Cout, K, stride, pad_left, x, dy, dwt, dbias, static_cast<float*>(ws));
   const int ntiles = ((Cout + 1) / 2) * ((Cin * K + 3) / 4);
   if (ntiles > kWgMaxTiles * kWgThreads) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: filter too large for the register tiles");
   const int chunk = 16;
   dim3 grid((Tout + chunk - 1) / chunk, B);
-  const size_t smem = ((size_t)K * Cin * 80 + (size_t)Cout * 80) * sizeof(float);
+  const size_t smem = ((size_t)K * Cin * 84 + (size_t)Cout * 84) * sizeof(float);
   if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: input window does not fit in shared memory");
   if (smem > 48 * 1024)
     W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_time_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

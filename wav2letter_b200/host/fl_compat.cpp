@@ -197,6 +197,7 @@ void Variable::setGradStorage(const af::array& buf) {
   impl_->gradLive = false;
   impl_->grad.reset();
 }
+af::array Variable::gradStorage() const { return impl_ ? impl_->boundGrad : af::array(); }
 void Variable::addGrad(const Variable& g) {
   if (!impl_ || !impl_->calcGrad) return;
   if (g.elements() != elements()) throw std::invalid_argument("addGrad: size mismatch");
@@ -427,8 +428,14 @@ Variable Conv2D::forwardMasked(const Variable& in, bool maskByConsumer) {
     }
     af::array ws2 = workspaceFor(g_conv_ws, w2l_conv_time_workspace_size(B, Tout, cin, cout, k));
     if (ins[1].isCalcGrad()) {
-      af::array dw = af::array::zeros(ins[1].dims());
-      af::array db = hasBias ? af::array::zeros(ins[2].dims()) : af::array();
+      // accumulate straight into the gradient arena slots when the parameters are arena-backed
+      af::array dw = ins[1].gradStorage();
+      if (dw.isEmpty()) dw = af::array::zeros(ins[1].dims());
+      af::array db;
+      if (hasBias) {
+        db = ins[2].gradStorage();
+        if (db.isEmpty()) db = af::array::zeros(ins[2].dims());
+      }
       check(w2l_conv_time_wgrad(currentStream(), B, T, Tout, W, cin, cout, k, s, pl, ins[0].array().f32(), dy.f32(), dw.f32(),
                                 hasBias ? db.f32() : nullptr, ws2.ptr(), ws2.bytes()));
       ins[1].addGrad(Variable(dw, false));
@@ -508,8 +515,13 @@ Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int br
     const int gi = hasRes ? 2 : 1;
     af::array d_branch = af::array::empty(ins[0].dims());
     af::array d_res = hasRes ? af::array::empty(ins[0].dims()) : af::array();
-    af::array dg = affine ? af::array::zeros(af::dim4(1)) : af::array();
-    af::array db = affine ? af::array::zeros(af::dim4(1)) : af::array();
+    af::array dg, db;
+    if (affine) {
+      dg = ins[gi].gradStorage();
+      if (dg.isEmpty()) dg = af::array::zeros(af::dim4(1));
+      db = ins[gi + 1].gradStorage();
+      if (db.isEmpty()) db = af::array::zeros(af::dim4(1));
+    }
     af::array sc = af::array::empty(af::dim4(2 * B), DType::f64);
     check(w2l_layernorm_bwd(currentStream(), B, R, ins[0].array().f32(), hasRes ? ins[1].array().f32() : nullptr, g.array().f32(),
                             affine ? ins[gi].array().f32() : nullptr, mr.f32(), d_branch.f32(), hasRes ? d_res.f32() : nullptr,
@@ -572,12 +584,15 @@ Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool m
       dy = m;
     }
     if (ins[1].isCalcGrad()) {  // dW[nout][nin] = dy^T x  (both operands MN-major, no transposition pass)
-      af::array dw = af::array::empty(ins[1].dims());
-      check(w2l_gemm_tf32_ex(currentStream(), 1, 1, nout, nin, M, dy.f32(), nout, ins[0].array().f32(), nin, dw.f32(), nin, nullptr, 0, 0,
-                             nullptr, 0, 0, 1.f, 0.f, 0ull));
+      af::array dw = ins[1].gradStorage();
+      const int accumulate = dw.isEmpty() ? 0 : 1;  // arena slot (zeroed by zeroGrad): C += in the GEMM epilogue
+      if (!accumulate) dw = af::array::empty(ins[1].dims());
+      check(w2l_gemm_tf32_ex(currentStream(), 1, 1, nout, nin, M, dy.f32(), nout, ins[0].array().f32(), nin, dw.f32(), nin, nullptr, 0,
+                             accumulate, nullptr, 0, 0, 1.f, 0.f, 0ull));
       ins[1].addGrad(Variable(dw, false));
       if (hasBias) {
-        af::array db = af::array::zeros(ins[2].dims());
+        af::array db = ins[2].gradStorage();
+        if (db.isEmpty()) db = af::array::zeros(ins[2].dims());
         check(w2l_colsum_accumulate(currentStream(), M, nout, dy.f32(), nout, db.f32()));
         ins[2].addGrad(Variable(db, false));
       }
