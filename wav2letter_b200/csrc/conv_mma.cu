@@ -60,63 +60,81 @@ __device__ __forceinline__ void stage_input(float* xs, int pitch, const float* _
 }
 
 // ------------------------------------------------------------------------------------------
-// forward: one CTA = TB output frames of one sample; work unit = (frame, half of the W tiles)
+// forward: one CTA = TB = 8*UPW output frames of one sample; warp w owns frames w, w+8 (all of W).
+// The K loop is chunked over ranges of kDeltaTaps taps: each chunk stages only the (TB-1)*stride + 8 input
+// frames it touches (<= 100 KB for every TDS shape -> two CTAs per SM), accumulators stay in registers
+// across chunks.  Weight fragments come straight from global memory (L1-resident, 50 KB at most).
 // ------------------------------------------------------------------------------------------
-template <int MT>  // m tiles of 16 output channels (1 or 2)
+constexpr int kDeltaTaps = 8;  // 8 * Cin is always a multiple of the MMA K (8)
+
+template <int MT, int UPW>  // m tiles of 16 output channels (1 or 2); frames per warp
 __global__ void __launch_bounds__(kMmaThreads) conv_mma_fwd_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
-                                                                    int pad_left, int TB, int Kpad, int apitch,
+                                                                    int pad_left, int Kpad, int apitch,
                                                                     const float* __restrict__ x, const float* __restrict__ wa,
                                                                     const float* __restrict__ bias, const float* __restrict__ add,
                                                                     float* __restrict__ y, int act, float drop_p,
                                                                     unsigned long long seed) {
   extern __shared__ __align__(16) float sm[];
   constexpr int kPitch = 88;  // 88 = 24 (mod 32): the 4 k-rows x 8 w of a B fragment hit 32 distinct banks
-  float* as = sm;                                 // [16*MT][apitch]   weights, k = dk*Cin + ci
-  float* xs = sm + (size_t)16 * MT * apitch;      // [(nframes*Cin) + 8][kPitch]
+  constexpr int TB = 8 * UPW;
+  float* xs = sm;  // [(nframes*Cin) + 8][kPitch]
   const int b = blockIdx.y, to0 = blockIdx.x * TB;
   const int nto = min(TB, Tout - to0);
-  const int nframes = (nto - 1) * stride + K;
-  const int tin0 = to0 * stride - pad_left;
-  for (int i = threadIdx.x; i < 16 * MT * apitch; i += blockDim.x) as[i] = wa[i];
-  stage_input(xs, kPitch, x + (size_t)b * T * Cin * W, T, Cin, W, tin0, nframes, 8);
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  const int wtiles = W / 8, half0 = (wtiles + 1) / 2;
-  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  for (int unit = warp; unit < 2 * nto; unit += kMmaThreads / 32) {
-    const int tl = unit >> 1, hw = unit & 1;
-    const int wt0 = hw ? half0 : 0, nwt = hw ? wtiles - half0 : half0;
-    float acc[MT][5][4];
+  const int wtiles = W / 8;  // <= 10
+  float acc[UPW][MT][10][4];
+#pragma unroll
+  for (int u = 0; u < UPW; ++u)
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-      for (int j = 0; j < 5; ++j)
+      for (int j = 0; j < 10; ++j)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
-    const float* xrow = xs + (size_t)(tl * stride * Cin) * kPitch;
-    for (int k0 = 0; k0 < Kpad; k0 += 8) {
+        for (int q = 0; q < 4; ++q) acc[u][m][j][q] = 0.f;
+  const float* xb = x + (size_t)b * T * Cin * W;
+  for (int d0 = 0; d0 * Cin < Kpad; d0 += kDeltaTaps) {
+    const int kbeg = d0 * Cin, kend = min(Kpad, (d0 + kDeltaTaps) * Cin);
+    // frames this chunk touches: outputs tl = 0..nto-1, taps d0 .. d0+7 (clipped to the padded K range)
+    const int taps = (kend - kbeg + Cin - 1) / Cin;
+    const int nframes = (nto - 1) * stride + taps;
+    __syncthreads();  // previous chunk fully consumed
+    stage_input(xs, kPitch, xb, T, Cin, W, to0 * stride - pad_left + d0, nframes, 8);
+    __syncthreads();
+    for (int k0 = kbeg; k0 < kend; k0 += 8) {
       float a[MT][4];
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const float* ap = as + (size_t)(16 * m + g) * apitch + k0 + t4;
-        a[m][0] = ap[0];
-        a[m][1] = ap[8 * apitch];
-        a[m][2] = ap[4];
-        a[m][3] = ap[8 * apitch + 4];
+        const float* ap = wa + (size_t)(16 * m + g) * apitch + k0 + t4;
+        a[m][0] = __ldg(ap);
+        a[m][1] = __ldg(ap + 8 * apitch);
+        a[m][2] = __ldg(ap + 4);
+        a[m][3] = __ldg(ap + 8 * apitch + 4);
       }
-      const float* bp = xrow + (size_t)(k0 + t4) * kPitch + 8 * wt0 + g;
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        if (j < nwt) {
-          float bf[2];
-          bf[0] = bp[8 * j];
-          bf[1] = bp[4 * kPitch + 8 * j];
+      for (int u = 0; u < UPW; ++u) {
+        const int tl = warp + 8 * u;
+        if (tl < nto) {
+          const float* bp = xs + (size_t)(tl * stride * Cin + (k0 - kbeg) + t4) * kPitch + g;
 #pragma unroll
-          for (int m = 0; m < MT; ++m) mma_tf32(acc[m][j], a[m], bf);
+          for (int j = 0; j < 10; ++j) {
+            if (j < wtiles) {
+              float bf[2];
+              bf[0] = bp[8 * j];
+              bf[1] = bp[4 * kPitch + 8 * j];
+#pragma unroll
+              for (int m = 0; m < MT; ++m) mma_tf32(acc[u][m][j], a[m], bf);
+            }
+          }
         }
       }
     }
-    // epilogue: d0 (co = g, w = 2 t4), d1 (g, 2 t4 + 1), d2 (g + 8, ..), d3
+  }
+  // epilogue: d0 (co = g, w = 2 t4), d1 (g, 2 t4 + 1), d2 (g + 8, ..), d3
+  const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+#pragma unroll
+  for (int u = 0; u < UPW; ++u) {
+    const int tl = warp + 8 * u;
+    if (tl >= nto) continue;
     const int to = to0 + tl;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
@@ -126,11 +144,11 @@ __global__ void __launch_bounds__(kMmaThreads) conv_mma_fwd_kernel(int T, int To
         if (co >= Cout) continue;
         const float bv = bias ? __ldg(bias + co) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          if (j < nwt) {
-            const int w = 8 * (wt0 + j) + 2 * t4;
+        for (int j = 0; j < 10; ++j) {
+          if (j < wtiles) {
+            const int w = 8 * j + 2 * t4;
             const size_t idx = (((size_t)b * Tout + to) * Cout + co) * W + w;
-            float v0 = acc[m][j][2 * hrow] + bv, v1 = acc[m][j][2 * hrow + 1] + bv;
+            float v0 = acc[u][m][j][2 * hrow] + bv, v1 = acc[u][m][j][2 * hrow + 1] + bv;
             if (act == 1) {
               v0 = fmaxf(v0, 0.f);
               v1 = fmaxf(v1, 0.f);
@@ -180,13 +198,25 @@ __global__ void __launch_bounds__(kMmaThreads) conv_mma_wgrad_kernel(int T, int 
                                                                       const float* __restrict__ dy, float* __restrict__ partial) {
   extern __shared__ __align__(16) float sm[];
   constexpr int kPitch = 84;  // 84 = 20 (mod 32): 8 rows x 4 consecutive w of a fragment hit 32 distinct banks
-  const int b = blockIdx.y, to0 = blockIdx.x * TC;
-  const int nto = min(TC, Tout - to0);
-  const int nframes = (nto - 1) * stride + K;
-  const int tin0 = to0 * stride - pad_left;
+  const int b = blockIdx.y;
   const int Kc = K * Cin, ktiles = (Kc + 7) / 8;
   float* xs = sm;                                                   // [(nframes*Cin) + 8][kPitch]
   float* ds = sm + ((size_t)((TC - 1) * stride + K) * Cin + 8) * kPitch;  // [TC][16*MT][kPitch]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  float acc[MT][kWgMaxNt][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int j = 0; j < kWgMaxNt; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+  float bias_acc = 0.f;
+  // a CTA walks chunks blockIdx.x, blockIdx.x + gridDim.x, ... of its sample, accumulating in registers
+  for (int to0 = blockIdx.x * TC; to0 < Tout; to0 += gridDim.x * TC) {
+  const int nto = min(TC, Tout - to0);
+  const int nframes = (nto - 1) * stride + K;
+  const int tin0 = to0 * stride - pad_left;
+  __syncthreads();  // the previous chunk's reads are done
   stage_input(xs, kPitch, x + (size_t)b * T * Cin * W, T, Cin, W, tin0, nframes, 8);
   {
     const int chunks = W / 4;
@@ -202,14 +232,6 @@ __global__ void __launch_bounds__(kMmaThreads) conv_mma_wgrad_kernel(int T, int 
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  float acc[MT][kWgMaxNt][4];
-#pragma unroll
-  for (int m = 0; m < MT; ++m)
-#pragma unroll
-    for (int j = 0; j < kWgMaxNt; ++j)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
   for (int tl = 0; tl < nto; ++tl) {
     const float* xrow = xs + (size_t)(tl * stride * Cin) * kPitch;
     const float* drow = ds + (size_t)tl * 16 * MT * kPitch;
@@ -237,6 +259,13 @@ __global__ void __launch_bounds__(kMmaThreads) conv_mma_wgrad_kernel(int T, int 
       }
     }
   }
+  if (threadIdx.x < Cout) {  // bias gradient: sum over (t', w) of dy
+    for (int tl = 0; tl < nto; ++tl) {
+      const float* r = ds + ((size_t)tl * 16 * MT + threadIdx.x) * kPitch;
+      for (int w = 0; w < W; ++w) bias_acc += r[w];
+    }
+  }
+  }  // chunk loop
   // CTA partial: layout of the final gradient wt[co][ci][dk], then Cout bias sums
   float* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)Cout * Cin * K + Cout);
 #pragma unroll
@@ -255,14 +284,7 @@ __global__ void __launch_bounds__(kMmaThreads) conv_mma_wgrad_kernel(int T, int 
         }
       }
     }
-  if (threadIdx.x < Cout) {  // bias gradient: sum over (t', w) of dy (fp32 values as staged)
-    float s = 0.f;
-    for (int tl = 0; tl < nto; ++tl) {
-      const float* r = ds + ((size_t)tl * 16 * MT + threadIdx.x) * kPitch;
-      for (int w = 0; w < W; ++w) s += r[w];
-    }
-    out[(size_t)Cout * Cin * K + threadIdx.x] = s;
-  }
+  if (threadIdx.x < Cout) out[(size_t)Cout * Cin * K + threadIdx.x] = bias_acc;
 }
 
 __global__ void conv_mma_wgrad_reduce_kernel(int n_parts, int n_w, int n_b, const float* __restrict__ partial,
@@ -309,22 +331,19 @@ int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, in
   const int apitch = apitch_for(Kpad);
   conv_mma_arrange_kernel<<<16, 256, 0, stream>>>(wt_cin, wt_cout, K, 16 * MT, apitch, wt, arranged, flip);
   W2L_LAUNCH_CHECK("conv_mma_arrange_kernel");
-  // frames per CTA from the shared-memory budget
-  const size_t a_bytes = (size_t)16 * MT * apitch * 4;
-  int TB = 8;
-  auto bytes_for = [&](int tb) { return a_bytes + ((size_t)((tb - 1) * stride + K) * Cin + 8) * 88 * 4; };
-  while (TB > 1 && bytes_for(TB) > 200 * 1024) TB >>= 1;
-  const size_t smem = bytes_for(TB);
+  // MT = 1: 16 frames per CTA (2 per warp); MT = 2: 8 frames per CTA — 80 accumulator registers either way
+  const int TB = MT == 1 ? 16 : 8;
+  const size_t smem = ((size_t)((TB - 1) * stride + kDeltaTaps) * Cin + 8) * 88 * 4;
   if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "conv_mma_fwd: window does not fit in shared memory");
   dim3 grid((Tout + TB - 1) / TB, B);
   if (MT == 1) {
-    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_mma_fwd_kernel<1><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TB, Kpad, apitch, x, arranged,
-                                                                bias, add, y, act, drop_p, seed);
+    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_mma_fwd_kernel<1, 2><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged,
+                                                                   bias, add, y, act, drop_p, seed);
   } else {
-    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_mma_fwd_kernel<2><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TB, Kpad, apitch, x, arranged,
-                                                                bias, add, y, act, drop_p, seed);
+    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_mma_fwd_kernel<2, 1><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged,
+                                                                   bias, add, y, act, drop_p, seed);
   }
   W2L_LAUNCH_CHECK("conv_mma_fwd_kernel");
   return W2L_OK;
@@ -336,7 +355,10 @@ size_t conv_mma_wgrad_parts(int B, int Tout, int Cin, int Cout, int K, int strid
   auto bytes_for = [&](int tc) { return (((size_t)((tc - 1) * stride + K) * Cin + 8) + (size_t)tc * 16 * MT) * 84 * 4; };
   while (TC > 1 && bytes_for(TC) > 200 * 1024) TC >>= 1;
   if (tc_out) *tc_out = TC;
-  return (size_t)B * ((Tout + TC - 1) / TC);
+  // CTAs per sample: enough to fill the chip ~twice, never more than there are chunks
+  const int chunks = (Tout + TC - 1) / TC;
+  const int per_sample = std::max(1, std::min(chunks, (2 * 148 + B - 1) / B));
+  return (size_t)B * per_sample;
 }
 
 int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
@@ -346,7 +368,7 @@ int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, 
   const size_t parts = conv_mma_wgrad_parts(B, Tout, Cin, Cout, K, stride, &TC);
   const size_t smem = (((size_t)((TC - 1) * stride + K) * Cin + 8) + (size_t)TC * 16 * MT) * 84 * 4;
   if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "conv_mma_wgrad: window does not fit in shared memory");
-  dim3 grid((Tout + TC - 1) / TC, B);
+  dim3 grid((unsigned)(parts / B), B);
   if (MT == 1) {
     if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv_mma_wgrad_kernel<1><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TC, x, dy, partial);

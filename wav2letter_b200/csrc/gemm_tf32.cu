@@ -14,7 +14,7 @@
 //
 // Structure (one CTA per 128 x 128 output tile, 192 threads):
 //   warp 4        TMA producer: cp.async.bulk.tensor 2D boxes (128B inner extent, SWIZZLE_128B, TF32
-//                 rounding on load) into a 6-stage shared-memory ring, mbarrier expect_tx
+//                 rounding on load) into a 3-stage shared-memory ring (2 CTAs per SM), mbarrier expect_tx
 //   warp 5        TMEM allocation (128 columns) + single-thread tcgen05.mma.cta_group::1.kind::tf32
 //                 issue (UMMA 128x128x8, 4 per 32-wide k block), tcgen05.commit onto the stage's
 //                 empty barrier, final commit onto the accumulator-full barrier
@@ -35,7 +35,8 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;  // tile; BK fp32 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;                   // tf32
-constexpr int kStages = 6;
+constexpr int kStages = 3;                  // 96 KB of operand ring per CTA -> two CTAs per SM: one tile's epilogue and
+                                            // prologue overlap the other's main loop (non-persistent kernel)
 constexpr int kTileBytes = BM * BK * 4;     // 16 KB per operand per stage
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 128;
@@ -128,7 +129,7 @@ __device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t
 }
 
 template <bool kAMn, bool kBMn>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
