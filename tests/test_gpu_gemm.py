@@ -51,3 +51,26 @@ def test_gemm_rejects_unaligned():
     B = torch.randn(8, 30, device="cuda")
     with pytest.raises(w.W2LError):
         w.capi.gemm_tf32(A, B)
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(1120, 1120, 4800, True, True), (360, 360, 9600, True, True),
+                                              (256, 200, 2052, False, False), (128, 128, 16 * 32, False, True)])
+def test_gemm_split_k(M, N, K, a_mn, b_mn, accumulate):
+    """few output tiles + long K (the weight-gradient shape): the k blocks are split over blockIdx.z and summed with
+    vector atomics; same TF32 bound, plus the accumulate-onto-C semantics"""
+    import wav2letter_b200 as w
+
+    g = torch.Generator(device="cuda").manual_seed(K)
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g)
+    B = torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g)
+    C0 = torch.randn(M, N, device="cuda", generator=g) * 10
+    C = C0.clone()
+    w.capi.gemm_tf32_ex(A, B, C, a_mn=a_mn, b_mn=b_mn, accumulate=accumulate)
+    torch.cuda.synchronize()
+    A64 = (A.t() if a_mn else A).double()
+    B64 = (B.t() if b_mn else B).double()
+    ref = A64 @ B64.t() + (C0.double() if accumulate else 0)
+    bound = 1.5e-3 * (A64.abs() @ B64.abs().t()) + 1e-4
+    ratio = float(((C.double() - ref).abs() / bound).max())
+    assert ratio <= 1.0, f"split-K M={M} N={N} K={K}: err/bound {ratio}"

@@ -109,6 +109,7 @@ struct GemmParams {
   const float* aux;
   float aux_scale, drop_p;
   unsigned long long seed;
+  int k_splits;  // > 1: blockIdx.z owns a slice of the k blocks and the epilogue adds atomically (few tiles, long K: wgrad)
 };
 
 __device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
@@ -143,7 +144,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb_per = (total_kb + p.k_splits - 1) / p.k_splits;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);
 
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -175,7 +179,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_expect_tx(&full[s], 2 * kTileBytes);
         unsigned char* sa = smem_a + s * kTileBytes;
         unsigned char* sb = smem_b + s * kTileBytes;
-        const int k0 = kb * BK;
+        const int k0 = (kb_begin + kb) * BK;
         if (!kAMn) {
           tma_load_2d(&map_a, &full[s], sa, k0, m0);  // box {32 k, 128 rows}
         } else {
@@ -211,7 +215,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         umma_commit(&empty[s]);  // frees the stage when the MMAs above have read it
       }
-      umma_commit(acc_full);
+      umma_commit(acc_full);  // with num_kb == 0 nothing is pending: the barrier completes immediately
     }
   } else {
     // ===== epilogue warps 0..3: TMEM lanes 32*warp .. +31 =====
@@ -276,12 +280,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               o[j] *= (p.aux_mode == 1 ? a > 0.f : a != 0.f) ? p.aux_scale : 0.f;
             }
         }
-        if (p.accumulate) {
+        if (p.accumulate && p.k_splits == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (nb + j < p.N) o[j] += crow[nb + j];
         }
-        if (vec_ok && nb + 32 <= p.N) {
+        if (p.k_splits > 1) {  // split-K: C was zeroed (or holds the value to accumulate onto) by the host wrapper
+          if (num_kb > 0) {
+            if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(crow + nb + j), make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) atomicAdd(crow + nb + j, o[j]);
+            }
+          }
+        } else if (vec_ok && nb + 32 <= p.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + nb + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         } else {
@@ -342,7 +357,7 @@ int launch(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, co
     W2L_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.k_splits);
   profile_kind(1);
     profile_start(stream);
   gemm_tf32_kernel<kAMn, kBMn><<<grid, kGemmThreads, smem, stream>>>(ma, mb, p);
@@ -393,7 +408,14 @@ extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, i
   else
     rc = make_map(&mb, B, K, N, ldb, BK, true);
   if (rc) return rc;
-  GemmParams p{M, N, K, ldc, act, C, bias, accumulate, aux_mode, ld_aux, aux, aux_scale, dropout_p, seed};
+  // split-K when the output has few tiles and K is long (weight gradients: 81 tiles, 150 k blocks): slices of
+  // >= 4 k blocks, ~2 CTAs per SM in total; only for plain epilogues (the partial sums are added atomically)
+  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM), total_kb = (K + BK - 1) / BK;
+  int splits = 1;
+  if (tiles < 148 && total_kb >= 16 && act == 0 && aux_mode == 0 && dropout_p == 0.f && bias == nullptr)
+    splits = std::max(1, std::min(std::min(296 / tiles, total_kb / 4), 32));
+  if (splits > 1 && !accumulate) W2L_CUDA_CHECK(cudaMemsetAsync(C, 0, sizeof(float) * ((size_t)(M - 1) * ldc + N), stream));
+  GemmParams p{M, N, K, ldc, act, C, bias, accumulate, aux_mode, ld_aux, aux, aux_scale, dropout_p, seed, splits};
   if (!a_mn_major && !b_mn_major) return launch<false, false>(stream, ma, mb, p);
   if (!a_mn_major && b_mn_major) return launch<false, true>(stream, ma, mb, p);
   if (a_mn_major && b_mn_major) return launch<true, true>(stream, ma, mb, p);
