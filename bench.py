@@ -407,6 +407,11 @@ def run_tds(args, rank, world, local_rank):
     ms, kern, launches, clocks = tm.run(step, args.steps, args.warmup, sample_clocks=True, profile=prof, profile_steps=prof_steps)
     ms_e2e, _, _, _ = tm.run(step_e2e, args.steps, args.warmup)
     final_loss = float(loss.sum().item())
+    # after the timed regions: one traced step (an event after every launch) -> warm in-situ share of each kernel
+    tr = capi.trace(lambda: step(0))
+    tr_total = sum(v[1] for v in tr.values()) or 1.0
+    breakdown = {k: {"launches": v[0], "ms": round(v[1], 4), "share": round(v[1] / tr_total, 4)}
+                 for k, v in sorted(tr.items(), key=lambda kv: -kv[1][1])}
     asg = asg_point(tm, rank, 10, 3, profile=False) if world == 1 else None
     if rank != 0:
         return
@@ -442,6 +447,8 @@ def run_tds(args, rank, world, local_rank):
                      "peak_source": src + " bf16_tflops_sustained; tf32 math has half the bf16 hardware ceiling",
                      "gemm_ms_per_step": gemm_ms_per_step, "gemm_launches_per_step": len(kern) / prof_steps,
                      "algorithmic_flops_per_step": gemm_flops, "gemm_share_of_step": gemm_ms_per_step / (ms / args.steps)},
+        "step_breakdown": {"method": "one extra traced step after the timed region, a CUDA event after every launch",
+                           "traced_ms": round(tr_total, 3), "kernels": dict(list(breakdown.items())[:14])},
         "cpu_baseline": ({"value": cpu_fps, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
                           "sample": f"2 train steps of B=2,T={T} on torch-CPU/oneDNN + C-oracle CTC ({cpu_s:.1f} s/step)"}
                          if cpu_fps is not None else None),

@@ -79,6 +79,11 @@ W2L_API void w2l_set_profile_events(void* start_event, void* stop_event);
  * caller-owned arrays (n pairs); w2l_profile_events_used() tells how many were consumed.  NULL clears. */
 W2L_API int w2l_set_profile_event_list(int kind, void** start_events, void** stop_events, int n);
 W2L_API int w2l_profile_events_used(void);
+/* Trace mode (measurement only): between begin and end every kernel launched by this thread records one event on
+ * `stream` (all work must be on that stream); end synchronises, sums the inter-event time per kernel name and writes
+ * "name\tlaunches\tms\n" lines into out.  Returns the byte count needed (call with NULL to size). */
+W2L_API int w2l_trace_begin(void* stream, int capacity);
+W2L_API long long w2l_trace_end(char* out, long long out_bytes);
 
 /* ----------------------------------------------------------------------------------------
  * ASG = FullConnectionCriterion - ForceAlignmentCriterion, fused forward + backward.

@@ -19,7 +19,7 @@ TERM_FCC, TERM_FAC, TERM_ASG = 1, 2, 3
 
 # every entry point include/w2l_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count", "w2l_set_profile_events", "w2l_set_profile_event_list", "w2l_profile_events_used",
+    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count", "w2l_set_profile_events", "w2l_set_profile_event_list", "w2l_profile_events_used", "w2l_trace_begin", "w2l_trace_end",
     "w2l_asg_workspace_size", "w2l_asg_forward_backward",
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
@@ -50,6 +50,9 @@ def _load() -> ctypes.CDLL:
     lib.w2l_launch_count.restype = ctypes.c_longlong
     lib.w2l_set_profile_events.argtypes = [vp, vp]
     lib.w2l_set_profile_event_list.argtypes = [i, vp, vp, i]
+    lib.w2l_trace_begin.argtypes = [vp, i]
+    lib.w2l_trace_end.restype = ctypes.c_longlong
+    lib.w2l_trace_end.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
     lib.w2l_asg_workspace_size.restype = sz
     lib.w2l_asg_workspace_size.argtypes = [i, i, i, i]
     lib.w2l_asg_forward_backward.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, sz]
@@ -261,6 +264,22 @@ class ProfileList:
 
     def times_ms(self, used: int):
         return [self.starts[k].elapsed_time(self.stops[k]) for k in range(used)]
+
+
+def trace(fn, capacity: int = 4096) -> dict:
+    """Run fn() (all work on the current stream) in trace mode; returns {kernel name: (launches, total ms)} measured
+    with one CUDA event after every launch — the warm, in-situ share of each kernel (measurement only)."""
+    _check(lib.w2l_trace_begin(_stream(), capacity))
+    try:
+        fn()
+    finally:
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.w2l_trace_end(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split("\t")
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def gemm_tf32(A, B, bias=None, act=0, a_mn=False, b_mn=False, out=None):

@@ -23,7 +23,7 @@ size_t conv_mma_arranged_floats(int Cin, int Cout, int K);
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                  const float* x, const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y,
                  int act, float drop_p, unsigned long long seed, float* arranged);
-size_t conv_mma_wgrad_parts(int B, int Tout, int Cin, int Cout, int K, int stride, int* tc_out);
+size_t conv_mma_wgrad_parts(int B, int Tout, int W, int Cin, int Cout, int K, int stride, int* tc_out, int* per_sample_out);
 int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                    const float* x, const float* dy, float* dwt, float* dbias, float* partial);
 
@@ -539,8 +539,8 @@ static int co_pad(int c) { return (c + 3) / 4 * 4; }
 static size_t conv_ws_partial_bytes(int B, int Tout, int Cin, int Cout, int K) {
   const size_t per = ((size_t)Cout * Cin * K + Cout) * sizeof(float);
   const size_t simt = (size_t)B * ((Tout + 15) / 16);
-  const size_t mma = conv_mma_wgrad_parts(B, Tout, Cin, Cout, K, 1, nullptr);  // stride 1 gives the smallest TC -> most parts
-  return align_up(std::max(simt, std::max(mma, (size_t)B * (size_t)Tout)) * per, 256);
+  const size_t mma = conv_mma_wgrad_parts(B, Tout, 0, Cin, Cout, K, 1, nullptr, nullptr);  // W unknown here: ten slices
+  return align_up(std::max(simt, std::max(mma, (size_t)B * (size_t)std::max(Tout, 16))) * per, 256);
 }
 extern "C" size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K) {
   const size_t arranged = std::max((size_t)std::max(Cin, Cout) * K * co_pad(std::max(Cin, Cout)), conv_mma_arranged_floats(Cin, Cout, K)) * sizeof(float);

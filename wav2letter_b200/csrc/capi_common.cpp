@@ -1,5 +1,8 @@
 // capi_common.cpp — error text, launch counter, version.
+#include <cstring>
+#include <map>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -38,6 +41,17 @@ void profile_stop(cudaStream_t s) {
   }
   g_cur_kind = 0;
 }
+// ---- trace mode: attribute the time of a single-stream call sequence to kernel names ---------------------
+static thread_local cudaStream_t g_trace_stream = nullptr;
+static thread_local bool g_trace_on = false;
+static thread_local std::vector<cudaEvent_t> g_trace_ev;
+static thread_local std::vector<const char*> g_trace_name;
+static thread_local size_t g_trace_used = 0;
+void trace_launch(const char* name) {
+  if (!g_trace_on || g_trace_used >= g_trace_ev.size()) return;
+  cudaEventRecord(g_trace_ev[g_trace_used], g_trace_stream);
+  g_trace_name[g_trace_used++] = name;
+}
 void set_profile_events(cudaEvent_t a, cudaEvent_t b) {
   g_ev_start = a;
   g_ev_stop = b;
@@ -63,4 +77,38 @@ int w2l_set_profile_event_list(int kind, void** starts, void** stops, int n) {
   return 0;
 }
 int w2l_profile_events_used(void) { return w2l::g_list_used; }
+int w2l_trace_begin(void* stream, int capacity) {
+  using namespace w2l;
+  while ((int)g_trace_ev.size() < capacity + 1) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return fail(W2L_ERR_CUDA, "w2l_trace_begin: cudaEventCreate");
+    g_trace_ev.push_back(e);
+  }
+  g_trace_name.assign(g_trace_ev.size(), "");
+  g_trace_stream = static_cast<cudaStream_t>(stream);
+  g_trace_used = 0;
+  g_trace_on = true;
+  trace_launch("(begin)");
+  return W2L_OK;
+}
+long long w2l_trace_end(char* out, long long out_bytes) {
+  using namespace w2l;
+  g_trace_on = false;
+  if (g_trace_used == 0) return 0;
+  cudaEventSynchronize(g_trace_ev[g_trace_used - 1]);
+  struct Acc { double ms = 0; long long n = 0; };
+  std::map<std::string, Acc> acc;
+  for (size_t i = 1; i < g_trace_used; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace_ev[i - 1], g_trace_ev[i]);
+    Acc& a = acc[g_trace_name[i]];
+    a.ms += ms;
+    a.n += 1;
+  }
+  std::string text;
+  for (const auto& kv : acc) text += kv.first + "\t" + std::to_string(kv.second.n) + "\t" + std::to_string(kv.second.ms) + "\n";
+  const long long need = (long long)text.size() + 1;
+  if (out && out_bytes >= need) memcpy(out, text.c_str(), (size_t)need);
+  return need;
+}
 }

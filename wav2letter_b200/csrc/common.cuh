@@ -15,6 +15,7 @@ namespace w2l {
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
+void trace_launch(const char* name);  // trace mode (w2l_trace_begin): one event after every launch, on the trace stream
 // bench hook: events recorded around a call's dominant kernel (nullptr when unset)
 void profile_kind(int kind);  // 1 = GEMM, 2 = criterion chains (set right before profile_start)
 void profile_start(cudaStream_t s);
@@ -30,6 +31,7 @@ void profile_stop(cudaStream_t s);
 #define W2L_LAUNCH_CHECK(name)                                                                    \
   do {                                                                                            \
     ::w2l::count_launch();                                                                        \
+    ::w2l::trace_launch(name);                                                                    \
     cudaError_t _e = cudaGetLastError();                                                          \
     if (_e != cudaSuccess)                                                                        \
       return ::w2l::fail(W2L_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \

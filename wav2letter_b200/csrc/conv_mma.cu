@@ -39,124 +39,163 @@ __device__ __forceinline__ float drop_scale(unsigned long long seed, unsigned lo
   return dropout_scale(seed, idx, p, inv_keep);
 }
 
-// stage rows [row0, row0 + nrows) of the input window: smem row r = (tin - tin0) * Cin + ci, pitch `pitch`
-__device__ __forceinline__ void stage_input(float* xs, int pitch, const float* __restrict__ xb, int T, int Cin, int W, int tin0,
-                                            int nframes, int pad_rows) {
-  const int nrows = nframes * Cin;
-  const int chunks = W / 4;  // W % 4 == 0
-  for (int i = threadIdx.x; i < nrows * chunks; i += blockDim.x) {
-    const int r = i / chunks, c4 = i % chunks;
-    const int tin = tin0 + r / Cin, ci = r % Cin;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tin >= 0 && tin < T) v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)tin * Cin + ci) * W) + c4);
-    float* dst = xs + (size_t)r * pitch + 4 * c4;
-    dst[0] = to_tf32(v.x);
-    dst[1] = to_tf32(v.y);
-    dst[2] = to_tf32(v.z);
-    dst[3] = to_tf32(v.w);
+// Stage `nrows` consecutive rows of a [rows][W] global matrix (slice columns [w_off, w_off + 8 WT)) into shared
+// memory, TF32-rounded, 16-byte stores.  Activations are [t][c][W], so the window rows (t, c) of a sample are
+// consecutive global rows: smem row r <- global row r + row_base, zero when outside [0, rows_total).
+// Lanes: 2 WT float4 per row, 32 / (2 WT) rows per warp pass — divisions by compile-time constants only.
+template <int WT>
+__device__ __forceinline__ void stage_rows(float* dst, int pitch, const float* __restrict__ src, int W, int row_base,
+                                           int rows_total, int nrows, int zero_rows) {
+  constexpr int q = 2 * WT, RPW = 32 / q, kWarps = kMmaThreads / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / q, c4 = lane % q;
+  if (sub < RPW) {
+#pragma unroll 4
+    for (int r = warp * RPW + sub; r < nrows; r += kWarps * RPW) {
+      const int gr = r + row_base;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr >= 0 && gr < rows_total) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * W) + c4);
+      *reinterpret_cast<float4*>(dst + (size_t)r * pitch + 4 * c4) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
   }
   // rows read by the zero-padded tail of K must be finite
-  for (int i = threadIdx.x; i < pad_rows * pitch; i += blockDim.x) xs[(size_t)nrows * pitch + i] = 0.f;
+  for (int i = threadIdx.x; i < zero_rows * pitch; i += blockDim.x) dst[(size_t)nrows * pitch + i] = 0.f;
 }
 
-// ------------------------------------------------------------------------------------------
-// forward: one CTA = TB = 8*UPW output frames of one sample; warp w owns frames w, w+8 (all of W).
-// The K loop is chunked over ranges of kDeltaTaps taps: each chunk stages only the (TB-1)*stride + 8 input
-// frames it touches (<= 100 KB for every TDS shape -> two CTAs per SM), accumulators stay in registers
-// across chunks.  Weight fragments come straight from global memory (L1-resident, 50 KB at most).
-// ------------------------------------------------------------------------------------------
-constexpr int kDeltaTaps = 8;  // 8 * Cin is always a multiple of the MMA K (8)
+// row pitch of a [k][w] operand slice 8*WT wide: = 8 or 24 (mod 32) so the 4 k-rows x 8 w of a B fragment hit 32 banks
+__host__ __device__ constexpr int fwd_pitch(int WT) { return (8 * WT) % 16 == 8 ? 8 * WT : 8 * WT + 8; }
+// weight-gradient operands ([row][w], fragments of 8 rows x 4 w): pitch = 4 (mod 8)
+__host__ __device__ constexpr int wg_pitch(int WT) { return 8 * WT + 4; }
 
-template <int MT, int UPW>  // m tiles of 16 output channels (1 or 2); frames per warp
-__global__ void __launch_bounds__(kMmaThreads) conv_mma_fwd_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
-                                                                    int pad_left, int Kpad, int apitch,
-                                                                    const float* __restrict__ x, const float* __restrict__ wa,
-                                                                    const float* __restrict__ bias, const float* __restrict__ add,
-                                                                    float* __restrict__ y, int act, float drop_p,
-                                                                    unsigned long long seed) {
+// ------------------------------------------------------------------------------------------
+// forward: one CTA = TB = 8*UPW output frames x one slice of 8*WT columns of one sample; warp w owns frames
+// w, w+8, ...  The whole (TB-1)*stride + K frame window of the slice is staged once (W = 80 is cut into two
+// slices of 40: 58-81 KB per CTA for every TDS shape -> 2-3 CTAs per SM).  Weight fragments come straight from
+// global memory (L1-resident, 50 KB at most), prefetched one k-step ahead.
+// ------------------------------------------------------------------------------------------
+template <int MT, int UPW, int WT>  // m tiles of 16 output channels (1 or 2); frames per warp; 8-column tiles per slice
+__global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                                                                       int pad_left, int Kpad, int apitch,
+                                                                       const float* __restrict__ x, const float* __restrict__ wa,
+                                                                       const float* __restrict__ bias, const float* __restrict__ add,
+                                                                       float* __restrict__ y, int act, float drop_p,
+                                                                       unsigned long long seed) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int kPitch = 88;  // 88 = 24 (mod 32): the 4 k-rows x 8 w of a B fragment hit 32 distinct banks
+  constexpr int kPitch = fwd_pitch(WT);
   constexpr int TB = 8 * UPW;
   float* xs = sm;  // [(nframes*Cin) + 8][kPitch]
-  const int b = blockIdx.y, to0 = blockIdx.x * TB;
+  const int b = blockIdx.z, w_off = blockIdx.y * 8 * WT, to0 = blockIdx.x * TB;
   const int nto = min(TB, Tout - to0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-  const int wtiles = W / 8;  // <= 10
-  float acc[UPW][MT][10][4];
+  float acc[UPW][MT][WT][4];
 #pragma unroll
   for (int u = 0; u < UPW; ++u)
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-      for (int j = 0; j < 10; ++j)
+      for (int j = 0; j < WT; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[u][m][j][q] = 0.f;
-  const float* xb = x + (size_t)b * T * Cin * W;
-  for (int d0 = 0; d0 * Cin < Kpad; d0 += kDeltaTaps) {
-    const int kbeg = d0 * Cin, kend = min(Kpad, (d0 + kDeltaTaps) * Cin);
-    // frames this chunk touches: outputs tl = 0..nto-1, taps d0 .. d0+7 (clipped to the padded K range)
-    const int taps = (kend - kbeg + Cin - 1) / Cin;
-    const int nframes = (nto - 1) * stride + taps;
-    __syncthreads();  // previous chunk fully consumed
-    stage_input(xs, kPitch, xb, T, Cin, W, to0 * stride - pad_left + d0, nframes, 8);
-    __syncthreads();
-    for (int k0 = kbeg; k0 < kend; k0 += 8) {
-      float a[MT][4];
+  const int nframes = (nto - 1) * stride + K;
+  stage_rows<WT>(xs, kPitch, x + (size_t)b * T * Cin * W + w_off, W, (to0 * stride - pad_left) * Cin, T * Cin, nframes * Cin, 8);
+  __syncthreads();
+  // frames past the end of the sample recompute the last valid one (their result is not stored): no divergent
+  // branch around the MMAs
+  const float* bp[UPW];
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        const float* ap = wa + (size_t)(16 * m + g) * apitch + k0 + t4;
-        a[m][0] = __ldg(ap);
-        a[m][1] = __ldg(ap + 8 * apitch);
-        a[m][2] = __ldg(ap + 4);
-        a[m][3] = __ldg(ap + 8 * apitch + 4);
-      }
+  for (int u = 0; u < UPW; ++u) bp[u] = xs + (size_t)(min(warp + 8 * u, nto - 1) * stride * Cin + t4) * kPitch + g;
+  const float* ap = wa + (size_t)g * apitch + t4;
+  float a[MT][4];
 #pragma unroll
-      for (int u = 0; u < UPW; ++u) {
-        const int tl = warp + 8 * u;
-        if (tl < nto) {
-          const float* bp = xs + (size_t)(tl * stride * Cin + (k0 - kbeg) + t4) * kPitch + g;
+  for (int m = 0; m < MT; ++m) {
+    a[m][0] = __ldg(ap + (size_t)16 * m * apitch);
+    a[m][1] = __ldg(ap + (size_t)(16 * m + 8) * apitch);
+    a[m][2] = __ldg(ap + (size_t)16 * m * apitch + 4);
+    a[m][3] = __ldg(ap + (size_t)(16 * m + 8) * apitch + 4);
+  }
+  for (int k0 = 0; k0 < Kpad; k0 += 8) {
+    float an[MT][4];
+    const int kn = min(k0 + 8, Kpad - 8);  // the last prefetch re-reads the last step
 #pragma unroll
-          for (int j = 0; j < 10; ++j) {
-            if (j < wtiles) {
-              float bf[2];
-              bf[0] = bp[8 * j];
-              bf[1] = bp[4 * kPitch + 8 * j];
+    for (int m = 0; m < MT; ++m) {
+      an[m][0] = __ldg(ap + (size_t)16 * m * apitch + kn);
+      an[m][1] = __ldg(ap + (size_t)(16 * m + 8) * apitch + kn);
+      an[m][2] = __ldg(ap + (size_t)16 * m * apitch + kn + 4);
+      an[m][3] = __ldg(ap + (size_t)(16 * m + 8) * apitch + kn + 4);
+    }
 #pragma unroll
-              for (int m = 0; m < MT; ++m) mma_tf32(acc[u][m][j], a[m], bf);
-            }
-          }
-        }
+    for (int u = 0; u < UPW; ++u) {
+      const float* bq = bp[u] + (size_t)k0 * kPitch;
+#pragma unroll
+      for (int j = 0; j < WT; ++j) {
+        float bf[2];
+        bf[0] = bq[8 * j];
+        bf[1] = bq[4 * kPitch + 8 * j];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mma_tf32(acc[u][m][j], a[m], bf);
       }
     }
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[m][q] = an[m][q];
   }
-  // epilogue: d0 (co = g, w = 2 t4), d1 (g, 2 t4 + 1), d2 (g + 8, ..), d3
+  // epilogue: d0 (co = g, w = 2 t4), d1 (g, 2 t4 + 1), d2 (g + 8, ..), d3.  Dropout: the keep mask is a function of
+  // the element index (Philox block idx >> 2, word idx & 3); a lane pair (t4 even, t4 odd) covers one block of four
+  // consecutive w, so the even lane generates the block of tile j, the odd lane the block of tile j + 1, and they
+  // swap the two words the other one needs.
   const float inv_keep = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  const bool odd = t4 & 1;
 #pragma unroll
   for (int u = 0; u < UPW; ++u) {
     const int tl = warp + 8 * u;
-    if (tl >= nto) continue;
-    const int to = to0 + tl;
+    const int to = to0 + min(tl, nto - 1);
+    const bool live = tl < nto;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
 #pragma unroll
       for (int hrow = 0; hrow < 2; ++hrow) {
         const int co = 16 * m + g + 8 * hrow;
-        if (co >= Cout) continue;
-        const float bv = bias ? __ldg(bias + co) : 0.f;
+        const bool ok = live && co < Cout;
+        const int coc = min(co, Cout - 1);
+        const float bv = bias ? __ldg(bias + coc) : 0.f;
+        const size_t base = (((size_t)b * Tout + to) * Cout + coc) * W + w_off + 2 * t4;
+        float keep[WT][2];
+        if (drop_p > 0.f) {
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          if (j < wtiles) {
-            const int w = 8 * j + 2 * t4;
-            const size_t idx = (((size_t)b * Tout + to) * Cout + co) * W + w;
-            float v0 = acc[u][m][j][2 * hrow] + bv, v1 = acc[u][m][j][2 * hrow + 1] + bv;
-            if (act == 1) {
-              v0 = fmaxf(v0, 0.f);
-              v1 = fmaxf(v1, 0.f);
+          for (int j = 0; j < WT; j += 2) {
+            const int jm = (odd && j + 1 < WT) ? j + 1 : j;  // the tile whose block this lane generates
+            const unsigned long long idx = base + 8 * jm;
+            const uint4 r = philox4x32((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)seed, (uint32_t)(seed >> 32));
+            const uint32_t s0 = odd ? r.x : r.z, s1 = odd ? r.y : r.w;  // words the partner lane needs
+            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            // own words of the generated block: even lane words 0,1 (tile j); odd lane words 2,3 (tile jm)
+            const uint32_t o0 = odd ? r.z : r.x, o1 = odd ? r.w : r.y;
+            auto k = [&](uint32_t v) { return ((float)(v >> 8) * (1.0f / 16777216.0f)) >= drop_p ? inv_keep : 0.f; };
+            if (j + 1 < WT) {
+              keep[j][0] = odd ? k(r0) : k(o0);
+              keep[j][1] = odd ? k(r1) : k(o1);
+              keep[j + 1][0] = odd ? k(o0) : k(r0);
+              keep[j + 1][1] = odd ? k(o1) : k(r1);
+            } else {  // unpaired last tile: both lanes generated the same block
+              keep[j][0] = k(o0);
+              keep[j][1] = k(o1);
             }
-            if (drop_p > 0.f) {
-              v0 *= drop_scale(seed, idx, drop_p, inv_keep);
-              v1 *= drop_scale(seed, idx + 1, drop_p, inv_keep);
-            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < WT; ++j) {
+          const size_t idx = base + 8 * j;
+          float v0 = acc[u][m][j][2 * hrow] + bv, v1 = acc[u][m][j][2 * hrow + 1] + bv;
+          if (act == 1) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          if (drop_p > 0.f) {
+            v0 *= keep[j][0];
+            v1 *= keep[j][1];
+          }
+          if (ok) {
             if (add != nullptr) {
               const float2 av = __ldg(reinterpret_cast<const float2*>(add + idx));
               v0 += av.x;
@@ -188,20 +227,23 @@ __global__ void conv_mma_arrange_kernel(int Cin, int Cout, int K, int rows, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// weight gradient: CTA = TC output frames of one sample; warps own disjoint 8-wide tiles of k
+// weight gradient: CTA = (sample, slice of 8*WT columns), walking chunks of TC output frames; warps own disjoint
+// 8-wide tiles of k (k tiles past the end recompute the last one, unstored, so no MMA sits behind a divergent
+// branch); dY rows are staged unpadded ([t'][Cout]) with one shared zero row standing in for channels >= Cout.
 // ------------------------------------------------------------------------------------------
 constexpr int kWgMaxNt = 8;  // k tiles per warp (Kc <= 8 * 8 * 8 = 512)
 
-template <int MT>
-__global__ void __launch_bounds__(kMmaThreads) conv_mma_wgrad_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
-                                                                      int pad_left, int TC, const float* __restrict__ x,
-                                                                      const float* __restrict__ dy, float* __restrict__ partial) {
+template <int MT, int WT>
+__global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_wgrad_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                                                                         int pad_left, int TC, int NT, const float* __restrict__ x,
+                                                                         const float* __restrict__ dy, float* __restrict__ partial) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int kPitch = 84;  // 84 = 20 (mod 32): 8 rows x 4 consecutive w of a fragment hit 32 distinct banks
-  const int b = blockIdx.y;
+  constexpr int kPitch = wg_pitch(WT);
+  const int b = blockIdx.z, w_off = blockIdx.y * 8 * WT;
   const int Kc = K * Cin, ktiles = (Kc + 7) / 8;
-  float* xs = sm;                                                   // [(nframes*Cin) + 8][kPitch]
-  float* ds = sm + ((size_t)((TC - 1) * stride + K) * Cin + 8) * kPitch;  // [TC][16*MT][kPitch]
+  float* xs = sm;                                                          // [(nframes*Cin) + 8][kPitch]
+  float* ds = sm + ((size_t)((TC - 1) * stride + K) * Cin + 8) * kPitch;   // [TC*Cout][kPitch] + 1 zero row
+  const float* zrow = ds + (size_t)TC * Cout * kPitch;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
   float acc[MT][kWgMaxNt][4];
 #pragma unroll
@@ -210,70 +252,73 @@ __global__ void __launch_bounds__(kMmaThreads) conv_mma_wgrad_kernel(int T, int 
     for (int j = 0; j < kWgMaxNt; ++j)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
-  float bias_acc = 0.f;
+  float bias_ch[4] = {0.f, 0.f, 0.f, 0.f};
+  // B-fragment row offsets of this warp's k tiles (clamped), relative to the frame's first row
+  int boff[kWgMaxNt];
+#pragma unroll
+  for (int j = 0; j < kWgMaxNt; ++j) boff[j] = (8 * min(warp + j * (kMmaThreads / 32), ktiles - 1) + g) * kPitch + t4;
   // a CTA walks chunks blockIdx.x, blockIdx.x + gridDim.x, ... of its sample, accumulating in registers
   for (int to0 = blockIdx.x * TC; to0 < Tout; to0 += gridDim.x * TC) {
-  const int nto = min(TC, Tout - to0);
-  const int nframes = (nto - 1) * stride + K;
-  const int tin0 = to0 * stride - pad_left;
-  __syncthreads();  // the previous chunk's reads are done
-  stage_input(xs, kPitch, x + (size_t)b * T * Cin * W, T, Cin, W, tin0, nframes, 8);
-  {
-    const int chunks = W / 4;
-    for (int i = threadIdx.x; i < nto * 16 * MT * chunks; i += blockDim.x) {
-      const int c4 = i % chunks, co = (i / chunks) % (16 * MT), tl = i / (chunks * 16 * MT);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (co < Cout) v = __ldg(reinterpret_cast<const float4*>(dy + (((size_t)b * Tout + to0 + tl) * Cout + co) * W) + c4);
-      float* dst = ds + ((size_t)tl * 16 * MT + co) * kPitch + 4 * c4;
-      dst[0] = to_tf32(v.x);
-      dst[1] = to_tf32(v.y);
-      dst[2] = to_tf32(v.z);
-      dst[3] = to_tf32(v.w);
-    }
-  }
-  __syncthreads();
-  for (int tl = 0; tl < nto; ++tl) {
-    const float* xrow = xs + (size_t)(tl * stride * Cin) * kPitch;
-    const float* drow = ds + (size_t)tl * 16 * MT * kPitch;
-    for (int w0 = 0; w0 < W; w0 += 8) {
-      float a[MT][4];
+    const int nto = min(TC, Tout - to0);
+    const int nframes = (nto - 1) * stride + K;
+    __syncthreads();  // the previous chunk's reads are done
+    stage_rows<WT>(xs, kPitch, x + (size_t)b * T * Cin * W + w_off, W, (to0 * stride - pad_left) * Cin, T * Cin, nframes * Cin, 8);
+    stage_rows<WT>(ds, kPitch, dy + (size_t)b * Tout * Cout * W + w_off, W, to0 * Cout, Tout * Cout, nto * Cout, 0);
+    if (to0 == blockIdx.x * TC)
+      for (int i = threadIdx.x; i < kPitch; i += blockDim.x) ds[(size_t)TC * Cout * kPitch + i] = 0.f;
+    __syncthreads();
+    for (int tl = 0; tl < nto; ++tl) {
+      const float* xrow = xs + (size_t)(tl * stride * Cin) * kPitch;
+      const float* drow = ds + (size_t)tl * Cout * kPitch;
+      const float* ar[MT][2];
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        const float* ap = drow + (size_t)(16 * m + g) * kPitch + w0 + t4;  // A[co][w] = dy
-        a[m][0] = ap[0];
-        a[m][1] = ap[8 * kPitch];
-        a[m][2] = ap[4];
-        a[m][3] = ap[8 * kPitch + 4];
+        ar[m][0] = (16 * m + g < Cout ? drow + (size_t)(16 * m + g) * kPitch : zrow) + t4;
+        ar[m][1] = (16 * m + g + 8 < Cout ? drow + (size_t)(16 * m + g + 8) * kPitch : zrow) + t4;
       }
 #pragma unroll
-      for (int j = 0; j < kWgMaxNt; ++j) {
-        const int kt = warp + j * (kMmaThreads / 32);
-        if (kt < ktiles) {
-          const float* bp = xrow + (size_t)(8 * kt + g) * kPitch + w0 + t4;  // B[w][k] = x[row k][w]
-          float bf[2];
-          bf[0] = bp[0];
-          bf[1] = bp[4];
+      for (int wt = 0; wt < WT; ++wt) {
+        float a[MT][4];
 #pragma unroll
-          for (int m = 0; m < MT; ++m) mma_tf32(acc[m][j], a[m], bf);
+        for (int m = 0; m < MT; ++m) {  // A[co][w] = dy
+          a[m][0] = ar[m][0][8 * wt];
+          a[m][1] = ar[m][1][8 * wt];
+          a[m][2] = ar[m][0][8 * wt + 4];
+          a[m][3] = ar[m][1][8 * wt + 4];
+        }
+#pragma unroll
+        for (int j = 0; j < kWgMaxNt; ++j) {
+          if (j < NT) {  // NT is a kernel argument: warp-uniform
+            const float* bp = xrow + boff[j] + 8 * wt;  // B[w][k] = x[row k][w]
+            float bf[2];
+            bf[0] = bp[0];
+            bf[1] = bp[4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) mma_tf32(acc[m][j], a[m], bf);
+          }
         }
       }
     }
-  }
-  if (threadIdx.x < Cout) {  // bias gradient: sum over (t', w) of dy
-    for (int tl = 0; tl < nto; ++tl) {
-      const float* r = ds + ((size_t)tl * 16 * MT + threadIdx.x) * kPitch;
-      for (int w = 0; w < W; ++w) bias_acc += r[w];
+    // bias gradient: sum over (t', w) of dy; warp w takes channels w, w + 8, ..
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int co = warp + 8 * c;
+      if (co < Cout) {
+        float sacc = 0.f;
+        for (int i = lane; i < nto * 8 * WT; i += 32) sacc += ds[((size_t)(i / (8 * WT)) * Cout + co) * kPitch + i % (8 * WT)];
+        bias_ch[c] += sacc;
+      }
     }
-  }
   }  // chunk loop
   // CTA partial: layout of the final gradient wt[co][ci][dk], then Cout bias sums
-  float* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)Cout * Cin * K + Cout);
+  const size_t part = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  float* out = partial + part * ((size_t)Cout * Cin * K + Cout);
 #pragma unroll
   for (int m = 0; m < MT; ++m)
 #pragma unroll
     for (int j = 0; j < kWgMaxNt; ++j) {
       const int kt = warp + j * (kMmaThreads / 32);
-      if (kt < ktiles) {
+      if (j < NT && kt < ktiles) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int co = 16 * m + g + 8 * (q >> 1), k = 8 * kt + 2 * t4 + (q & 1);
@@ -284,7 +329,14 @@ __global__ void __launch_bounds__(kMmaThreads) conv_mma_wgrad_kernel(int T, int 
         }
       }
     }
-  if (threadIdx.x < Cout) out[(size_t)Cout * Cin * K + threadIdx.x] = bias_acc;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int co = warp + 8 * c;
+    if (co < Cout) {
+      const float tot = warp_sum(bias_ch[c]);
+      if (lane == 0) out[(size_t)Cout * Cin * K + co] = tot;
+    }
+  }
 }
 
 __global__ void conv_mma_wgrad_reduce_kernel(int n_parts, int n_w, int n_b, const float* __restrict__ partial,
@@ -321,6 +373,24 @@ size_t conv_mma_arranged_floats(int Cin, int Cout, int K) {
   const int Kpad = (K * kin + 7) / 8 * 8;
   return (size_t)32 * apitch_for(Kpad);
 }
+// 8-column tiles per slice: the largest of 5..1 that divides W / 8 (W = 80 -> two slices of 40)
+static int slice_tiles(int W) {
+  for (int wt = 5; wt > 1; --wt)
+    if ((W / 8) % wt == 0) return wt;
+  return 1;
+}
+constexpr size_t kConvSmemTarget = 112 * 1024;  // two CTAs per SM
+
+template <int MT, int UPW, int WT>
+static int launch_fwd(cudaStream_t stream, dim3 grid, size_t smem, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                      int pad_left, int Kpad, int apitch, const float* x, const float* arranged, const float* bias,
+                      const float* add, float* y, int act, float drop_p, unsigned long long seed) {
+  if (smem > 48 * 1024)
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<MT, UPW, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_mma_fwd_kernel<MT, UPW, WT><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x,
+                                                                        arranged, bias, add, y, act, drop_p, seed);
+  return W2L_OK;
+}
 
 // flip = 0: y = conv(x) ; flip = 1: stride-1 data gradient (x := dy, roles of Cin/Cout swapped by the caller)
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
@@ -331,51 +401,75 @@ int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, in
   const int apitch = apitch_for(Kpad);
   conv_mma_arrange_kernel<<<16, 256, 0, stream>>>(wt_cin, wt_cout, K, 16 * MT, apitch, wt, arranged, flip);
   W2L_LAUNCH_CHECK("conv_mma_arrange_kernel");
-  // MT = 1: 16 frames per CTA (2 per warp); MT = 2: 8 frames per CTA — 80 accumulator registers either way
-  const int TB = MT == 1 ? 16 : 8;
-  const size_t smem = ((size_t)((TB - 1) * stride + kDeltaTaps) * Cin + 8) * 88 * 4;
+  const int WT = slice_tiles(W);
+  auto bytes_for = [&](int tb) { return ((size_t)((tb - 1) * stride + K) * Cin + 8) * fwd_pitch(WT) * 4; };
+  // frames per warp: MT = 1 -> 2 (16 frames per CTA) when the window leaves room for two CTAs per SM, else 1
+  const int UPW = (MT == 1 && bytes_for(16) <= kConvSmemTarget) ? 2 : 1;
+  const int TB = 8 * UPW;
+  const size_t smem = bytes_for(TB);
   if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "conv_mma_fwd: window does not fit in shared memory");
-  dim3 grid((Tout + TB - 1) / TB, B);
-  if (MT == 1) {
-    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_mma_fwd_kernel<1, 2><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged,
-                                                                   bias, add, y, act, drop_p, seed);
-  } else {
-    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_mma_fwd_kernel<2, 1><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged,
-                                                                   bias, add, y, act, drop_p, seed);
-  }
+  dim3 grid((Tout + TB - 1) / TB, W / (8 * WT), B);
+  int rc = W2L_OK;
+#define W2L_FWD_CASE(MT_, UPW_, WT_)                                                                                  \
+  if (MT == MT_ && UPW == UPW_ && WT == WT_)                                                                         \
+    rc = launch_fwd<MT_, UPW_, WT_>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged, \
+                                    bias, add, y, act, drop_p, seed);
+#define W2L_FWD_WT(WT_) W2L_FWD_CASE(1, 1, WT_) W2L_FWD_CASE(1, 2, WT_) W2L_FWD_CASE(2, 1, WT_)
+  W2L_FWD_WT(1) W2L_FWD_WT(2) W2L_FWD_WT(3) W2L_FWD_WT(4) W2L_FWD_WT(5)
+#undef W2L_FWD_WT
+#undef W2L_FWD_CASE
+  if (rc != W2L_OK) return rc;
   W2L_LAUNCH_CHECK("conv_mma_fwd_kernel");
   return W2L_OK;
 }
 
-size_t conv_mma_wgrad_parts(int B, int Tout, int Cin, int Cout, int K, int stride, int* tc_out) {
-  const int MT = (Cout + 15) / 16;
-  int TC = 8;
-  auto bytes_for = [&](int tc) { return (((size_t)((tc - 1) * stride + K) * Cin + 8) + (size_t)tc * 16 * MT) * 84 * 4; };
-  while (TC > 1 && bytes_for(TC) > 200 * 1024) TC >>= 1;
+static size_t wgrad_smem(int tc, int stride, int K, int Cin, int Cout, int WT) {
+  return (((size_t)((tc - 1) * stride + K) * Cin + 8) + (size_t)tc * Cout + 1) * wg_pitch(WT) * 4;
+}
+// number of CTA partials of the weight gradient (upper bound over W when W <= 0: ten slices)
+size_t conv_mma_wgrad_parts(int B, int Tout, int W, int Cin, int Cout, int K, int stride, int* tc_out, int* per_sample_out) {
+  const int WT = W > 0 ? slice_tiles(W) : 1;
+  const int nslices = W > 0 ? W / (8 * WT) : 10;
+  int TC = 16;
+  while (TC > 1 && wgrad_smem(TC, stride, K, Cin, Cout, WT) > kConvSmemTarget) TC >>= 1;
   if (tc_out) *tc_out = TC;
-  // CTAs per sample: enough to fill the chip ~twice, never more than there are chunks
+  // CTAs per (sample, slice): enough to fill the chip ~twice, never more than there are chunks; the partial buffer
+  // is sized for B * max(Tout, 16) parts
   const int chunks = (Tout + TC - 1) / TC;
-  const int per_sample = std::max(1, std::min(chunks, (2 * 148 + B - 1) / B));
-  return (size_t)B * per_sample;
+  int per_sample = std::max(1, std::min(chunks, (2 * 148 + B * nslices - 1) / (B * nslices)));
+  per_sample = std::max(1, std::min(per_sample, std::max(Tout, 16) / nslices));
+  if (per_sample_out) *per_sample_out = per_sample;
+  return (size_t)B * nslices * per_sample;
+}
+
+template <int MT, int WT>
+static int launch_wgrad(cudaStream_t stream, dim3 grid, size_t smem, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
+                        int pad_left, int TC, int NT, const float* x, const float* dy, float* partial) {
+  if (smem > 48 * 1024)
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_wgrad_kernel<MT, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_mma_wgrad_kernel<MT, WT><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TC, NT, x, dy, partial);
+  return W2L_OK;
 }
 
 int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                    const float* x, const float* dy, float* dwt, float* dbias, float* partial) {
   const int MT = (Cout + 15) / 16;
-  int TC = 8;
-  const size_t parts = conv_mma_wgrad_parts(B, Tout, Cin, Cout, K, stride, &TC);
-  const size_t smem = (((size_t)((TC - 1) * stride + K) * Cin + 8) + (size_t)TC * 16 * MT) * 84 * 4;
+  const int WT = slice_tiles(W);
+  int TC = 8, per_sample = 1;
+  const size_t parts = conv_mma_wgrad_parts(B, Tout, W, Cin, Cout, K, stride, &TC, &per_sample);
+  const size_t smem = wgrad_smem(TC, stride, K, Cin, Cout, WT);
   if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "conv_mma_wgrad: window does not fit in shared memory");
-  dim3 grid((unsigned)(parts / B), B);
-  if (MT == 1) {
-    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_mma_wgrad_kernel<1><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TC, x, dy, partial);
-  } else {
-    if (smem > 48 * 1024) W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_mma_wgrad_kernel<2><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TC, x, dy, partial);
-  }
+  const int ktiles = (K * Cin + 7) / 8, NT = (ktiles + kMmaThreads / 32 - 1) / (kMmaThreads / 32);
+  if (NT > kWgMaxNt) return fail(W2L_ERR_UNSUPPORTED, "conv_mma_wgrad: filter too large for the register tiles");
+  dim3 grid((unsigned)per_sample, W / (8 * WT), B);
+  int rc = W2L_OK;
+#define W2L_WG_CASE(MT_, WT_) \
+  if (MT == MT_ && WT == WT_) rc = launch_wgrad<MT_, WT_>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, TC, NT, x, dy, partial);
+#define W2L_WG_WT(WT_) W2L_WG_CASE(1, WT_) W2L_WG_CASE(2, WT_)
+  W2L_WG_WT(1) W2L_WG_WT(2) W2L_WG_WT(3) W2L_WG_WT(4) W2L_WG_WT(5)
+#undef W2L_WG_WT
+#undef W2L_WG_CASE
+  if (rc != W2L_OK) return rc;
   W2L_LAUNCH_CHECK("conv_mma_wgrad_kernel");
   const int n_w = Cout * Cin * K;
   conv_mma_wgrad_reduce_kernel<<<(n_w + Cout + 255) / 256, 256, 0, stream>>>((int)parts, n_w, Cout, partial, dwt, dbias);
