@@ -149,6 +149,8 @@ W2L_API int w2l_linseg_target(void* stream, int B, int T, int L, const int32_t* 
  *   (0,1) with B = W; wgrad dW = dY^T X : (1,1) with A = dY, B = X.  bias nullable; act 0 none,
  *   1 ReLU.  lda/ldb must be multiples of 4 floats and A/B 16-byte aligned (TMA).
  * ---------------------------------------------------------------------------------------- */
+/* Pin the GEMM tile width (128 / 160 / 224 / 256; 0 = choose per shape, the default).  Thread-local; for tests and tuning. */
+W2L_API int w2l_gemm_set_tile(int bn);
 W2L_API int w2l_gemm_tf32(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
                           const float* B, int ldb, float* C, int ldc, const float* bias, int act);
 

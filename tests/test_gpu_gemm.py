@@ -74,3 +74,18 @@ def test_gemm_split_k(M, N, K, a_mn, b_mn, accumulate):
     bound = 1.5e-3 * (A64.abs() @ B64.abs().t()) + 1e-4
     ratio = float(((C.double() - ref).abs() / bound).max())
     assert ratio <= 1.0, f"split-K M={M} N={N} K={K}: err/bound {ratio}"
+
+
+@pytest.mark.parametrize("bn", [128, 160, 224, 256])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(1000, 800, 800, False, False), (700, 1120, 1120, False, True),
+                                              (300, 1440, 1440, False, False), (1120, 1120, 2400, True, True),
+                                              (200, 456, 100, False, True), (130, 10000, 64, False, False)])
+def test_gemm_tile_widths(M, N, K, a_mn, b_mn, bn):
+    """every tile width the host heuristic can pick (w2l_gemm_set_tile pins it), tails in M, N and K included"""
+    import wav2letter_b200 as w
+
+    w.capi.gemm_set_tile(bn)
+    try:
+        run(M, N, K, a_mn, b_mn, bias=not a_mn, act=0 if a_mn else 1, seed=bn + M)
+    finally:
+        w.capi.gemm_set_tile(0)

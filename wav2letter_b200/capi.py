@@ -24,7 +24,7 @@ EXPORTS = [
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
     "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
-    "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
+    "w2l_gemm_set_tile", "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
     "w2l_conv_time_wgrad", "w2l_layernorm_fwd", "w2l_layernorm_bwd", "w2l_colsum_accumulate", "w2l_sq_norm_accumulate",
     "w2l_sgd_step", "w2l_transpose_input", "w2l_axpy", "w2l_fill", "w2l_act_fwd", "w2l_mask_mul",
     "w2l_trainer_create", "w2l_trainer_destroy", "w2l_trainer_step", "w2l_trainer_forward", "w2l_trainer_num_params",
@@ -264,6 +264,10 @@ class ProfileList:
 
     def times_ms(self, used: int):
         return [self.starts[k].elapsed_time(self.stops[k]) for k in range(used)]
+
+
+def gemm_set_tile(bn: int = 0):
+    _check(lib.w2l_gemm_set_tile(int(bn)))
 
 
 def trace(fn, capacity: int = 4096) -> dict:

@@ -35,10 +35,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], con
       : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
         "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
 }
-__device__ __forceinline__ float drop_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
-  return dropout_scale(seed, idx, p, inv_keep);
-}
-
 // Stage `nrows` consecutive rows of a [rows][W] global matrix (slice columns [w_off, w_off + 8 WT)) into shared
 // memory, TF32-rounded, 16-byte stores.  Activations are [t][c][W], so the window rows (t, c) of a sample are
 // consecutive global rows: smem row r <- global row r + row_base, zero when outside [0, rows_total).

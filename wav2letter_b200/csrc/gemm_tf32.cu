@@ -28,18 +28,25 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace w2l {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;  // tile; BK fp32 = 128 bytes = one swizzle row
+constexpr int BM = 128, BK = 32;            // tile rows; BK fp32 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;                   // tf32
-constexpr int kStages = 3;                  // 96 KB of operand ring per CTA -> two CTAs per SM: one tile's epilogue and
-                                            // prologue overlap the other's main loop (non-persistent kernel)
-constexpr int kTileBytes = BM * BK * 4;     // 16 KB per operand per stage
+constexpr int kTileBytes = BM * BK * 4;     // 16 KB of A per stage
 constexpr int kGemmThreads = 192;
-constexpr int kTmemCols = 128;
+// The tile width BN is a template parameter (128 / 160 / 224 / 256).  The kernel is fed from L2 at ~42 B/clk per SM,
+// so tensor-pipe time per k block scales with the operand bytes (128 + BN) * 128 B while the work scales with
+// 128 * BN: wider tiles raise MAC/byte, and the host picks the BN that minimises waves x bytes for each shape
+// (e.g. 160 divides 800/1120/1440 exactly).  BN <= 160: 3 stages, 2 CTAs per SM (one tile's epilogue overlaps the
+// other's main loop); BN > 160: 4 stages, 1 CTA per SM.
+__host__ __device__ constexpr int stages_for(int bn) { return bn <= 160 ? 3 : 4; }
+__host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 128 ? 128 : 256; }
+__host__ __device__ constexpr size_t smem_for(int bn) { return (size_t)stages_for(bn) * (kTileBytes + bn * 128) + 256 + 1024; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -129,14 +136,15 @@ __device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t
   return make_uint4(c0, c1, c2, c3);
 }
 
-template <bool kAMn, bool kBMn>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+template <bool kAMn, bool kBMn, int BN>
+__global__ void __launch_bounds__(kGemmThreads, BN <= 160 ? 2 : 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kStages = stages_for(BN), kTileBytesB = BN * BK * 4, kTmemCols = tmem_cols_for(BN);
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + kStages * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStages * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kTileBytes + kTileBytesB));
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
@@ -176,9 +184,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], 2 * kTileBytes);
+        mbar_expect_tx(&full[s], kTileBytes + kTileBytesB);
         unsigned char* sa = smem_a + s * kTileBytes;
-        unsigned char* sb = smem_b + s * kTileBytes;
+        unsigned char* sb = smem_b + s * kTileBytesB;
         const int k0 = (kb_begin + kb) * BK;
         if (!kAMn) {
           tma_load_2d(&map_a, &full[s], sa, k0, m0);  // box {32 k, 128 rows}
@@ -204,7 +212,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&full[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem_a + s * kTileBytes);
-        const uint32_t sb = smem_u32(smem_b + s * kTileBytes);
+        const uint32_t sb = smem_u32(smem_b + s * kTileBytesB);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // K-major: +32 B per UMMA_K inside the 128 B swizzle row; MN-major: +8 k-rows = 1024 B
@@ -349,21 +357,63 @@ int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols,
   return W2L_OK;
 }
 
-template <bool kAMn, bool kBMn>
-int launch(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
-  const size_t smem = 2 * kStages * kTileBytes + 256 + 1024;
+template <bool kAMn, bool kBMn, int BN>
+int launch_bn(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  constexpr size_t smem = smem_for(BN);
   static bool configured = false;
   if (!configured) {
-    W2L_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_kernel<kAMn, kBMn, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.k_splits);
   profile_kind(1);
-    profile_start(stream);
-  gemm_tf32_kernel<kAMn, kBMn><<<grid, kGemmThreads, smem, stream>>>(ma, mb, p);
+  profile_start(stream);
+  gemm_tf32_kernel<kAMn, kBMn, BN><<<grid, kGemmThreads, smem, stream>>>(ma, mb, p);
   profile_stop(stream);
   W2L_LAUNCH_CHECK("gemm_tf32_kernel");
   return W2L_OK;
+}
+template <bool kAMn, bool kBMn>
+int launch(cudaStream_t stream, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  switch (bn) {
+    case 128: return launch_bn<kAMn, kBMn, 128>(stream, ma, mb, p);
+    case 160: return launch_bn<kAMn, kBMn, 160>(stream, ma, mb, p);
+    case 224: return launch_bn<kAMn, kBMn, 224>(stream, ma, mb, p);
+    default: return launch_bn<kAMn, kBMn, 256>(stream, ma, mb, p);
+  }
+}
+
+// split-K factor for a tile count: when the tiles alone under-fill the chip and K is long (weight gradients),
+// slices of >= 4 k blocks; only for plain epilogues (the partial sums are added atomically)
+int splits_for(int tiles, int total_kb, int bn, bool plain) {
+  const int slots = 148 * (bn <= 160 ? 2 : 1);
+  if (!plain || tiles >= 148 || total_kb < 16) return 1;
+  return std::max(1, std::min(std::min(slots / tiles, total_kb / 4), 32));
+}
+// tile width: minimise (waves over 148 SMs) x (operand bytes per tile + exposed epilogue), see the note at the top
+thread_local int g_force_bn = 0;  // w2l_gemm_set_tile: tests pin the tile width
+int choose_bn(int M, int N, int total_kb, bool plain, int* splits_out) {
+  if (g_force_bn) {
+    const int tiles = ((N + g_force_bn - 1) / g_force_bn) * ((M + BM - 1) / BM);
+    *splits_out = splits_for(tiles, total_kb, g_force_bn, plain);
+    return g_force_bn;
+  }
+  const int cands[4] = {128, 160, 224, 256};
+  double best = 1e300;
+  int best_bn = 128;
+  for (int bn : cands) {
+    const int tiles = ((N + bn - 1) / bn) * ((M + BM - 1) / BM);
+    const int splits = splits_for(tiles, total_kb, bn, plain);
+    const int kb_local = (total_kb + splits - 1) / splits;
+    const double waves = std::ceil((double)tiles * splits / 148.0);
+    const double cost = waves * ((double)(128 + bn) * kb_local + (bn <= 160 ? 1.0 : 3.0) * bn);
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_bn = bn;
+      *splits_out = splits;
+    }
+  }
+  return best_bn;
 }
 
 }  // namespace
@@ -375,6 +425,12 @@ extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, i
                                 const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
                                 const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
                                 unsigned long long seed);
+
+extern "C" int w2l_gemm_set_tile(int bn) {
+  if (bn != 0 && bn != 128 && bn != 160 && bn != 224 && bn != 256) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: tile width must be 0 (auto), 128, 160, 224 or 256");
+  g_force_bn = bn;
+  return W2L_OK;
+}
 
 extern "C" int w2l_gemm_tf32(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
                              const float* B, int ldb, float* C, int ldc, const float* bias, int act) {
@@ -396,6 +452,10 @@ extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, i
     return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: operand rows must be 16-byte aligned (ld % 4 == 0)");
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N)
     return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: leading dimension smaller than the row length");
+  const int total_kb = (K + BK - 1) / BK;
+  const bool plain = act == 0 && aux_mode == 0 && dropout_p == 0.f && bias == nullptr;
+  int splits = 1;
+  const int BN = choose_bn(M, N, total_kb, plain, &splits);
   CUtensorMap ma, mb;
   int rc;
   if (!a_mn_major)
@@ -408,16 +468,10 @@ extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, i
   else
     rc = make_map(&mb, B, K, N, ldb, BK, true);
   if (rc) return rc;
-  // split-K when the output has few tiles and K is long (weight gradients: 81 tiles, 150 k blocks): slices of
-  // >= 4 k blocks, ~2 CTAs per SM in total; only for plain epilogues (the partial sums are added atomically)
-  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM), total_kb = (K + BK - 1) / BK;
-  int splits = 1;
-  if (tiles < 148 && total_kb >= 16 && act == 0 && aux_mode == 0 && dropout_p == 0.f && bias == nullptr)
-    splits = std::max(1, std::min(std::min(296 / tiles, total_kb / 4), 32));
-  if (splits > 1 && !accumulate) W2L_CUDA_CHECK(cudaMemsetAsync(C, 0, sizeof(float) * ((size_t)(M - 1) * ldc + N), stream));
+  if (splits > 1 && !accumulate) W2L_CUDA_CHECK(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, stream));
   GemmParams p{M, N, K, ldc, act, C, bias, accumulate, aux_mode, ld_aux, aux, aux_scale, dropout_p, seed, splits};
-  if (!a_mn_major && !b_mn_major) return launch<false, false>(stream, ma, mb, p);
-  if (!a_mn_major && b_mn_major) return launch<false, true>(stream, ma, mb, p);
-  if (a_mn_major && b_mn_major) return launch<true, true>(stream, ma, mb, p);
-  return launch<true, false>(stream, ma, mb, p);
+  if (!a_mn_major && !b_mn_major) return launch<false, false>(stream, BN, ma, mb, p);
+  if (!a_mn_major && b_mn_major) return launch<false, true>(stream, BN, ma, mb, p);
+  if (a_mn_major && b_mn_major) return launch<true, true>(stream, BN, ma, mb, p);
+  return launch<true, false>(stream, BN, ma, mb, p);
 }
