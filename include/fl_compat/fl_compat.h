@@ -124,7 +124,9 @@ class Variable {
   bool isCalcGrad() const;
   bool isGradAvailable() const;
   Variable& grad() const;  // throws std::logic_error if absent, like flashlight
-  void addGrad(const Variable& g);
+  // fresh = g's buffer is aliased by nothing else: later contributions may be accumulated into it in place
+  void addGrad(const Variable& g, bool fresh = false);
+  af::array accumulableGrad() const;  // the gradient buffer a producer may add into (empty when there is none)
   void setGradStorage(const af::array& buf);  // pre-bound accumulation buffer (flat gradient arena)
   af::array gradStorage() const;              // that buffer (empty if none): kernels accumulate into it directly
   void zeroGrad(bool zeroStorage = true);  // zeroStorage = false: the caller cleared the gradient arena itself

@@ -169,7 +169,8 @@ W2L_API int w2l_gemm_tf32_ex(void* stream, int a_mn_major, int b_mn_major, int M
  * float [B][T][C][W] (W <= 80 innermost), weights float wt[Cout][Cin][K] (= fl's [kw,1,cin,cout]
  * column-major), out frame `to` reads input frames to*stride + dk - pad_left.
  *   fwd   : y = dropout(act(conv(x) + bias)) (+ add)          act 0 none / 1 ReLU
- *   dgrad : dx = conv^T(dy) (+ add)
+ *   dgrad : dx = conv^T(dy) (+ add)                           add may be dx itself (in-place accumulation;
+ *                                                            likewise add == y in fwd)
  *   wgrad : dwt += ..., dbias += ...  (deterministic two-stage reduction)
  * The workspace size call covers all three.
  * ---------------------------------------------------------------------------------------- */

@@ -61,6 +61,9 @@ def test_conv_time_fwd_dgrad_wgrad(B, T, Cin, Cout, K, stride, W):
     addx = torch.randn((B, T, Cin, W), device="cuda", generator=g)
     dx = capi.conv_time_dgrad(dy, wt, T, stride, pl, add=addx)
     assert rel(dx, x64.grad + addx.double()) < tol
+    inplace = addx.clone()  # add == dx: the residual gradient is accumulated in place (fl_compat's autograd does this)
+    capi.conv_time_dgrad(dy, wt, T, stride, pl, add=inplace, out=inplace)
+    assert torch.equal(inplace, dx)
     dwt, dbias = capi.conv_time_wgrad(x, dy, K, stride, pl)
     assert rel(dwt, w64.grad) < tol
     assert rel(dbias, b64.grad) < tol

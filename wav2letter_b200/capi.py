@@ -326,10 +326,11 @@ def conv_time_fwd(x, wt, bias, Tout, stride, pad_left, act=0, dropout_p=0.0, see
     return y
 
 
-def conv_time_dgrad(dy, wt, T, stride, pad_left, add=None):
+def conv_time_dgrad(dy, wt, T, stride, pad_left, add=None, out=None):
+    """dx = conv^T(dy) (+ add); out may be the same tensor as add (in-place accumulation)."""
     B, Tout, Cout, W = dy.shape
     _, Cin, K = wt.shape
-    dx = torch.empty((B, T, Cin, W), dtype=torch.float32, device=dy.device)
+    dx = out if out is not None else torch.empty((B, T, Cin, W), dtype=torch.float32, device=dy.device)
     ws = conv_time_ws(B, Tout, Cin, Cout, K, dy.device)
     _check(lib.w2l_conv_time_dgrad(_stream(), B, T, Tout, W, Cin, Cout, K, stride, pad_left, _ptr(dy), _ptr(wt), _ptr(add),
                                    _ptr(dx), _ptr(ws), ws.numel()))

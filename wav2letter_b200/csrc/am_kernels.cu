@@ -44,8 +44,8 @@ constexpr int kConvRows = 4;  // thread rows per CTA; a thread computes TT conse
 template <int CO, int TT>
 __global__ void __launch_bounds__(96 * kConvRows) conv_time_fwd_kernel(
     int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left, const float* __restrict__ x,
-    const float* __restrict__ wt_arranged, const float* __restrict__ bias, const float* __restrict__ add,
-    float* __restrict__ y, int act, float drop_p, unsigned long long seed) {
+    const float* __restrict__ wt_arranged, const float* __restrict__ bias, const float* add,
+    float* y, int act, float drop_p, unsigned long long seed) {
   extern __shared__ __align__(16) float wsm[];  // [Cin][K][CO]
   const int b = blockIdx.y;
   const int w = threadIdx.x;                   // 0..95, active < W
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(96 * kConvRows) conv_time_fwd_kernel(
         float v = acc[h][c];
         if (act == 1) v = fmaxf(v, 0.f);
         if (drop_p > 0.f) v *= dropout_scale(seed, idx, drop_p, inv_keep);
-        if (add != nullptr) v += __ldg(add + idx);
+        if (add != nullptr) v += add[idx];  // add may alias y (in-place accumulation): plain load, same thread writes idx
         y[idx] = v;
       }
     }
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(96 * 4) conv_time_dgrad_strided_kernel(int T, 
                                                                         int stride, int pad_left,
                                                                         const float* __restrict__ dy,
                                                                         const float* __restrict__ wt,
-                                                                        const float* __restrict__ add,
-                                                                        float* __restrict__ dx) {
+                                                                        const float* add,
+                                                                        float* dx) {
   extern __shared__ __align__(16) float wsm[];  // [K][Cout][CI]
   const int b = blockIdx.y, w = threadIdx.x, t = blockIdx.x * 4 + threadIdx.y;
   for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < K * Cout * CI; i += blockDim.x * blockDim.y) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(96 * 4) conv_time_dgrad_strided_kernel(int T, 
   for (int c = 0; c < CI; ++c)
     if (c < Cin) {
       const size_t idx = (((size_t)b * T + t) * Cin + c) * W + w;
-      dx[idx] = acc[c] + (add ? __ldg(add + idx) : 0.f);
+      dx[idx] = acc[c] + (add ? add[idx] : 0.f);  // add may alias dx
     }
 }
 
@@ -302,17 +302,12 @@ __global__ void conv_wgrad_reduce_kernel(int n_parts, int n_w, int n_b, const fl
 // LayerNorm over a whole sample (R = T*C*W elements) with scalar gain/bias, fused residual:
 //   s = a + r ; y = (s - mean) * rstd * gain + bias
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ln_stats_kernel(long long R, const float* __restrict__ a, const float* __restrict__ r,
-                                                       double* __restrict__ stats /*[B][2] sum, sumsq*/) {
-  const int b = blockIdx.y;
-  const float* ab = a + (size_t)b * R;
-  const float* rb = r ? r + (size_t)b * R : nullptr;
-  double s = 0.0, q = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
-    const float v = ab[i] + (rb ? rb[i] : 0.f);
-    s += v;
-    q += (double)v * v;
-  }
+// All four passes stream float4 (R % 4 == 0 and 16-byte aligned bases: `vec`), two loads in flight per operand;
+// the per-sample sums are accumulated in double from 4-element fp32 partials.
+__device__ __forceinline__ float4 ld4(const float* p, long long i) { return *reinterpret_cast<const float4*>(p + i); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__device__ __forceinline__ void block_sum2_atomic(double s, double q, double* out) {
   s = warp_sum(s);
   q = warp_sum(q);
   __shared__ double ss[8], qq[8];
@@ -327,12 +322,37 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(long long R, const float*
       S += ss[w];
       Q += qq[w];
     }
-    atomicAdd(stats + 2 * b, S);
-    atomicAdd(stats + 2 * b + 1, Q);
+    atomicAdd(out, S);
+    atomicAdd(out + 1, Q);
   }
 }
 
-__global__ void __launch_bounds__(256) ln_apply_kernel(long long R, float eps, const float* __restrict__ a,
+__global__ void __launch_bounds__(256) ln_stats_kernel(long long R, int vec, const float* __restrict__ a, const float* __restrict__ r,
+                                                       double* __restrict__ stats /*[B][2] sum, sumsq*/) {
+  const int b = blockIdx.y;
+  const float* ab = a + (size_t)b * R;
+  const float* rb = r ? r + (size_t)b * R : nullptr;
+  double s = 0.0, q = 0.0;
+  const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+#pragma unroll 2
+    for (long long i = 4 * start; i < R; i += 4 * step) {
+      float4 v = ld4(ab, i);
+      if (rb) v = add4(v, ld4(rb, i));
+      s += (double)((v.x + v.y) + (v.z + v.w));
+      q += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+    }
+  } else {
+    for (long long i = start; i < R; i += step) {
+      const float v = ab[i] + (rb ? rb[i] : 0.f);
+      s += v;
+      q += (double)v * v;
+    }
+  }
+  block_sum2_atomic(s, q, stats + 2 * b);
+}
+
+__global__ void __launch_bounds__(256) ln_apply_kernel(long long R, int vec, float eps, const float* __restrict__ a,
                                                        const float* __restrict__ r, const float* __restrict__ gain,
                                                        const float* __restrict__ bias, const double* __restrict__ stats,
                                                        float* __restrict__ y, float* __restrict__ mean_rstd /*[B][2]*/) {
@@ -348,14 +368,26 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(long long R, float eps, c
   const float* ab = a + (size_t)b * R;
   const float* rb = r ? r + (size_t)b * R : nullptr;
   float* yb = y + (size_t)b * R;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
-    const float v = ab[i] + (rb ? rb[i] : 0.f);
-    yb[i] = (v - mu) * rstd * g + bi;
+  const float sc = rstd * g;
+  const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+#pragma unroll 2
+    for (long long i = 4 * start; i < R; i += 4 * step) {
+      float4 v = ld4(ab, i);
+      if (rb) v = add4(v, ld4(rb, i));
+      *reinterpret_cast<float4*>(yb + i) =
+          make_float4((v.x - mu) * sc + bi, (v.y - mu) * sc + bi, (v.z - mu) * sc + bi, (v.w - mu) * sc + bi);
+    }
+  } else {
+    for (long long i = start; i < R; i += step) {
+      const float v = ab[i] + (rb ? rb[i] : 0.f);
+      yb[i] = (v - mu) * sc + bi;
+    }
   }
 }
 
 // backward pass 1: per-sample sums of dy and dy * xhat
-__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(long long R, const float* __restrict__ a,
+__global__ void __launch_bounds__(256) ln_bwd_stats_kernel(long long R, int vec, const float* __restrict__ a,
                                                            const float* __restrict__ r, const float* __restrict__ dy,
                                                            const float* __restrict__ mean_rstd,
                                                            double* __restrict__ sums /*[B][2]*/) {
@@ -365,35 +397,34 @@ __global__ void __launch_bounds__(256) ln_bwd_stats_kernel(long long R, const fl
   const float* rb = r ? r + (size_t)b * R : nullptr;
   const float* db = dy + (size_t)b * R;
   double s = 0.0, q = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
-    const float xh = (ab[i] + (rb ? rb[i] : 0.f) - mu) * rstd;
-    const float d = db[i];
-    s += d;
-    q += (double)d * xh;
-  }
-  s = warp_sum(s);
-  q = warp_sum(q);
-  __shared__ double ss[8], qq[8];
-  if ((threadIdx.x & 31) == 0) {
-    ss[threadIdx.x >> 5] = s;
-    qq[threadIdx.x >> 5] = q;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double S = 0, Q = 0;
-    for (int w = 0; w < 8; ++w) {
-      S += ss[w];
-      Q += qq[w];
+  const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+#pragma unroll 2
+    for (long long i = 4 * start; i < R; i += 4 * step) {
+      float4 v = ld4(ab, i);
+      const float4 d = ld4(db, i);
+      if (rb) v = add4(v, ld4(rb, i));
+      s += (double)((d.x + d.y) + (d.z + d.w));
+      q += (double)((d.x * ((v.x - mu) * rstd) + d.y * ((v.y - mu) * rstd)) + (d.z * ((v.z - mu) * rstd) + d.w * ((v.w - mu) * rstd)));
     }
-    atomicAdd(sums + 2 * b, S);
-    atomicAdd(sums + 2 * b + 1, Q);
+  } else {
+    for (long long i = start; i < R; i += step) {
+      const float xh = (ab[i] + (rb ? rb[i] : 0.f) - mu) * rstd;
+      const float d = db[i];
+      s += d;
+      q += (double)d * xh;
+    }
   }
+  block_sum2_atomic(s, q, sums + 2 * b);
 }
 
 // backward pass 2: ds = rstd * gain * (dy - mean(dy) - xhat * mean(dy*xhat));
 //   d_res = ds ; d_branch = ds * mask(a) where mask undoes the branch's fused ReLU / dropout:
 //   branch_mode 0: 1 ; 1: (a > 0) * scale ; 2: (a != 0) * scale
-__global__ void __launch_bounds__(256) ln_bwd_apply_kernel(long long R, const float* __restrict__ a,
+__device__ __forceinline__ float ln_mask(int mode, float av, float scale) {
+  return mode == 0 ? 1.f : ((mode == 1 ? av > 0.f : av != 0.f) ? scale : 0.f);
+}
+__global__ void __launch_bounds__(256) ln_bwd_apply_kernel(long long R, int vec, const float* __restrict__ a,
                                                            const float* __restrict__ r, const float* __restrict__ dy,
                                                            const float* __restrict__ gain, const float* __restrict__ mean_rstd,
                                                            const double* __restrict__ sums, float* __restrict__ d_branch,
@@ -409,15 +440,35 @@ __global__ void __launch_bounds__(256) ln_bwd_apply_kernel(long long R, const fl
   const float* ab = a + (size_t)b * R;
   const float* rb = r ? r + (size_t)b * R : nullptr;
   const float* db = dy + (size_t)b * R;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (long long)gridDim.x * blockDim.x) {
-    const float av = ab[i];
-    const float xh = (av + (rb ? rb[i] : 0.f) - mu) * rstd;
-    const float ds = rstd * g * (db[i] - m1 - xh * m2);
-    if (d_res) d_res[(size_t)b * R + i] = ds;
-    float m = 1.f;
-    if (branch_mode == 1) m = av > 0.f ? branch_scale : 0.f;
-    if (branch_mode == 2) m = av != 0.f ? branch_scale : 0.f;
-    d_branch[(size_t)b * R + i] = ds * m;
+  float* ob = d_branch + (size_t)b * R;
+  float* orr = d_res ? d_res + (size_t)b * R : nullptr;
+  const float rg = rstd * g;
+  const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+#pragma unroll 2
+    for (long long i = 4 * start; i < R; i += 4 * step) {
+      const float4 av = ld4(ab, i);
+      const float4 d = ld4(db, i);
+      float4 v = av;
+      if (rb) v = add4(v, ld4(rb, i));
+      float4 ds;
+      ds.x = rg * (d.x - m1 - (v.x - mu) * rstd * m2);
+      ds.y = rg * (d.y - m1 - (v.y - mu) * rstd * m2);
+      ds.z = rg * (d.z - m1 - (v.z - mu) * rstd * m2);
+      ds.w = rg * (d.w - m1 - (v.w - mu) * rstd * m2);
+      if (orr) *reinterpret_cast<float4*>(orr + i) = ds;
+      *reinterpret_cast<float4*>(ob + i) =
+          make_float4(ds.x * ln_mask(branch_mode, av.x, branch_scale), ds.y * ln_mask(branch_mode, av.y, branch_scale),
+                      ds.z * ln_mask(branch_mode, av.z, branch_scale), ds.w * ln_mask(branch_mode, av.w, branch_scale));
+    }
+  } else {
+    for (long long i = start; i < R; i += step) {
+      const float av = ab[i];
+      const float xh = (av + (rb ? rb[i] : 0.f) - mu) * rstd;
+      const float ds = rg * (db[i] - m1 - xh * m2);
+      if (orr) orr[i] = ds;
+      ob[i] = ds * ln_mask(branch_mode, av, branch_scale);
+    }
   }
 }
 
@@ -499,9 +550,22 @@ __global__ void transpose_bft_kernel(int F, int T, const float* __restrict__ in,
     if (t < T && f < F) ob[(size_t)t * F + f] = tile[threadIdx.x][j];
   }
 }
-__global__ void axpy_kernel(long long n, float a, const float* __restrict__ x, float* __restrict__ y) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    y[i] = fmaf(a, x[i], y[i]);
+__global__ void axpy_kernel(long long n, int vec, float a, const float* __restrict__ x, float* __restrict__ y) {
+  const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+#pragma unroll 2
+    for (long long i = 4 * start; i < n; i += 4 * step) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + i);
+      float4 yv = *reinterpret_cast<float4*>(y + i);
+      yv.x = fmaf(a, xv.x, yv.x);
+      yv.y = fmaf(a, xv.y, yv.y);
+      yv.z = fmaf(a, xv.z, yv.z);
+      yv.w = fmaf(a, xv.w, yv.w);
+      *reinterpret_cast<float4*>(y + i) = yv;
+    }
+  } else {
+    for (long long i = start; i < n; i += step) y[i] = fmaf(a, x[i], y[i]);
+  }
 }
 __global__ void fill_kernel(long long n, float v, float* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = v;
@@ -671,9 +735,10 @@ extern "C" int w2l_layernorm_fwd(void* stream_, int B, long long R, float eps, c
   if (B <= 0 || R <= 0 || !a || !y || !mean_rstd || !scratch) return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_fwd: bad arguments");
   W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
   dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
-  ln_stats_kernel<<<grid, 256, 0, stream>>>(R, a, r, scratch);
+  const int vec = (R % 4 == 0) && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(y)) & 15);
+  ln_stats_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, scratch);
   W2L_LAUNCH_CHECK("ln_stats_kernel");
-  ln_apply_kernel<<<grid, 256, 0, stream>>>(R, eps, a, r, gain, bias, scratch, y, mean_rstd);
+  ln_apply_kernel<<<grid, 256, 0, stream>>>(R, vec, eps, a, r, gain, bias, scratch, y, mean_rstd);
   W2L_LAUNCH_CHECK("ln_apply_kernel");
   return W2L_OK;
 }
@@ -687,9 +752,11 @@ extern "C" int w2l_layernorm_bwd(void* stream_, int B, long long R, const float*
   if (branch_mode < 0 || branch_mode > 2) return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_bwd: bad branch mode");
   W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
   dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
-  ln_bwd_stats_kernel<<<grid, 256, 0, stream>>>(R, a, r, dy, mean_rstd, scratch);
+  const int vec = (R % 4 == 0) && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(dy) |
+                                      reinterpret_cast<uintptr_t>(d_branch) | reinterpret_cast<uintptr_t>(d_res)) & 15);
+  ln_bwd_stats_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, dy, mean_rstd, scratch);
   W2L_LAUNCH_CHECK("ln_bwd_stats_kernel");
-  ln_bwd_apply_kernel<<<grid, 256, 0, stream>>>(R, a, r, dy, gain, mean_rstd, scratch, d_branch, d_res, branch_mode, branch_scale,
+  ln_bwd_apply_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, dy, gain, mean_rstd, scratch, d_branch, d_res, branch_mode, branch_scale,
                                                 dgain, dbias);
   W2L_LAUNCH_CHECK("ln_bwd_apply_kernel");
   return W2L_OK;
@@ -734,7 +801,8 @@ extern "C" int w2l_transpose_input(void* stream_, int B, int F, int T, const flo
 extern "C" int w2l_axpy(void* stream_, long long n, float a, const float* x, float* y) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n <= 0 || !x || !y) return fail(W2L_ERR_INVALID_ARGUMENT, "axpy: bad arguments");
-  axpy_kernel<<<blocks_for(n), 256, 0, stream>>>(n, a, x, y);
+  const int vec = (n % 4 == 0) && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15);
+  axpy_kernel<<<blocks_for(n), 256, 0, stream>>>(n, vec, a, x, y);
   W2L_LAUNCH_CHECK("axpy_kernel");
   return W2L_OK;
 }

@@ -73,8 +73,8 @@ template <int MT, int UPW, int WT>  // m tiles of 16 output channels (1 or 2); f
 __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                                                                        int pad_left, int Kpad, int apitch,
                                                                        const float* __restrict__ x, const float* __restrict__ wa,
-                                                                       const float* __restrict__ bias, const float* __restrict__ add,
-                                                                       float* __restrict__ y, int act, float drop_p,
+                                                                       const float* __restrict__ bias, const float* add,
+                                                                       float* y, int act, float drop_p,
                                                                        unsigned long long seed) {
   extern __shared__ __align__(16) float sm[];
   constexpr int kPitch = fwd_pitch(WT);
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
           }
           if (ok) {
             if (add != nullptr) {
-              const float2 av = __ldg(reinterpret_cast<const float2*>(add + idx));
+              const float2 av = *reinterpret_cast<const float2*>(add + idx);  // add may alias y (in-place accumulation)
               v0 += av.x;
               v1 += av.y;
             }

@@ -164,6 +164,7 @@ struct Variable::Impl {
   af::array boundGrad;  // pre-bound accumulation buffer (gradient arena)
   bool gradLive = false;  // boundGrad holds a valid (accumulated) gradient
   bool onesSeed = false;
+  bool gradOwned = false;  // grad is a buffer no other variable aliases: later contributions may be added in place
 };
 
 Variable::Variable(const af::array& data, bool calcGrad) : impl_(std::make_shared<Impl>()) {
@@ -198,7 +199,11 @@ void Variable::setGradStorage(const af::array& buf) {
   impl_->grad.reset();
 }
 af::array Variable::gradStorage() const { return impl_ ? impl_->boundGrad : af::array(); }
-void Variable::addGrad(const Variable& g) {
+af::array Variable::accumulableGrad() const {
+  if (impl_ && impl_->calcGrad && impl_->boundGrad.isEmpty() && impl_->grad && impl_->gradOwned) return impl_->grad->array();
+  return af::array();
+}
+void Variable::addGrad(const Variable& g, bool fresh) {
   if (!impl_ || !impl_->calcGrad) return;
   if (g.elements() != elements()) throw std::invalid_argument("addGrad: size mismatch");
   if (!impl_->boundGrad.isEmpty()) {
@@ -211,18 +216,25 @@ void Variable::addGrad(const Variable& g) {
   if (!impl_->grad) {
     impl_->grad = std::make_shared<Variable>(g.array(), false);
     impl_->grad->impl_->onesSeed = g.isOnesSeed();
+    impl_->gradOwned = fresh;
+  } else if (impl_->gradOwned) {
+    // second consumer, and the first producer handed over a buffer nobody else aliases: add in place
+    if (g.array().ptr() != impl_->grad->array().ptr())
+      check(w2l_axpy(currentStream(), elements(), 1.0f, g.array().f32(), impl_->grad->array().f32()));
   } else {
     // second consumer: out-of-place sum (keeps the first producer's buffer intact)
     af::array sum = af::array::empty(array().dims());
     sum.copyFrom(impl_->grad->array());
     check(w2l_axpy(currentStream(), elements(), 1.0f, g.array().f32(), sum.f32()));
     impl_->grad = std::make_shared<Variable>(sum, false);
+    impl_->gradOwned = true;
   }
 }
 void Variable::zeroGrad(bool zeroStorage) {
   if (!impl_) return;
   impl_->grad.reset();
   impl_->gradLive = false;
+  impl_->gradOwned = false;
   if (zeroStorage && !impl_->boundGrad.isEmpty()) impl_->boundGrad.zero();
 }
 void Variable::backward(bool retainGraph) {
@@ -442,10 +454,12 @@ Variable Conv2D::forwardMasked(const Variable& in, bool maskByConsumer) {
       if (hasBias) ins[2].addGrad(Variable(db, false));
     }
     if (ins[0].isCalcGrad()) {
-      af::array dx = af::array::empty(ins[0].dims());
-      check(w2l_conv_time_dgrad(currentStream(), B, T, Tout, W, cin, cout, k, s, pl, dy.f32(), ins[1].array().f32(), nullptr, dx.f32(),
-                                ws2.ptr(), ws2.bytes()));
-      ins[0].addGrad(Variable(dx, false));
+      // a gradient already sitting on the input (the residual path of a TDS block) is summed in the kernel's epilogue
+      af::array acc = ins[0].accumulableGrad();
+      af::array dx = acc.isEmpty() ? af::array::empty(ins[0].dims()) : acc;
+      check(w2l_conv_time_dgrad(currentStream(), B, T, Tout, W, cin, cout, k, s, pl, dy.f32(), ins[1].array().f32(),
+                                acc.isEmpty() ? nullptr : acc.f32(), dx.f32(), ws2.ptr(), ws2.bytes()));
+      if (acc.isEmpty()) ins[0].addGrad(Variable(dx, false), true);
     }
   });
 }
@@ -526,8 +540,8 @@ Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int br
     check(w2l_layernorm_bwd(currentStream(), B, R, ins[0].array().f32(), hasRes ? ins[1].array().f32() : nullptr, g.array().f32(),
                             affine ? ins[gi].array().f32() : nullptr, mr.f32(), d_branch.f32(), hasRes ? d_res.f32() : nullptr,
                             branchMode, keepScale, affine ? dg.f32() : nullptr, affine ? db.f32() : nullptr, sc.f64()));
-    ins[0].addGrad(Variable(d_branch, false));
-    if (hasRes) ins[1].addGrad(Variable(d_res, false));
+    ins[0].addGrad(Variable(d_branch, false), true);
+    if (hasRes) ins[1].addGrad(Variable(d_res, false), true);
     if (affine) {
       ins[gi].addGrad(Variable(dg, false));
       ins[gi + 1].addGrad(Variable(db, false));
@@ -598,10 +612,11 @@ Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool m
       }
     }
     if (ins[0].isCalcGrad()) {  // dx[M][nin] = dy W  (B = W MN-major)
-      af::array dx = af::array::empty(ins[0].dims());
-      check(w2l_gemm_tf32_ex(currentStream(), 0, 1, M, nin, nout, dy.f32(), nout, ins[1].array().f32(), nin, dx.f32(), nin, nullptr, 0, 0,
-                             inMaskMode ? ins[0].array().f32() : nullptr, nin, inMaskMode, inMaskScale, 0.f, 0ull));
-      ins[0].addGrad(Variable(dx, false));
+      af::array acc = ins[0].accumulableGrad();  // e.g. LN2's residual gradient: C += in the GEMM epilogue
+      af::array dx = acc.isEmpty() ? af::array::empty(ins[0].dims()) : acc;
+      check(w2l_gemm_tf32_ex(currentStream(), 0, 1, M, nin, nout, dy.f32(), nout, ins[1].array().f32(), nin, dx.f32(), nin, nullptr, 0,
+                             acc.isEmpty() ? 0 : 1, inMaskMode ? ins[0].array().f32() : nullptr, nin, inMaskMode, inMaskScale, 0.f, 0ull));
+      if (acc.isEmpty()) ins[0].addGrad(Variable(dx, false), true);
     }
   });
 }
