@@ -84,6 +84,8 @@ W2L_API int w2l_profile_events_used(void);
  * "name\tlaunches\tms\n" lines into out.  Returns the byte count needed (call with NULL to size). */
 W2L_API int w2l_trace_begin(void* stream, int capacity);
 W2L_API long long w2l_trace_end(char* out, long long out_bytes);
+/* after w2l_trace_end: every traced launch in order, "name\tms\n" (same sizing convention) */
+W2L_API long long w2l_trace_list(char* out, long long out_bytes);
 
 /* ----------------------------------------------------------------------------------------
  * ASG = FullConnectionCriterion - ForceAlignmentCriterion, fused forward + backward.

@@ -19,7 +19,7 @@ TERM_FCC, TERM_FAC, TERM_ASG = 1, 2, 3
 
 # every entry point include/w2l_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count", "w2l_set_profile_events", "w2l_set_profile_event_list", "w2l_profile_events_used", "w2l_trace_begin", "w2l_trace_end",
+    "w2l_version", "w2l_last_error", "w2l_launch_count", "w2l_reset_launch_count", "w2l_set_profile_events", "w2l_set_profile_event_list", "w2l_profile_events_used", "w2l_trace_begin", "w2l_trace_end", "w2l_trace_list",
     "w2l_asg_workspace_size", "w2l_asg_forward_backward",
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
@@ -53,6 +53,8 @@ def _load() -> ctypes.CDLL:
     lib.w2l_trace_begin.argtypes = [vp, i]
     lib.w2l_trace_end.restype = ctypes.c_longlong
     lib.w2l_trace_end.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
+    lib.w2l_trace_list.restype = ctypes.c_longlong
+    lib.w2l_trace_list.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
     lib.w2l_asg_workspace_size.restype = sz
     lib.w2l_asg_workspace_size.argtypes = [i, i, i, i]
     lib.w2l_asg_forward_backward.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, sz]
@@ -264,6 +266,13 @@ class ProfileList:
 
     def times_ms(self, used: int):
         return [self.starts[k].elapsed_time(self.stops[k]) for k in range(used)]
+
+
+def trace_list() -> list:
+    """every launch of the last trace() in order: [(kernel name, ms)]"""
+    buf = ctypes.create_string_buffer(1 << 18)
+    lib.w2l_trace_list(buf, len(buf))
+    return [(ln.split("\t")[0], float(ln.split("\t")[1])) for ln in buf.value.decode().splitlines()]
 
 
 def gemm_set_tile(bn: int = 0):

@@ -91,6 +91,18 @@ int w2l_trace_begin(void* stream, int capacity) {
   trace_launch("(begin)");
   return W2L_OK;
 }
+long long w2l_trace_list(char* out, long long out_bytes) {  // after w2l_trace_end: every launch in order, "name\tms\n"
+  using namespace w2l;
+  std::string text;
+  for (size_t i = 1; i < g_trace_used; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace_ev[i - 1], g_trace_ev[i]);
+    text += std::string(g_trace_name[i]) + "\t" + std::to_string(ms) + "\n";
+  }
+  const long long need = (long long)text.size() + 1;
+  if (out && out_bytes >= need) memcpy(out, text.c_str(), (size_t)need);
+  return need;
+}
 long long w2l_trace_end(char* out, long long out_bytes) {
   using namespace w2l;
   g_trace_on = false;

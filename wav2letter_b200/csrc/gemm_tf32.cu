@@ -46,7 +46,7 @@ constexpr int kGemmThreads = 192;
 // other's main loop); BN > 160: 4 stages, 1 CTA per SM.
 __host__ __device__ constexpr int stages_for(int bn) { return bn <= 160 ? 3 : 4; }
 __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 128 ? 128 : 256; }
-__host__ __device__ constexpr size_t smem_for(int bn) { return (size_t)stages_for(bn) * (kTileBytes + bn * 128) + 256 + 1024; }
+__host__ __device__ constexpr size_t smem_for(int bn) { return (size_t)stages_for(bn) * (kTileBytes + bn * 128) + 128 + 1024 + 1024; }  // ring + barriers + bias row + alignment slack
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -137,7 +137,7 @@ __device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t
 }
 
 template <bool kAMn, bool kBMn, int BN>
-__global__ void __launch_bounds__(kGemmThreads, BN <= 160 ? 2 : 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)  // 168-register cap for every width (BN > 160 runs 1 CTA per SM anyway: smem)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -227,90 +227,119 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ===== epilogue warps 0..3: TMEM lanes 32*warp .. +31 =====
+    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per chunk).  Bias, ReLU and the
+    // dropout mask (one Philox block per 4 consecutive columns) are applied in that layout; the chunk is then
+    // transposed through shared memory (the idle operand ring; 33-float pitch, conflict-free both ways) so that
+    // every global access of the rest — mask read, C read for accumulation, store / red — is one row x 32
+    // consecutive columns per warp instruction: 128 B coalesced instead of 32 sectors.
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 128);  // [BN]
+    if (p.bias != nullptr) {
+      for (int j = threadIdx.x; j < BN; j += 128) sbias[j] = n0 + j < p.N ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // while the main loop runs: pull the tile's mask / C lines into L2 so the epilogue's reads are L2 hits
+    if (p.aux_mode != 0 || (p.accumulate && p.k_splits == 1)) {
+      const int lines = (BN * 4 + 127) / 128;  // 128-byte lines per tile row
+      for (int i = threadIdx.x; i < BM * lines; i += 128) {
+        const int r = m0 + i / lines, cc = n0 + (i % lines) * 32;
+        if (r < p.M && cc < p.N) {
+          if (p.aux_mode != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux + (size_t)r * p.ld_aux + cc));
+          if (p.accumulate && p.k_splits == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.C + (size_t)r * p.ldc + cc));
+        }
+      }
+    }
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + warp * 32 + lane;
-    float* crow = p.C + (size_t)row * p.ldc;
-    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    float* tbuf = reinterpret_cast<float*>(smem_a) + warp * (32 * 33);  // all TMA writes / UMMA reads of the ring are complete
+    const int row_own = m0 + warp * 32 + lane;
+    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const bool rd_aux = p.aux_mode != 0, rd_c = p.accumulate && p.k_splits == 1;
+    if (num_kb > 0 || p.k_splits == 1) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nb = n0 + c * 32;
-      if (row < p.M && nb < p.N) {
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb >= p.N) break;  // warp-uniform
+        const int col = nb + lane;
+        const bool col_ok = col < p.N;
+        const int rows_here = min(32, p.M - (m0 + warp * 32));  // warp-uniform; may be <= 0
+        // the chunk's mask (or, without a mask, its C values to accumulate onto) is requested first, in the coalesced
+        // layout (lane = column, one row per instruction), and lands while the accumulator is read and transposed
+        float pre[32];
+        if (rd_aux || rd_c) {
+          const float* src = rd_aux ? p.aux : p.C;
+          const size_t ld = rd_aux ? (size_t)p.ld_aux : (size_t)p.ldc;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            pre[rr] = (rr < rows_here && col_ok) ? src[(size_t)(m0 + warp * 32 + rr) * ld + col] : 0.f;
+        }
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float o[32];
-        const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]);
-          if (p.bias != nullptr && nb + j < p.N) x += __ldg(p.bias + nb + j);
+          if (p.bias != nullptr) x += sbias[c * 32 + j];  // broadcast read
           if (p.act == 1) x = fmaxf(x, 0.f);
           o[j] = x;
         }
         if (p.drop_p > 0.f) {
-          // element index row * N + n; one Philox call covers 4 consecutive columns (nb % 4 == 0)
-          const unsigned long long base_idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)nb;
+          // element index row * N + n; nb % 4 == 0, and N % 4 == 0 is required for dropout (checked by the host), so one
+          // Philox block covers the 4 consecutive columns j .. j+3
+          const unsigned long long base_idx = (unsigned long long)row_own * (unsigned long long)p.N + (unsigned long long)nb;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const unsigned long long idx = base_idx + j;
             const uint4 r = philox4x32_g((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // lane of element idx+e inside its Philox block is (idx+e) & 3
-              const unsigned long long ie = idx + e;
-              uint32_t rv = rr[(int)(ie & 3ull)];
-              if ((ie >> 2) != (idx >> 2)) {
-                const uint4 r2 = philox4x32_g((uint32_t)(ie >> 2), (uint32_t)(ie >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                const uint32_t rr2[4] = {r2.x, r2.y, r2.z, r2.w};
-                rv = rr2[(int)(ie & 3ull)];
-              }
-              o[j + e] *= ((float)(rv >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-            }
+            o[j] *= ((float)(r.x >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+            o[j + 1] *= ((float)(r.y >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+            o[j + 2] *= ((float)(r.z >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+            o[j + 3] *= ((float)(r.w >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
           }
         }
-        if (p.aux_mode != 0) {
-          const float* arow = p.aux + (size_t)row * p.ld_aux + nb;
+        __syncwarp();  // the previous chunk's transposed reads are done
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) {
-              const float a = __ldg(arow + j);
-              o[j] *= (p.aux_mode == 1 ? a > 0.f : a != 0.f) ? p.aux_scale : 0.f;
-            }
-        }
-        if (p.accumulate && p.k_splits == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) o[j] += crow[nb + j];
-        }
-        if (p.k_splits > 1) {  // split-K: C was zeroed (or holds the value to accumulate onto) by the host wrapper
-          if (num_kb > 0) {
-            if (vec_ok && nb + 32 <= p.N) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(crow + nb + j), make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) atomicAdd(crow + nb + j, o[j]);
+        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = o[j];
+        __syncwarp();
+        if (!rd_aux && !rd_c) {  // no global reads: stream the rows out
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < rows_here && col_ok) {
+              float* dst = p.C + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
+              const float x = tbuf[rr * 33 + lane];
+              if (p.k_splits > 1)
+                atomicAdd(dst, x);  // split-K: C was zeroed (or holds the value to accumulate onto) by the host wrapper
+              else
+                *dst = x;
             }
           }
-        } else if (vec_ok && nb + 32 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + nb + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) crow[nb + j] = o[j];
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < rows_here && col_ok) {
+              float* dst = p.C + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
+              float x = tbuf[rr * 33 + lane];
+              if (rd_aux) {
+                x *= (p.aux_mode == 1 ? pre[rr] > 0.f : pre[rr] != 0.f) ? p.aux_scale : 0.f;
+                if (rd_c) x += *dst;  // mask and accumulation together (not on the TDS path): C is read here
+              } else {
+                x += pre[rr];
+              }
+              if (p.k_splits > 1)
+                atomicAdd(dst, x);
+              else
+                *dst = x;
+            }
+          }
         }
       }
     }
@@ -448,6 +477,7 @@ extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, i
   if (aux_mode < 0 || aux_mode > 2 || (aux_mode != 0 && (!aux || ld_aux < N)))
     return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: bad aux mask arguments");
   if (dropout_p < 0.f || dropout_p >= 1.f) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: dropout_p must be in [0, 1)");
+  if (dropout_p > 0.f && N % 4 != 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: dropout needs N % 4 == 0 (one Philox block per 4 columns)");
   if ((lda % 4) || (ldb % 4) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: operand rows must be 16-byte aligned (ld % 4 == 0)");
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N)
