@@ -26,6 +26,10 @@
 #include <string>
 #include <vector>
 
+// every name below is part of the library's C++ surface (the .so is built with -fvisibility=hidden): arch plugins and
+// a Train.cpp built against this header link to them
+#pragma GCC visibility push(default)
+
 namespace w2l {
 
 enum class DType { f32, i32, f64, u8 };
@@ -248,6 +252,7 @@ class LayerNorm : public UnaryModule {
  private:
   std::vector<int> axes_;
   double eps_;
+  bool perFrame_ = false;
 };
 
 class Linear : public UnaryModule {
@@ -379,6 +384,22 @@ void initDistributed(int worldRank, int worldSize, const void* id128);
 // arch DSL -> fl::Sequential (opcodes V RO PD C2 R DO LN TDS L SAUG; cpc/SequentialBuilder.cpp:29-57,92-626)
 std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, int64_t nFeatures, int64_t nClasses);
 std::shared_ptr<Sequential> buildSequentialModuleFromFile(const std::string& path, int64_t nFeatures, int64_t nClasses);
+
+// fl::pkg::runtime::ModulePlugin — architecture plugins: a shared object exporting
+//   extern "C" fl::Module* createModule(int64_t nFeature, int64_t nLabel);
+// loaded as `ModulePlugin(FLAGS_arch).arch(numFeatures, numClasses)` (recipes/slimIPL/src/Train.cpp:390-395; plugin
+// sources: recipes/slimIPL/100h_supervised.cpp:84-87).  The caller owns the returned module; the library handle stays
+// open for the life of the process (the module's code lives in it).
+class ModulePlugin {
+ public:
+  explicit ModulePlugin(const std::string& path);
+  std::shared_ptr<Module> arch(int64_t nFeatures, int64_t nClasses);
+
+ private:
+  void* handle_ = nullptr;
+  void* create_ = nullptr;
+  std::string path_;
+};
 }  // namespace runtime
 
 namespace speech {
@@ -440,3 +461,5 @@ using LinSegCriterion = LinearSegmentationCriterion;
 }  // namespace speech
 }  // namespace pkg
 }  // namespace fl
+
+#pragma GCC visibility pop

@@ -106,7 +106,8 @@ def test_dropout_in_conv_and_gemm():
     assert abs(kept - 0.5) < 0.01 and torch.allclose(out[out != 0], torch.tensor(64.0, device="cuda"))
 
 
-@pytest.mark.parametrize("B,R", [(1, 17), (3, 5000), (4, 50 * 800), (2, 250 * 1440)])
+@pytest.mark.parametrize("B,R", [(1, 17), (3, 5000), (4, 50 * 800), (2, 250 * 1440),
+                                 (2400, 1200), (1500, 2160), (1300, 30)])  # many short groups: the one-warp-per-group kernels
 def test_layernorm_fwd_bwd(B, R):
     from wav2letter_b200 import capi
 

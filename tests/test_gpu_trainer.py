@@ -95,6 +95,63 @@ class TorchTDS:
         return x.reshape(B, T, -1) @ W.view(N, 640).t() + b
 
 
+# streaming TDS family (recipes/streaming_convnets/librispeech/am_500ms_future_context.arch): explicit PD padding
+# before valid strided convolutions, per-frame LayerNorm (`LN 1 2`, TDS lNormIncludeTime = 0), limited right context
+STREAMING_ARCH = """V -1 NFEAT 1 0
+PD 0 5 3
+C2 1 4 10 1 2 1 0 0
+R
+DO 0.0
+LN 1 2
+TDS 4 9 80 0.0 0 1 0
+PD 0 7 1
+C2 4 8 10 1 2 1 0 0
+R
+DO 0.0
+LN 1 2
+TDS 8 9 80 0.0 0 1 0
+TDS 8 5 80 0.0 0 0 0
+V 0 640 1 0
+RO 1 0 3 2
+L 640 NLABEL
+"""
+
+
+class TorchStreamingTDS(TorchTDS):
+    def forward(self, feat):
+        it = iter(range(len(self.p)))
+        P = lambda: self.p[next(it)]
+        x = feat.double().permute(0, 3, 1, 2)  # [B,T,1,F]
+
+        def conv(x, cin, cout, k, s, pl, pr):
+            xin = F.pad(x.permute(0, 2, 1, 3), (0, 0, pl, pr))
+            return F.conv2d(xin, P().view(cout, cin, k).unsqueeze(-1), P().view(cout), stride=(s, 1)).permute(0, 2, 1, 3)
+
+        def ln(x, g, b):  # per frame over (C, W)
+            return F.layer_norm(x, x.shape[2:], eps=1e-5) * g + b
+
+        def tds(x, c, k, rpad):
+            y1 = conv(x, c, c, k, 1, k - 1 - rpad, rpad).clamp_min(0)
+            z = ln(x + y1, P(), P())
+            B, T = z.shape[:2]
+            W1, b1, W2, b2 = P().view(c * 80, c * 80), P(), P().view(c * 80, c * 80), P()
+            h = (z.reshape(B, T, -1) @ W1.t() + b1).clamp_min(0)
+            u = h @ W2.t() + b2
+            return ln(z + u.view_as(z), P(), P())
+
+        x = conv(x, 1, 4, 10, 2, 5, 3).clamp_min(0)
+        x = ln(x, P(), P())
+        x = tds(x, 4, 9, 1)
+        x = conv(x, 4, 8, 10, 2, 7, 1).clamp_min(0)
+        x = ln(x, P(), P())
+        x = tds(x, 8, 9, 1)
+        x = tds(x, 8, 5, 0)
+        B, T = x.shape[:2]
+        W, b = P(), P()
+        N = b.numel()
+        return x.reshape(B, T, -1) @ W.view(N, 640).t() + b
+
+
 def make_batch(B, T, N, L, seed, blank):
     g = torch.Generator(device="cuda").manual_seed(seed)
     feat = torch.randn((B, 1, 80, T), device="cuda", generator=g)
@@ -104,19 +161,20 @@ def make_batch(B, T, N, L, seed, blank):
     return feat, tgt
 
 
-@pytest.mark.parametrize("criterion,N", [("ctc", 12), ("asg", 8)])
-def test_train_step_matches_torch_reference(criterion, N):
+@pytest.mark.parametrize("criterion,N,arch_name", [("ctc", 12, "tds"), ("asg", 8, "tds"), ("ctc", 12, "streaming")])
+def test_train_step_matches_torch_reference(criterion, N, arch_name):
     from wav2letter_b200.trainer import Trainer
 
     B, T, L = 3, 64, 5
-    tr = Trainer(ARCH, 80, N, criterion, "target_sz" if criterion == "ctc" else "none", transdiag=1.0, lr=0.0, lrcrit=0.0)
+    arch_text, ref_cls = (ARCH, TorchTDS) if arch_name == "tds" else (STREAMING_ARCH, TorchStreamingTDS)
+    tr = Trainer(arch_text, 80, N, criterion, "target_sz" if criterion == "ctc" else "none", transdiag=1.0, lr=0.0, lrcrit=0.0)
     feat, tgt = make_batch(B, T, N, L, 1, criterion == "ctc")
     flat0 = tr.get_flat(0, 0).clone()
     loss = tr.step(feat, tgt, train=True)
     torch.cuda.synchronize()
     grads = tr.get_flat(0, 1)
     assert torch.equal(tr.get_flat(0, 0), flat0)  # lr = 0
-    ref = TorchTDS(flat0, tr.layout(0))
+    ref = ref_cls(flat0, tr.layout(0))
     logits = ref.forward(feat)
     e = logits.detach().float().cpu().numpy()
     y = tgt.cpu().numpy()

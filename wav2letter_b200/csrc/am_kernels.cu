@@ -472,6 +472,129 @@ __global__ void __launch_bounds__(256) ln_bwd_apply_kernel(long long R, int vec,
   }
 }
 
+// ---- per-row variant: many short groups (per-frame LayerNorm of the streaming TDS family: R = C*W <= a few
+// thousand, groups = T*B).  One warp per group, two sweeps inside one kernel (the second hits L1), no scratch.
+__global__ void __launch_bounds__(256) ln_row_fwd_kernel(long long G, int R, int vec, float eps, const float* __restrict__ a,
+                                                         const float* __restrict__ r, const float* __restrict__ gain,
+                                                         const float* __restrict__ bias, float* __restrict__ y,
+                                                         float* __restrict__ mean_rstd) {
+  const long long grp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (grp >= G) return;
+  const float* ab = a + grp * R;
+  const float* rb = r ? r + grp * R : nullptr;
+  float* yb = y + grp * R;
+  float s = 0.f, q = 0.f;
+  if (vec) {
+    for (int i = 4 * lane; i < R; i += 128) {
+      float4 v = ld4(ab, i);
+      if (rb) v = add4(v, ld4(rb, i));
+      s += (v.x + v.y) + (v.z + v.w);
+      q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  } else {
+    for (int i = lane; i < R; i += 32) {
+      const float v = ab[i] + (rb ? rb[i] : 0.f);
+      s += v;
+      q += v * v;
+    }
+  }
+  const double S = warp_sum((double)s), Q = warp_sum((double)q);
+  const double mean = S / R, var = fmax(Q / R - mean * mean, 0.0);
+  const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = rstd * (gain ? *gain : 1.f), bi = bias ? *bias : 0.f;
+  if (lane == 0) {
+    mean_rstd[2 * grp] = mu;
+    mean_rstd[2 * grp + 1] = rstd;
+  }
+  if (vec) {
+    for (int i = 4 * lane; i < R; i += 128) {
+      float4 v = ld4(ab, i);
+      if (rb) v = add4(v, ld4(rb, i));
+      *reinterpret_cast<float4*>(yb + i) = make_float4((v.x - mu) * sc + bi, (v.y - mu) * sc + bi, (v.z - mu) * sc + bi, (v.w - mu) * sc + bi);
+    }
+  } else {
+    for (int i = lane; i < R; i += 32) yb[i] = (ab[i] + (rb ? rb[i] : 0.f) - mu) * sc + bi;
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_row_bwd_kernel(long long G, int R, int vec, const float* __restrict__ a,
+                                                         const float* __restrict__ r, const float* __restrict__ dy,
+                                                         const float* __restrict__ gain, const float* __restrict__ mean_rstd,
+                                                         float* __restrict__ d_branch, float* __restrict__ d_res, int branch_mode,
+                                                         float branch_scale, float* __restrict__ dgain, float* __restrict__ dbias) {
+  const long long grp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float sh_s[8], sh_q[8];
+  float S = 0.f, Q = 0.f;
+  if (grp < G) {
+    const float mu = mean_rstd[2 * grp], rstd = mean_rstd[2 * grp + 1], g = gain ? *gain : 1.f;
+    const float* ab = a + grp * R;
+    const float* rb = r ? r + grp * R : nullptr;
+    const float* db = dy + grp * R;
+    float* ob = d_branch + grp * R;
+    float* orr = d_res ? d_res + grp * R : nullptr;
+    float s = 0.f, q = 0.f;
+    if (vec) {
+      for (int i = 4 * lane; i < R; i += 128) {
+        float4 v = ld4(ab, i);
+        const float4 d = ld4(db, i);
+        if (rb) v = add4(v, ld4(rb, i));
+        s += (d.x + d.y) + (d.z + d.w);
+        q += (d.x * ((v.x - mu) * rstd) + d.y * ((v.y - mu) * rstd)) + (d.z * ((v.z - mu) * rstd) + d.w * ((v.w - mu) * rstd));
+      }
+    } else {
+      for (int i = lane; i < R; i += 32) {
+        const float d = db[i];
+        s += d;
+        q += d * ((ab[i] + (rb ? rb[i] : 0.f) - mu) * rstd);
+      }
+    }
+    S = warp_sum(s);
+    Q = warp_sum(q);
+    const float m1 = S / R, m2 = Q / R, rg = rstd * g;
+    if (vec) {
+      for (int i = 4 * lane; i < R; i += 128) {
+        const float4 av = ld4(ab, i);
+        const float4 d = ld4(db, i);
+        float4 v = av;
+        if (rb) v = add4(v, ld4(rb, i));
+        float4 ds;
+        ds.x = rg * (d.x - m1 - (v.x - mu) * rstd * m2);
+        ds.y = rg * (d.y - m1 - (v.y - mu) * rstd * m2);
+        ds.z = rg * (d.z - m1 - (v.z - mu) * rstd * m2);
+        ds.w = rg * (d.w - m1 - (v.w - mu) * rstd * m2);
+        if (orr) *reinterpret_cast<float4*>(orr + i) = ds;
+        *reinterpret_cast<float4*>(ob + i) =
+            make_float4(ds.x * ln_mask(branch_mode, av.x, branch_scale), ds.y * ln_mask(branch_mode, av.y, branch_scale),
+                        ds.z * ln_mask(branch_mode, av.z, branch_scale), ds.w * ln_mask(branch_mode, av.w, branch_scale));
+      }
+    } else {
+      for (int i = lane; i < R; i += 32) {
+        const float av = ab[i];
+        const float ds = rg * (db[i] - m1 - (av + (rb ? rb[i] : 0.f) - mu) * rstd * m2);
+        if (orr) orr[i] = ds;
+        ob[i] = ds * ln_mask(branch_mode, av, branch_scale);
+      }
+    }
+  }
+  // scalar affine gradients: one atomic per CTA
+  if (lane == 0) {
+    sh_s[warp] = S;
+    sh_q[warp] = Q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      ts += sh_s[w];
+      tq += sh_q[w];
+    }
+    if (dbias) atomicAdd(dbias, ts);
+    if (dgain) atomicAdd(dgain, tq);
+  }
+}
+
 // out[n] += sum_m X[m][n]   (bias gradients of Linear)
 __global__ void __launch_bounds__(256) colsum_kernel(int M, int N, const float* __restrict__ X, int ld, int rows_per_cta,
                                                      float* __restrict__ out) {
@@ -729,13 +852,22 @@ extern "C" int w2l_conv_time_wgrad(void* stream_, int B, int T, int Tout, int W,
   return W2L_OK;
 }
 
+// many short groups -> the one-warp-per-group kernels; few long groups -> the two-pass kernels
+static bool ln_use_rows(int B, long long R) { return R <= 8192 && (long long)B * 32 >= 148 * 256; }
+
 extern "C" int w2l_layernorm_fwd(void* stream_, int B, long long R, float eps, const float* a, const float* r,
                                  const float* gain, const float* bias, float* y, float* mean_rstd, double* scratch) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (B <= 0 || R <= 0 || !a || !y || !mean_rstd || !scratch) return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_fwd: bad arguments");
+  const int vec = (R % 4 == 0) && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(y)) & 15);
+  if (ln_use_rows(B, R)) {  // many short groups (per-frame LayerNorm): one warp per group
+    ln_row_fwd_kernel<<<(B + 7) / 8, 256, 0, stream>>>(B, (int)R, vec, eps, a, r, gain, bias, y, mean_rstd);
+    W2L_LAUNCH_CHECK("ln_row_fwd_kernel");
+    return W2L_OK;
+  }
+  if (B > 65535) return fail(W2L_ERR_UNSUPPORTED, "layernorm_fwd: more than 65535 long groups");
   W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
   dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
-  const int vec = (R % 4 == 0) && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(y)) & 15);
   ln_stats_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, scratch);
   W2L_LAUNCH_CHECK("ln_stats_kernel");
   ln_apply_kernel<<<grid, 256, 0, stream>>>(R, vec, eps, a, r, gain, bias, scratch, y, mean_rstd);
@@ -750,10 +882,17 @@ extern "C" int w2l_layernorm_bwd(void* stream_, int B, long long R, const float*
   if (B <= 0 || R <= 0 || !a || !dy || !mean_rstd || !d_branch || !scratch)
     return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_bwd: bad arguments");
   if (branch_mode < 0 || branch_mode > 2) return fail(W2L_ERR_INVALID_ARGUMENT, "layernorm_bwd: bad branch mode");
-  W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
-  dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
   const int vec = (R % 4 == 0) && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(dy) |
                                       reinterpret_cast<uintptr_t>(d_branch) | reinterpret_cast<uintptr_t>(d_res)) & 15);
+  if (ln_use_rows(B, R)) {
+    ln_row_bwd_kernel<<<(B + 7) / 8, 256, 0, stream>>>(B, (int)R, vec, a, r, dy, gain, mean_rstd, d_branch, d_res, branch_mode, branch_scale,
+                                                       dgain, dbias);
+    W2L_LAUNCH_CHECK("ln_row_bwd_kernel");
+    return W2L_OK;
+  }
+  if (B > 65535) return fail(W2L_ERR_UNSUPPORTED, "layernorm_bwd: more than 65535 long groups");
+  W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
+  dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
   ln_bwd_stats_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, dy, mean_rstd, scratch);
   W2L_LAUNCH_CHECK("ln_bwd_stats_kernel");
   ln_bwd_apply_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, dy, gain, mean_rstd, scratch, d_branch, d_res, branch_mode, branch_scale,

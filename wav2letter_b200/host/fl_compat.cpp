@@ -2,6 +2,8 @@
 // Host code only: every arithmetic operation is a call into libw2l_b200's sm_100a kernels.
 #include "fl_compat/fl_compat.h"
 
+#include <dlfcn.h>
+
 #include <cuda_runtime.h>
 #include <nccl.h>
 
@@ -496,19 +498,27 @@ LayerNorm::LayerNorm(const std::vector<int>& axes, double eps, bool affine) : ax
   std::vector<int> s = axes;
   std::sort(s.begin(), s.end());
   // `LN 0 1 2`, and the legacy `LN 3` (= feature axis 3 -> normalise over 0,1,2) of seq2seq_tds/librispeech/network.arch
+  // Axes are the reference's ([T, W, C, B] after the arch's head view): {1,2} = over (W, C) of every frame
+  // (streaming TDS: `LN 1 2`, TDSBlock with lNormIncludeTime = false), {0,1,2} = over the whole sample.
   const bool whole = (s == std::vector<int>{0, 1, 2}) || (s == std::vector<int>{3});
-  if (!whole) throw std::invalid_argument("LayerNorm: only normalisation over the whole sample (axes 0 1 2) is covered");
+  perFrame_ = (s == std::vector<int>{1, 2});
+  if (!whole && !perFrame_) throw std::invalid_argument("LayerNorm: axes must be {0,1,2} (whole sample) or {1,2} (per frame)");
   if (affine) {
     params_.push_back(Variable(af::array::zeros(af::dim4(1)), true));
     params_[0].array().fill(1.0f);
     params_.push_back(Variable(af::array::zeros(af::dim4(1)), true));
   }
 }
-std::string LayerNorm::prettyString() const { return "LayerNorm ( axis : { 0 1 2 } , size : -1)"; }
+std::string LayerNorm::prettyString() const {
+  return perFrame_ ? "LayerNorm ( axis : { 1 2 } , size : -1)" : "LayerNorm ( axis : { 0 1 2 } , size : -1)";
+}
 Variable LayerNorm::forward(const Variable& in) { return forwardResidual(in, Variable(), 0, 1.0f); }
 Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int branchMode, float keepScale) {
   requireInternal(a, "LayerNorm");
-  const int B = (int)a.dims(3);
+  // groups: samples, or (frame, sample) pairs — in the internal [W, C, T, B] layout both are contiguous runs of R floats
+  const long long groups = perFrame_ ? a.dims(2) * a.dims(3) : a.dims(3);
+  if (groups > 0x7fffffffLL) throw std::invalid_argument("LayerNorm: too many groups");
+  const int B = (int)groups;
   const long long R = a.elements() / B;
   const bool hasRes = !r.isEmpty();
   if (hasRes && r.elements() != a.elements()) throw std::invalid_argument("LayerNorm: residual size mismatch");
@@ -626,7 +636,6 @@ Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool m
 // ================================================================================================
 TDSBlock::TDSBlock(int channels, int kernelSize, int width, double dropout, int innerLinearDim, int rightPadding, bool lNormIncludeTime)
     : c_(channels), k_(kernelSize), w_(width), inner_(innerLinearDim > 0 ? innerLinearDim : channels * width), dropout_(dropout) {
-  if (!lNormIncludeTime) throw std::invalid_argument("TDSBlock: lNormIncludeTime = false (per-frame LayerNorm) is not covered yet");
   conv_ = std::make_shared<Conv2D>(c_, c_, k_, 1, 1, 1, (int)PaddingMode::SAME, 0);
   if (rightPadding >= 0) {
     if (rightPadding > k_ - 1) throw std::invalid_argument("TDSBlock: rightPadding exceeds kernel - 1");
@@ -634,8 +643,10 @@ TDSBlock::TDSBlock(int channels, int kernelSize, int width, double dropout, int 
   }
   conv_->fuseRelu();
   conv_->fuseDropout((float)dropout);
-  ln1_ = std::make_shared<LayerNorm>(std::vector<int>{0, 1, 2});
-  ln2_ = std::make_shared<LayerNorm>(std::vector<int>{0, 1, 2});
+  // lNormIncludeTime = false (streaming TDS): normalise every frame over (W, C) instead of the whole sample
+  const std::vector<int> lnAxes = lNormIncludeTime ? std::vector<int>{0, 1, 2} : std::vector<int>{1, 2};
+  ln1_ = std::make_shared<LayerNorm>(lnAxes);
+  ln2_ = std::make_shared<LayerNorm>(lnAxes);
   lin1_ = std::make_shared<Linear>(c_ * w_, inner_);
   lin2_ = std::make_shared<Linear>(inner_, c_ * w_);
 }
@@ -935,6 +946,21 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
     }
   }
   return net;
+}
+ModulePlugin::ModulePlugin(const std::string& path) : path_(path) {
+  handle_ = dlopen(path.c_str(), RTLD_NOW | RTLD_GLOBAL);
+  if (!handle_) {
+    const char* e = dlerror();
+    throw std::runtime_error("ModulePlugin: cannot load " + path + ": " + (e ? e : "unknown error"));
+  }
+  create_ = dlsym(handle_, "createModule");
+  if (!create_) throw std::runtime_error("ModulePlugin: " + path + " does not export createModule(int64_t, int64_t)");
+}
+std::shared_ptr<Module> ModulePlugin::arch(int64_t nFeatures, int64_t nClasses) {
+  using Fn = Module* (*)(int64_t, int64_t);
+  Module* m = reinterpret_cast<Fn>(create_)(nFeatures, nClasses);
+  if (!m) throw std::runtime_error("ModulePlugin: createModule returned null (" + path_ + ")");
+  return std::shared_ptr<Module>(m);  // ownership passes to the caller (100h_supervised.cpp:84-87)
 }
 std::shared_ptr<Sequential> buildSequentialModuleFromFile(const std::string& path, int64_t nFeatures, int64_t nClasses) {
   std::ifstream f(path);

@@ -27,7 +27,7 @@ using namespace fl::pkg::speech;
 
 namespace {
 struct Trainer {
-  std::shared_ptr<Sequential> net;
+  std::shared_ptr<fl::Module> net;
   std::shared_ptr<SequenceCriterion> crit;
   ParameterArena netArena, critArena;
   af::array sqnorm;
@@ -57,7 +57,12 @@ W2L_API void* w2l_trainer_create(void* stream, const char* arch_text, int n_feat
   const int rc = guarded([&] {
     w2l::setCurrentStream(stream);
     auto tr = std::make_unique<Trainer>();
-    tr->net = fl::pkg::runtime::buildSequentialModule(arch_text, n_feat, n_label);
+    // --arch is either the text of an .arch file or the path of a plugin exporting createModule (Train.cpp:390-395)
+    const std::string arch = arch_text;
+    if (arch.size() > 3 && arch.compare(arch.size() - 3, 3, ".so") == 0 && arch.find('\n') == std::string::npos)
+      tr->net = fl::pkg::runtime::ModulePlugin(arch).arch(n_feat, n_label);
+    else
+      tr->net = fl::pkg::runtime::buildSequentialModule(arch, n_feat, n_label);
     const auto mode = static_cast<CriterionScaleMode>(scale_mode);
     const std::string c = criterion;
     if (c == "ctc") {
