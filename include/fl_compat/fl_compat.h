@@ -99,6 +99,8 @@ class Tensor {
 };
 
 void* currentStream();            // cudaStream_t used by every fl_compat call on this thread
+// device-to-device strided copy on the current stream (cudaMemcpy2DAsync): `height` rows of `width` bytes
+void copyRows(void* dst, size_t dstPitch, const void* src, size_t srcPitch, size_t width, size_t height);
 void setCurrentStream(void* s);   // (the Python harness passes torch's current stream)
 void sync();                      // af::sync()
 
@@ -214,10 +216,18 @@ class Conv2D : public UnaryModule {
   float fusedDropout() const { return dropP_; }
   void fuseDropout(float p) { dropP_ = p; }
   void setAsymmetricPad(int left, int right) { padL_ = left; padR_ = right; explicitPad_ = true; }
+  // Functional form (used by WeightNorm): the same layer with the weight / bias taken from the given variables.
+  Variable forwardWith(const Variable& in, const Variable& weight, const Variable& bias, bool maskByConsumer);
+  // `C cin cout kw 1 pad` of the conv_glu archs: W = 1, hundreds of channels — the convolution is the tcgen05 GEMM on a
+  // zero-copy im2col view (w2l_gemm_tf32_view).  Channel counts are carried padded to multiples of 4 (zero channels);
+  // with gluSplit the two halves of the output channels are padded separately for the GLU that follows.
+  void setGluSplit(bool on) { gluSplit_ = on; }
+  bool hasBias() const { return hasBias_; }
   int nIn, nOut, kw, stride, pad;
 
  private:
-  bool relu_ = false, explicitPad_ = false, hasBias_ = true;
+  Variable forwardGemm(const Variable& in, const Variable& weight, const Variable& bias);
+  bool relu_ = false, explicitPad_ = false, hasBias_ = true, gluSplit_ = false;
   float dropP_ = 0.f;
   int padL_ = 0, padR_ = 0;
 };
@@ -264,11 +274,46 @@ class Linear : public UnaryModule {
   // data-gradient GEMM's epilogue on behalf of the producer.
   Variable forwardFused(const Variable& in, bool relu, float dropP, bool maskByConsumer = false, int inMaskMode = 0,
                         float inMaskScale = 1.0f);
+  // functional form (WeightNorm): weight [nIn, nOut] (stored [nOut][nIn]) and bias from the given variables
+  Variable forwardWith(const Variable& in, const Variable& weight, const Variable& bias, bool relu = false, float dropP = 0.f,
+                       bool maskByConsumer = false, int inMaskMode = 0, float inMaskScale = 1.0f);
+  bool hasBias() const { return hasBias_; }
   std::string prettyString() const override;
   int nIn, nOut;
 
  private:
   bool hasBias_;
+};
+
+// fl::GatedLinearUnit(dim): y = x[first half] * sigmoid(x[second half]) along the channel axis (`GLU 2` after a conv,
+// `GLU 0` after the Linear head: in the internal layout both are the fastest-varying run of C floats per frame).
+// A following Dropout is fused (fuseDropout).
+class GatedLinearUnit : public UnaryModule {
+ public:
+  explicit GatedLinearUnit(int dim) : dim_(dim) {}
+  Variable forward(const Variable& in) override;
+  void fuseDropout(float p) { dropP_ = p; }
+  std::string prettyString() const override;
+
+ private:
+  int dim_;
+  float dropP_ = 0.f;
+};
+
+// fl::WeightNorm(module, dim): w = g * v / ||v|| with the norm taken per output unit (dim 3 of a Conv2D weight
+// [kw,1,cin,cout], dim 0 of flashlight's Linear weight [out,in]).  params(): v, g, then the wrapped layer's bias.
+class WeightNorm : public UnaryModule {
+ public:
+  WeightNorm(std::shared_ptr<Module> module, int dim);
+  Variable forward(const Variable& in) override;
+  std::shared_ptr<Module> module() const { return module_; }
+  void train() override;
+  void eval() override;
+  std::string prettyString() const override;
+
+ private:
+  std::shared_ptr<Module> module_;
+  int dim_, rows_ = 0, len_ = 0;
 };
 
 // fl::View / fl::Reorder: the TDS archs use them only to move between [T,F,1,B], [T,W,C,B] and

@@ -151,6 +151,15 @@ W2L_API int w2l_linseg_target(void* stream, int B, int T, int L, const int32_t* 
  *   (0,1) with B = W; wgrad dW = dY^T X : (1,1) with A = dY, B = X.  bias nullable; act 0 none,
  *   1 ReLU.  lda/ldb must be multiples of 4 floats and A/B 16-byte aligned (TMA).
  * ---------------------------------------------------------------------------------------- */
+/* w2l_gemm_tf32 with OVERLAPPING operand rows allowed (lda / ldb may be smaller than the row length; still % 4):
+ * the im2col matrix of a stride-1 time convolution over [T][Cin] activations — row t = the kw*Cin contiguous floats
+ * starting at frame t, row stride Cin — is then a zero-copy TMA view.  This is how the large-channel `C` convolutions
+ * of the conv_glu archs (recipes/conv_glu/librispeech/network.arch) run on the tcgen05 GEMM:
+ *   fwd   Y[t][co]  = sum_k Xview[t][k] Warr[co][k]            (A = Xview K-major, lda = Cin;  B = Warr K-major)
+ *   dgrad dX[t][ci] = sum_k dYview[t][k] Wflip[ci][k]          (A = zero-padded dY view, lda = Cout)
+ *   wgrad dWarr[co][k] += sum_t dY[t][co] Xview[t][k]          (A = dY MN-major; B = Xview MN-major, ldb = Cin) */
+W2L_API int w2l_gemm_tf32_view(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                               const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate);
 /* Pin the GEMM tile width (128 / 160 / 224 / 256; 0 = choose per shape, the default).  Thread-local; for tests and tuning. */
 W2L_API int w2l_gemm_set_tile(int bn);
 W2L_API int w2l_gemm_tf32(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
@@ -186,6 +195,30 @@ W2L_API int w2l_conv_time_dgrad(void* stream, int B, int T, int Tout, int W, int
 W2L_API int w2l_conv_time_wgrad(void* stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                                 int pad_left, const float* x, const float* dy, float* dwt, float* dbias, void* ws,
                                 size_t ws_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Conv1D + GLU family (recipes/conv_glu/{wsj,librispeech}/network.arch: `WN 3 C cin cout kw 1 pad`, `GLU 2`, `DO p`,
+ * `RO 2 0 3 1`, `WN 0 L in out`, `GLU 0`).  Activations are [rows = B*T][C] row-major (internal layout with W = 1).
+ *   weightnorm : w[r][:] = g[r] v[r][:] / ||v[r][:]|| per output unit r (rows of the [cout][cin*kw] / [out][in] weight);
+ *                bwd ADDS into dv, dg.  inv_norm [rows] is saved by fwd for bwd.
+ *   conv1d_arrange : w [cout][cin][kw] (= fl's [kw,1,cin,cout]) -> GEMM operands fwd [cout_p][kw*cin_p] and (nullable)
+ *                flip [cin_p][kw*cout_p] (data gradient), bias -> bias_p [cout_p]; padded channels are zero.  glu_split:
+ *                the two halves of cout are padded separately (cout_p/2 each) so a following GLU stays aligned.
+ *                The convolution itself is w2l_gemm_tf32_view on these operands.
+ *   conv1d_unarrange_grad : dw[co][ci][dk] += dfwd[row(co)][dk*cin_p+ci]; dbias[co] += sum_rows dy[row][col(co)]
+ *   glu        : y[r][c] = x[r][c] * sigmoid(x[r][half+c]) * dropout-mask(r*half+c)   (x has 2*half columns)
+ * ---------------------------------------------------------------------------------------- */
+W2L_API int w2l_weightnorm_fwd(void* stream, int rows, int len, const float* v, const float* g, float* w, float* inv_norm);
+W2L_API int w2l_weightnorm_bwd(void* stream, int rows, int len, const float* v, const float* g, const float* inv_norm,
+                               const float* dw, float* dv, float* dg);
+W2L_API int w2l_conv1d_arrange(void* stream, int cin, int cout, int kw, int cin_p, int cout_p, int glu_split, const float* w,
+                               const float* bias, float* fwd, float* flip, float* bias_p);
+W2L_API int w2l_conv1d_unarrange_grad(void* stream, int cin, int cout, int kw, int cin_p, int cout_p, int glu_split,
+                                      const float* dfwd, float* dw, long long rows, const float* dy, float* dbias);
+W2L_API int w2l_glu_fwd(void* stream, long long rows, int half, const float* x, float* y, float dropout_p,
+                        unsigned long long seed);
+W2L_API int w2l_glu_bwd(void* stream, long long rows, int half, const float* x, const float* dy, float* dx, float dropout_p,
+                        unsigned long long seed);
 
 /* fl::LayerNorm over a whole sample (R = T*C*W elements; `LN 0 1 2` / TDSBlock with lnIncludeTime)
  * with scalar gain/bias (device scalars, nullable = 1/0) and a fused residual: y = LN(a + r).

@@ -89,3 +89,26 @@ def test_gemm_tile_widths(M, N, K, a_mn, b_mn, bn):
         run(M, N, K, a_mn, b_mn, bias=not a_mn, act=0 if a_mn else 1, seed=bn + M)
     finally:
         w.capi.gemm_set_tile(0)
+
+
+@pytest.mark.parametrize("T,Cin,Cout,kw", [(300, 40, 200, 13), (257, 100, 136, 5), (64, 244, 96, 21)])
+def test_gemm_overlapping_rows_is_a_time_convolution(T, Cin, Cout, kw):
+    """w2l_gemm_tf32_view: the im2col matrix of a stride-1 conv over [T][Cin] is rows of kw*Cin floats with row stride Cin
+    (a zero-copy TMA view).  fwd (K-major view as A) and wgrad (MN-major view as B) against conv1d in float64."""
+    import wav2letter_b200 as w
+
+    g = torch.Generator(device="cuda").manual_seed(T)
+    x = torch.randn(T, Cin, device="cuda", generator=g)
+    wt = torch.randn(Cout, kw, Cin, device="cuda", generator=g) * 0.1   # arranged [co][dk*Cin + ci]
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    Tout = T - kw + 1
+    y = torch.empty(Tout, Cout, device="cuda")
+    w.capi.gemm_tf32_view(x, Cin, wt.view(Cout, kw * Cin), kw * Cin, y, Tout, Cout, kw * Cin, bias=bias)
+    ref = torch.nn.functional.conv1d(x.double().t().unsqueeze(0), wt.double().permute(0, 2, 1), bias.double())[0].t()
+    assert float((y.double() - ref).abs().max()) < 3e-3 * float(ref.abs().max()) + 1e-3
+    dy = torch.randn(Tout, Cout, device="cuda", generator=g)
+    dw = torch.zeros(Cout, kw * Cin, device="cuda")
+    w.capi.gemm_tf32_view(dy, Cout, x, Cin, dw, Cout, kw * Cin, Tout, a_mn=True, b_mn=True)
+    cols = torch.stack([x[dk:dk + Tout] for dk in range(kw)], 1).reshape(Tout, kw * Cin).double()
+    refw = dy.double().t() @ cols
+    assert float((dw.double() - refw).abs().max()) < 3e-3 * float(refw.abs().max()) + 1e-3

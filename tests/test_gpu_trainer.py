@@ -220,6 +220,6 @@ def test_arch_errors():
     from wav2letter_b200.trainer import Trainer
 
     with pytest.raises(W2LError):
-        Trainer("GLU 2\n", 80, 12)
+        Trainer("TR 4 4 8 2 100\n", 80, 12)  # transformer blocks are outside the hot-path subset
     with pytest.raises(W2LError):
-        Trainer("V -1 NFEAT 1 0\nL 80 13\n", 80, 13)  # Linear sizes must be multiples of 4
+        Trainer("V -1 NFEAT 1 0\nL 78 12\n", 78, 12)  # Linear input rows must be multiples of 4 floats (TMA)

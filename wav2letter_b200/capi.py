@@ -24,9 +24,10 @@ EXPORTS = [
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
     "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
-    "w2l_gemm_set_tile", "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
+    "w2l_gemm_set_tile", "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_gemm_tf32_view", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
     "w2l_conv_time_wgrad", "w2l_layernorm_fwd", "w2l_layernorm_bwd", "w2l_colsum_accumulate", "w2l_sq_norm_accumulate",
-    "w2l_sgd_step", "w2l_transpose_input", "w2l_axpy", "w2l_fill", "w2l_act_fwd", "w2l_mask_mul",
+    "w2l_sgd_step", "w2l_weightnorm_fwd", "w2l_weightnorm_bwd", "w2l_conv1d_arrange", "w2l_conv1d_unarrange_grad",
+    "w2l_glu_fwd", "w2l_glu_bwd", "w2l_transpose_input", "w2l_axpy", "w2l_fill", "w2l_act_fwd", "w2l_mask_mul",
     "w2l_trainer_create", "w2l_trainer_destroy", "w2l_trainer_step", "w2l_trainer_forward", "w2l_trainer_num_params",
     "w2l_trainer_param_layout", "w2l_trainer_get_flat", "w2l_trainer_set_flat", "w2l_trainer_sync_parameters",
     "w2l_trainer_describe", "w2l_nccl_unique_id", "w2l_init_distributed",
@@ -71,6 +72,14 @@ def _load() -> ctypes.CDLL:
     lib.w2l_linseg_target.argtypes = [vp, i, i, i, vp, vp]
     lib.w2l_gemm_tf32.argtypes = [vp, i, i, i, i, i, vp, i, vp, i, vp, i, vp, i]
     f32, u64, ll = ctypes.c_float, ctypes.c_ulonglong, ctypes.c_longlong
+    ll = ctypes.c_longlong
+    lib.w2l_weightnorm_fwd.argtypes = [vp, i, i, vp, vp, vp, vp]
+    lib.w2l_weightnorm_bwd.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp]
+    lib.w2l_conv1d_arrange.argtypes = [vp, i, i, i, i, i, i, vp, vp, vp, vp, vp]
+    lib.w2l_conv1d_unarrange_grad.argtypes = [vp, i, i, i, i, i, i, vp, vp, ll, vp, vp]
+    lib.w2l_glu_fwd.argtypes = [vp, ll, i, vp, vp, f32, u64]
+    lib.w2l_glu_bwd.argtypes = [vp, ll, i, vp, vp, vp, f32, u64]
+    lib.w2l_gemm_tf32_view.argtypes = [vp, i, i, i, i, i, vp, i, vp, i, vp, i, vp, i, i]
     lib.w2l_gemm_tf32_ex.argtypes = [vp, i, i, i, i, i, vp, i, vp, i, vp, i, vp, i, i, vp, i, i, f32, f32, u64]
     lib.w2l_conv_time_workspace_size.restype = sz
     lib.w2l_conv_time_workspace_size.argtypes = [i, i, i, i, i]
@@ -317,6 +326,13 @@ def gemm_tf32_ex(A, B, out, bias=None, act=0, a_mn=False, b_mn=False, accumulate
                                 _ptr(out), out.stride(0), _ptr(bias), int(act), int(accumulate), _ptr(aux),
                                 0 if aux is None else aux.stride(0), int(aux_mode), float(aux_scale), float(dropout_p),
                                 int(seed)))
+    return out
+
+
+def gemm_tf32_view(A, lda, B, ldb, out, M, N, K, a_mn=False, b_mn=False, bias=None, act=0, accumulate=False):
+    """GEMM on raw (possibly overlapping-row) operand views: A/B are any CUDA float tensors, lda/ldb explicit."""
+    _check(lib.w2l_gemm_tf32_view(_stream(), int(a_mn), int(b_mn), M, N, K, _ptr(A), lda, _ptr(B), ldb, _ptr(out), out.stride(0),
+                                  _ptr(bias), int(act), int(accumulate)))
     return out
 
 

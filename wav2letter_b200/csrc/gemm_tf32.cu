@@ -466,10 +466,10 @@ extern "C" int w2l_gemm_tf32(void* stream_, int a_mn_major, int b_mn_major, int 
   return w2l_gemm_tf32_ex(stream_, a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, bias, act, 0, nullptr, 0, 0, 1.f, 0.f, 0ull);
 }
 
-extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
-                                const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
-                                const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
-                                unsigned long long seed) {
+static int gemm_impl(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                     const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
+                     const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
+                     unsigned long long seed, bool allow_overlap) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: M, N, K must be positive");
   if (!A || !B || !C) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: null pointer");
@@ -480,8 +480,9 @@ extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, i
   if (dropout_p > 0.f && N % 4 != 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: dropout needs N % 4 == 0 (one Philox block per 4 columns)");
   if ((lda % 4) || (ldb % 4) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: operand rows must be 16-byte aligned (ld % 4 == 0)");
-  if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N)
+  if (ldc < N || (!allow_overlap && (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K))))
     return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: leading dimension smaller than the row length");
+  if (lda <= 0 || ldb <= 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: non-positive leading dimension");
   const int total_kb = (K + BK - 1) / BK;
   const bool plain = act == 0 && aux_mode == 0 && dropout_p == 0.f && bias == nullptr;
   int splits = 1;
@@ -504,4 +505,21 @@ extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, i
   if (!a_mn_major && b_mn_major) return launch<false, true>(stream, BN, ma, mb, p);
   if (a_mn_major && b_mn_major) return launch<true, true>(stream, BN, ma, mb, p);
   return launch<true, false>(stream, BN, ma, mb, p);
+}
+
+extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                                const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
+                                const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
+                                unsigned long long seed) {
+  return gemm_impl(stream_, a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, aux, ld_aux, aux_mode, aux_scale,
+                   dropout_p, seed, false);
+}
+
+// Same contraction with OVERLAPPING operand rows allowed (lda / ldb smaller than the row length): the TMA tensor map
+// takes any 16-byte-multiple row stride, so the im2col matrix of a time convolution over [T][Cin] activations —
+// row t = frames t .. t+kw-1, i.e. kw*Cin contiguous floats starting at frame t, row stride Cin — is a zero-copy view.
+extern "C" int w2l_gemm_tf32_view(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                                  const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate) {
+  return gemm_impl(stream_, a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, nullptr, 0, 0, 1.f, 0.f, 0ull,
+                   true);
 }

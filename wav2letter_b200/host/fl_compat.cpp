@@ -36,6 +36,9 @@ void check(int rc) {  // C ABI status -> the reference's exception style
 }
 
 void* currentStream() { return g_stream; }
+void copyRows(void* dst, size_t dstPitch, const void* src, size_t srcPitch, size_t width, size_t height) {
+  cudaCheck(cudaMemcpy2DAsync(dst, dstPitch, src, srcPitch, width, height, cudaMemcpyDeviceToDevice, g_stream), "copyRows");
+}
 void setCurrentStream(void* s) { g_stream = static_cast<cudaStream_t>(s); }
 void sync() { cudaCheck(cudaStreamSynchronize(g_stream), "af::sync"); }
 
@@ -374,6 +377,14 @@ Variable View::forward(const Variable& in) {
     check(w2l_transpose_input(currentStream(), (int)B, (int)F, (int)T, in.array().f32(), out.f32()));
     return Variable(out, in.isCalcGrad());
   }
+  // head of a conv_glu arch: `V -1 1 NFEAT 0` -> [T,1,F,B]: the features are CHANNELS (W = 1); same transposition
+  if (dims_[1] == 1 && dims_[0] == -1 && dims_[2] > 1 && in.dims(2) == 1 && in.dims(1) == dims_[2]) {
+    const long long T = in.dims(0), F = in.dims(1), B = in.dims(3);
+    if (F % 4) throw std::invalid_argument("View: the channel-major head needs a feature count that is a multiple of 4");
+    af::array out = af::array::empty(af::dim4(1, F, T, B));
+    check(w2l_transpose_input(currentStream(), (int)B, (int)F, (int)T, in.array().f32(), out.f32()));
+    return Variable(out, in.isCalcGrad());
+  }
   return in;  // [T,W,C,B] <-> [C*W,T,B] <-> [N,T,B] are the same memory in the internal layout
 }
 std::string View::prettyString() const { return "View (" + dims_.str() + ")"; }
@@ -403,8 +414,13 @@ std::string Conv2D::prettyString() const {
   return o.str();
 }
 Variable Conv2D::forwardMasked(const Variable& in, bool maskByConsumer) {
+  return forwardWith(in, params_[0], hasBias_ ? params_[1] : Variable(), maskByConsumer);
+}
+Variable Conv2D::forwardWith(const Variable& in, const Variable& weight, const Variable& biasVar, bool maskByConsumer) {
   requireInternal(in, "Conv2D");
   const int W = (int)in.dims(0), Cin = (int)in.dims(1), T = (int)in.dims(2), B = (int)in.dims(3);
+  // W = 1 (`V -1 1 NFEAT 0` archs: features are channels): the large-channel GEMM path
+  if (W == 1 && Cin == (nIn + 3) / 4 * 4) return forwardGemm(in, weight, biasVar);
   if (Cin != nIn) throw std::invalid_argument("Conv2D: input has " + std::to_string(Cin) + " channels, expected " + std::to_string(nIn));
   int pl, pr;
   if (explicitPad_) {
@@ -424,8 +440,8 @@ Variable Conv2D::forwardMasked(const Variable& in, bool maskByConsumer) {
   af::array ws = workspaceFor(g_conv_ws, wsb);
   const float dp = (train_ && dropP_ > 0) ? dropP_ : 0.f;
   const unsigned long long seed = nextSeed();
-  Variable wv = params_[0];
-  Variable bv = hasBias_ ? params_[1] : Variable();
+  Variable wv = weight;
+  Variable bv = hasBias_ ? biasVar : Variable();
   check(w2l_conv_time_fwd(currentStream(), B, T, Tout, W, nIn, nOut, kw, stride, pl, in.array().f32(), wv.array().f32(),
                           hasBias_ ? bv.array().f32() : nullptr, nullptr, y.f32(), relu_ ? 1 : 0, dp, seed, ws.ptr(), ws.bytes()));
   const bool relu = relu_;
@@ -464,6 +480,182 @@ Variable Conv2D::forwardMasked(const Variable& in, bool maskByConsumer) {
       if (acc.isEmpty()) ins[0].addGrad(Variable(dx, false), true);
     }
   });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large-channel time convolution (conv_glu archs): one tcgen05 GEMM per sample on a zero-copy im2col view.
+//   activations [B][T][Cp] (Cp = channels padded to a multiple of 4 with zero channels), stride 1
+//   fwd   y_b [Tout][Cout_p]   = Xp_b view [Tout][kw*Cp] (row stride Cp)  x  Warr [Cout_p][kw*Cp]^T + bias
+//   wgrad dWarr               += dY_b^T [Cout_p][Tout]  x  Xp_b view                      (accumulated over b)
+//   dgrad dXp_b [Tp][Cp]       = dYp_b view [Tp][kw*Cout_p] (dY with kw-1 zero frames either side)  x  Wflip^T
+// ------------------------------------------------------------------------------------------------
+namespace {
+void copyFrames(const af::array& src, long long srcFrames, long long srcOff, af::array& dst, long long dstFrames, long long dstOff,
+                long long frames, long long C, long long B) {
+  // per sample: `frames` frames of C floats from frame srcOff of src to frame dstOff of dst
+  w2l::copyRows(dst.f32() + dstOff * C, sizeof(float) * dstFrames * C, src.f32() + srcOff * C, sizeof(float) * srcFrames * C,
+                sizeof(float) * frames * C, (size_t)B);
+}
+}  // namespace
+Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const Variable& biasVar) {
+  if (stride != 1) throw std::invalid_argument("Conv2D: the large-channel path covers stride 1 only");
+  const int Cp = (int)in.dims(1), T = (int)in.dims(2), B = (int)in.dims(3);
+  int pl, pr;
+  if (explicitPad_) {
+    pl = padL_;
+    pr = padR_;
+  } else if (pad == (int)PaddingMode::SAME) {
+    pl = pr = kw / 2;  // flashlight derivePadding, stride 1: ceil((kw - 1) / 2) each side
+  } else {
+    pl = pr = pad;
+  }
+  const int Tp = T + pl + pr, Tout = Tp - kw + 1;
+  if (Tout <= 0) throw std::invalid_argument("Conv2D: input shorter than the kernel");
+  const bool glu = gluSplit_;
+  if (glu && (nOut % 2)) throw std::invalid_argument("Conv2D: a GLU needs an even channel count");
+  const int CoutP = glu ? 2 * ((nOut / 2 + 3) / 4 * 4) : (nOut + 3) / 4 * 4;
+  const int cin = nIn, cout = nOut, k = kw;
+  const bool hasBias = hasBias_, relu = relu_;
+  af::array fwdW = af::array::empty(af::dim4((long long)k * Cp, CoutP));
+  af::array flipW = af::array::empty(af::dim4((long long)k * CoutP, Cp));
+  af::array biasP = af::array::empty(af::dim4(CoutP));
+  check(w2l_conv1d_arrange(currentStream(), cin, cout, k, Cp, CoutP, glu ? 1 : 0, weight.array().f32(),
+                           hasBias ? biasVar.array().f32() : nullptr, fwdW.f32(), flipW.f32(), biasP.f32()));
+  af::array xp = in.array();
+  if (pl || pr) {
+    xp = af::array::zeros(af::dim4(1, Cp, Tp, B));
+    copyFrames(in.array(), T, 0, xp, Tp, pl, T, Cp, B);
+  }
+  af::array y = af::array::empty(af::dim4(1, CoutP, Tout, B));
+  for (int b = 0; b < B; ++b)
+    check(w2l_gemm_tf32_view(currentStream(), 0, 0, Tout, CoutP, k * Cp, xp.f32() + (size_t)b * Tp * Cp, Cp, fwdW.f32(), k * Cp,
+                             y.f32() + (size_t)b * Tout * CoutP, CoutP, biasP.f32(), relu ? 1 : 0, 0));
+  std::vector<Variable> inputs{in, weight};
+  if (hasBias) inputs.push_back(biasVar);
+  return Variable(y, inputs, [=](std::vector<Variable>& ins, const Variable& gout) {
+    af::array dy = gout.array();
+    if (relu) {
+      af::array m = af::array::empty(y.dims());
+      check(w2l_mask_mul(currentStream(), y.elements(), dy.f32(), y.f32(), 1, 1.0f, m.f32()));
+      dy = m;
+    }
+    if (ins[1].isCalcGrad()) {
+      af::array dWarr = af::array::zeros(af::dim4((long long)k * Cp, CoutP));
+      for (int b = 0; b < B; ++b)
+        check(w2l_gemm_tf32_view(currentStream(), 1, 1, CoutP, k * Cp, Tout, dy.f32() + (size_t)b * Tout * CoutP, CoutP,
+                                 xp.f32() + (size_t)b * Tp * Cp, Cp, dWarr.f32(), k * Cp, nullptr, 0, 1));
+      af::array dw = ins[1].gradStorage();
+      if (dw.isEmpty()) dw = af::array::zeros(ins[1].dims());
+      af::array db;
+      if (hasBias) {
+        db = ins[2].gradStorage();
+        if (db.isEmpty()) db = af::array::zeros(ins[2].dims());
+      }
+      check(w2l_conv1d_unarrange_grad(currentStream(), cin, cout, k, Cp, CoutP, glu ? 1 : 0, dWarr.f32(), dw.f32(), (long long)B * Tout,
+                                      dy.f32(), hasBias ? db.f32() : nullptr));
+      ins[1].addGrad(Variable(dw, false));
+      if (hasBias) ins[2].addGrad(Variable(db, false));
+    }
+    if (ins[0].isCalcGrad()) {
+      const int Td = Tout + 2 * (k - 1);
+      af::array dyp = af::array::zeros(af::dim4(1, CoutP, Td, B));
+      copyFrames(dy, Tout, 0, dyp, Td, k - 1, Tout, CoutP, B);
+      af::array dxp = af::array::empty(af::dim4(1, Cp, Tp, B));
+      for (int b = 0; b < B; ++b)
+        check(w2l_gemm_tf32_view(currentStream(), 0, 0, Tp, Cp, k * CoutP, dyp.f32() + (size_t)b * Td * CoutP, CoutP, flipW.f32(), k * CoutP,
+                                 dxp.f32() + (size_t)b * Tp * Cp, Cp, nullptr, 0, 0));
+      af::array dx = dxp;
+      if (pl || pr) {
+        dx = af::array::empty(af::dim4(1, Cp, T, B));
+        copyFrames(dxp, Tp, pl, dx, T, 0, T, Cp, B);
+      }
+      ins[0].addGrad(Variable(dx, false), true);
+    }
+  });
+}
+
+// ================================================================================================
+// GatedLinearUnit / WeightNorm (conv_glu archs)
+// ================================================================================================
+std::string GatedLinearUnit::prettyString() const {
+  return "GatedLinearUnit (" + std::to_string(dim_) + ")" + (dropP_ > 0 ? " +Dropout" : "");
+}
+Variable GatedLinearUnit::forward(const Variable& in) {
+  requireInternal(in, "GatedLinearUnit");
+  // the channel axis is the fastest-varying non-unit axis of the internal layout: [1, C, T, B] after a conv, [C, T, B] after Linear
+  const bool lead = in.dims(0) > 1;
+  const long long C = lead ? in.dims(0) : in.dims(1);
+  if (C % 2) throw std::invalid_argument("GatedLinearUnit: odd channel count " + std::to_string(C));
+  const long long rows = in.elements() / C, H = C / 2;
+  af::dim4 od = in.dims();
+  od[lead ? 0 : 1] = H;
+  af::array y = af::array::empty(od);
+  const float dp = (train_ && dropP_ > 0) ? dropP_ : 0.f;
+  const unsigned long long seed = nextSeed();
+  check(w2l_glu_fwd(currentStream(), rows, (int)H, in.array().f32(), y.f32(), dp, seed));
+  return Variable(y, {in}, [=](std::vector<Variable>& ins, const Variable& g) {
+    af::array dx = af::array::empty(ins[0].dims());
+    check(w2l_glu_bwd(currentStream(), rows, (int)H, ins[0].array().f32(), g.array().f32(), dx.f32(), dp, seed));
+    ins[0].addGrad(Variable(dx, false), true);
+  });
+}
+
+WeightNorm::WeightNorm(std::shared_ptr<Module> module, int dim) : module_(std::move(module)), dim_(dim) {
+  Variable v, b;
+  bool hasBias = false;
+  if (auto conv = std::dynamic_pointer_cast<Conv2D>(module_)) {
+    if (dim != 3) throw std::invalid_argument("WeightNorm: a Conv2D is normalised along dim 3 (output channels)");
+    rows_ = conv->nOut;
+    len_ = conv->nIn * conv->kw;
+    hasBias = conv->hasBias();
+  } else if (auto lin = std::dynamic_pointer_cast<Linear>(module_)) {
+    if (dim != 0) throw std::invalid_argument("WeightNorm: a Linear is normalised along dim 0 (output units)");
+    rows_ = lin->nOut;
+    len_ = lin->nIn;
+    hasBias = lin->hasBias();
+  } else {
+    throw std::invalid_argument("WeightNorm: only Conv2D and Linear are covered");
+  }
+  v = module_->param(0);
+  // g starts at ||v|| so that the wrapped layer's function is unchanged at initialisation (flashlight's WeightNorm)
+  af::array g = af::array::empty(af::dim4(rows_));
+  af::array tmpw = af::array::empty(v.dims()), ones = af::array::empty(af::dim4(rows_));
+  ones.fill(1.0f);
+  check(w2l_weightnorm_fwd(currentStream(), rows_, len_, v.array().f32(), ones.f32(), tmpw.f32(), g.f32()));  // g := 1/||v||
+  std::vector<float> h = g.host<float>();
+  for (auto& x : h) x = 1.0f / x;
+  g = af::array::fromHost(h.data(), af::dim4(rows_));
+  params_.push_back(v);
+  params_.push_back(Variable(g, true));
+  if (hasBias) params_.push_back(module_->param(1));
+}
+void WeightNorm::train() {
+  train_ = true;
+  module_->train();
+}
+void WeightNorm::eval() {
+  train_ = false;
+  module_->eval();
+}
+std::string WeightNorm::prettyString() const { return "WeightNorm (" + std::to_string(dim_) + ") of " + module_->prettyString(); }
+Variable WeightNorm::forward(const Variable& in) {
+  Variable v = params_[0], g = params_[1];
+  Variable b = params_.size() > 2 ? params_[2] : Variable();
+  af::array w = af::array::empty(v.dims());
+  af::array inv = af::array::empty(af::dim4(rows_));
+  const int rows = rows_, len = len_;
+  check(w2l_weightnorm_fwd(currentStream(), rows, len, v.array().f32(), g.array().f32(), w.f32(), inv.f32()));
+  Variable wv(w, {v, g}, [=](std::vector<Variable>& ins, const Variable& gw) {
+    af::array dv = ins[0].gradStorage(), dg = ins[1].gradStorage();
+    if (dv.isEmpty()) dv = af::array::zeros(ins[0].dims());
+    if (dg.isEmpty()) dg = af::array::zeros(ins[1].dims());
+    check(w2l_weightnorm_bwd(currentStream(), rows, len, ins[0].array().f32(), ins[1].array().f32(), inv.f32(), gw.array().f32(), dv.f32(),
+                             dg.f32()));
+    ins[0].addGrad(Variable(dv, false));
+    ins[1].addGrad(Variable(dg, false));
+  });
+  if (auto conv = std::dynamic_pointer_cast<Conv2D>(module_)) return conv->forwardWith(in, wv, b, false);
+  return std::static_pointer_cast<Linear>(module_)->forwardWith(in, wv, b);
 }
 
 // ================================================================================================
@@ -564,8 +756,9 @@ Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int br
 // ================================================================================================
 Linear::Linear(int nIn_, int nOut_, bool bias) : nIn(nIn_), nOut(nOut_), hasBias_(bias) {
   if (nIn <= 0 || nOut <= 0) throw std::invalid_argument("Linear: non-positive size");
-  if (nIn % 4 || nOut % 4)
-    throw std::invalid_argument("Linear: in/out sizes must be multiples of 4 (16-byte rows for the TMA loads)");
+  // the input rows are TMA operands (16-byte row stride); an output size that is not a multiple of 4 (e.g. ~30 letter
+  // classes) is handled in backward by a zero-padded copy of the incoming gradient
+  if (nIn % 4) throw std::invalid_argument("Linear: the input size must be a multiple of 4 (16-byte rows for the TMA loads)");
   const double bound = std::sqrt(1.0 / (double)nIn);
   // memory [nOut][nIn] (nIn fastest) == column-major dims [nIn, nOut]: the K-major B operand of the forward
   // GEMM.  Upstream stores the transpose ([out, in] column-major); INTEGRATION.md lists the conversion.
@@ -577,6 +770,10 @@ std::string Linear::prettyString() const {
 }
 Variable Linear::forward(const Variable& in) { return forwardFused(in, false, 0.f); }
 Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool maskByConsumer, int inMaskMode, float inMaskScale) {
+  return forwardWith(in, params_[0], hasBias_ ? params_[1] : Variable(), relu, dropP, maskByConsumer, inMaskMode, inMaskScale);
+}
+Variable Linear::forwardWith(const Variable& in, const Variable& weight, const Variable& bias, bool relu, float dropP, bool maskByConsumer,
+                             int inMaskMode, float inMaskScale) {
   requireInternal(in, "Linear");
   long long T, B;
   if (in.dims(0) == nIn) {  // flattened [K, T, B]
@@ -590,8 +787,8 @@ Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool m
   }
   const int M = (int)(T * B);
   af::array y = af::array::empty(af::dim4(nOut, T, B));
-  Variable wv = params_[0];
-  Variable bv = hasBias_ ? params_[1] : Variable();
+  Variable wv = weight;
+  Variable bv = hasBias_ ? bias : Variable();
   const float dp = (train_ && dropP > 0) ? dropP : 0.f;
   // NOTE: the weight is stored [nOut][nIn] row-major (K-major B operand)
   check(w2l_gemm_tf32_ex(currentStream(), 0, 0, M, nOut, nIn, in.array().f32(), nIn, wv.array().f32(), nIn, y.f32(), nOut,
@@ -607,24 +804,31 @@ Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool m
       check(w2l_mask_mul(currentStream(), y.elements(), dy.f32(), y.f32(), relu ? 1 : 2, dp > 0.f ? 1.0f / (1.0f - dp) : 1.0f, m.f32()));
       dy = m;
     }
+    int ldy = nout;  // row stride of dy as a TMA operand
+    if (nout % 4) {  // pad the rows to a multiple of 4 floats (zero columns)
+      ldy = (nout + 3) / 4 * 4;
+      af::array dyp = af::array::zeros(af::dim4(ldy, M));
+      w2l::copyRows(dyp.f32(), sizeof(float) * ldy, dy.f32(), sizeof(float) * nout, sizeof(float) * nout, (size_t)M);
+      dy = dyp;
+    }
     if (ins[1].isCalcGrad()) {  // dW[nout][nin] = dy^T x  (both operands MN-major, no transposition pass)
       af::array dw = ins[1].gradStorage();
       const int accumulate = dw.isEmpty() ? 0 : 1;  // arena slot (zeroed by zeroGrad): C += in the GEMM epilogue
       if (!accumulate) dw = af::array::empty(ins[1].dims());
-      check(w2l_gemm_tf32_ex(currentStream(), 1, 1, nout, nin, M, dy.f32(), nout, ins[0].array().f32(), nin, dw.f32(), nin, nullptr, 0,
+      check(w2l_gemm_tf32_ex(currentStream(), 1, 1, nout, nin, M, dy.f32(), ldy, ins[0].array().f32(), nin, dw.f32(), nin, nullptr, 0,
                              accumulate, nullptr, 0, 0, 1.f, 0.f, 0ull));
       ins[1].addGrad(Variable(dw, false));
       if (hasBias) {
         af::array db = ins[2].gradStorage();
         if (db.isEmpty()) db = af::array::zeros(ins[2].dims());
-        check(w2l_colsum_accumulate(currentStream(), M, nout, dy.f32(), nout, db.f32()));
+        check(w2l_colsum_accumulate(currentStream(), M, nout, dy.f32(), ldy, db.f32()));
         ins[2].addGrad(Variable(db, false));
       }
     }
     if (ins[0].isCalcGrad()) {  // dx[M][nin] = dy W  (B = W MN-major)
       af::array acc = ins[0].accumulableGrad();  // e.g. LN2's residual gradient: C += in the GEMM epilogue
       af::array dx = acc.isEmpty() ? af::array::empty(ins[0].dims()) : acc;
-      check(w2l_gemm_tf32_ex(currentStream(), 0, 1, M, nin, nout, dy.f32(), nout, ins[1].array().f32(), nin, dx.f32(), nin, nullptr, 0,
+      check(w2l_gemm_tf32_ex(currentStream(), 0, 1, M, nin, nout, dy.f32(), ldy, ins[1].array().f32(), nin, dx.f32(), nin, nullptr, 0,
                              acc.isEmpty() ? 0 : 1, inMaskMode ? ins[0].array().f32() : nullptr, nin, inMaskMode, inMaskScale, 0.f, 0ull));
       if (acc.isEmpty()) ins[0].addGrad(Variable(dx, false), true);
     }
@@ -868,6 +1072,8 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
   std::istringstream in(archText);
   std::string line;
   std::shared_ptr<Conv2D> lastConv;  // candidate for ReLU / Dropout fusion
+  std::shared_ptr<Conv2D> lastBigConv;        // `C` conv that a following GLU splits
+  std::shared_ptr<GatedLinearUnit> lastGlu;   // candidate for Dropout fusion
   int pendingPadL = -1, pendingPadR = -1;
   int lineNo = 0;
   while (std::getline(in, line)) {
@@ -911,6 +1117,48 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
       }
       net->add(conv);
       lastConv = conv;
+    } else if (op == "C" || op == "C1" || op == "WN") {
+      // `C cin cout kw stride [pad dil bias groups]` (cpc/SequentialBuilder.cpp:203-251) — 1-D convolution over time;
+      // `WN dim <C ...|L ...>` wraps the layer in WeightNorm (:379-386)
+      size_t o = 0;
+      int wnDim = -1;
+      if (op == "WN") {
+        if (p.size() < 4) throw bad("WN expects dim and a layer");
+        wnDim = num(1);
+        o = 2;
+      }
+      std::shared_ptr<Module> layer;
+      std::shared_ptr<Conv2D> conv;
+      if (p[o] == "C" || p[o] == "C1") {
+        if (p.size() < o + 5) throw bad("C expects cin cout kw stride [pad dil bias groups]");
+        const int px = p.size() > o + 5 ? num(o + 5) : 0, dil = p.size() > o + 6 ? num(o + 6) : 1;
+        const bool cb = p.size() > o + 7 ? num(o + 7) != 0 : true;
+        const int groups = p.size() > o + 8 ? num(o + 8) : 1;
+        conv = std::make_shared<Conv2D>(num(o + 1), num(o + 2), num(o + 3), 1, num(o + 4), 1, px, 0, dil, 1, cb, groups);
+        layer = conv;
+      } else if (p[o] == "L") {
+        if (p.size() < o + 3) throw bad("L expects in out [bias]");
+        layer = std::make_shared<Linear>(num(o + 1), num(o + 2), p.size() > o + 3 ? num(o + 3) != 0 : true);
+      } else {
+        throw bad("WN wraps C or L only");
+      }
+      if (wnDim >= 0) layer = std::make_shared<WeightNorm>(layer, wnDim);
+      net->add(layer);
+      lastConv.reset();
+      lastBigConv = conv;
+      lastGlu.reset();
+    } else if (op == "GLU") {
+      if (p.size() != 2) throw bad("GLU expects the axis");
+      auto glu = std::make_shared<GatedLinearUnit>(num(1));
+      if (lastBigConv) lastBigConv->setGluSplit(true);  // the conv pads its two channel halves separately
+      net->add(glu);
+      lastConv.reset();
+      lastBigConv.reset();
+      lastGlu = glu;
+    } else if (op == "DO" && lastGlu) {
+      if (p.size() != 2) throw bad("DO expects the probability");
+      lastGlu->fuseDropout((float)std::stod(p[1]));
+      lastGlu.reset();
     } else if (op == "R") {
       if (lastConv)
         lastConv->fuseRelu();  // fused into the convolution's epilogue
@@ -942,7 +1190,7 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
       // SpecAugment is data augmentation ahead of the hot path: identity here
       lastConv.reset();
     } else {
-      throw bad("opcode '" + op + "' is outside the hot-path subset (V RO PD C2 R DO LN TDS L SAUG)");
+      throw bad("opcode '" + op + "' is outside the hot-path subset (V RO PD C C2 WN GLU R DO LN TDS L SAUG)");
     }
   }
   return net;
