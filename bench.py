@@ -356,6 +356,70 @@ def run_asg(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def conv_glu_flops(arch_text, B, T, n_feat, n_label):
+    """2*M*N*K over every convolution / Linear of a conv_glu arch, x3 (forward, data gradient, weight gradient)."""
+    total, t = 0, T
+    for line in arch_text.splitlines():
+        p = line.replace("NFEAT", str(n_feat)).replace("NLABEL", str(n_label)).split()
+        if p and p[0] == "WN" and p[2] == "C":
+            cin, cout, kw, pad = int(p[3]), int(p[4]), int(p[5]), int(p[7])
+            t = t + 2 * pad - kw + 1
+            total += 2 * B * t * cout * cin * kw
+        elif p and p[0] == "WN" and p[2] == "L":
+            total += 2 * B * t * int(p[3]) * int(p[4])
+    return 3 * total, t
+
+
+def run_conv_glu(args, rank, world, local_rank):
+    """conv_glu LibriSpeech 17-layer GLU model + ASG, full train step (BASELINE.json configs[2] shape, TF32 math, 1 GPU per
+    rank; not the default workload).  GEMM time is measured with an event pair around every GEMM launch."""
+    import torch
+
+    from wav2letter_b200 import capi
+    from wav2letter_b200.trainer import Trainer, conv_glu_librispeech_arch
+
+    tm = Timed(world, local_rank)
+    B, T, F, N, L = 8, 1000, 40, 30, 160
+    arch = conv_glu_librispeech_arch()
+    trainer = Trainer(arch, F, N, "asg", "target_sz_sqrt", transdiag=4.0, lr=0.1, lrcrit=0.001, maxgradnorm=0.2)
+    rng = np.random.default_rng(1234 + rank)
+    sets = []
+    for _ in range(4):
+        f = rng.standard_normal((B, 1, F, T), dtype=np.float32)
+        y = rng.integers(0, N, (B, L)).astype(np.int32)
+        sets.append((torch.from_numpy(f).to(tm.dev), torch.from_numpy(y).to(tm.dev)))
+    loss = torch.empty(B, dtype=torch.float32, device=tm.dev)
+
+    def step(i):
+        trainer.step(sets[i % 4][0], sets[i % 4][1], True, float(B * world), loss)
+
+    prof_steps = min(args.steps, 2)
+    prof = capi.ProfileList(1, 1200 * prof_steps)
+    ms, kern, launches, clocks = tm.run(step, args.steps, args.warmup, sample_clocks=True, profile=prof, profile_steps=prof_steps)
+    if rank != 0:
+        return
+    flops, t_out = conv_glu_flops(arch, B, T, F, N)
+    peaks, src = measured_peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    gemm_ms = sum(kern) / prof_steps
+    line = {
+        "metric": "frames_per_sec", "value": B * T * world * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 storage, tf32 tensor-core math with f32 accumulation", "data": "synthetic",
+        "config": {"workload": "conv_glu LibriSpeech 17-layer Conv1D+GLU acoustic model (WeightNorm) + ASG, full train step, "
+                               f"B={B} x T={T} frames x {F} filterbanks per GPU, {N} letter classes "
+                               "(BASELINE.json configs[2] shape; recipes/conv_glu/librispeech/network.arch)",
+                   "global_batch": B * world, "output_frames": t_out, "parallelism": f"dp{world}", "params": trainer.num_params(0)},
+        "final_loss_sum": float(loss.sum().item()), "clocks": clocks, "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (time convolutions as im2col-view GEMMs)",
+                     "achieved": flops / (gemm_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": flops / (gemm_ms * 1e-3) / 1e12 / peak, "traffic": None, "peak_source": src,
+                     "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": len(kern) / prof_steps,
+                     "algorithmic_flops_per_step": flops, "gemm_share_of_step": gemm_ms / (ms / args.steps)},
+    }
+    print(json.dumps(line))
+
+
 def run_tds(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -468,7 +532,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="tds_ctc", choices=["tds_ctc", "asg"])
+    ap.add_argument("--workload", default="tds_ctc", choices=["tds_ctc", "asg", "conv_glu_asg"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -486,7 +550,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        (run_tds if args.workload == "tds_ctc" else run_asg)(args, rank, world, local_rank)
+        {"tds_ctc": run_tds, "asg": run_asg, "conv_glu_asg": run_conv_glu}[args.workload](args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -133,6 +133,10 @@ class Variable {
   // fresh = g's buffer is aliased by nothing else: later contributions may be accumulated into it in place
   void addGrad(const Variable& g, bool fresh = false);
   af::array accumulableGrad() const;  // the gradient buffer a producer may add into (empty when there is none)
+  // Frames of each sample that hold data (<= dims(2)); the rest of the sample's frame slots are slack that the
+  // batched large-channel convolutions leave behind (-1: all).  Producers that understand it propagate it.
+  long long validFrames() const;
+  void setValidFrames(long long n);
   void setGradStorage(const af::array& buf);  // pre-bound accumulation buffer (flat gradient arena)
   af::array gradStorage() const;              // that buffer (empty if none): kernels accumulate into it directly
   void zeroGrad(bool zeroStorage = true);  // zeroStorage = false: the caller cleared the gradient arena itself
@@ -330,7 +334,8 @@ class View : public UnaryModule {
 class Reorder : public UnaryModule {
  public:
   Reorder(int d0, int d1, int d2, int d3) : perm_{d0, d1, d2, d3} {}
-  Variable forward(const Variable& in) override { return in; }
+  // a relabelling in the internal layout; if the input carries slack frames (validFrames) they are dropped here
+  Variable forward(const Variable& in) override;
   std::string prettyString() const override;
 
  private:

@@ -112,3 +112,24 @@ def test_gemm_overlapping_rows_is_a_time_convolution(T, Cin, Cout, kw):
     cols = torch.stack([x[dk:dk + Tout] for dk in range(kw)], 1).reshape(Tout, kw * Cin).double()
     refw = dy.double().t() @ cols
     assert float((dw.double() - refw).abs().max()) < 3e-3 * float(refw.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("T,Cin,Cout,kw", [(52, 16, 40, 4), (300, 44, 200, 13)])
+def test_gemm_view_data_gradient(T, Cin, Cout, kw):
+    """data gradient of a stride-1 valid convolution: the view of dY padded with kw-1 zero rows in front (row t = frames
+    t-(kw-1) .. t) times the flipped weights"""
+    import wav2letter_b200 as w
+
+    g = torch.Generator(device="cuda").manual_seed(T + kw)
+    Tout = T - kw + 1
+    dyp = torch.zeros(T + kw - 1, Cout, device="cuda")
+    dyp[kw - 1:kw - 1 + Tout] = torch.randn(Tout, Cout, device="cuda", generator=g)
+    wt = torch.randn(Cout, Cin, kw, device="cuda", generator=g) * 0.1   # [co][ci][dk]
+    flip = wt.flip(2).permute(1, 2, 0).contiguous()                      # [ci][j][co], j = kw-1-dk
+    dx = torch.empty(T, Cin, device="cuda")
+    w.capi.gemm_tf32_view(dyp, Cout, flip.view(Cin, kw * Cout), kw * Cout, dx, T, Cin, kw * Cout)
+    x64 = torch.zeros(1, Cin, T, dtype=torch.float64, device="cuda", requires_grad=True)
+    y = torch.nn.functional.conv1d(x64, wt.double())
+    y.backward(dyp[kw - 1:kw - 1 + Tout].double().t().unsqueeze(0))
+    ref = x64.grad[0].t()
+    assert float((dx.double() - ref).abs().max()) < 3e-3 * float(ref.abs().max()) + 1e-3

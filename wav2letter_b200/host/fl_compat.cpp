@@ -170,6 +170,7 @@ struct Variable::Impl {
   bool gradLive = false;  // boundGrad holds a valid (accumulated) gradient
   bool onesSeed = false;
   bool gradOwned = false;  // grad is a buffer no other variable aliases: later contributions may be added in place
+  long long validFrames = -1;
 };
 
 Variable::Variable(const af::array& data, bool calcGrad) : impl_(std::make_shared<Impl>()) {
@@ -204,6 +205,10 @@ void Variable::setGradStorage(const af::array& buf) {
   impl_->grad.reset();
 }
 af::array Variable::gradStorage() const { return impl_ ? impl_->boundGrad : af::array(); }
+long long Variable::validFrames() const { return impl_ ? impl_->validFrames : -1; }
+void Variable::setValidFrames(long long n) {
+  if (impl_) impl_->validFrames = n;
+}
 af::array Variable::accumulableGrad() const {
   if (impl_ && impl_->calcGrad && impl_->boundGrad.isEmpty() && impl_->grad && impl_->gradOwned) return impl_->grad->array();
   return af::array();
@@ -498,8 +503,12 @@ void copyFrames(const af::array& src, long long srcFrames, long long srcOff, af:
 }
 }  // namespace
 Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const Variable& biasVar) {
+  // The whole batch is ONE GEMM per direction: the samples keep a constant frame stride Ts, and output rows whose
+  // window straddles two samples are slack (computed, finite, never read as data): each sample's valid frame count
+  // shrinks by kw-1 per layer and travels with the variable (validFrames); fl::Reorder drops the slack at the end.
   if (stride != 1) throw std::invalid_argument("Conv2D: the large-channel path covers stride 1 only");
-  const int Cp = (int)in.dims(1), T = (int)in.dims(2), B = (int)in.dims(3);
+  const int Cp = (int)in.dims(1), TsIn = (int)in.dims(2), B = (int)in.dims(3);
+  const int TvIn = in.validFrames() >= 0 ? (int)in.validFrames() : TsIn;
   int pl, pr;
   if (explicitPad_) {
     pl = padL_;
@@ -509,7 +518,10 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
   } else {
     pl = pr = pad;
   }
-  const int Tp = T + pl + pr, Tout = Tp - kw + 1;
+  const bool padded = pl || pr;
+  const int Ts = padded ? TvIn + pl + pr : TsIn;  // frame stride of this layer's operands
+  const int Tv = padded ? Ts : TvIn;              // frames of each sample that are real input (incl. the zero padding)
+  const int Tout = Tv - kw + 1;
   if (Tout <= 0) throw std::invalid_argument("Conv2D: input shorter than the kernel");
   const bool glu = gluSplit_;
   if (glu && (nOut % 2)) throw std::invalid_argument("Conv2D: a GLU needs an even channel count");
@@ -522,17 +534,20 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
   check(w2l_conv1d_arrange(currentStream(), cin, cout, k, Cp, CoutP, glu ? 1 : 0, weight.array().f32(),
                            hasBias ? biasVar.array().f32() : nullptr, fwdW.f32(), flipW.f32(), biasP.f32()));
   af::array xp = in.array();
-  if (pl || pr) {
-    xp = af::array::zeros(af::dim4(1, Cp, Tp, B));
-    copyFrames(in.array(), T, 0, xp, Tp, pl, T, Cp, B);
+  if (padded) {
+    xp = af::array::zeros(af::dim4(1, Cp, Ts, B));
+    copyFrames(in.array(), TsIn, 0, xp, Ts, pl, TvIn, Cp, B);
   }
-  af::array y = af::array::empty(af::dim4(1, CoutP, Tout, B));
-  for (int b = 0; b < B; ++b)
-    check(w2l_gemm_tf32_view(currentStream(), 0, 0, Tout, CoutP, k * Cp, xp.f32() + (size_t)b * Tp * Cp, Cp, fwdW.f32(), k * Cp,
-                             y.f32() + (size_t)b * Tout * CoutP, CoutP, biasP.f32(), relu ? 1 : 0, 0));
+  const long long rowsAll = (long long)B * Ts, M = rowsAll - k + 1;  // output rows that have a full window in the buffer
+  if (rowsAll > 0x7fffffffLL / 2) throw std::invalid_argument("Conv2D: batch too long for one GEMM");
+  af::array y = af::array::empty(af::dim4(1, CoutP, Ts, B));
+  cudaMemsetAsync(y.f32() + (size_t)M * CoutP, 0, sizeof(float) * (size_t)(k - 1) * CoutP, static_cast<cudaStream_t>(currentStream()));
+  check(w2l_gemm_tf32_view(currentStream(), 0, 0, (int)M, CoutP, k * Cp, xp.f32(), Cp, fwdW.f32(), k * Cp, y.f32(), CoutP, biasP.f32(),
+                           relu ? 1 : 0, 0));
   std::vector<Variable> inputs{in, weight};
   if (hasBias) inputs.push_back(biasVar);
-  return Variable(y, inputs, [=](std::vector<Variable>& ins, const Variable& gout) {
+  Variable out(y, inputs, [=](std::vector<Variable>& ins, const Variable& gout) {
+    // gout's slack rows (frames >= Tout of every sample) are zero: every producer of this gradient keeps them so
     af::array dy = gout.array();
     if (relu) {
       af::array m = af::array::empty(y.dims());
@@ -540,10 +555,8 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
       dy = m;
     }
     if (ins[1].isCalcGrad()) {
-      af::array dWarr = af::array::zeros(af::dim4((long long)k * Cp, CoutP));
-      for (int b = 0; b < B; ++b)
-        check(w2l_gemm_tf32_view(currentStream(), 1, 1, CoutP, k * Cp, Tout, dy.f32() + (size_t)b * Tout * CoutP, CoutP,
-                                 xp.f32() + (size_t)b * Tp * Cp, Cp, dWarr.f32(), k * Cp, nullptr, 0, 1));
+      af::array dWarr = af::array::empty(af::dim4((long long)k * Cp, CoutP));
+      check(w2l_gemm_tf32_view(currentStream(), 1, 1, CoutP, k * Cp, (int)M, dy.f32(), CoutP, xp.f32(), Cp, dWarr.f32(), k * Cp, nullptr, 0, 0));
       af::array dw = ins[1].gradStorage();
       if (dw.isEmpty()) dw = af::array::zeros(ins[1].dims());
       af::array db;
@@ -551,26 +564,47 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
         db = ins[2].gradStorage();
         if (db.isEmpty()) db = af::array::zeros(ins[2].dims());
       }
-      check(w2l_conv1d_unarrange_grad(currentStream(), cin, cout, k, Cp, CoutP, glu ? 1 : 0, dWarr.f32(), dw.f32(), (long long)B * Tout,
-                                      dy.f32(), hasBias ? db.f32() : nullptr));
+      check(w2l_conv1d_unarrange_grad(currentStream(), cin, cout, k, Cp, CoutP, glu ? 1 : 0, dWarr.f32(), dw.f32(), rowsAll, dy.f32(),
+                                      hasBias ? db.f32() : nullptr));
       ins[1].addGrad(Variable(dw, false));
       if (hasBias) ins[2].addGrad(Variable(db, false));
     }
     if (ins[0].isCalcGrad()) {
-      const int Td = Tout + 2 * (k - 1);
-      af::array dyp = af::array::zeros(af::dim4(1, CoutP, Td, B));
-      copyFrames(dy, Tout, 0, dyp, Td, k - 1, Tout, CoutP, B);
-      af::array dxp = af::array::empty(af::dim4(1, Cp, Tp, B));
-      for (int b = 0; b < B; ++b)
-        check(w2l_gemm_tf32_view(currentStream(), 0, 0, Tp, Cp, k * CoutP, dyp.f32() + (size_t)b * Td * CoutP, CoutP, flipW.f32(), k * CoutP,
-                                 dxp.f32() + (size_t)b * Tp * Cp, Cp, nullptr, 0, 0));
+      // dXp[m][ci] = sum_j dY[m - (kw-1) + j][..] Wflip: a copy of dY with kw-1 zero rows in front gives the view its
+      // left context; a sample's first frames see the previous sample's slack rows, which are zero
+      af::array dyp = af::array::empty(af::dim4(CoutP, rowsAll + k - 1));
+      cudaMemsetAsync(dyp.f32(), 0, sizeof(float) * (size_t)(k - 1) * CoutP, static_cast<cudaStream_t>(currentStream()));
+      w2l::copyRows(dyp.f32() + (size_t)(k - 1) * CoutP, sizeof(float) * (size_t)rowsAll * CoutP, dy.f32(), sizeof(float) * (size_t)rowsAll * CoutP,
+                    sizeof(float) * (size_t)rowsAll * CoutP, 1);
+      af::array dxp = af::array::empty(af::dim4(1, Cp, Ts, B));
+      check(w2l_gemm_tf32_view(currentStream(), 0, 0, (int)rowsAll, Cp, k * CoutP, dyp.f32(), CoutP, flipW.f32(), k * CoutP, dxp.f32(), Cp,
+                               nullptr, 0, 0));
+      if (Tv < Ts)  // gradients of slack input frames must not reach the previous layer
+        cudaMemset2DAsync(dxp.f32() + (size_t)Tv * Cp, sizeof(float) * (size_t)Ts * Cp, 0, sizeof(float) * (size_t)(Ts - Tv) * Cp, (size_t)B,
+                          static_cast<cudaStream_t>(currentStream()));
       af::array dx = dxp;
-      if (pl || pr) {
-        dx = af::array::empty(af::dim4(1, Cp, T, B));
-        copyFrames(dxp, Tp, pl, dx, T, 0, T, Cp, B);
+      if (padded) {
+        dx = af::array::zeros(af::dim4(1, Cp, TsIn, B));
+        copyFrames(dxp, Ts, pl, dx, TsIn, 0, TvIn, Cp, B);
       }
       ins[0].addGrad(Variable(dx, false), true);
     }
+  });
+  out.setValidFrames(Tout);
+  return out;
+}
+
+// fl::Reorder: a relabelling — except that slack frames left by the batched convolutions are dropped here
+Variable Reorder::forward(const Variable& in) {
+  const long long Tv = in.validFrames(), Ts = in.dims(2);
+  if (Tv < 0 || Tv == Ts) return in;
+  const long long C = in.dims(0) * in.dims(1), B = in.dims(3);
+  af::array y = af::array::empty(af::dim4(in.dims(0), in.dims(1), Tv, B));
+  w2l::copyRows(y.f32(), sizeof(float) * Tv * C, in.array().f32(), sizeof(float) * Ts * C, sizeof(float) * Tv * C, (size_t)B);
+  return Variable(y, {in}, [=](std::vector<Variable>& ins, const Variable& g) {
+    af::array dx = af::array::zeros(ins[0].dims());  // slack rows of the gradient are zero by construction
+    w2l::copyRows(dx.f32(), sizeof(float) * Ts * C, g.array().f32(), sizeof(float) * Tv * C, sizeof(float) * Tv * C, (size_t)B);
+    ins[0].addGrad(Variable(dx, false), true);
   });
 }
 
@@ -593,11 +627,13 @@ Variable GatedLinearUnit::forward(const Variable& in) {
   const float dp = (train_ && dropP_ > 0) ? dropP_ : 0.f;
   const unsigned long long seed = nextSeed();
   check(w2l_glu_fwd(currentStream(), rows, (int)H, in.array().f32(), y.f32(), dp, seed));
-  return Variable(y, {in}, [=](std::vector<Variable>& ins, const Variable& g) {
+  Variable out(y, {in}, [=](std::vector<Variable>& ins, const Variable& g) {
     af::array dx = af::array::empty(ins[0].dims());
     check(w2l_glu_bwd(currentStream(), rows, (int)H, ins[0].array().f32(), g.array().f32(), dx.f32(), dp, seed));
     ins[0].addGrad(Variable(dx, false), true);
   });
+  out.setValidFrames(in.validFrames());  // row-wise: slack rows stay slack (and zero gradients stay zero)
+  return out;
 }
 
 WeightNorm::WeightNorm(std::shared_ptr<Module> module, int dim) : module_(std::move(module)), dim_(dim) {
@@ -775,6 +811,8 @@ Variable Linear::forwardFused(const Variable& in, bool relu, float dropP, bool m
 Variable Linear::forwardWith(const Variable& in, const Variable& weight, const Variable& bias, bool relu, float dropP, bool maskByConsumer,
                              int inMaskMode, float inMaskScale) {
   requireInternal(in, "Linear");
+  if (in.validFrames() >= 0 && in.validFrames() != in.dims(2))
+    throw std::invalid_argument("Linear: the input carries slack frames (large-channel convolutions); a Reorder must come first");
   long long T, B;
   if (in.dims(0) == nIn) {  // flattened [K, T, B]
     T = in.dims(1);
