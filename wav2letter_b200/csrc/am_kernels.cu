@@ -22,7 +22,8 @@ bool conv_mma_supported(int W, int Cin, int Cout, int K, int stride);
 size_t conv_mma_arranged_floats(int Cin, int Cout, int K);
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                  const float* x, const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y,
-                 int act, float drop_p, unsigned long long seed, float* arranged);
+                 int act, float drop_p, unsigned long long seed, float* arranged, int Kfull, int tap_step, int tap_off,
+                 int out_fstride, int out_foff, int out_frames);
 size_t conv_mma_wgrad_parts(int B, int Tout, int W, int Cin, int Cout, int K, int stride, int* tc_out, int* per_sample_out);
 int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                    const float* x, const float* dy, float* dwt, float* dbias, float* partial);
@@ -766,7 +767,7 @@ extern "C" int w2l_conv_time_fwd(void* stream_, int B, int T, int Tout, int W, i
   float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
   if (conv_mma_supported(W, Cin, Cout, K, stride))
     return conv_mma_fwd(stream, B, T, Tout, W, Cin, Cout, K, stride, pad_left, x, wt, Cin, Cout, 0, bias, add, y, act, dropout_p, seed,
-                        arranged);
+                        arranged, K, 1, 0, 1, 0, Tout);
   conv_arrange_weights_kernel<<<8, 256, 0, stream>>>(Cin, Cout, K, CO, wt, arranged, 0);
   W2L_LAUNCH_CHECK("conv_arrange_weights_kernel");
   const size_t smem = (size_t)Cin * K * CO * sizeof(float);
@@ -793,7 +794,24 @@ extern "C" int w2l_conv_time_dgrad(void* stream_, int B, int T, int Tout, int W,
     // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped — on the tensor-core path
     float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
     return conv_mma_fwd(stream, B, Tout, T, W, Cout, Cin, K, 1, K - 1 - pad_left, dy, wt, Cin, Cout, 1, nullptr, add, dx, 0, 0.f, 0ull,
-                        arranged);
+                        arranged, K, 1, 0, 1, 0, T);
+  }
+  if (stride > 1 && stride <= K && conv_mma_supported(W, Cout, Cin, (K + stride - 1) / stride, 1)) {
+    // polyphase: input frames t with (t + pad_left) % stride == p only see taps p, p + stride, ...; each phase is a
+    // stride-1 correlation of dy with those taps reversed, written to every stride-th frame of dx
+    float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
+    for (int p = 0; p < stride; ++p) {
+      const int Kp = (K - p + stride - 1) / stride;
+      const int d = pad_left - p;
+      const int u_min = d > 0 ? (d + stride - 1) / stride : 0;  // first u with t = stride*u + p - pad_left >= 0
+      const int t0 = stride * u_min + p - pad_left;
+      const int n_u = t0 < T ? (T - 1 - t0) / stride + 1 : 0;
+      if (n_u <= 0) continue;
+      if (int rc = conv_mma_fwd(stream, B, Tout, n_u, W, Cout, Cin, Kp, 1, Kp - 1 - u_min, dy, wt, Cin, Cout, 1, nullptr, add, dx, 0, 0.f, 0ull,
+                                arranged, K, stride, p, stride, t0, T))
+        return rc;
+    }
+    return W2L_OK;
   }
   if (stride == 1 && Tout == T) {
     // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped

@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
                                                                        const float* __restrict__ x, const float* __restrict__ wa,
                                                                        const float* __restrict__ bias, const float* add,
                                                                        float* y, int act, float drop_p,
-                                                                       unsigned long long seed) {
+                                                                       unsigned long long seed, int out_fstride, int out_foff,
+                                                                       int out_frames) {
+  // output frame `to` of this launch lands at frame to*out_fstride + out_foff of a sample with out_frames frames
+  // (1, 0, Tout for a plain convolution; the polyphase data gradient of a strided convolution interleaves its phases)
   extern __shared__ __align__(16) float sm[];
   constexpr int kPitch = fwd_pitch(WT);
   constexpr int TB = 8 * UPW;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
         const bool ok = live && co < Cout;
         const int coc = min(co, Cout - 1);
         const float bv = bias ? __ldg(bias + coc) : 0.f;
-        const size_t base = (((size_t)b * Tout + to) * Cout + coc) * W + w_off + 2 * t4;
+        const size_t base = (((size_t)b * out_frames + (size_t)to * out_fstride + out_foff) * Cout + coc) * W + w_off + 2 * t4;
         float keep[WT][2];
         if (drop_p > 0.f) {
 #pragma unroll
@@ -206,9 +209,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
 }
 
 // weights wt[Cout][Cin][K] -> wa[16*MT][apitch] with k = dk*Cin + ci (TF32-rounded, zero padded);
-// flip != 0 builds the stride-1 data-gradient operator: wa[ci][dk'*Cout + co] = wt[co][ci][K-1-dk']
-__global__ void conv_mma_arrange_kernel(int Cin, int Cout, int K, int rows, int apitch, const float* __restrict__ wt,
-                                        float* __restrict__ wa, int flip) {
+// flip != 0 builds a data-gradient operator: wa[ci][dk'*Cout + co] = wt[co][ci][tap_off + tap_step*(K-1-dk')] — all
+// taps reversed for stride 1 (tap_step 1), or the taps of one phase of a strided convolution (K = taps of the phase)
+__global__ void conv_mma_arrange_kernel(int Cin, int Cout, int Kfull, int K, int tap_step, int tap_off, int rows, int apitch,
+                                        const float* __restrict__ wt, float* __restrict__ wa, int flip) {
   const int kin = flip ? Cout : Cin;  // channel count that plays "input" in the arranged operator
   const int mout = flip ? Cin : Cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * apitch; i += gridDim.x * blockDim.x) {
@@ -216,7 +220,7 @@ __global__ void conv_mma_arrange_kernel(int Cin, int Cout, int K, int rows, int 
     float v = 0.f;
     if (m < mout && k < K * kin) {
       const int dk = k / kin, c = k % kin;
-      v = flip ? wt[((size_t)c * Cin + m) * K + (K - 1 - dk)] : wt[((size_t)m * Cin + c) * K + dk];
+      v = flip ? wt[((size_t)c * Cin + m) * Kfull + tap_off + tap_step * (K - 1 - dk)] : wt[((size_t)m * Cin + c) * Kfull + dk];
     }
     wa[i] = to_tf32(v);
   }
@@ -335,21 +339,33 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_wgrad_kernel(int T, i
   }
 }
 
-__global__ void conv_mma_wgrad_reduce_kernel(int n_parts, int n_w, int n_b, const float* __restrict__ partial,
-                                             float* __restrict__ dwt, float* __restrict__ dbias) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_w + n_b) return;
+// deterministic second stage: thread (kx, py) of a 32 x 8 block sums parts py, py+8, ... of element k (coalesced over kx),
+// the 8 partial sums are combined through shared memory in a fixed order
+__global__ void __launch_bounds__(256) conv_mma_wgrad_reduce_kernel(int n_parts, int n_w, int n_b, const float* __restrict__ partial,
+                                                                    float* __restrict__ dwt, float* __restrict__ dbias) {
+  __shared__ float red[8][33];
+  const int kx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx, n = n_w + n_b;
   float s0 = 0.f, s1 = 0.f;
-  int q = 0;
-  for (; q + 1 < n_parts; q += 2) {
-    s0 += partial[(size_t)q * (n_w + n_b) + k];
-    s1 += partial[(size_t)(q + 1) * (n_w + n_b) + k];
+  if (k < n) {
+    int q = py;
+    for (; q + 8 < n_parts; q += 16) {
+      s0 += partial[(size_t)q * n + k];
+      s1 += partial[(size_t)(q + 8) * n + k];
+    }
+    if (q < n_parts) s0 += partial[(size_t)q * n + k];
   }
-  if (q < n_parts) s0 += partial[(size_t)q * (n_w + n_b) + k];
-  if (k < n_w)
-    dwt[k] += s0 + s1;
-  else if (dbias != nullptr)
-    dbias[k - n_w] += s0 + s1;
+  red[py][kx] = s0 + s1;
+  __syncthreads();
+  if (py == 0 && k < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][kx];
+    if (k < n_w)
+      dwt[k] += t;
+    else if (dbias != nullptr)
+      dbias[k - n_w] += t;
+  }
 }
 
 int apitch_for(int Kpad) {  // row pitch of the weight operand: = 4 (mod 32) -> conflict-free A fragments
@@ -380,22 +396,27 @@ constexpr size_t kConvSmemTarget = 112 * 1024;  // two CTAs per SM
 template <int MT, int UPW, int WT>
 static int launch_fwd(cudaStream_t stream, dim3 grid, size_t smem, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                       int pad_left, int Kpad, int apitch, const float* x, const float* arranged, const float* bias,
-                      const float* add, float* y, int act, float drop_p, unsigned long long seed) {
+                      const float* add, float* y, int act, float drop_p, unsigned long long seed, int out_fstride, int out_foff,
+                      int out_frames) {
   if (smem > 48 * 1024)
     W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<MT, UPW, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv_mma_fwd_kernel<MT, UPW, WT><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x,
-                                                                        arranged, bias, add, y, act, drop_p, seed);
+                                                                        arranged, bias, add, y, act, drop_p, seed, out_fstride, out_foff,
+                                                                        out_frames);
   return W2L_OK;
 }
 
-// flip = 0: y = conv(x) ; flip = 1: stride-1 data gradient (x := dy, roles of Cin/Cout swapped by the caller)
+// flip = 0: y = conv(x) ; flip = 1: data gradient (x := dy, roles of Cin/Cout swapped by the caller): all K = Kfull
+// taps reversed for a stride-1 convolution, or one phase (taps tap_off, tap_off + tap_step, ...; K of them) of a strided
+// one, whose outputs land at frames to*out_fstride + out_foff of the out_frames-frame gradient
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                  const float* x, const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y,
-                 int act, float drop_p, unsigned long long seed, float* arranged) {
+                 int act, float drop_p, unsigned long long seed, float* arranged, int Kfull, int tap_step, int tap_off,
+                 int out_fstride, int out_foff, int out_frames) {
   const int MT = (Cout + 15) / 16;
   const int Kpad = (K * Cin + 7) / 8 * 8;
   const int apitch = apitch_for(Kpad);
-  conv_mma_arrange_kernel<<<16, 256, 0, stream>>>(wt_cin, wt_cout, K, 16 * MT, apitch, wt, arranged, flip);
+  conv_mma_arrange_kernel<<<16, 256, 0, stream>>>(wt_cin, wt_cout, Kfull, K, tap_step, tap_off, 16 * MT, apitch, wt, arranged, flip);
   W2L_LAUNCH_CHECK("conv_mma_arrange_kernel");
   const int WT = slice_tiles(W);
   auto bytes_for = [&](int tb) { return ((size_t)((tb - 1) * stride + K) * Cin + 8) * fwd_pitch(WT) * 4; };
@@ -409,7 +430,7 @@ int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, in
 #define W2L_FWD_CASE(MT_, UPW_, WT_)                                                                                  \
   if (MT == MT_ && UPW == UPW_ && WT == WT_)                                                                         \
     rc = launch_fwd<MT_, UPW_, WT_>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged, \
-                                    bias, add, y, act, drop_p, seed);
+                                    bias, add, y, act, drop_p, seed, out_fstride, out_foff, out_frames);
 #define W2L_FWD_WT(WT_) W2L_FWD_CASE(1, 1, WT_) W2L_FWD_CASE(1, 2, WT_) W2L_FWD_CASE(2, 1, WT_)
   W2L_FWD_WT(1) W2L_FWD_WT(2) W2L_FWD_WT(3) W2L_FWD_WT(4) W2L_FWD_WT(5)
 #undef W2L_FWD_WT
@@ -468,7 +489,7 @@ int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, 
   if (rc != W2L_OK) return rc;
   W2L_LAUNCH_CHECK("conv_mma_wgrad_kernel");
   const int n_w = Cout * Cin * K;
-  conv_mma_wgrad_reduce_kernel<<<(n_w + Cout + 255) / 256, 256, 0, stream>>>((int)parts, n_w, Cout, partial, dwt, dbias);
+  conv_mma_wgrad_reduce_kernel<<<(n_w + Cout + 31) / 32, 256, 0, stream>>>((int)parts, n_w, Cout, partial, dwt, dbias);
   W2L_LAUNCH_CHECK("conv_mma_wgrad_reduce_kernel");
   return W2L_OK;
 }
