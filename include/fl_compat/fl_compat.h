@@ -409,6 +409,39 @@ int getWorldSize();
 bool isDistributedInit();
 void allReduce(af::array& arr, double scale = 1.0);  // in-place sum over ranks (NCCL)
 void allReduceParameters(const std::shared_ptr<const Module>& module);  // average, Train.cpp:1078-1079
+// Gradient all-reduce overlapped with the backward pass (the reference registers a reducer callback on every parameter's
+// gradient for this, recipes/joint_training_vox_populi/cpc/Train.cpp:972-976).  The parameters must be bound to one
+// gradient arena (flattenParameters); the arena is cut into buckets of whole parameters in arena order.  Backward
+// produces gradients from the last layer to the first, so buckets complete back to front: when every parameter of a
+// bucket has received its gradient, an event is recorded on the compute stream and the bucket's NCCL all-reduce is
+// enqueued on a separate communication stream behind it.  finalize() launches what is left and makes the compute
+// stream wait for all reductions.
+class OverlappedArenaReducer {
+ public:
+  OverlappedArenaReducer(const std::vector<Variable>& params, const af::array& arenaGrads, size_t bucketBytes = (size_t)8 << 20);
+  ~OverlappedArenaReducer();
+  void arm();       // call after zeroGrad, before loss.backward()
+  void finalize();  // call after backward
+  int buckets() const { return (int)bucket_.size(); }
+  void onGradReady(const void* id);  // called by Variable::addGrad for arena-bound parameters
+
+ private:
+  struct Bucket {
+    size_t offset = 0, count = 0;  // floats
+    int params = 0, remaining = 0;
+    bool launched = false;
+    void* event = nullptr;
+  };
+  void launch(Bucket& b);
+  af::array grads_;
+  std::vector<Bucket> bucket_;
+  std::vector<std::pair<const void*, int>> owner_;  // sorted (variable id, bucket)
+  std::vector<char> seen_;
+  void* comm_stream_ = nullptr;
+  void* done_ = nullptr;
+  bool armed_ = false;
+};
+
 class Reducer {
  public:
   virtual ~Reducer() = default;

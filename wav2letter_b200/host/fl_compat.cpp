@@ -160,6 +160,8 @@ using w2l::DType;
 // ================================================================================================
 // Variable / autograd
 // ================================================================================================
+thread_local OverlappedArenaReducer* g_active_reducer = nullptr;  // set between arm() and finalize()
+
 struct Variable::Impl {
   af::array data;
   bool calcGrad = false;
@@ -221,6 +223,7 @@ void Variable::addGrad(const Variable& g, bool fresh) {
     if (g.array().ptr() != impl_->boundGrad.ptr())
       check(w2l_axpy(currentStream(), elements(), 1.0f, g.array().f32(), impl_->boundGrad.f32()));
     if (!impl_->grad) impl_->grad = std::make_shared<Variable>(impl_->boundGrad, false);
+    if (g_active_reducer) g_active_reducer->onGradReady(impl_.get());
     return;
   }
   if (!impl_->grad) {
@@ -1069,6 +1072,97 @@ void CoalescingReducer::finalize() {
     }
   pending_.clear();
 }
+// ---- overlapped bucketed all-reduce ---------------------------------------------------------------------
+OverlappedArenaReducer::OverlappedArenaReducer(const std::vector<Variable>& params, const af::array& arenaGrads, size_t bucketBytes)
+    : grads_(arenaGrads) {
+  const char* base = static_cast<const char*>(arenaGrads.ptr());
+  const size_t total = arenaGrads.bytes();
+  Bucket cur;
+  bool open = false;
+  for (const auto& p : params) {
+    af::array g = p.gradStorage();
+    if (g.isEmpty()) throw std::invalid_argument("OverlappedArenaReducer: a parameter is not bound to the gradient arena");
+    const size_t off = (size_t)(static_cast<const char*>(g.ptr()) - base);
+    if (off >= total) throw std::invalid_argument("OverlappedArenaReducer: parameter outside the arena");
+    if (!open) {
+      cur = Bucket();
+      cur.offset = off / 4;
+      open = true;
+    }
+    cur.count = (off + g.bytes()) / 4 - cur.offset;
+    cur.params += 1;
+    owner_.emplace_back(p.id(), (int)bucket_.size());
+    if (cur.count * 4 >= bucketBytes) {
+      bucket_.push_back(cur);
+      open = false;
+    }
+  }
+  if (open) bucket_.push_back(cur);
+  std::sort(owner_.begin(), owner_.end());
+  seen_.assign(owner_.size(), 0);
+  cudaStream_t cs;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, hi) != cudaSuccess) throw std::runtime_error("OverlappedArenaReducer: stream");
+  comm_stream_ = cs;
+  for (auto& b : bucket_) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) throw std::runtime_error("OverlappedArenaReducer: event");
+    b.event = e;
+  }
+  cudaEvent_t d;
+  if (cudaEventCreateWithFlags(&d, cudaEventDisableTiming) != cudaSuccess) throw std::runtime_error("OverlappedArenaReducer: event");
+  done_ = d;
+}
+OverlappedArenaReducer::~OverlappedArenaReducer() {
+  if (g_active_reducer == this) g_active_reducer = nullptr;
+  for (auto& b : bucket_)
+    if (b.event) cudaEventDestroy(static_cast<cudaEvent_t>(b.event));
+  if (done_) cudaEventDestroy(static_cast<cudaEvent_t>(done_));
+  if (comm_stream_) cudaStreamDestroy(static_cast<cudaStream_t>(comm_stream_));
+}
+void OverlappedArenaReducer::arm() {
+  for (auto& b : bucket_) {
+    b.remaining = b.params;
+    b.launched = false;
+  }
+  std::fill(seen_.begin(), seen_.end(), 0);
+  armed_ = true;
+  g_active_reducer = this;
+}
+void OverlappedArenaReducer::launch(Bucket& b) {
+  b.launched = true;
+  if (!g_comm) return;
+  cudaStream_t compute = static_cast<cudaStream_t>(currentStream()), comm = static_cast<cudaStream_t>(comm_stream_);
+  cudaEvent_t e = static_cast<cudaEvent_t>(b.event);
+  if (cudaEventRecord(e, compute) != cudaSuccess || cudaStreamWaitEvent(comm, e, 0) != cudaSuccess)
+    throw std::runtime_error("OverlappedArenaReducer: event record/wait failed");
+  float* ptr = grads_.f32() + b.offset;
+  ncclCheck(ncclAllReduce(ptr, ptr, b.count, ncclFloat32, ncclSum, g_comm, comm), "ncclAllReduce (bucket)");
+}
+void OverlappedArenaReducer::onGradReady(const void* id) {
+  if (!armed_) return;
+  auto it = std::lower_bound(owner_.begin(), owner_.end(), std::make_pair(id, -1));
+  if (it == owner_.end() || it->first != id) return;
+  const size_t k = (size_t)(it - owner_.begin());
+  if (seen_[k]) return;  // only the first arrival of a step counts (a shared parameter would arrive again)
+  seen_[k] = 1;
+  Bucket& b = bucket_[(size_t)it->second];
+  if (--b.remaining == 0 && !b.launched) launch(b);
+}
+void OverlappedArenaReducer::finalize() {
+  if (!armed_) return;
+  armed_ = false;
+  g_active_reducer = nullptr;
+  for (size_t i = bucket_.size(); i-- > 0;)
+    if (!bucket_[i].launched) launch(bucket_[i]);
+  if (!g_comm) return;
+  cudaStream_t compute = static_cast<cudaStream_t>(currentStream()), comm = static_cast<cudaStream_t>(comm_stream_);
+  if (cudaEventRecord(static_cast<cudaEvent_t>(done_), comm) != cudaSuccess ||
+      cudaStreamWaitEvent(compute, static_cast<cudaEvent_t>(done_), 0) != cudaSuccess)
+    throw std::runtime_error("OverlappedArenaReducer: final wait failed");
+}
+
 namespace pkg {
 namespace runtime {
 void createUniqueId(void* id128) {

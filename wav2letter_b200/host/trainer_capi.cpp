@@ -28,6 +28,7 @@ using namespace fl::pkg::speech;
 namespace {
 struct Trainer {
   std::shared_ptr<fl::Module> net;
+  std::unique_ptr<fl::OverlappedArenaReducer> reducer;  // created at the first distributed step
   std::shared_ptr<SequenceCriterion> crit;
   ParameterArena netArena, critArena;
   af::array sqnorm;
@@ -155,12 +156,13 @@ W2L_API int w2l_trainer_step(void* h, void* stream, int B, int T, const float* f
       t->critArena.grads.zero();
       for (auto& p : t->crit->params()) p.zeroGrad(false);
     }
+    // reducer: Train.cpp:1721-1735 adds every gradient after backward; here the network's gradient arena is reduced in
+    // buckets WHILE backward runs (the callback pattern of cpc/Train.cpp:972-976), on a separate stream
+    if (fl::isDistributedInit() && !t->reducer) t->reducer = std::make_unique<fl::OverlappedArenaReducer>(t->net->params(), t->netArena.grads);
+    if (t->reducer) t->reducer->arm();
     loss.backward();
-    // reducer->add(grad) for every param; finalize()   Train.cpp:1721-1735 — the arenas are contiguous
-    if (fl::isDistributedInit()) {
-      fl::allReduce(t->netArena.grads);
-      if (t->critArena.elements) fl::allReduce(t->critArena.grads);
-    }
+    if (t->reducer) t->reducer->finalize();
+    if (fl::isDistributedInit() && t->critArena.elements) fl::allReduce(t->critArena.grads);
     // [opt]  grads /= totalBatch (Train.cpp:1752,1783), clipGradNorm(net U crit) (:1791-1798), step (:1801-1802)
     const float gscale = 1.0f / total_batch;
     const double* sq = nullptr;
