@@ -443,9 +443,21 @@ int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, in
 static size_t wgrad_smem(int tc, int stride, int K, int Cin, int Cout, int WT) {
   return (((size_t)((tc - 1) * stride + K) * Cin + 8) + (size_t)tc * Cout + 1) * wg_pitch(WT) * 4;
 }
+// slice width for the weight gradient: the widest slice (fewest CTAs re-staging the same frames) that still lets a CTA
+// take 16 output frames per chunk inside the shared-memory target — a chunk of TC frames stages TC-1+K input frames,
+// so short chunks multiply the staging traffic (18 channels: 40-wide slices allow TC = 4, 16-wide ones TC = 16)
+static int wgrad_slice_tiles(int W, int stride, int K, int Cin, int Cout) {
+  int best = 1;
+  for (int wt = 5; wt >= 1; --wt) {
+    if ((W / 8) % wt) continue;
+    best = wt;
+    if (wgrad_smem(16, stride, K, Cin, Cout, wt) <= kConvSmemTarget) return wt;
+  }
+  return best;
+}
 // number of CTA partials of the weight gradient (upper bound over W when W <= 0: ten slices)
 size_t conv_mma_wgrad_parts(int B, int Tout, int W, int Cin, int Cout, int K, int stride, int* tc_out, int* per_sample_out) {
-  const int WT = W > 0 ? slice_tiles(W) : 1;
+  const int WT = W > 0 ? wgrad_slice_tiles(W, stride, K, Cin, Cout) : 1;
   const int nslices = W > 0 ? W / (8 * WT) : 10;
   int TC = 16;
   while (TC > 1 && wgrad_smem(TC, stride, K, Cin, Cout, WT) > kConvSmemTarget) TC >>= 1;
@@ -471,7 +483,7 @@ static int launch_wgrad(cudaStream_t stream, dim3 grid, size_t smem, int T, int 
 int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                    const float* x, const float* dy, float* dwt, float* dbias, float* partial) {
   const int MT = (Cout + 15) / 16;
-  const int WT = slice_tiles(W);
+  const int WT = wgrad_slice_tiles(W, stride, K, Cin, Cout);
   int TC = 8, per_sample = 1;
   const size_t parts = conv_mma_wgrad_parts(B, Tout, W, Cin, Cout, K, stride, &TC, &per_sample);
   const size_t smem = wgrad_smem(TC, stride, K, Cin, Cout, WT);
