@@ -223,9 +223,12 @@ W2L_API int w2l_glu_bwd(void* stream, long long rows, int half, const float* x, 
 
 /* fl::LayerNorm over a whole sample (R = T*C*W elements; `LN 0 1 2` / TDSBlock with lnIncludeTime)
  * with scalar gain/bias (device scalars, nullable = 1/0) and a fused residual: y = LN(a + r).
- * mean_rstd [B][2] is saved for the backward pass; scratch = 2*B doubles.
+ * mean_rstd [B][2] is saved for the backward pass; scratch = W2L_LN_SCRATCH_DOUBLES(B) doubles (one partial
+ * pair per CTA: no zero-fill, no atomics, deterministic).
  * Backward: d_res = ds, d_branch = ds * mask(a) where the mask undoes the fused ReLU/dropout of the
  * branch that produced `a` (branch_mode 0 none, 1 (a>0)*scale, 2 (a!=0)*scale); dgain/dbias accumulate. */
+#define W2L_LN_MAX_PARTS 80
+#define W2L_LN_SCRATCH_DOUBLES(B) (2 * W2L_LN_MAX_PARTS * (size_t)(B))
 W2L_API int w2l_layernorm_fwd(void* stream, int B, long long R, float eps, const float* a, const float* r,
                               const float* gain, const float* bias, float* y, float* mean_rstd, double* scratch);
 W2L_API int w2l_layernorm_bwd(void* stream, int B, long long R, const float* a, const float* r, const float* dy,

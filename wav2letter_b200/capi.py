@@ -379,7 +379,7 @@ def layernorm_fwd(a, r, gain, bias, eps=1e-5):
     R = a[0].numel()
     y = torch.empty_like(a)
     mr = torch.empty((B, 2), dtype=torch.float32, device=a.device)
-    scratch = torch.empty(2 * B, dtype=torch.float64, device=a.device)
+    scratch = torch.empty(160 * B, dtype=torch.float64, device=a.device)
     _check(lib.w2l_layernorm_fwd(_stream(), B, R, float(eps), _ptr(a), _ptr(r), _ptr(gain), _ptr(bias), _ptr(y), _ptr(mr),
                                  _ptr(scratch)))
     return y, mr
@@ -392,7 +392,7 @@ def layernorm_bwd(a, r, dy, gain, mr, branch_mode=0, branch_scale=1.0):
     d_res = torch.empty_like(a)
     dgain = torch.zeros(1, dtype=torch.float32, device=a.device)
     dbias = torch.zeros(1, dtype=torch.float32, device=a.device)
-    scratch = torch.empty(2 * B, dtype=torch.float64, device=a.device)
+    scratch = torch.empty(160 * B, dtype=torch.float64, device=a.device)
     _check(lib.w2l_layernorm_bwd(_stream(), B, R, _ptr(a), _ptr(r), _ptr(dy), _ptr(gain), _ptr(mr), _ptr(d_branch),
                                  _ptr(d_res), int(branch_mode), float(branch_scale), _ptr(dgain), _ptr(dbias),
                                  _ptr(scratch)))

@@ -308,7 +308,9 @@ __global__ void conv_wgrad_reduce_kernel(int n_parts, int n_w, int n_b, const fl
 __device__ __forceinline__ float4 ld4(const float* p, long long i) { return *reinterpret_cast<const float4*>(p + i); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-__device__ __forceinline__ void block_sum2_atomic(double s, double q, double* out) {
+// CTA partial (sum, sum of squares / products) -> out[0..1]; the consumer kernel adds the CTAs' partials in a fixed order
+// (no zero-fill of the scratch, no atomics, deterministic)
+__device__ __forceinline__ void block_sum2_store(double s, double q, double* out) {
   s = warp_sum(s);
   q = warp_sum(q);
   __shared__ double ss[8], qq[8];
@@ -323,9 +325,29 @@ __device__ __forceinline__ void block_sum2_atomic(double s, double q, double* ou
       S += ss[w];
       Q += qq[w];
     }
-    atomicAdd(out, S);
-    atomicAdd(out + 1, Q);
+    out[0] = S;
+    out[1] = Q;
   }
+}
+// sum of the gridDim.x CTA partials of sample b (every thread gets the totals)
+__device__ __forceinline__ void sum_partials(const double* __restrict__ parts, int nparts, double& S, double& Q) {
+  __shared__ double tot[2];
+  if (threadIdx.x < 32) {
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 32) {
+      s += parts[2 * i];
+      q += parts[2 * i + 1];
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (threadIdx.x == 0) {
+      tot[0] = s;
+      tot[1] = q;
+    }
+  }
+  __syncthreads();
+  S = tot[0];
+  Q = tot[1];
 }
 
 __global__ void __launch_bounds__(256) ln_stats_kernel(long long R, int vec, const float* __restrict__ a, const float* __restrict__ r,
@@ -336,7 +358,7 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(long long R, int vec, con
   double s = 0.0, q = 0.0;
   const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
   if (vec) {
-#pragma unroll 2
+#pragma unroll 4
     for (long long i = 4 * start; i < R; i += 4 * step) {
       float4 v = ld4(ab, i);
       if (rb) v = add4(v, ld4(rb, i));
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(long long R, int vec, con
       q += (double)v * v;
     }
   }
-  block_sum2_atomic(s, q, stats + 2 * b);
+  block_sum2_store(s, q, stats + 2 * ((size_t)b * gridDim.x + blockIdx.x));
 }
 
 __global__ void __launch_bounds__(256) ln_apply_kernel(long long R, int vec, float eps, const float* __restrict__ a,
@@ -358,8 +380,10 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(long long R, int vec, flo
                                                        const float* __restrict__ bias, const double* __restrict__ stats,
                                                        float* __restrict__ y, float* __restrict__ mean_rstd /*[B][2]*/) {
   const int b = blockIdx.y;
-  const double mean = stats[2 * b] / (double)R;
-  const double var = fmax(stats[2 * b + 1] / (double)R - mean * mean, 0.0);
+  double S, Q;
+  sum_partials(stats + 2 * (size_t)b * gridDim.x, gridDim.x, S, Q);
+  const double mean = S / (double)R;
+  const double var = fmax(Q / (double)R - mean * mean, 0.0);
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float mu = (float)mean, g = gain ? *gain : 1.f, bi = bias ? *bias : 0.f;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -400,7 +424,7 @@ __global__ void __launch_bounds__(256) ln_bwd_stats_kernel(long long R, int vec,
   double s = 0.0, q = 0.0;
   const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
   if (vec) {
-#pragma unroll 2
+#pragma unroll 4
     for (long long i = 4 * start; i < R; i += 4 * step) {
       float4 v = ld4(ab, i);
       const float4 d = ld4(db, i);
@@ -416,7 +440,7 @@ __global__ void __launch_bounds__(256) ln_bwd_stats_kernel(long long R, int vec,
       q += (double)d * xh;
     }
   }
-  block_sum2_atomic(s, q, sums + 2 * b);
+  block_sum2_store(s, q, sums + 2 * ((size_t)b * gridDim.x + blockIdx.x));
 }
 
 // backward pass 2: ds = rstd * gain * (dy - mean(dy) - xhat * mean(dy*xhat));
@@ -433,10 +457,12 @@ __global__ void __launch_bounds__(256) ln_bwd_apply_kernel(long long R, int vec,
                                                            float* __restrict__ dgain, float* __restrict__ dbias) {
   const int b = blockIdx.y;
   const float mu = mean_rstd[2 * b], rstd = mean_rstd[2 * b + 1], g = gain ? *gain : 1.f;
-  const float m1 = (float)(sums[2 * b] / (double)R), m2 = (float)(sums[2 * b + 1] / (double)R);
+  double S, Q;
+  sum_partials(sums + 2 * (size_t)b * gridDim.x, gridDim.x, S, Q);
+  const float m1 = (float)(S / (double)R), m2 = (float)(Q / (double)R);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (dbias) atomicAdd(dbias, (float)sums[2 * b]);
-    if (dgain) atomicAdd(dgain, (float)sums[2 * b + 1]);
+    if (dbias) atomicAdd(dbias, (float)S);
+    if (dgain) atomicAdd(dgain, (float)Q);
   }
   const float* ab = a + (size_t)b * R;
   const float* rb = r ? r + (size_t)b * R : nullptr;
@@ -884,8 +910,9 @@ extern "C" int w2l_layernorm_fwd(void* stream_, int B, long long R, float eps, c
     return W2L_OK;
   }
   if (B > 65535) return fail(W2L_ERR_UNSUPPORTED, "layernorm_fwd: more than 65535 long groups");
-  W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
-  dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
+  // whole multiples of the 148 SMs at full occupancy (8 CTAs of 256 threads per SM) when the samples are long enough;
+  // at most W2L_LN_MAX_PARTS CTAs per sample (the scratch holds one partial pair per CTA)
+  dim3 grid(std::max(1, std::min(std::min(blocks_for(R, 256 * 4 * 4), W2L_LN_MAX_PARTS), 148 * 8 / std::max(1, std::min(B, 148 * 8)))), B);
   ln_stats_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, scratch);
   W2L_LAUNCH_CHECK("ln_stats_kernel");
   ln_apply_kernel<<<grid, 256, 0, stream>>>(R, vec, eps, a, r, gain, bias, scratch, y, mean_rstd);
@@ -909,8 +936,9 @@ extern "C" int w2l_layernorm_bwd(void* stream_, int B, long long R, const float*
     return W2L_OK;
   }
   if (B > 65535) return fail(W2L_ERR_UNSUPPORTED, "layernorm_bwd: more than 65535 long groups");
-  W2L_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, stream));
-  dim3 grid(std::max(1, std::min(blocks_for(R), 148 * 4 / std::max(1, std::min(B, 148 * 4)) + 1)), B);
+  // whole multiples of the 148 SMs at full occupancy (8 CTAs of 256 threads per SM) when the samples are long enough;
+  // at most W2L_LN_MAX_PARTS CTAs per sample (the scratch holds one partial pair per CTA)
+  dim3 grid(std::max(1, std::min(std::min(blocks_for(R, 256 * 4 * 4), W2L_LN_MAX_PARTS), 148 * 8 / std::max(1, std::min(B, 148 * 8)))), B);
   ln_bwd_stats_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, dy, mean_rstd, scratch);
   W2L_LAUNCH_CHECK("ln_bwd_stats_kernel");
   ln_bwd_apply_kernel<<<grid, 256, 0, stream>>>(R, vec, a, r, dy, gain, mean_rstd, scratch, d_branch, d_res, branch_mode, branch_scale,

@@ -755,7 +755,7 @@ Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int br
   if (hasRes && r.elements() != a.elements()) throw std::invalid_argument("LayerNorm: residual size mismatch");
   af::array y = af::array::empty(a.dims());
   af::array mr = af::array::empty(af::dim4(2, B));
-  af::array scratch = af::array::empty(af::dim4(2 * B), DType::f64);
+  af::array scratch = af::array::empty(af::dim4((long long)W2L_LN_SCRATCH_DOUBLES(B)), DType::f64);
   const bool affine = !params_.empty();
   check(w2l_layernorm_fwd(currentStream(), B, R, (float)eps_, a.array().f32(), hasRes ? r.array().f32() : nullptr,
                           affine ? params_[0].array().f32() : nullptr, affine ? params_[1].array().f32() : nullptr, y.f32(), mr.f32(),
@@ -777,7 +777,7 @@ Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int br
       db = ins[gi + 1].gradStorage();
       if (db.isEmpty()) db = af::array::zeros(af::dim4(1));
     }
-    af::array sc = af::array::empty(af::dim4(2 * B), DType::f64);
+    af::array sc = af::array::empty(af::dim4((long long)W2L_LN_SCRATCH_DOUBLES(B)), DType::f64);
     check(w2l_layernorm_bwd(currentStream(), B, R, ins[0].array().f32(), hasRes ? ins[1].array().f32() : nullptr, g.array().f32(),
                             affine ? ins[gi].array().f32() : nullptr, mr.f32(), d_branch.f32(), hasRes ? d_res.f32() : nullptr,
                             branchMode, keepScale, affine ? dg.f32() : nullptr, affine ? db.f32() : nullptr, sc.f64()));
