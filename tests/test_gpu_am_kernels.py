@@ -154,6 +154,10 @@ def test_colsum_sqnorm_sgd():
     out = torch.ones(77, device="cuda")
     capi._check(capi.lib.w2l_colsum_accumulate(capi._stream(), 1000, 77, capi._ptr(X), 77, capi._ptr(out)))
     assert rel(out, 1 + X.double().sum(0)) < 1e-5
+    X4 = torch.randn((2403, 1120), device="cuda", generator=g)   # float4 path (N % 4 == 0), sub-matrix with ld > N
+    out4 = torch.ones(1000, device="cuda")
+    capi._check(capi.lib.w2l_colsum_accumulate(capi._stream(), 2403, 1000, capi._ptr(X4), 1120, capi._ptr(out4)))
+    assert rel(out4, 1 + X4[:, :1000].double().sum(0)) < 1e-5
     n = 100003
     p = torch.randn(n, device="cuda", generator=g)
     gr = torch.randn(n, device="cuda", generator=g)

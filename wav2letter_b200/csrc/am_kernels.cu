@@ -641,6 +641,42 @@ __global__ void __launch_bounds__(256) colsum_kernel(int M, int N, const float* 
   }
 }
 
+// float4 variant (N, ld multiples of 4, 16-byte aligned base): a block covers 128 columns x rows_per_cta rows
+__global__ void __launch_bounds__(256) colsum4_kernel(int M, int N, const float* __restrict__ X, int ld, int rows_per_cta,
+                                                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + 4 * lane;
+  const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+#pragma unroll 4
+    for (int m = m0 + warp; m < m1; m += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(X + (size_t)m * ld + n);
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+  }
+  __shared__ float4 red[8][32];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      t.x += red[w][lane].x;
+      t.y += red[w][lane].y;
+      t.z += red[w][lane].z;
+      t.w += red[w][lane].w;
+    }
+    atomicAdd(out + n, t.x);
+    atomicAdd(out + n + 1, t.y);
+    atomicAdd(out + n + 2, t.z);
+    atomicAdd(out + n + 3, t.w);
+  }
+}
+
 // ---- optimizer on a flat parameter arena -------------------------------------------------------
 __global__ void __launch_bounds__(256) sq_norm_kernel(long long n, const float* __restrict__ g, double* __restrict__ out) {
   double s = 0.0;
@@ -950,6 +986,15 @@ extern "C" int w2l_layernorm_bwd(void* stream_, int B, long long R, const float*
 extern "C" int w2l_colsum_accumulate(void* stream_, int M, int N, const float* X, int ld, float* out) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || !X || !out) return fail(W2L_ERR_INVALID_ARGUMENT, "colsum: bad arguments");
+  if (N % 4 == 0 && ld % 4 == 0 && !(reinterpret_cast<uintptr_t>(X) & 15)) {
+    const int col_blocks = (N + 127) / 128;
+    // ~4 CTAs per SM: rows per CTA so that col_blocks * row_blocks ~ 600, at least 64 rows each
+    const int rows_per_cta = std::max(64, (int)(((long long)M * col_blocks + 599) / 600));
+    dim3 grid(col_blocks, (M + rows_per_cta - 1) / rows_per_cta);
+    colsum4_kernel<<<grid, 256, 0, stream>>>(M, N, X, ld, rows_per_cta, out);
+    W2L_LAUNCH_CHECK("colsum_kernel");
+    return W2L_OK;
+  }
   const int rows_per_cta = 256;
   dim3 grid((N + 31) / 32, (M + rows_per_cta - 1) / rows_per_cta);
   colsum_kernel<<<grid, 256, 0, stream>>>(M, N, X, ld, rows_per_cta, out);
