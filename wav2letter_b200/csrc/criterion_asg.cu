@@ -431,12 +431,34 @@ struct FacWalk {
   }
 };
 
-// flush warp: occupancy of frame t per label from the group's gamma row, through the label-sorted index
-__device__ __forceinline__ void fac_flush(const float* gm, const int* order, const int* start, int lane, float* Grow,
+// flush warp: occupancy of frame t per label from the group's gamma row, through the label-sorted index.  The index is
+// loop-invariant, so each lane keeps the first kFlushRegs positions of its label in registers: the per-frame work is then
+// up to kFlushRegs INDEPENDENT shared-memory loads instead of a chain of dependent (order[i] -> gamma[order[i]]) pairs —
+// that chain (8 positions per label on average for L = 250, N = 30) used to set the length of every phase-2 step.
+constexpr int kFlushRegs = 16;
+struct FlushIndex {
+  int cnt, rest0, rest1;
+  int pos[kFlushRegs];
+  __device__ __forceinline__ void load(const int* order, const int* start, int lane) {
+    const int i0 = start[lane], i1 = start[lane + 1];
+    cnt = min(kFlushRegs, i1 - i0);
+    rest0 = i0 + kFlushRegs;
+    rest1 = i1;
+#pragma unroll
+    for (int j = 0; j < kFlushRegs; ++j) pos[j] = j < cnt ? order[i0 + j] : 0;
+  }
+};
+__device__ __forceinline__ void fac_flush(const float* gm, const int* order, const FlushIndex& fx, int lane, float* Grow,
                                           float* rnorm_slot) {
-  float s = 0.f;
-  const int i0 = start[lane], i1 = start[lane + 1];
-  for (int i = i0; i < i1; ++i) s += gm[order[i]];
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kFlushRegs; j += 2) {
+    const float v0 = gm[fx.pos[j]], v1 = gm[fx.pos[j + 1]];  // pos is 0 (a valid slot) past cnt
+    s0 += j < fx.cnt ? v0 : 0.f;
+    s1 += j + 1 < fx.cnt ? v1 : 0.f;
+  }
+  for (int i = fx.rest0; i < fx.rest1; ++i) s0 += gm[order[i]];  // labels with more than kFlushRegs positions
+  const float s = s0 + s1;
   const int tot_i = __reduce_add_sync(0xffffffffu, __float2int_rn(s * kFix));
   Grow[lane] = s;
   if (lane == 0) *rnorm_slot = tot_i > 0 ? __fdividef(kFix, (float)tot_i) : 0.f;
@@ -514,15 +536,17 @@ __device__ void fac_role(const AsgParams& p, int b, float* smem) {
     __syncthreads();  // S2 (mid-point)
     __syncthreads();  // S3
     __syncthreads();  // S4 (phase 2 open)
+    FlushIndex fx;
+    fx.load(order_s, start_s, lane);
     if (grp == 0) {
       for (int t = h; t < T; ++t) {
         named_barrier_sync(4, kGroup + 32);
-        fac_flush(gam_g + (t & 1) * Lp, order_s, start_s, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
+        fac_flush(gam_g + (t & 1) * Lp, order_s, fx, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
       }
     } else {
       for (int t = h - 1; t >= 0; --t) {
         named_barrier_sync(5, kGroup + 32);
-        fac_flush(gam_g + (t & 1) * Lp, order_s, start_s, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
+        fac_flush(gam_g + (t & 1) * Lp, order_s, fx, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
       }
     }
     __syncthreads();  // S5
