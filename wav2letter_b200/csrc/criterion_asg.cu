@@ -331,6 +331,8 @@ __device__ __forceinline__ float max4_guard(const float* w) {
 }
 
 // State of one group's walk; every method is force-inlined so the fields live in registers.
+// Everything a step addresses is carried as a running pointer / ring slot that advances by a constant per step
+// (the walks visit consecutive frames): the step loop was issue-bound with ~60 % integer address arithmetic.
 template <int KMAX>
 struct FacWalk {
   const AsgParams& p;
@@ -344,13 +346,43 @@ struct FacWalk {
   double C;
   int yk[KMAX];
   float s1k[KMAX], s2k[KMAX], ds1k[KMAX], ds2k[KMAX];
+  // running state of the copy pipeline: `it` is the next frame to issue
+  int it, islot;
+  const float* e_it;    // eb + it*N + gt
+  const float* o_it;    // other group's stored row of frame `it` (valid once phase 2 is open)
+  const double* oc_it;  // other_c + it
+  // running state of the walk itself: frame of the NEXT step
+  int slot;             // frame & (kFRing-1)
+  float* srow_run;      // half-lattice row the next mode-1 step stores
+  double* c_run;        // offset slot the next mode-1 step stores
+  const float* o_cur;   // other group's row of the next step's frame (direct path, no ring)
 
   __device__ __forceinline__ explicit FacWalk(const AsgParams& p_) : p(p_) {}
   __device__ __forceinline__ const float* other_row(int t) const {
     return other_base + (size_t)(grp == 0 ? t - p.h : t) * Lp;
   }
   __device__ __forceinline__ float* row(int k) const { return rowbase + k * (Lp + 4); }
-  __device__ __forceinline__ void issue_other(int t) {
+  // start the copy pipeline at frame t0 and the walk at frame t0 + dir
+  __device__ __forceinline__ void prime(int t0) {
+    it = t0;
+    islot = t0 & (kFRing - 1);
+    e_it = eb + (size_t)t0 * N + gt;
+    o_it = nullptr;
+    oc_it = nullptr;
+    const int t1 = t0 + dir;
+    slot = t1 & (kFRing - 1);
+    srow_run = grp == 0 ? p.facA + ((size_t)b * p.h + t1) * Lp : p.facB + ((size_t)b * (T - p.h) + (t1 - p.h)) * Lp;
+    c_run = (grp == 0 ? p.cA : p.cB) + (size_t)b * T + t1;
+    o_cur = nullptr;
+  }
+  // the other group's half lattice is complete: phase 2 may read it (t_next = frame of the next step)
+  __device__ __forceinline__ void open_phase2(int t_next) {
+    p2_open = true;
+    o_it = other_row(it);
+    oc_it = other_c + it;
+    o_cur = other_row(t_next);
+  }
+  __device__ __forceinline__ void issue_other(int t) {  // explicit frame (catch-up at the junction only)
     if (t >= p2_lo && t <= p2_hi) {
       if (use_oring) {
         const float* src = other_row(t);
@@ -364,13 +396,28 @@ struct FacWalk {
       if (gt == 0) cp_async8(cring + (t & (kFRing - 1)), other_c + t);
     }
   }
-  // issue (one commit group) the asynchronous copies that step `t` of this walk will consume
-  __device__ __forceinline__ void issue(int t) {
-    if (t >= 0 && t < T) {
-      if (gt < N) cp_async4(ering + (t & (kFRing - 1)) * 32 + gt, eb + (size_t)t * N + gt);
-      if (p2_open) issue_other(t);
+  // issue (one commit group) the asynchronous copies of the next frame in walk order
+  __device__ __forceinline__ void issue_next() {
+    if (it >= 0 && it < T) {
+      if (gt < N) cp_async4(ering + islot * 32 + gt, e_it);
+      if (p2_open && it >= p2_lo && it <= p2_hi) {
+        if (use_oring) {
+          float* dst = oring + islot * Lp;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const int l = gt + k * kGroup;
+            if (l < L) cp_async4(dst + l, o_it + l);
+          }
+        }
+        if (gt == 0) cp_async8(cring + islot, oc_it);
+      }
     }
     cp_async_commit();
+    it += dir;
+    islot = (islot + dir) & (kFRing - 1);
+    e_it += dir * N;
+    o_it += dir * Lp;   // only dereferenced while phase 2 is open (re-based by open_phase2)
+    oc_it += dir;
   }
   // One step of this group's walk at frame t: computes row[cur^1] from row[cur] (re-centred by
   // the previous row's maximum).  kMode 0: plain; 1: also store the row to the half lattice;
@@ -378,21 +425,18 @@ struct FacWalk {
   template <int kMode>
   __device__ __forceinline__ void step(int t, double logZ) {
     const float delta = max4_guard(wmax + cur * 4);
-    issue(t + dir * kFDepth);
+    issue_next();
     const int lo = max(0, L - (T - t)), hi = min(t, L - 1);
     const float* rp = row(cur);
     float* rn = row(cur ^ 1);
-    const float* fr = ering + (t & (kFRing - 1)) * 32;
+    const float* fr = ering + slot * 32;
     float Kd = 0.f, rn_lag = 1.f;
     const float* orow = nullptr;
     float* gm = nullptr;
-    float* srow = nullptr;
-    if (kMode == 1)
-      srow = grp == 0 ? p.facA + ((size_t)b * p.h + t) * Lp : p.facB + ((size_t)b * (T - p.h) + (t - p.h)) * Lp;
     if (kMode == 2) {
       // K = C_prev + C_other(t) - logZ ; xi = exp(a + o + K + delta) with a already re-centred
-      Kd = (float)(C + cring[t & (kFRing - 1)] - logZ) + delta;
-      orow = use_oring ? oring + (size_t)(t & (kFRing - 1)) * Lp : other_row(t);
+      Kd = (float)(C + cring[slot] - logZ) + delta;
+      orow = use_oring ? oring + slot * Lp : o_cur;
       gm = gam + (t & 1) * Lp;
       rn_lag = rnorm[t & 1];  // normaliser of two steps ago (written by the flush warp)
     }
@@ -408,7 +452,7 @@ struct FacWalk {
         if (l >= lo && l <= hi) val = fr[yk[k]] + lse2f(a0, a1);
         rn[l] = val;
         lmax = fmaxf(lmax, val);
-        if (kMode == 1) srow[l] = val;
+        if (kMode == 1) srow_run[l] = val;
         if (kMode == 2) {
           const float o = orow[l] + Kd;
           const float xs = __expf(a0 + o);
@@ -421,8 +465,12 @@ struct FacWalk {
     }
     const float wm = warp_max(lmax);
     if (lane == 0) wmax[(cur ^ 1) * 4 + gw] = wm;
-    if (kMode == 1 && gt == 0) (grp == 0 ? p.cA : p.cB)[(size_t)b * T + t] = C;
+    if (kMode == 1 && gt == 0) *c_run = C;
     cur ^= 1;
+    slot = (slot + dir) & (kFRing - 1);
+    srow_run += dir * Lp;
+    c_run += dir;
+    o_cur += dir * Lp;
     cp_async_wait<kFDepth - 1>();  // everything the next step needs has landed (this thread's copies)
     if (kMode == 2)
       named_barrier_sync(4 + grp, kGroup + 32);  // compute warps + flush warp
@@ -606,7 +654,8 @@ __device__ void fac_role(const AsgParams& p, int b, float* smem) {
   // group g (0-based) carries the frame at walk offset g; offsets 0..kFDepth are issued here,
   // step at offset q issues offset q + kFDepth and, before its barrier, waits until at most
   // kFDepth-1 groups are pending, i.e. offset q+1 has landed.
-  for (int q = 0; q <= kFDepth; ++q) w.issue(t_first + dir * q);
+  w.prime(t_first);
+  for (int q = 0; q <= kFDepth; ++q) w.issue_next();
   cp_async_wait<kFDepth - 1>();
   named_barrier_sync(bar_c, kGroup);
 
@@ -708,8 +757,8 @@ __device__ void fac_role(const AsgParams& p, int b, float* smem) {
   // rows for the first kFDepth steps (their frame copies are already in flight), one extra
   // commit group, drained before the walks resume.
   {
-    w.p2_open = true;
     const int t_next = grp == 0 ? h + 1 : h - 1;
+    w.open_phase2(t_next);
     for (int q = 0; q < kFDepth; ++q) w.issue_other(t_next + dir * q);
     cp_async_commit();
     cp_async_wait<0>();
