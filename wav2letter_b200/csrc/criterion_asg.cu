@@ -87,6 +87,41 @@ template <int kPending>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
 }
+// 32-bit shared-window addresses: the FAC step loop addresses ~15 shared locations per step; through generic pointers the
+// compiler re-derived every one of them from the layout arithmetic (and a generic->shared conversion for each cp.async).
+// (the value is laundered through an empty asm so that ptxas keeps it in a register instead of re-deriving it from the
+// thread index and the layout constants inside the loop)
+__device__ __forceinline__ uint32_t sa_of(const void* smem_ptr) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("" : "+r"(a));
+  return a;
+}
+__device__ __forceinline__ int opaque_i(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_d(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void cp_async4_sa(uint32_t dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8_sa(uint32_t dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // 1. prep
@@ -325,10 +360,6 @@ __host__ __device__ inline FacLayout fac_layout(int Lp, int oring) {
 }
 __host__ __device__ inline size_t fac_smem_bytes(int Lp, int oring) { return (size_t)fac_layout(Lp, oring).total * 4; }
 
-__device__ __forceinline__ float max4_guard(const float* w) {
-  float d = fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3]));
-  return (d > -1e30f) ? d : 0.0f;
-}
 
 // State of one group's walk; every method is force-inlined so the fields live in registers.
 // Everything a step addresses is carried as a running pointer / ring slot that advances by a constant per step
@@ -356,12 +387,33 @@ struct FacWalk {
   float* srow_run;      // half-lattice row the next mode-1 step stores
   double* c_run;        // offset slot the next mode-1 step stores
   const float* o_cur;   // other group's row of the next step's frame (direct path, no ring)
+  // shared-window byte addresses (set by bind_shared): rows / warp maxima ping-pong between two fixed addresses
+  uint32_t rp_sa, rn_sa, wm_cur_sa, wm_nxt_sa, ering_sa, oring_sa, cring_sa, gam_cur_sa, gam_oth_sa, rno_cur_sa, rno_oth_sa;
+  uint32_t gt4;         // 4 * gt
+  int Lp4;              // 4 * Lp
+  int yk4[KMAX];        // 4 * label
 
   __device__ __forceinline__ explicit FacWalk(const AsgParams& p_) : p(p_) {}
   __device__ __forceinline__ const float* other_row(int t) const {
     return other_base + (size_t)(grp == 0 ? t - p.h : t) * Lp;
   }
   __device__ __forceinline__ float* row(int k) const { return rowbase + k * (Lp + 4); }
+  // call once the pointer fields, cur (= 0) and yk are set
+  __device__ __forceinline__ void bind_shared() {
+    rp_sa = sa_of(row(0));
+    rn_sa = sa_of(row(1));
+    wm_cur_sa = sa_of(wmax);
+    wm_nxt_sa = sa_of(wmax + 4);
+    ering_sa = sa_of(ering);
+    oring_sa = sa_of(oring);
+    cring_sa = sa_of(cring);
+    gam_cur_sa = gam_oth_sa = sa_of(gam);
+    rno_cur_sa = rno_oth_sa = sa_of(rnorm);
+    gt4 = (uint32_t)opaque_i(4 * gt);
+    Lp4 = opaque_i(4 * Lp);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) yk4[k] = 4 * yk[k];
+  }
   // start the copy pipeline at frame t0 and the walk at frame t0 + dir
   __device__ __forceinline__ void prime(int t0) {
     it = t0;
@@ -381,6 +433,12 @@ struct FacWalk {
     o_it = other_row(it);
     oc_it = other_c + it;
     o_cur = other_row(t_next);
+    const uint32_t g0 = sa_of(gam), r0 = sa_of(rnorm);
+    const int par = t_next & 1;
+    gam_cur_sa = (uint32_t)opaque_i((int)(g0 + par * Lp4));
+    gam_oth_sa = (uint32_t)opaque_i((int)(g0 + (par ^ 1) * Lp4));
+    rno_cur_sa = (uint32_t)opaque_i((int)(r0 + par * 4));
+    rno_oth_sa = (uint32_t)opaque_i((int)(r0 + (par ^ 1) * 4));
   }
   __device__ __forceinline__ void issue_other(int t) {  // explicit frame (catch-up at the junction only)
     if (t >= p2_lo && t <= p2_hi) {
@@ -399,17 +457,17 @@ struct FacWalk {
   // issue (one commit group) the asynchronous copies of the next frame in walk order
   __device__ __forceinline__ void issue_next() {
     if (it >= 0 && it < T) {
-      if (gt < N) cp_async4(ering + islot * 32 + gt, e_it);
+      if (gt < N) cp_async4_sa(ering_sa + islot * 128 + gt4, e_it);
       if (p2_open && it >= p2_lo && it <= p2_hi) {
         if (use_oring) {
-          float* dst = oring + islot * Lp;
+          const uint32_t dst = oring_sa + islot * Lp4 + gt4;
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) {
             const int l = gt + k * kGroup;
-            if (l < L) cp_async4(dst + l, o_it + l);
+            if (l < L) cp_async4_sa(dst + k * (4 * kGroup), o_it + l);
           }
         }
-        if (gt == 0) cp_async8(cring + islot, oc_it);
+        if (gt == 0) cp_async8_sa(cring_sa + islot * 8, oc_it);
       }
     }
     cp_async_commit();
@@ -424,49 +482,65 @@ struct FacWalk {
   // 2: phase 2 — also emit occupancies / transition statistics from the other group's row.
   template <int kMode>
   __device__ __forceinline__ void step(int t, double logZ) {
-    const float delta = max4_guard(wmax + cur * 4);
+    const float4 w4 = lds_f4(wm_cur_sa);
+    const float dmx = fmaxf(fmaxf(w4.x, w4.y), fmaxf(w4.z, w4.w));
+    const float delta = (dmx > -1e30f) ? dmx : 0.0f;
     issue_next();
     const int lo = max(0, L - (T - t)), hi = min(t, L - 1);
-    const float* rp = row(cur);
-    float* rn = row(cur ^ 1);
-    const float* fr = ering + slot * 32;
+    const uint32_t fr_sa = ering_sa + slot * 128;
     float Kd = 0.f, rn_lag = 1.f;
-    const float* orow = nullptr;
-    float* gm = nullptr;
+    uint32_t orow_sa = 0;
     if (kMode == 2) {
       // K = C_prev + C_other(t) - logZ ; xi = exp(a + o + K + delta) with a already re-centred
-      Kd = (float)(C + cring[slot] - logZ) + delta;
-      orow = use_oring ? oring + slot * Lp : o_cur;
-      gm = gam + (t & 1) * Lp;
-      rn_lag = rnorm[t & 1];  // normaliser of two steps ago (written by the flush warp)
+      Kd = (float)(C + lds_d(cring_sa + slot * 8) - logZ) + delta;
+      orow_sa = oring_sa + slot * Lp4 + gt4;
+      rn_lag = lds_f(rno_cur_sa);  // normaliser of two steps ago (written by the flush warp)
     }
     C += (double)delta;
     float lmax = kNegInf;
+    const uint32_t rp_l = rp_sa + gt4, rn_l = rn_sa + gt4, gm_l = gam_cur_sa + gt4;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       const int l = gt + k * kGroup;
+      constexpr int kb = 4 * kGroup;  // byte distance between this thread's consecutive labels
       if (l < L) {
-        const float a0 = rp[l] + (s1k[k] - delta);
-        const float a1 = rp[l - dir] + (s2k[k] - delta);  // pads and missing transitions are -inf
+        const float a0 = lds_f(rp_l + k * kb) + (s1k[k] - delta);
+        const float a1 = lds_f(rp_l + k * kb - 4 * dir) + (s2k[k] - delta);  // pads and missing transitions are -inf
         float val = kNegInf;
-        if (l >= lo && l <= hi) val = fr[yk[k]] + lse2f(a0, a1);
-        rn[l] = val;
+        if (l >= lo && l <= hi) val = lds_f(fr_sa + yk4[k]) + lse2f(a0, a1);
+        sts_f(rn_l + k * kb, val);
         lmax = fmaxf(lmax, val);
         if (kMode == 1) srow_run[l] = val;
         if (kMode == 2) {
-          const float o = orow[l] + Kd;
+          const float o = (use_oring ? lds_f(orow_sa + k * kb) : o_cur[l]) + Kd;
           const float xs = __expf(a0 + o);
           const float xa = __expf(a1 + o);
           ds1k[k] = fmaf(xs, rn_lag, ds1k[k]);
           ds2k[k] = fmaf(xa, rn_lag, ds2k[k]);
-          gm[l] = xs + xa;
+          sts_f(gm_l + k * kb, xs + xa);
         }
       }
     }
     const float wm = warp_max(lmax);
-    if (lane == 0) wmax[(cur ^ 1) * 4 + gw] = wm;
+    if (lane == 0) sts_f(wm_nxt_sa + 4 * gw, wm);
     if (kMode == 1 && gt == 0) *c_run = C;
     cur ^= 1;
+    {
+      uint32_t x = rp_sa;
+      rp_sa = rn_sa;
+      rn_sa = x;
+      x = wm_cur_sa;
+      wm_cur_sa = wm_nxt_sa;
+      wm_nxt_sa = x;
+      if (kMode == 2) {
+        x = gam_cur_sa;
+        gam_cur_sa = gam_oth_sa;
+        gam_oth_sa = x;
+        x = rno_cur_sa;
+        rno_cur_sa = rno_oth_sa;
+        rno_oth_sa = x;
+      }
+    }
     slot = (slot + dir) & (kFRing - 1);
     srow_run += dir * Lp;
     c_run += dir;
@@ -649,6 +723,7 @@ __device__ void fac_role(const AsgParams& p, int b, float* smem) {
     w.ds1k[k] = 0.f;
     w.ds2k[k] = 0.f;
   }
+  w.bind_shared();
   const int bar_c = 2 + grp, dir = w.dir;
   const int t_first = grp == 0 ? 0 : T - 1;
   // group g (0-based) carries the frame at walk offset g; offsets 0..kFDepth are issued here,
