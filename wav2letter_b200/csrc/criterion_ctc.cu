@@ -23,9 +23,24 @@ namespace {
 
 constexpr int kCtcThreads = 256;
 constexpr int kCtcWarps = kCtcThreads / 32;
+// Every per-step global read of the chains (the gathered activations e_t[z_s], the stored alpha row in the beta walk) is
+// requested kCtcDepth steps ahead with cp.async into shared-memory rings; the per-frame scalars live in shared memory.
+// With one-step-ahead register prefetch the step time was one DRAM latency (~0.9 us): 0.28 ms for T' = 150.
+// The depth is a template parameter (8 / 4 / 2 / 1, ring = 2 x depth slots): long targets shrink the rings to fit.
+
+__device__ __forceinline__ void ctc_cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ctc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void ctc_cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
 
 struct CtcParams {
   int B, T, N, L, Sp, scale_mode, need_grad;
+  int t_smem;     // per-frame scalars (lz, alpha offsets) of a sample fit in shared memory
   const float* emis;
   const int32_t* target;
   const float* dloss;
@@ -93,15 +108,20 @@ __device__ __forceinline__ float lse3f(float a, float b, float c) {
 }
 
 // block-wide max of per-thread values through per-warp slots (caller supplies the barrier)
-template <bool kGrad>
+template <bool kGrad, int kCtcDepth>
 __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
+  constexpr int kCtcRing = 2 * kCtcDepth;  // slots, power of two > depth
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = p.T, N = p.N, Sp = p.Sp, blank = N - 1;
   float* row0 = reinterpret_cast<float*>(smem_raw) + 4;  // index -2..Sp+1 valid
   float* row1 = row0 + Sp + 8;
   int32_t* z = reinterpret_cast<int32_t*>(row1 + Sp + 4);
-  uint8_t* skip = reinterpret_cast<uint8_t*>(z + Sp);  // skip[s]: s-2 -> s allowed
+  float* ering = reinterpret_cast<float*>(z + Sp);              // [kCtcRing][Sp] gathered activations
+  float* lring = ering + (size_t)kCtcRing * Sp;                  // [kCtcRing][Sp] stored alpha rows (beta walk)
+  double* cA_s = reinterpret_cast<double*>(lring + (size_t)kCtcRing * Sp);  // [T] when p.t_smem
+  float* lz_s = reinterpret_cast<float*>(cA_s + (p.t_smem ? p.T : 0));     // [T] when p.t_smem
+  uint8_t* skip = reinterpret_cast<uint8_t*>(lz_s + (p.t_smem ? p.T : 0));  // skip[s]: s-2 -> s allowed
   __shared__ float wmax[2][kCtcWarps];
   __shared__ float wsum[2][kCtcWarps];
   __shared__ double ll_s;
@@ -124,6 +144,9 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     row0[s - 4] = kNegInf;
     row1[s - 4] = kNegInf;
   }
+  const bool ts = p.t_smem != 0;
+  if (ts)
+    for (int t = tid; t < T; t += kCtcThreads) lz_s[t] = lzb[t];
   __syncthreads();
   for (int s = tid; s < Sp; s += kCtcThreads) skip[s] = (s >= 2 && s < S && z[s] != blank && z[s] != z[s - 2]) ? 1 : 0;
   // t = 0
@@ -137,57 +160,58 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     }
     lm = warp_max(lm);
     if (lane == 0) wmax[0][warp] = lm;
-    if (kGrad && tid == 0) p.cA[(size_t)b * T] = 0.0;
+    if (kGrad && tid == 0) {
+      p.cA[(size_t)b * T] = 0.0;
+      if (p.t_smem) cA_s[0] = 0.0;
+    }
   }
   __syncthreads();
   float* rp = row0;
   float* rn = row1;
   double C = 0.0;
   int par = 0;
-  // gathered activations e_t[z_s] of the NEXT step are prefetched into registers (first kPf
-  // states of a thread); longer targets fall back to a direct load.
-  constexpr int kPf = 4;
-  float epf[kPf];
-#pragma unroll
-  for (int k = 0; k < kPf; ++k) {
-    const int s = tid + k * kCtcThreads;
-    epf[k] = (T > 1 && s < S) ? eb[(size_t)1 * N + z[s]] : 0.f;
-  }
+  // one commit group per frame: the activations e_f[z_s] of this thread's states
+  auto issue_a = [&](int f) {
+    if (f < T) {
+      float* dst = ering + (size_t)(f & (kCtcRing - 1)) * Sp;
+      const float* src = eb + (size_t)f * N;
+      for (int s = tid; s < S; s += kCtcThreads) ctc_cp_async4(dst + s, src + z[s]);
+    }
+    ctc_cp_commit();
+  };
+  for (int q = 1; q <= kCtcDepth; ++q) issue_a(q);
   for (int t = 1; t < T; ++t) {
+    ctc_cp_wait<kCtcDepth - 1>();  // frame t has landed (own copies: no barrier needed)
+    issue_a(t + kCtcDepth);
     float d = wmax[par][0];
 #pragma unroll
     for (int w = 1; w < kCtcWarps; ++w) d = fmaxf(d, wmax[par][w]);
     if (!(d > -1e30f)) d = 0.f;
     C += (double)d;
-    const float lzt = lzb[t] + d;
+    const float lzt = (ts ? lz_s[t] : lzb[t]) + d;
     float lm = kNegInf;
-    auto body = [&](int s, float ev) {
+    const float* er = ering + (size_t)(t & (kCtcRing - 1)) * Sp;
+    for (int s = tid; s < S; s += kCtcThreads) {
       const float a2 = skip[s] ? rp[s - 2] : kNegInf;
       const float v = lse3f(rp[s], rp[s - 1], a2);
-      const float val = (v == kNegInf) ? kNegInf : v + (ev - lzt);
+      const float val = (v == kNegInf) ? kNegInf : v + (er[s] - lzt);
       rn[s] = val;
       lm = fmaxf(lm, val);
       if (kGrad) lat[(size_t)t * Sp + s] = val;
-    };
-#pragma unroll
-    for (int k = 0; k < kPf; ++k) {
-      const int s = tid + k * kCtcThreads;
-      if (s < S) {
-        const float ev = epf[k];
-        if (t + 1 < T) epf[k] = eb[(size_t)(t + 1) * N + z[s]];
-        body(s, ev);
-      }
     }
-    for (int s = tid + kPf * kCtcThreads; s < S; s += kCtcThreads) body(s, eb[(size_t)t * N + z[s]]);
     lm = warp_max(lm);
     if (lane == 0) wmax[par ^ 1][warp] = lm;
-    if (kGrad && tid == 0) p.cA[(size_t)b * T + t] = C;
+    if (kGrad && tid == 0) {
+      p.cA[(size_t)b * T + t] = C;
+      if (ts) cA_s[t] = C;
+    }
     __syncthreads();
     float* tmp = rp;
     rp = rn;
     rn = tmp;
     par ^= 1;
   }
+  ctc_cp_wait<0>();
   if (tid == 0) {
     const float a = rp[S - 1], a2 = S > 1 ? rp[S - 2] : kNegInf;
     const double ll = (double)lse2f(a, a2) + C;
@@ -237,12 +261,23 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kPf; ++k) {
-    const int s = tid + k * kCtcThreads;
-    epf[k] = (T > 1 && s < S) ? eb[(size_t)(T - 2) * N + z[s]] : 0.f;
-  }
+  // one commit group per frame: activations and the stored alpha row of this thread's states
+  auto issue_b = [&](int f) {
+    if (f >= 0) {
+      const size_t slot = (size_t)(f & (kCtcRing - 1)) * Sp;
+      const float* src = eb + (size_t)f * N;
+      const float* lsrc = lat + (size_t)f * Sp;
+      for (int s = tid; s < S; s += kCtcThreads) {
+        ctc_cp_async4(ering + slot + s, src + z[s]);
+        ctc_cp_async4(lring + slot + s, lsrc + s);
+      }
+    }
+    ctc_cp_commit();
+  };
+  for (int q = 0; q < kCtcDepth; ++q) issue_b(T - 2 - q);
   for (int t = T - 2; t >= 0; --t) {
+    ctc_cp_wait<kCtcDepth - 1>();
+    issue_b(t - kCtcDepth);
     float d = wmax[par][0], psm = wsum[par][0];
 #pragma unroll
     for (int w = 1; w < kCtcWarps; ++w) {
@@ -252,31 +287,22 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     if (tid == 0) p.psum[(size_t)b * T + t + 1] = psm;
     if (!(d > -1e30f)) d = 0.f;
     CB += (double)d;
-    const float lz_t = lzb[t];
-    const float K = (float)(p.cA[(size_t)b * T + t] + CB - ll);
+    const float lz_t = ts ? lz_s[t] : lzb[t];
+    const float K = (float)((ts ? cA_s[t] : p.cA[(size_t)b * T + t]) + CB - ll);
     float lm = kNegInf, ps = 0.f;
-    auto body = [&](int s, float ev) {
+    const size_t slot = (size_t)(t & (kCtcRing - 1)) * Sp;
+    for (int s = tid; s < S; s += kCtcThreads) {
       const float b2 = (s + 2 < S && skip[s + 2]) ? rp[s + 2] : kNegInf;
       const float v = lse3f(rp[s], rp[s + 1], b2);
-      const float lp = ev - lz_t;
+      const float lp = ering[slot + s] - lz_t;
       const float val = (v == kNegInf) ? kNegInf : v + (lp - d);
       rn[s] = val;
       lm = fmaxf(lm, val);
-      const float q = lat[(size_t)t * Sp + s] + val - lp + K;
+      const float q = lring[slot + s] + val - lp + K;
       const float post = (val == kNegInf) ? 0.f : __expf(q);
       lat[(size_t)t * Sp + s] = post;
       ps += post;
-    };
-#pragma unroll
-    for (int k = 0; k < kPf; ++k) {
-      const int s = tid + k * kCtcThreads;
-      if (s < S) {
-        const float ev = epf[k];
-        if (t >= 1) epf[k] = eb[(size_t)(t - 1) * N + z[s]];
-        body(s, ev);
-      }
     }
-    for (int s = tid + kPf * kCtcThreads; s < S; s += kCtcThreads) body(s, eb[(size_t)t * N + z[s]]);
     lm = warp_max(lm);
     ps = warp_sum(ps);
     if (lane == 0) {
@@ -289,6 +315,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     rn = tmp;
     par ^= 1;
   }
+  ctc_cp_wait<0>();
   if (tid == 0) {
     float psm = 0.f;
     for (int w = 0; w < kCtcWarps; ++w) psm += wsum[par][w];
@@ -387,26 +414,40 @@ extern "C" int w2l_ctc_forward_backward(void* stream_, int B, int T, int N, int 
   carve(p, workspace, need);
   if (!workspace || workspace_bytes < need)
     return fail(W2L_ERR_WORKSPACE, "ctc: workspace too small (need " + std::to_string(need) + " bytes)");
-  const size_t smem = (size_t)(2 * (p.Sp + 8) + p.Sp) * 4 + p.Sp + 64;
+  const size_t smem_base = (size_t)(2 * (p.Sp + 8) + p.Sp) * 4 + p.Sp + 64;
+  int depth = 8;
+  while (depth > 1 && smem_base + (size_t)4 * depth * p.Sp * 4 > 200 * 1024) depth >>= 1;
+  size_t smem = smem_base + (size_t)4 * depth * p.Sp * 4;  // two rings of 2*depth slots
   if (smem > 200 * 1024) return fail(W2L_ERR_UNSUPPORTED, "ctc: target too long for the shared-memory rows");
+  p.t_smem = smem + (size_t)T * 12 <= 200 * 1024 ? 1 : 0;
+  if (p.t_smem) smem += (size_t)T * 12;
   const long long nframes = (long long)B * T;
   const int frame_blocks = (int)std::min<long long>((nframes + 7) / 8, 148 * 8);
   ctc_prep_kernel<<<frame_blocks + (B + 255) / 256, 256, 0, stream>>>(p, frame_blocks);
   W2L_LAUNCH_CHECK("ctc_prep_kernel");
   if (p.need_grad) {
-    if (smem > 48 * 1024)
-      W2L_CUDA_CHECK(cudaFuncSetAttribute(ctc_chains_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define W2L_CTC_LAUNCH(GRAD, D)                                                                                               \
+  do {                                                                                                                         \
+    if (smem > 48 * 1024)                                                                                                      \
+      W2L_CUDA_CHECK(cudaFuncSetAttribute(ctc_chains_kernel<GRAD, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_chains_kernel<GRAD, D><<<B, kCtcThreads, smem, stream>>>(p);                                                           \
+  } while (0)
+#define W2L_CTC_DISPATCH(GRAD)                \
+  do {                                        \
+    if (depth == 8) W2L_CTC_LAUNCH(GRAD, 8);  \
+    else if (depth == 4) W2L_CTC_LAUNCH(GRAD, 4); \
+    else if (depth == 2) W2L_CTC_LAUNCH(GRAD, 2); \
+    else W2L_CTC_LAUNCH(GRAD, 1);             \
+  } while (0)
     profile_kind(2);
     profile_start(stream);
-    ctc_chains_kernel<true><<<B, kCtcThreads, smem, stream>>>(p);
+    W2L_CTC_DISPATCH(true);
     profile_stop(stream);
     W2L_LAUNCH_CHECK("ctc_chains_kernel<grad>");
     ctc_grad_kernel<<<(unsigned)nframes, 256, 0, stream>>>(p);
     W2L_LAUNCH_CHECK("ctc_grad_kernel");
   } else {
-    if (smem > 48 * 1024)
-      W2L_CUDA_CHECK(cudaFuncSetAttribute(ctc_chains_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_chains_kernel<false><<<B, kCtcThreads, smem, stream>>>(p);
+    W2L_CTC_DISPATCH(false);
     W2L_LAUNCH_CHECK("ctc_chains_kernel<fwd>");
   }
   return W2L_OK;
