@@ -112,7 +112,8 @@ template <bool kGrad, int kCtcDepth>
 __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
   constexpr int kCtcRing = 2 * kCtcDepth;  // slots, power of two > depth
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the block is sized to the state count (32 .. 256 threads): idle warps would still spend issue slots on every step
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = blockDim.x >> 5;
   const int T = p.T, N = p.N, Sp = p.Sp, blank = N - 1;
   float* row0 = reinterpret_cast<float*>(smem_raw) + 4;  // index -2..Sp+1 valid
   float* row1 = row0 + Sp + 8;
@@ -135,26 +136,26 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
   const float* eb = p.emis + (size_t)b * T * N;
   const float* lzb = p.lz + (size_t)b * T;
   float* lat = p.lat + (size_t)b * T * Sp;
-  for (int s = tid; s < Sp; s += kCtcThreads) {
+  for (int s = tid; s < Sp; s += nthr) {
     int zs = blank;
     if (s < S && (s & 1)) zs = yg[s >> 1];
     z[s] = zs;
   }
-  for (int s = tid; s < Sp + 8; s += kCtcThreads) {
+  for (int s = tid; s < Sp + 8; s += nthr) {
     row0[s - 4] = kNegInf;
     row1[s - 4] = kNegInf;
   }
   const bool ts = p.t_smem != 0;
   if (ts)
-    for (int t = tid; t < T; t += kCtcThreads) lz_s[t] = lzb[t];
+    for (int t = tid; t < T; t += nthr) lz_s[t] = lzb[t];
   __syncthreads();
-  for (int s = tid; s < Sp; s += kCtcThreads) skip[s] = (s >= 2 && s < S && z[s] != blank && z[s] != z[s - 2]) ? 1 : 0;
+  for (int s = tid; s < Sp; s += nthr) skip[s] = (s >= 2 && s < S && z[s] != blank && z[s] != z[s - 2]) ? 1 : 0;
   // t = 0
   if (tid < 2 && tid < S) row0[tid] = eb[z[tid]] - lzb[0];
   __syncthreads();
   {
     float lm = kNegInf;
-    for (int s = tid; s < S; s += kCtcThreads) {
+    for (int s = tid; s < S; s += nthr) {
       lm = fmaxf(lm, row0[s]);
       if (kGrad) lat[s] = row0[s];
     }
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     if (f < T) {
       float* dst = ering + (size_t)(f & (kCtcRing - 1)) * Sp;
       const float* src = eb + (size_t)f * N;
-      for (int s = tid; s < S; s += kCtcThreads) ctc_cp_async4(dst + s, src + z[s]);
+      for (int s = tid; s < S; s += nthr) ctc_cp_async4(dst + s, src + z[s]);
     }
     ctc_cp_commit();
   };
@@ -185,13 +186,13 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     issue_a(t + kCtcDepth);
     float d = wmax[par][0];
 #pragma unroll
-    for (int w = 1; w < kCtcWarps; ++w) d = fmaxf(d, wmax[par][w]);
+    for (int w = 1; w < nw; ++w) d = fmaxf(d, wmax[par][w]);
     if (!(d > -1e30f)) d = 0.f;
     C += (double)d;
     const float lzt = (ts ? lz_s[t] : lzb[t]) + d;
     float lm = kNegInf;
     const float* er = ering + (size_t)(t & (kCtcRing - 1)) * Sp;
-    for (int s = tid; s < S; s += kCtcThreads) {
+    for (int s = tid; s < S; s += nthr) {
       const float a2 = skip[s] ? rp[s - 2] : kNegInf;
       const float v = lse3f(rp[s], rp[s - 1], a2);
       const float val = (v == kNegInf) ? kNegInf : v + (er[s] - lzt);
@@ -222,12 +223,12 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
   __syncthreads();
   const double ll = ll_s;
   if (!(ll > -1e30)) {  // infeasible: zero gradient
-    for (size_t k = tid; k < (size_t)T * Sp; k += kCtcThreads) lat[k] = 0.f;
-    for (int t = tid; t < T; t += kCtcThreads) p.psum[(size_t)b * T + t] = 1.f;
+    for (size_t k = tid; k < (size_t)T * Sp; k += nthr) lat[k] = 0.f;
+    for (int t = tid; t < T; t += nthr) p.psum[(size_t)b * T + t] = 1.f;
     return;
   }
   // ---- beta walk; posteriors overwrite the alpha lattice ------------------------------------------
-  for (int s = tid; s < Sp + 8; s += kCtcThreads) {
+  for (int s = tid; s < Sp + 8; s += nthr) {
     row0[s - 4] = kNegInf;
     row1[s - 4] = kNegInf;
   }
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
   {
     const float K = (float)(p.cA[(size_t)b * T + T - 1] + 0.0 - ll);
     float lm = kNegInf, ps = 0.f;
-    for (int s = tid; s < S; s += kCtcThreads) {
+    for (int s = tid; s < S; s += nthr) {
       const float bt = rp[s];
       lm = fmaxf(lm, bt);
       const float lp = eb[(size_t)(T - 1) * N + z[s]] - lzb[T - 1];
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
       const size_t slot = (size_t)(f & (kCtcRing - 1)) * Sp;
       const float* src = eb + (size_t)f * N;
       const float* lsrc = lat + (size_t)f * Sp;
-      for (int s = tid; s < S; s += kCtcThreads) {
+      for (int s = tid; s < S; s += nthr) {
         ctc_cp_async4(ering + slot + s, src + z[s]);
         ctc_cp_async4(lring + slot + s, lsrc + s);
       }
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     issue_b(t - kCtcDepth);
     float d = wmax[par][0], psm = wsum[par][0];
 #pragma unroll
-    for (int w = 1; w < kCtcWarps; ++w) {
+    for (int w = 1; w < nw; ++w) {
       d = fmaxf(d, wmax[par][w]);
       psm += wsum[par][w];
     }
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
     const float K = (float)((ts ? cA_s[t] : p.cA[(size_t)b * T + t]) + CB - ll);
     float lm = kNegInf, ps = 0.f;
     const size_t slot = (size_t)(t & (kCtcRing - 1)) * Sp;
-    for (int s = tid; s < S; s += kCtcThreads) {
+    for (int s = tid; s < S; s += nthr) {
       const float b2 = (s + 2 < S && skip[s + 2]) ? rp[s + 2] : kNegInf;
       const float v = lse3f(rp[s], rp[s + 1], b2);
       const float lp = ering[slot + s] - lz_t;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
   ctc_cp_wait<0>();
   if (tid == 0) {
     float psm = 0.f;
-    for (int w = 0; w < kCtcWarps; ++w) psm += wsum[par][w];
+    for (int w = 0; w < nw; ++w) psm += wsum[par][w];
     p.psum[(size_t)b * T] = psm;
   }
 }
@@ -430,7 +431,7 @@ extern "C" int w2l_ctc_forward_backward(void* stream_, int B, int T, int N, int 
   do {                                                                                                                         \
     if (smem > 48 * 1024)                                                                                                      \
       W2L_CUDA_CHECK(cudaFuncSetAttribute(ctc_chains_kernel<GRAD, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ctc_chains_kernel<GRAD, D><<<B, kCtcThreads, smem, stream>>>(p);                                                           \
+    ctc_chains_kernel<GRAD, D><<<B, std::min(kCtcThreads, p.Sp), smem, stream>>>(p);                                                          \
   } while (0)
 #define W2L_CTC_DISPATCH(GRAD)                \
   do {                                        \
