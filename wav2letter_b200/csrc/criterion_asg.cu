@@ -559,15 +559,19 @@ struct FacWalk {
 // that chain (8 positions per label on average for L = 250, N = 30) used to set the length of every phase-2 step.
 constexpr int kFlushRegs = 16;
 struct FlushIndex {
-  int cnt, rest0, rest1;
-  int pos[kFlushRegs];
+  int rest0, rest1;
+  int pos[kFlushRegs];     // j-th position of this lane's label inside a gamma row (0 past the count)
+  float use[kFlushRegs];   // 1 for a real position, 0 past the count (the load then reads slot 0 and is multiplied away)
   __device__ __forceinline__ void load(const int* order, const int* start, int lane) {
     const int i0 = start[lane], i1 = start[lane + 1];
-    cnt = min(kFlushRegs, i1 - i0);
+    const int cnt = min(kFlushRegs, i1 - i0);
     rest0 = i0 + kFlushRegs;
     rest1 = i1;
 #pragma unroll
-    for (int j = 0; j < kFlushRegs; ++j) pos[j] = j < cnt ? order[i0 + j] : 0;
+    for (int j = 0; j < kFlushRegs; ++j) {
+      pos[j] = j < cnt ? order[i0 + j] : 0;
+      use[j] = j < cnt ? 1.f : 0.f;
+    }
   }
 };
 __device__ __forceinline__ void fac_flush(const float* gm, const int* order, const FlushIndex& fx, int lane, float* Grow,
@@ -575,10 +579,10 @@ __device__ __forceinline__ void fac_flush(const float* gm, const int* order, con
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int j = 0; j < kFlushRegs; j += 2) {
-    const float v0 = gm[fx.pos[j]], v1 = gm[fx.pos[j + 1]];  // pos is 0 (a valid slot) past cnt
-    s0 += j < fx.cnt ? v0 : 0.f;
-    s1 += j + 1 < fx.cnt ? v1 : 0.f;
+    s0 = fmaf(fx.use[j], gm[fx.pos[j]], s0);
+    s1 = fmaf(fx.use[j + 1], gm[fx.pos[j + 1]], s1);
   }
+#pragma unroll 1
   for (int i = fx.rest0; i < fx.rest1; ++i) s0 += gm[order[i]];  // labels with more than kFlushRegs positions
   const float s = s0 + s1;
   const int tot_i = __reduce_add_sync(0xffffffffu, __float2int_rn(s * kFix));
