@@ -405,7 +405,7 @@ def run_conv_glu(args, rank, world, local_rank):
     line = {
         "metric": "frames_per_sec", "value": B * T * world * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 storage, tf32 tensor-core math with f32 accumulation", "data": "synthetic",
+        "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
         "config": {"workload": "conv_glu LibriSpeech 17-layer Conv1D+GLU acoustic model (WeightNorm) + ASG, full train step, "
                                f"B={B} x T={T} frames x {F} filterbanks per GPU, {N} letter classes "
                                "(BASELINE.json configs[2] shape; recipes/conv_glu/librispeech/network.arch)",
@@ -492,7 +492,8 @@ def run_tds(args, rank, world, local_rank):
     line = {
         "metric": "frames_per_sec", "value": frames * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 storage, tf32 tensor-core math with f32 accumulation (dense), f32 elsewhere",
+        "vs_baseline": None, "dtype": "tf32",
+        "dtype_note": "f32 storage; dense contractions (Linear, time convolution) multiply TF32 operands on the tensor cores with f32 accumulation (what north_star asks of the TDS blocks; >= the bf16 of BASELINE configs 2-3); criterion, LayerNorm, optimizer in f32/f64",
         "data": "synthetic",
         "config": {"workload": "seq2seq_tds LibriSpeech TDS acoustic model + CTC, full train step (fwd, CTC, bwd, all-reduce, clip, SGD), "
                                f"B={B} x T={T} frames x {F} filterbanks per GPU, {N} word-piece classes, targets <= {L} "
