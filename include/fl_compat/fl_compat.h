@@ -418,7 +418,7 @@ void allReduceParameters(const std::shared_ptr<const Module>& module);  // avera
 // stream wait for all reductions.
 class OverlappedArenaReducer {
  public:
-  OverlappedArenaReducer(const std::vector<Variable>& params, const af::array& arenaGrads, size_t bucketBytes = (size_t)8 << 20);
+  OverlappedArenaReducer(const std::vector<Variable>& params, const af::array& arenaGrads, size_t bucketBytes = (size_t)24 << 20);
   ~OverlappedArenaReducer();
   void arm();       // call after zeroGrad, before loss.backward()
   void finalize();  // call after backward
