@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <functional>
 #include <memory>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -32,7 +33,7 @@
 
 namespace w2l {
 
-enum class DType { f32, i32, f64, u8 };
+enum class DType { f32, i32, f64, u8, bf16 };
 size_t dtypeSize(DType t);
 
 struct Storage;
@@ -253,6 +254,21 @@ class Dropout : public UnaryModule {
   double p_;
 };
 
+// fl::SpecAugment(tWarpW, fMaskF, nFMask, tMaskT, tMaskP, nTMask) — arch opcode `SAUG` (cpc/SequentialBuilder.cpp:602-613;
+// recipes/streaming_convnets/librispeech/am_500ms_future_context.arch:2).  Training mode: nFMask frequency bands and
+// nTMask time bands of the filterbank input are zeroed (the same bands for the whole batch); eval mode: identity.
+class SpecAugment : public UnaryModule {
+ public:
+  SpecAugment(int tWarpW, int fMaskF, int nFMask, int tMaskT, double tMaskP, int nTMask);
+  Variable forward(const Variable& in) override;
+  std::string prettyString() const override;
+
+ private:
+  int tWarpW_, fMaskF_, nFMask_, tMaskT_, nTMask_;
+  double tMaskP_;
+  std::mt19937_64 rng_;
+};
+
 // fl::LayerNorm over axes {0,1,2} (whole sample) with the scalar affine the TDS archs use.
 class LayerNorm : public UnaryModule {
  public:
@@ -389,6 +405,7 @@ class SGDOptimizer : public FirstOrderOptimizer {
 
  private:
   double mu_, wd_;
+  bool nesterov_ = false;
   std::vector<af::array> velocities_;
 };
 
@@ -424,6 +441,7 @@ class OverlappedArenaReducer {
   void finalize();  // call after backward
   int buckets() const { return (int)bucket_.size(); }
   void onGradReady(const void* id);  // called by Variable::addGrad for arena-bound parameters
+  void expectContribution(const void* id);  // called by Variable::backward once per graph node that consumes the parameter
 
  private:
   struct Bucket {
@@ -436,7 +454,7 @@ class OverlappedArenaReducer {
   af::array grads_;
   std::vector<Bucket> bucket_;
   std::vector<std::pair<const void*, int>> owner_;  // sorted (variable id, bucket)
-  std::vector<char> seen_;
+  std::vector<int> seen_, expected_;  // contributions landed / announced per parameter (a shared parameter has several)
   void* comm_stream_ = nullptr;
   void* done_ = nullptr;
   bool armed_ = false;
@@ -464,6 +482,9 @@ namespace runtime {
 // rendezvous: `id128` = ncclUniqueId bytes created by rank 0 (createUniqueId) and shipped by the launcher
 void createUniqueId(void* id128);
 void initDistributed(int worldRank, int worldSize, const void* id128);
+// the reference's call (Train.cpp:189-193): initDistributed(FLAGS_world_rank, FLAGS_world_size, FLAGS_max_devices_per_node,
+// FLAGS_rndv_filepath) — rank 0 publishes the id in a file under rndvFilepath, the others wait for it
+void initDistributed(int worldRank, int worldSize, int maxDevicesPerNode, const std::string& rndvFilepath);
 // arch DSL -> fl::Sequential (opcodes V RO PD C2 R DO LN TDS L SAUG; cpc/SequentialBuilder.cpp:29-57,92-626)
 std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, int64_t nFeatures, int64_t nClasses);
 std::shared_ptr<Sequential> buildSequentialModuleFromFile(const std::string& path, int64_t nFeatures, int64_t nClasses);
@@ -525,8 +546,8 @@ class ConnectionistTemporalClassificationCriterion : public SequenceCriterion {
 };
 using CTCLoss = ConnectionistTemporalClassificationCriterion;
 
-// LinSegCriterion(numClasses, scalemode): FAC on the linearly stretched target, sharing the ASG
-// transitions through setParams(asg->param(0), 0) — Train.cpp:589-617
+// LinSegCriterion(numClasses, scalemode): ASG (FCC - FAC) on the linearly stretched target, sharing the ASG
+// transitions through setParams(asg->param(0), 0) — Train.cpp:589-617, warm start :1867-1883
 class LinearSegmentationCriterion : public SequenceCriterion {
  public:
   LinearSegmentationCriterion(int N, CriterionScaleMode scalemode = CriterionScaleMode::NONE);

@@ -60,7 +60,7 @@ enum {
 /* which terms of the ASG criterion a call evaluates */
 enum {
   W2L_TERM_FCC = 1, /* FullConnectionCriterion: loss = +FCC                       */
-  W2L_TERM_FAC = 2, /* ForceAlignmentCriterion: loss = +FAC (LinSeg uses this)    */
+  W2L_TERM_FAC = 2, /* ForceAlignmentCriterion: loss = +FAC                       */
   W2L_TERM_ASG = 3  /* AutoSegmentationCriterion: loss = FCC - FAC                */
 };
 
@@ -139,14 +139,14 @@ W2L_API int w2l_ctc_forward_backward(void* stream, int B, int T, int N, int L, i
 W2L_API int w2l_argmax_path(void* stream, int B, int T, int N, const float* emis, int32_t* path);
 
 /* LinearSegmentationCriterion's target stretch (Train.cpp:589-617, --linseg): out[b][t] =
- * target[b][floor(t * L_b / T)]; feed it to w2l_asg_forward_backward(W2L_TERM_FAC, L = T). */
+ * target[b][floor(t * L_b / T)]; LinSeg = w2l_asg_forward_backward(W2L_TERM_ASG, L = T) on it (loss FCC - FAC). */
 W2L_API int w2l_linseg_target(void* stream, int B, int T, int L, const int32_t* target, int32_t* out);
 
 /* ----------------------------------------------------------------------------------------
  * Dense contraction of the acoustic model (replaces fl::Linear's af::matmul -> cuBLAS and the
  * GEMM inside cuDNN's convolutions; forward at Train.cpp:1470, backward at :1720).
- *   C[m][n] = act( sum_k A(m,k) * B(n,k) + bias[n] ),  fp32 storage, TF32 tcgen05 math, fp32
- *   accumulation.  a_mn_major = 0: A stored [M][K] (lda), 1: A stored [K][M];  b_mn_major = 0:
+ *   C[m][n] = act( sum_k A(m,k) * B(n,k) + bias[n] ),  fp32 storage, tcgen05 math in the kind the thread's precision
+ *   setting selects (TF32 by default, F32X3 under W2L_PRECISION_F32), fp32 accumulation.  a_mn_major = 0: A stored [M][K] (lda), 1: A stored [K][M];  b_mn_major = 0:
  *   B stored [N][K] (ldb), 1: B stored [K][N].  forward Y = X W^T : (0,0); dgrad dX = dY W :
  *   (0,1) with B = W; wgrad dW = dY^T X : (1,1) with A = dY, B = X.  bias nullable; act 0 none,
  *   1 ReLU.  lda/ldb must be multiples of 4 floats and A/B 16-byte aligned (TMA).
@@ -161,6 +161,31 @@ W2L_API int w2l_linseg_target(void* stream, int B, int T, int L, const int32_t* 
  * (the data gradient's kw-1 frames of left context are kw-1 zero rows in front of dY: the caller pads a copy) */
 W2L_API int w2l_gemm_tf32_view(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
                                const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate);
+/* Operand kinds of the tcgen05 GEMM (csrc/gemm_umma.cu) and the precision setting that selects among them.
+ *   TF32  : fp32 operands in HBM, TF32 products (10-bit mantissa), fp32 accumulation — what cuDNN/cuBLAS do by default
+ *           for fp32 tensors on Ampere+; the default.
+ *   F32X3 : fp32 operands in HBM, fp32-ACCURATE contraction: each staged tile is split hi/lo in shared memory and the
+ *           tensor core accumulates Al*Bh + Ah*Bl + Ah*Bh (error-compensated 3xTF32, products good to ~2^-21) — the
+ *           precision BASELINE.json configs[1] ("fp32") states; the time convolutions use the fp32 SIMT kernels.
+ *   BF16  : bf16 operands in HBM (activations / weights cast by their producers), fp32 accumulation — the AMP mode of
+ *           the reference (recipes/slimIPL/src/Train.cpp:211-219) with bf16 instead of fp16, configs[2]/[3].
+ * w2l_set_precision is thread-local and selects the kind used by the fp32-operand entry points (w2l_gemm_tf32*,
+ * w2l_conv_time_*) and by the fl_compat modules (which cast their GEMM operands in BF16 mode). */
+enum { W2L_GEMM_TF32 = 0, W2L_GEMM_F32X3 = 1, W2L_GEMM_BF16 = 2 };
+enum { W2L_PRECISION_TF32 = 0, W2L_PRECISION_F32 = 1, W2L_PRECISION_BF16 = 2 };
+W2L_API int w2l_set_precision(int precision);
+W2L_API int w2l_get_precision(void);
+/* General form: A / B are fp32 (kinds TF32, F32X3) or bf16 (kind BF16) with lda / ldb in ELEMENTS (rows 16-byte aligned:
+ * ld % 4 for fp32, ld % 8 for bf16); C is fp32 or bf16 (c_bf16; no accumulate / split-K then); aux (the backward mask
+ * source) fp32 or bf16 (aux_bf16).  allow_overlap: operand rows may overlap (im2col views, see w2l_gemm_tf32_view). */
+W2L_API int w2l_gemm(void* stream, int kind, int a_mn_major, int b_mn_major, int M, int N, int K, const void* A, int lda,
+                     const void* B, int ldb, void* C, int ldc, int c_bf16, const float* bias, int act, int accumulate,
+                     const void* aux, int ld_aux, int aux_bf16, int aux_mode, float aux_scale, float dropout_p,
+                     unsigned long long seed, int allow_overlap);
+/* fp32 -> bf16 (round to nearest even): flat, and row-wise with zero-padded columns (rows of `cols` floats, row stride
+ * ld_in, to rows of cols_padded bf16) */
+W2L_API int w2l_cast_bf16(void* stream, long long n, const float* x, void* y);
+W2L_API int w2l_cast_bf16_rows(void* stream, long long rows, int cols, int ld_in, int cols_padded, const float* x, void* y);
 /* Pin the GEMM tile width (128 / 160 / 224 / 256; 0 = choose per shape, the default).  Thread-local; for tests and tuning. */
 W2L_API int w2l_gemm_set_tile(int bn);
 W2L_API int w2l_gemm_tf32(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
@@ -242,6 +267,18 @@ W2L_API int w2l_colsum_accumulate(void* stream, int M, int N, const float* X, in
 W2L_API int w2l_sq_norm_accumulate(void* stream, long long n, const float* g, double* out);
 W2L_API int w2l_sgd_step(void* stream, long long n, float* params, const float* grads, float* velocity, float lr,
                          float momentum, float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm);
+/* + Nesterov momentum (fl::SGDOptimizer useNesterov: g += momentum * v after the velocity update) and a device-side guard:
+ * guard[0] != 0 -> the update is skipped.  w2l_finite_guard sets guard[0] = (any loss[i] or *sq_norm is NaN / Inf) and
+ * adds 1 to guard[1] when it is: the NaN check of Train.cpp:1686-1698 and the mixed-precision overflow check of
+ * :1753-1771 without a host round trip (the host reads the counter when it wants to). */
+W2L_API int w2l_sgd_step_ex(void* stream, long long n, float* params, const float* grads, float* velocity, float lr, float momentum,
+                            float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm, int nesterov,
+                            const int* guard);
+W2L_API int w2l_finite_guard(void* stream, int n_loss, const float* loss, const double* sq_norm, int* guard);
+/* fl::SpecAugment masking (arch opcode SAUG, cpc/SequentialBuilder.cpp:602-613) on [B][T][C][W] activations: frequency
+ * bands [f0,f1) of W and time bands [t0,t1) of T (host arrays, <= 8 each; the same bands for the whole batch) := value */
+W2L_API int w2l_mask_bands(void* stream, int B, int T, int C, int W, const float* x, float* y, int n_f, const int* f0_host,
+                           const int* f1_host, int n_t, const int* t0_host, const int* t1_host, float value);
 
 /* small element-wise helpers of the host layer: network input [T,F,1,B] (ArrayFire, T fastest) -> internal
  * [B][T][1][F]; y += a*x; y = v; standalone ReLU/Dropout forward and their backward mask. */
@@ -267,6 +304,11 @@ W2L_API int w2l_trainer_step(void* trainer, void* stream, int B, int T, const fl
                              float* loss_out, int train, float total_batch);
 W2L_API int w2l_trainer_forward(void* trainer, void* stream, int B, int T, const float* features, float* emissions_out,
                                 long long capacity, int* t_out);
+/* precision of the trainer's dense contractions (W2L_PRECISION_*; default: the creating thread's w2l_set_precision) */
+W2L_API int w2l_trainer_set_precision(void* trainer, int precision);
+/* steps whose update was skipped on the device because the loss or a gradient was NaN / Inf (Train.cpp:1686-1698,
+ * :1753-1771); synchronises `stream` */
+W2L_API int w2l_trainer_status(void* trainer, void* stream, long long* skipped_steps);
 W2L_API long long w2l_trainer_num_params(void* trainer, int which /*0 network, 1 criterion*/);
 W2L_API int w2l_trainer_param_layout(void* trainer, int which, int max_params, long long* elements, long long* dims4);
 W2L_API int w2l_trainer_get_flat(void* trainer, void* stream, int which, int what /*0 values, 1 gradients*/, float* out);

@@ -24,6 +24,8 @@ EXPORTS = [
     "w2l_fcc_viterbi_workspace_size", "w2l_fcc_viterbi",
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
     "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
+    "w2l_set_precision", "w2l_get_precision", "w2l_gemm", "w2l_cast_bf16", "w2l_cast_bf16_rows", "w2l_sgd_step_ex", "w2l_finite_guard",
+    "w2l_mask_bands", "w2l_trainer_set_precision", "w2l_trainer_status",
     "w2l_gemm_set_tile", "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_gemm_tf32_view", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
     "w2l_conv_time_wgrad", "w2l_layernorm_fwd", "w2l_layernorm_bwd", "w2l_colsum_accumulate", "w2l_sq_norm_accumulate",
     "w2l_sgd_step", "w2l_weightnorm_fwd", "w2l_weightnorm_bwd", "w2l_conv1d_arrange", "w2l_conv1d_unarrange_grad",
@@ -91,6 +93,15 @@ def _load() -> ctypes.CDLL:
     lib.w2l_colsum_accumulate.argtypes = [vp, i, i, vp, i, vp]
     lib.w2l_sq_norm_accumulate.argtypes = [vp, ll, vp, vp]
     lib.w2l_sgd_step.argtypes = [vp, ll, vp, vp, vp, f32, f32, f32, f32, f32, vp]
+    lib.w2l_set_precision.argtypes = [i]
+    lib.w2l_gemm.argtypes = [vp, i, i, i, i, i, i, vp, i, vp, i, vp, i, i, vp, i, i, vp, i, i, i, f32, f32, u64, i]
+    lib.w2l_cast_bf16.argtypes = [vp, ll, vp, vp]
+    lib.w2l_cast_bf16_rows.argtypes = [vp, ll, i, i, i, vp, vp]
+    lib.w2l_sgd_step_ex.argtypes = [vp, ll, vp, vp, vp, f32, f32, f32, f32, f32, vp, i, vp]
+    lib.w2l_finite_guard.argtypes = [vp, i, vp, vp, vp]
+    lib.w2l_mask_bands.argtypes = [vp, i, i, i, i, vp, vp, i, vp, vp, i, vp, vp, f32]
+    lib.w2l_trainer_set_precision.argtypes = [vp, i]
+    lib.w2l_trainer_status.argtypes = [vp, vp, vp]
     lib.w2l_trainer_create.restype = vp
     lib.w2l_trainer_create.argtypes = [vp, ctypes.c_char_p, i, i, ctypes.c_char_p, i, f32, f32, f32, f32, f32]
     lib.w2l_trainer_destroy.argtypes = [vp]
@@ -282,6 +293,43 @@ def trace_list() -> list:
     buf = ctypes.create_string_buffer(1 << 18)
     lib.w2l_trace_list(buf, len(buf))
     return [(ln.split("\t")[0], float(ln.split("\t")[1])) for ln in buf.value.decode().splitlines()]
+
+
+PRECISIONS = {"tf32": 0, "f32": 1, "fp32": 1, "bf16": 2}
+GEMM_KINDS = {"tf32": 0, "f32x3": 1, "bf16": 2}
+
+
+def set_precision(p) -> None:
+    """tf32 (default) | f32 (fp32-accurate 3xTF32 GEMMs + fp32 SIMT time convolutions) | bf16 (bf16 GEMM operands)."""
+    _check(lib.w2l_set_precision(PRECISIONS[p] if isinstance(p, str) else int(p)))
+
+
+def get_precision() -> int:
+    return int(lib.w2l_get_precision())
+
+
+def gemm(A, B, kind="tf32", a_mn=False, b_mn=False, bias=None, act=0, out=None, out_bf16=False, accumulate=False, aux=None,
+         aux_mode=0, aux_scale=1.0, dropout_p=0.0, seed=0, M=None, N=None, K=None, lda=None, ldb=None, allow_overlap=False):
+    """General tcgen05 GEMM (w2l_gemm): A/B fp32 (kinds tf32, f32x3) or bfloat16 (kind bf16); C fp32 or bfloat16."""
+    if M is None:
+        M, K = (A.shape[1], A.shape[0]) if a_mn else A.shape
+        N = B.shape[1] if b_mn else B.shape[0]
+    lda = A.stride(0) if lda is None else lda
+    ldb = B.stride(0) if ldb is None else ldb
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=A.device)
+    _check(lib.w2l_gemm(_stream(), GEMM_KINDS[kind], int(a_mn), int(b_mn), M, N, K, _ptr(A), lda, _ptr(B), ldb, _ptr(out),
+                        out.stride(0), int(out.dtype == torch.bfloat16), _ptr(bias), int(act), int(accumulate), _ptr(aux),
+                        0 if aux is None else aux.stride(0), int(aux is not None and aux.dtype == torch.bfloat16),
+                        int(aux_mode), float(aux_scale), float(dropout_p), int(seed), int(allow_overlap)))
+    return out
+
+
+def cast_bf16(x):
+    x = _req(x, torch.float32, "x")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _check(lib.w2l_cast_bf16(_stream(), x.numel(), _ptr(x), _ptr(y)))
+    return y
 
 
 def gemm_set_tile(bn: int = 0):

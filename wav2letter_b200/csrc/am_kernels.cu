@@ -11,7 +11,7 @@
 //     and into the LayerNorm backward (the mask is read back from the stored activation sign)
 //   fl::SGDOptimizer / fl::clipGradNorm (Train.cpp:1791-1803) -> w2l_sq_norm / w2l_sgd_step on a flat arena
 // These passes are HBM-bound (the k x 1 convolution has only 10-27 channels: SURVEY.md §7.4-3);
-// the dense contractions live in gemm_tf32.cu.
+// the dense contractions live in gemm_umma.cu.
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -19,6 +19,10 @@
 namespace w2l {
 // tensor-core path (conv_mma.cu)
 bool conv_mma_supported(int W, int Cin, int Cout, int K, int stride);
+// the TF32 tensor-core path, unless the thread asked for fp32-accurate contractions (w2l_set_precision): then the fp32 SIMT kernels
+static bool use_conv_mma(int W, int Cin, int Cout, int K, int stride) {
+  return current_precision() != W2L_PRECISION_F32 && conv_mma_supported(W, Cin, Cout, K, stride);
+}
 size_t conv_mma_arranged_floats(int Cin, int Cout, int K);
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                  const float* x, const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y,
@@ -697,10 +701,13 @@ __global__ void __launch_bounds__(256) sq_norm_kernel(long long n, const float* 
 
 // fl::SGDOptimizer::step with the loop's gradient scaling and fl::clipGradNorm folded in:
 //   g = grad * grad_scale * min(1, max_norm / (sqrt(sq_norm) * grad_scale))   (max_norm <= 0: no clip)
-//   g += wd * p ; v = momentum * v + g ; p -= lr * v      (momentum == 0: p -= lr * g)
+//   g += wd * p ; v = momentum * v + g ; (Nesterov: g += momentum * v, else g = v) ; p -= lr * g
+// guard (nullable): guard[0] != 0 -> the step is skipped (non-finite loss / gradients, set by finite_guard_kernel)
 __global__ void __launch_bounds__(256) sgd_step_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ v, float lr, float momentum, float wd,
-                                                       float grad_scale, float max_norm, const double* __restrict__ sq_norm) {
+                                                       float grad_scale, float max_norm, const double* __restrict__ sq_norm,
+                                                       int nesterov, const int* __restrict__ guard) {
+  if (guard != nullptr && guard[0] != 0) return;
   float scale = grad_scale;
   if (max_norm > 0.f && sq_norm != nullptr) {
     const float nrm = sqrtf((float)*sq_norm) * grad_scale;
@@ -713,9 +720,42 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(long long n, float* __res
     if (momentum != 0.f) {
       const float vi = fmaf(momentum, v[i], gi);
       v[i] = vi;
-      gi = vi;
+      gi = nesterov ? fmaf(momentum, vi, gi) : vi;
     }
     p[i] = pi - lr * gi;
+  }
+}
+// the loop's numerical guards without a host round trip: Train.cpp:1686-1698 (NaN / Inf in the loss) and
+// :1753-1771 (non-finite gradients under mixed precision: skip the update).  guard[0] = this step is bad,
+// guard[1] += 1 per bad step (read by the host whenever it wants).
+__global__ void finite_guard_kernel(int n_loss, const float* __restrict__ loss, const double* __restrict__ sq_norm, int* __restrict__ guard) {
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = (sq_norm != nullptr && !isfinite(*sq_norm)) ? 1 : 0;
+  __syncthreads();
+  int b = 0;
+  for (int i = threadIdx.x; i < n_loss; i += blockDim.x) b |= !isfinite(loss[i]);
+  if (b) atomicOr(&bad, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    guard[0] = bad;
+    if (bad) guard[1] += 1;
+  }
+}
+
+// fl::SpecAugment's masking on the internal layout [B][T][C][W]: frequency bands [f0, f1) of W and time bands
+// [t0, t1) of T are replaced by `val` (the same bands for every sample of the batch, as upstream)
+struct BandMasks {
+  int nf, nt;
+  int f0[8], f1[8], t0[8], t1[8];
+};
+__global__ void __launch_bounds__(256) mask_bands_kernel(long long n, int W, int CW, int T, const float* __restrict__ x, float* __restrict__ y,
+                                                         BandMasks m, float val) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W), t = (int)((i / CW) % T);
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hit = hit || (k < m.nf && w >= m.f0[k] && w < m.f1[k]) || (k < m.nt && t >= m.t0[k] && t < m.t1[k]);
+    y[i] = hit ? val : x[i];
   }
 }
 
@@ -827,7 +867,7 @@ extern "C" int w2l_conv_time_fwd(void* stream_, int B, int T, int Tout, int W, i
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_fwd: workspace too small");
   const int CO = co_pad(Cout);
   float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
-  if (conv_mma_supported(W, Cin, Cout, K, stride))
+  if (use_conv_mma(W, Cin, Cout, K, stride))
     return conv_mma_fwd(stream, B, T, Tout, W, Cin, Cout, K, stride, pad_left, x, wt, Cin, Cout, 0, bias, add, y, act, dropout_p, seed,
                         arranged, K, 1, 0, 1, 0, Tout);
   conv_arrange_weights_kernel<<<8, 256, 0, stream>>>(Cin, Cout, K, CO, wt, arranged, 0);
@@ -852,13 +892,13 @@ extern "C" int w2l_conv_time_dgrad(void* stream_, int B, int T, int Tout, int W,
   if (int rc = conv_check(B, T, Tout, W, Cin, Cout, K, stride)) return rc;
   if (!dy || !wt || !dx || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_dgrad: null pointer");
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_dgrad: workspace too small");
-  if (stride == 1 && conv_mma_supported(W, Cout, Cin, K, 1)) {
+  if (stride == 1 && use_conv_mma(W, Cout, Cin, K, 1)) {
     // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped — on the tensor-core path
     float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
     return conv_mma_fwd(stream, B, Tout, T, W, Cout, Cin, K, 1, K - 1 - pad_left, dy, wt, Cin, Cout, 1, nullptr, add, dx, 0, 0.f, 0ull,
                         arranged, K, 1, 0, 1, 0, T);
   }
-  if (stride > 1 && stride <= K && conv_mma_supported(W, Cout, Cin, (K + stride - 1) / stride, 1)) {
+  if (stride > 1 && stride <= K && use_conv_mma(W, Cout, Cin, (K + stride - 1) / stride, 1)) {
     // polyphase: input frames t with (t + pad_left) % stride == p only see taps p, p + stride, ...; each phase is a
     // stride-1 correlation of dy with those taps reversed, written to every stride-th frame of dx
     float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
@@ -913,7 +953,7 @@ extern "C" int w2l_conv_time_wgrad(void* stream_, int B, int T, int Tout, int W,
   if (!x || !dy || !dwt || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_wgrad: null pointer");
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_wgrad: workspace too small");
   if (stride > K) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: stride > kernel width");
-  if (conv_mma_supported(W, Cin, Cout, K, stride))
+  if (use_conv_mma(W, Cin, Cout, K, stride))
     return conv_mma_wgrad(stream, B, T, Tout, W, Cin, Cout, K, stride, pad_left, x, dy, dwt, dbias, static_cast<float*>(ws));
   const int ntiles = ((Cout + 1) / 2) * ((Cin * K + 3) / 4);
   if (ntiles > kWgMaxTiles * kWgThreads) return fail(W2L_ERR_UNSUPPORTED, "conv_time_wgrad: filter too large for the register tiles");
@@ -1010,13 +1050,47 @@ extern "C" int w2l_sq_norm_accumulate(void* stream_, long long n, const float* g
   return W2L_OK;
 }
 
-extern "C" int w2l_sgd_step(void* stream_, long long n, float* params, const float* grads, float* velocity, float lr,
-                            float momentum, float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm) {
+extern "C" int w2l_sgd_step_ex(void* stream_, long long n, float* params, const float* grads, float* velocity, float lr, float momentum,
+                               float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm, int nesterov,
+                               const int* guard) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n <= 0 || !params || !grads || (momentum != 0.f && !velocity)) return fail(W2L_ERR_INVALID_ARGUMENT, "sgd_step: bad arguments");
+  if (nesterov && momentum <= 0.f) return fail(W2L_ERR_INVALID_ARGUMENT, "sgd_step: Nesterov momentum needs momentum > 0");
   sgd_step_kernel<<<blocks_for(n), 256, 0, stream>>>(n, params, grads, velocity, lr, momentum, weight_decay, grad_scale,
-                                                     max_grad_norm, sq_norm);
+                                                     max_grad_norm, sq_norm, nesterov, guard);
   W2L_LAUNCH_CHECK("sgd_step_kernel");
+  return W2L_OK;
+}
+extern "C" int w2l_sgd_step(void* stream_, long long n, float* params, const float* grads, float* velocity, float lr,
+                            float momentum, float weight_decay, float grad_scale, float max_grad_norm, const double* sq_norm) {
+  return w2l_sgd_step_ex(stream_, n, params, grads, velocity, lr, momentum, weight_decay, grad_scale, max_grad_norm, sq_norm, 0, nullptr);
+}
+extern "C" int w2l_finite_guard(void* stream_, int n_loss, const float* loss, const double* sq_norm, int* guard) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_loss < 0 || (n_loss > 0 && !loss) || !guard) return fail(W2L_ERR_INVALID_ARGUMENT, "finite_guard: bad arguments");
+  finite_guard_kernel<<<1, 256, 0, stream>>>(n_loss, loss, sq_norm, guard);
+  W2L_LAUNCH_CHECK("finite_guard_kernel");
+  return W2L_OK;
+}
+extern "C" int w2l_mask_bands(void* stream_, int B, int T, int C, int W, const float* x, float* y, int n_f, const int* f0_host,
+                              const int* f1_host, int n_t, const int* t0_host, const int* t1_host, float value) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (B <= 0 || T <= 0 || C <= 0 || W <= 0 || !x || !y) return fail(W2L_ERR_INVALID_ARGUMENT, "mask_bands: bad arguments");
+  if (n_f < 0 || n_f > 8 || n_t < 0 || n_t > 8) return fail(W2L_ERR_UNSUPPORTED, "mask_bands: at most 8 frequency and 8 time masks");
+  BandMasks m{};
+  m.nf = n_f;
+  m.nt = n_t;
+  for (int k = 0; k < n_f; ++k) {
+    m.f0[k] = f0_host[k];
+    m.f1[k] = f1_host[k];
+  }
+  for (int k = 0; k < n_t; ++k) {
+    m.t0[k] = t0_host[k];
+    m.t1[k] = t1_host[k];
+  }
+  const long long n = (long long)B * T * C * W;
+  mask_bands_kernel<<<blocks_for(n), 256, 0, stream>>>(n, W, C * W, T, x, y, m, value);
+  W2L_LAUNCH_CHECK("mask_bands_kernel");
   return W2L_OK;
 }
 

@@ -17,6 +17,9 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 void count_launch(int n) { g_launches += n; }
+static thread_local int g_precision = W2L_PRECISION_TF32;
+int current_precision() { return g_precision; }
+void set_precision_value(int p) { g_precision = p; }
 static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 // event LIST mode: the k-th profiled launch of the selected kind records pair k
 static thread_local cudaEvent_t* g_list_start = nullptr;
@@ -60,7 +63,14 @@ void set_profile_events(cudaEvent_t a, cudaEvent_t b) {
 }  // namespace w2l
 
 extern "C" {
-int w2l_version(void) { return 100; }
+int w2l_version(void) { return 200; }
+int w2l_set_precision(int precision) {
+  if (precision != W2L_PRECISION_TF32 && precision != W2L_PRECISION_F32 && precision != W2L_PRECISION_BF16)
+    return w2l::fail(W2L_ERR_INVALID_ARGUMENT, "precision must be W2L_PRECISION_TF32, W2L_PRECISION_F32 or W2L_PRECISION_BF16");
+  w2l::set_precision_value(precision);
+  return W2L_OK;
+}
+int w2l_get_precision(void) { return w2l::current_precision(); }
 const char* w2l_last_error(void) { return w2l::g_err.c_str(); }
 long long w2l_launch_count(void) { return w2l::g_launches; }
 void w2l_reset_launch_count(void) { w2l::g_launches = 0; }

@@ -15,6 +15,7 @@ namespace w2l {
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
+int current_precision();  // W2L_PRECISION_* of the calling thread (w2l_set_precision)
 void trace_launch(const char* name);  // trace mode (w2l_trace_begin): one event after every launch, on the trace stream
 // bench hook: events recorded around a call's dominant kernel (nullptr when unset)
 void profile_kind(int kind);  // 1 = GEMM, 2 = criterion chains (set right before profile_start)

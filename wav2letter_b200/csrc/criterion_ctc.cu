@@ -222,9 +222,9 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
   if (!kGrad) return;
   __syncthreads();
   const double ll = ll_s;
-  if (!(ll > -1e30)) {  // infeasible: zero gradient
-    for (size_t k = tid; k < (size_t)T * Sp; k += nthr) lat[k] = 0.f;
-    for (int t = tid; t < T; t += nthr) p.psum[(size_t)b * T + t] = 1.f;
+  if (!(ll > -1e30)) {  // infeasible (loss = +inf, e.g. -inf activations on every path): zero gradient —
+    // ctc_grad_kernel zeroes the rows of samples whose `valid` flag is clear (it runs after this kernel)
+    if (tid == 0) p.valid[b] = 0;
     return;
   }
   // ---- beta walk; posteriors overwrite the alpha lattice ------------------------------------------

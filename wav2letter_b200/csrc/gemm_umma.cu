@@ -1,0 +1,736 @@
+// gemm_umma.cu — hand-written sm_100a GEMM (tcgen05 / TMEM / TMA) for the dense contractions of the acoustic
+// model: TDS fully-connected layers, the output Linear, and the large-channel Conv1D layers of the conv_glu
+// archs as zero-copy im2col views (reference: fl::Linear / fl::Conv2D -> af::matmul / cuDNN through cuBLAS,
+// reached from recipes/slimIPL/src/Train.cpp:1470 (forward) and :1720 (backward)).
+//
+//   C[m][n] = act( sum_k A(m,k) * B(n,k) + bias[n] )        fp32 accumulation in TMEM
+//
+// Three operand kinds, one kernel template (the "precision" of BASELINE.json's configs):
+//   W2L_GEMM_TF32   fp32 operands in HBM, kind::tf32 (10-bit mantissa products)  — cuDNN/cuBLAS default for fp32
+//   W2L_GEMM_F32X3  fp32 operands in HBM, fp32-ACCURATE: every staged tile is split in shared memory into
+//                   hi = tf32(x) and lo = tf32(x - hi) by the (otherwise idle) epilogue warps and the tensor core
+//                   accumulates Al*Bh + Ah*Bl + Ah*Bh — products good to ~2^-21, i.e. SGEMM-grade (configs[1] "fp32")
+//   W2L_GEMM_BF16   bf16 operands in HBM, kind::f16 — half the operand bytes through L2 -> SM, twice the MAC rate
+//                   (configs[2]/[3] "bf16 convs / fp32 loss"; the reference's AMP switch, Train.cpp:211-219)
+// C is fp32 or bf16 (c_bf16); bias/ReLU/dropout/mask/accumulate epilogue as before.
+//
+// Operand storage ("major"):
+//   A K-major : A stored [M][K] (row stride lda)      A MN-major : A stored [K][M]
+//   B K-major : B stored [N][K] (row stride ldb)      B MN-major : B stored [K][N]
+// so one kernel family covers  forward  Y = X W^T            (A = X  K-major,  B = W  K-major)
+//                              dgrad    dX = dY W            (A = dY K-major,  B = W  MN-major)
+//                              wgrad    dW = dY^T X          (A = dY MN-major, B = X  MN-major)
+// without any transposition pass.
+//
+// Structure (one CTA per 128 x BN output tile, 192 threads):
+//   warp 4        TMA producer: cp.async.bulk.tensor 2D boxes (128 B inner extent, 128B swizzle) into a 3/4-stage
+//                 shared-memory ring, mbarrier expect_tx
+//   warp 5        TMEM allocation + single-thread tcgen05.mma.cta_group::1 issue (UMMA 128 x BN x 32 B of k, 4 per
+//                 k block; 12 in F32X3 mode), tcgen05.commit onto the stage's empty barrier, final commit onto the
+//                 accumulator-full barrier
+//   warps 0..3    F32X3: hi/lo split of every stage (generic-proxy writes + fence.proxy.async + `ready` barrier);
+//                 epilogue: tcgen05.ld 32x32b (thread = accumulator row), bias + ReLU + dropout, transposition through
+//                 shared memory, coalesced global stores
+// Shared-memory operand layouts are the canonical UMMA ones (cute/atom/mma_traits_sm100.hpp):
+//   K-major  SW128: rows of 128 B (32 fp32 / 64 bf16 along k), 8-row groups 1024 B apart (SBO), LBO unused
+//   MN-major 32-bit: SW128_BASE32B (the only MN-major layout valid for 32-bit operands; TMA swizzle 128B_ATOM_32B):
+//                   boxes of [32 k-rows][128 B = 32 elements along m/n]; LBO = box size (4096 B), SBO = 512 B (4 k-rows);
+//                   one UMMA (k = 8) advances the start by 1024 B
+//   MN-major 16-bit: SW128: boxes of [64 k-rows][128 B = 64 elements along m/n]; LBO = box size (8192 B),
+//                   SBO = 1024 B (8 k-rows); one UMMA (k = 16) advances the start by 2048 B
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+#include "common.cuh"
+
+namespace w2l {
+namespace {
+
+constexpr int BM = 128;                     // tile rows
+constexpr int kRowBytes = 128;              // one swizzle row of k: 32 fp32 or 64 bf16
+constexpr int kTileBytes = BM * kRowBytes;  // 16 KB of A per stage
+constexpr int kGemmThreads = 192;
+enum { kTf32 = W2L_GEMM_TF32, kF32x3 = W2L_GEMM_F32X3, kBf16 = W2L_GEMM_BF16 };
+
+// The tile width BN is a template parameter (128 / 160 / 224 / 256).  The kernel is fed from L2 (~42 B/clk per SM is
+// the chip-wide L2 throughput cap), so tensor-pipe time per k block scales with the operand bytes (128 + BN) * 128 B
+// while the work scales with 128 * BN: wider tiles raise MAC/byte, and the host picks the BN that minimises
+// waves x bytes for each shape (e.g. 160 divides 800/1120/1440 exactly).  BN <= 160: 3 stages, 2 CTAs per SM (one
+// tile's epilogue overlaps the other's main loop); BN > 160: 4 stages, 1 CTA per SM.  F32X3 doubles every stage
+// (hi + lo tiles): BN = 128, 3 stages, 1 CTA per SM.
+__host__ __device__ constexpr int stages_for(int mode, int bn) { return mode == kF32x3 ? 3 : (bn <= 160 ? 3 : 4); }
+__host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 128 ? 128 : 256; }
+__host__ __device__ constexpr size_t stage_bytes(int mode, int bn) { return (size_t)(mode == kF32x3 ? 2 : 1) * (kTileBytes + bn * kRowBytes); }
+__host__ __device__ constexpr size_t smem_for(int mode, int bn) { return stages_for(mode, bn) * stage_bytes(mode, bn) + 128 + 1024 + 1024; }  // ring + barriers + bias row + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// layout_type: 2 = SWIZZLE_128B (K-major operands; MN-major 16-bit operands), 1 = SWIZZLE_128B_BASE32B (the only
+// layout the tensor core accepts for MN-major 32-bit operands: Swizzle<2,5,2>, atoms of 4 k-rows x 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// instruction descriptor: D = f32; A = B = tf32 (format 2, kind::tf32) or bf16 (format 1, kind::f16); M x N; majors
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16, int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+template <bool kIsBf16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  if (kIsBf16) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+struct GemmParams {
+  int M, N, K, ldc, act;
+  void* C;
+  const float* bias;
+  // epilogue extensions: forward dropout, backward mask read from a stored activation, C += acc
+  int accumulate, aux_mode, ld_aux;  // aux_mode 0: none, 1: (aux > 0) * aux_scale, 2: (aux != 0) * aux_scale
+  const void* aux;
+  float aux_scale, drop_p;
+  unsigned long long seed;
+  int k_splits;  // > 1: blockIdx.z owns a slice of the k blocks and the epilogue adds atomically (few tiles, long K: wgrad)
+  int c_bf16, aux_bf16;
+};
+
+__device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0, c3 = 0;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+template <int kMode, bool kAMn, bool kBMn, int BN>
+__global__ void __launch_bounds__(kGemmThreads, (kMode == kF32x3 || BN > 160) ? 1 : 2)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool kIsBf16 = kMode == kBf16, kSplit = kMode == kF32x3;
+  constexpr int ES = kIsBf16 ? 2 : 4;                 // operand element size
+  constexpr int BKE = kRowBytes / ES;                 // elements of k per k block: 32 fp32 / 64 bf16
+  constexpr int kMnAtom = kRowBytes / ES;             // elements of m/n per MN-major box: 32 / 64
+  constexpr int kMnBoxBytes = BKE * kRowBytes;        // one MN-major box [BKE k-rows][128 B]: 4096 / 8192
+  constexpr int kMnStep = kIsBf16 ? 2048 : 1024;      // MN-major start advance per UMMA (k = 16 / 8 rows)
+  constexpr int kMnSbo = kIsBf16 ? 1024 : 512;        // k-row group stride (8 / 4 rows)
+  constexpr int kMnLayout = kIsBf16 ? 2 : 1;          // SWIZZLE_128B / SWIZZLE_128B_BASE32B
+  constexpr int kStages = stages_for(kMode, BN), kTileBytesB = BN * kRowBytes, kTmemCols = tmem_cols_for(BN);
+  constexpr int kOperandBytes = kTileBytes + kTileBytesB;
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + kStages * kTileBytes;
+  unsigned char* smem_lo = smem + kStages * kOperandBytes;  // F32X3: [stage][A lo | B lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes(kMode, BN));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* ready = bars + 2 * kStages;  // F32X3 only
+  uint64_t* acc_full = bars + 3 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int total_kb = (p.K + BKE - 1) / BKE;
+  const int kb_per = (total_kb + p.k_splits - 1) / p.k_splits;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&ready[s], 128);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kOperandBytes);
+        unsigned char* sa = smem_a + s * kTileBytes;
+        unsigned char* sb = smem_b + s * kTileBytesB;
+        const int k0 = (kb_begin + kb) * BKE;
+        if (!kAMn) {
+          tma_load_2d(&map_a, &full[s], sa, k0, m0);  // box {128 B of k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / kMnAtom; ++j) tma_load_2d(&map_a, &full[s], sa + j * kMnBoxBytes, m0 + kMnAtom * j, k0);  // box {128 B of m, BKE k}
+        }
+        if (!kBMn) {
+          tma_load_2d(&map_b, &full[s], sb, k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / kMnAtom; ++j) tma_load_2d(&map_b, &full[s], sb + j * kMnBoxBytes, n0 + kMnAtom * j, k0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (one elected thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kIsBf16, BM, BN, kAMn, kBMn);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(kSplit ? &ready[s] : &full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem_a + s * kTileBytes);
+        const uint32_t sb = smem_u32(smem_b + s * kTileBytesB);
+        const uint32_t la = smem_u32(smem_lo + s * kOperandBytes), lb = la + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 UMMAs of 32 B of k per 128 B swizzle row
+          // K-major: +32 B per step inside the 128 B swizzle row; MN-major: + one k group of boxes' rows
+          auto adesc = [&](uint32_t base) { return kAMn ? make_smem_desc(base + k * kMnStep, kMnBoxBytes, kMnSbo, kMnLayout) : make_smem_desc(base + k * 32, 16, 1024, 2); };
+          auto bdesc = [&](uint32_t base) { return kBMn ? make_smem_desc(base + k * kMnStep, kMnBoxBytes, kMnSbo, kMnLayout) : make_smem_desc(base + k * 32, 16, 1024, 2); };
+          if (kSplit) {
+            umma<false>(tmem_base, adesc(la), bdesc(sb), idesc, (kb | k) != 0);  // Al * Bh
+            umma<false>(tmem_base, adesc(sa), bdesc(lb), idesc, 1);              // Ah * Bl
+            umma<false>(tmem_base, adesc(sa), bdesc(sb), idesc, 1);              // Ah * Bh
+          } else {
+            umma<kIsBf16>(tmem_base, adesc(sa), bdesc(sb), idesc, (kb | k) != 0);
+          }
+        }
+        umma_commit(&empty[s]);  // frees the stage when the MMAs above have read it
+      }
+      umma_commit(acc_full);  // with num_kb == 0 nothing is pending: the barrier completes immediately
+    }
+  } else {
+    // ===== warps 0..3: (F32X3: operand split,) epilogue on TMEM lanes 32*warp .. +31 =====
+    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per chunk).  Bias, ReLU and the
+    // dropout mask (one Philox block per 4 consecutive columns) are applied in that layout; the chunk is then
+    // transposed through shared memory (the idle operand ring; 33-float pitch, conflict-free both ways) so that
+    // every global access of the rest — mask read, C read for accumulation, store / red — is one row x 32
+    // consecutive columns per warp instruction: 128 B coalesced instead of 32 sectors.
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 128);  // [BN]
+    if (p.bias != nullptr) {
+      for (int j = threadIdx.x; j < BN; j += 128) sbias[j] = n0 + j < p.N ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // while the main loop runs: pull the tile's mask / C lines into L2 so the epilogue's reads are L2 hits
+    if (p.aux_mode != 0 || (p.accumulate && p.k_splits == 1)) {
+      const int lines = (BN * 4 + 127) / 128;  // 128-byte lines per tile row (fp32 columns; bf16 masks touch half of them)
+      for (int i = threadIdx.x; i < BM * lines; i += 128) {
+        const int r = m0 + i / lines, cc = n0 + (i % lines) * 32;
+        if (r < p.M && cc < p.N) {
+          if (p.aux_mode != 0) {
+            if (p.aux_bf16) {
+              if (((i % lines) & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const __nv_bfloat16*>(p.aux) + (size_t)r * p.ld_aux + cc));
+            } else {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const float*>(p.aux) + (size_t)r * p.ld_aux + cc));
+            }
+          }
+          if (p.accumulate && p.k_splits == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const float*>(p.C) + (size_t)r * p.ldc + cc));
+        }
+      }
+    }
+    if (kSplit) {
+      // fp32-accurate mode: x = hi + lo with hi = tf32(x) (written back in place) and lo = tf32(x - hi) (second tile
+      // of the stage); elementwise, so the swizzled / MN-major tile layouts are irrelevant here
+      constexpr int kVecA = kTileBytes / 16 / 128, kVecB = kTileBytesB / 16 / 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        uint4* ta = reinterpret_cast<uint4*>(smem_a + s * kTileBytes);
+        uint4* tb = reinterpret_cast<uint4*>(smem_b + s * kTileBytesB);
+        uint4* la = reinterpret_cast<uint4*>(smem_lo + s * kOperandBytes);
+        uint4* lb = reinterpret_cast<uint4*>(smem_lo + s * kOperandBytes + kTileBytes);
+        auto split = [](uint4* hi, uint4* lo, int i) {
+          const uint4 v = hi[i];
+          uint4 h, l;
+          h.x = rna_tf32(__uint_as_float(v.x));
+          h.y = rna_tf32(__uint_as_float(v.y));
+          h.z = rna_tf32(__uint_as_float(v.z));
+          h.w = rna_tf32(__uint_as_float(v.w));
+          l.x = rna_tf32(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = rna_tf32(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = rna_tf32(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = rna_tf32(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[i] = h;
+          lo[i] = l;
+        };
+#pragma unroll
+        for (int i = 0; i < kVecA; ++i) split(ta, la, i * 128 + threadIdx.x);
+#pragma unroll
+        for (int i = 0; i < kVecB; ++i) split(tb, lb, i * 128 + threadIdx.x);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(&ready[s]);
+      }
+    }
+    mbar_wait(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* tbuf = reinterpret_cast<float*>(smem_a) + warp * (32 * 33);  // all TMA writes / UMMA reads of the ring are complete
+    const int row_own = m0 + warp * 32 + lane;
+    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const bool rd_aux = p.aux_mode != 0, rd_c = p.accumulate && p.k_splits == 1;
+    float* Cf = static_cast<float*>(p.C);
+    __nv_bfloat16* Ch = static_cast<__nv_bfloat16*>(p.C);
+    if (num_kb > 0 || p.k_splits == 1) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb >= p.N) break;  // warp-uniform
+        const int col = nb + lane;
+        const bool col_ok = col < p.N;
+        const int rows_here = min(32, p.M - (m0 + warp * 32));  // warp-uniform; may be <= 0
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (p.bias != nullptr) x += sbias[c * 32 + j];  // broadcast read
+          if (p.act == 1) x = fmaxf(x, 0.f);
+          o[j] = x;
+        }
+        if (p.drop_p > 0.f) {
+          // element index row * N + n; nb % 4 == 0, and N % 4 == 0 is required for dropout (checked by the host), so one
+          // Philox block covers the 4 consecutive columns j .. j+3
+          const unsigned long long base_idx = (unsigned long long)row_own * (unsigned long long)p.N + (unsigned long long)nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const unsigned long long idx = base_idx + j;
+            const uint4 r = philox4x32_g((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+            o[j] *= ((float)(r.x >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+            o[j + 1] *= ((float)(r.y >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+            o[j + 2] *= ((float)(r.z >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+            o[j + 3] *= ((float)(r.w >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+          }
+        }
+        __syncwarp();  // the previous chunk's transposed reads are done
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = o[j];
+        // the chunk's mask (or, without a mask, its C values to accumulate onto) in the coalesced layout (lane = column,
+        // one row per instruction); the lines were prefetched into L2 during the main loop
+        float pre[32];
+        if (rd_aux) {
+          if (p.aux_bf16) {
+            const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(p.aux) + (size_t)(m0 + warp * 32) * p.ld_aux + col;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? __bfloat162float(src[(size_t)rr * p.ld_aux]) : 0.f;
+          } else {
+            const float* src = static_cast<const float*>(p.aux) + (size_t)(m0 + warp * 32) * p.ld_aux + col;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? src[(size_t)rr * p.ld_aux] : 0.f;
+          }
+        } else if (rd_c) {
+          const float* src = Cf + (size_t)(m0 + warp * 32) * p.ldc + col;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? src[(size_t)rr * p.ldc] : 0.f;
+        }
+        __syncwarp();
+        if (p.c_bf16 && rd_aux) {  // bf16 C behind a mask: column layout (the mask was fetched in it), 2-byte stores
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < rows_here && col_ok) {
+              float x = tbuf[rr * 33 + lane];
+              x *= (p.aux_mode == 1 ? pre[rr] > 0.f : pre[rr] != 0.f) ? p.aux_scale : 0.f;
+              Ch[(size_t)(m0 + warp * 32 + rr) * p.ldc + col] = __float2bfloat16_rn(x);
+            }
+          }
+        } else if (p.c_bf16) {  // bf16 C (no accumulate / split-K: checked by the host): a lane stores two adjacent columns
+          const int sub = lane >> 4, cp = (lane & 15) * 2;
+          const bool pair_ok = nb + cp + 1 < p.N, one_ok = nb + cp < p.N;
+#pragma unroll 8
+          for (int r2 = 0; r2 < 16; ++r2) {
+            const int rr = 2 * r2 + sub;
+            if (rr < rows_here && one_ok) {
+              const float x0 = tbuf[rr * 33 + cp], x1 = tbuf[rr * 33 + cp + 1];
+              __nv_bfloat16* dst = Ch + (size_t)(m0 + warp * 32 + rr) * p.ldc + nb + cp;
+              if (pair_ok && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+                *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(x0, x1);
+              } else {
+                dst[0] = __float2bfloat16_rn(x0);
+                if (pair_ok) dst[1] = __float2bfloat16_rn(x1);
+              }
+            }
+          }
+        } else if (!rd_aux && !rd_c) {  // no global reads: stream the rows out
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < rows_here && col_ok) {
+              float* dst = Cf + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
+              const float x = tbuf[rr * 33 + lane];
+              if (p.k_splits > 1)
+                atomicAdd(dst, x);  // split-K: C was zeroed (or holds the value to accumulate onto) by the host wrapper
+              else
+                *dst = x;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < rows_here && col_ok) {
+              float* dst = Cf + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
+              float x = tbuf[rr * 33 + lane];
+              if (rd_aux) {
+                x *= (p.aux_mode == 1 ? pre[rr] > 0.f : pre[rr] != 0.f) ? p.aux_scale : 0.f;
+                if (rd_c) x += *dst;  // mask and accumulation together (not on the TDS path): C is read here
+              } else {
+                x += pre[rr];
+              }
+              if (p.k_splits > 1)
+                atomicAdd(dst, x);
+              else
+                *dst = x;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2D map over a row-major matrix [rows][cols] (row stride ld elements); box {128 B of columns, box_rows}
+int make_map(CUtensorMap* map, int mode, const void* ptr, long long rows, long long cols, long long ld, int box_rows, bool mn_major) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(W2L_ERR_CUDA, "gemm: cuTensorMapEncodeTiled entry point not found");
+  const int es = mode == kBf16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(kRowBytes / es), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  // TF32: rounding on load; F32X3: the raw fp32 bits (the split happens in shared memory)
+  const CUtensorMapDataType dt = mode == kBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                               : (mode == kF32x3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32);
+  const CUtensorMapSwizzle sw = (mn_major && mode != kBf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(W2L_ERR_CUDA, "gemm: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return W2L_OK;
+}
+
+const char* kernel_name(int mode) { return mode == kBf16 ? "gemm_umma_kernel<bf16>" : (mode == kF32x3 ? "gemm_umma_kernel<f32x3>" : "gemm_umma_kernel<tf32>"); }
+
+template <int kMode, bool kAMn, bool kBMn, int BN>
+int launch_bn(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  constexpr size_t smem = smem_for(kMode, BN);
+  static_assert(smem <= 227 * 1024, "gemm: shared-memory budget");
+  static bool configured = false;
+  if (!configured) {
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_kernel<kMode, kAMn, kBMn, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.k_splits);
+  profile_kind(1);
+  profile_start(stream);
+  gemm_umma_kernel<kMode, kAMn, kBMn, BN><<<grid, kGemmThreads, smem, stream>>>(ma, mb, p);
+  profile_stop(stream);
+  W2L_LAUNCH_CHECK(kernel_name(kMode));
+  return W2L_OK;
+}
+template <int kMode, bool kAMn, bool kBMn>
+int launch_mode(cudaStream_t stream, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  if constexpr (kMode == kF32x3) {
+    return launch_bn<kMode, kAMn, kBMn, 128>(stream, ma, mb, p);
+  } else if constexpr (kMode == kBf16 && kBMn) {  // 64-wide MN-major boxes: BN a multiple of 64
+    return bn <= 128 ? launch_bn<kMode, kAMn, kBMn, 128>(stream, ma, mb, p) : launch_bn<kMode, kAMn, kBMn, 256>(stream, ma, mb, p);
+  } else {
+    switch (bn) {
+      case 128: return launch_bn<kMode, kAMn, kBMn, 128>(stream, ma, mb, p);
+      case 160: return launch_bn<kMode, kAMn, kBMn, 160>(stream, ma, mb, p);
+      case 224: return launch_bn<kMode, kAMn, kBMn, 224>(stream, ma, mb, p);
+      default: return launch_bn<kMode, kAMn, kBMn, 256>(stream, ma, mb, p);
+    }
+  }
+}
+template <int kMode>
+int launch(cudaStream_t stream, bool a_mn, bool b_mn, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  if (!a_mn && !b_mn) return launch_mode<kMode, false, false>(stream, bn, ma, mb, p);
+  if (!a_mn && b_mn) return launch_mode<kMode, false, true>(stream, bn, ma, mb, p);
+  if (a_mn && b_mn) return launch_mode<kMode, true, true>(stream, bn, ma, mb, p);
+  return launch_mode<kMode, true, false>(stream, bn, ma, mb, p);
+}
+
+// split-K factor for a tile count: when the tiles alone under-fill the chip and K is long (weight gradients),
+// slices of >= 4 k blocks; only for plain epilogues (the partial sums are added atomically)
+int splits_for(int tiles, int total_kb, int slots_per_sm, bool plain) {
+  const int slots = 148 * slots_per_sm;
+  if (!plain || tiles >= 148 || total_kb < 16) return 1;
+  return std::max(1, std::min(std::min(slots / tiles, total_kb / 4), 32));
+}
+// tile width: minimise (waves over 148 SMs) x (operand bytes per tile + exposed epilogue), see the note at the top
+thread_local int g_force_bn = 0;  // w2l_gemm_set_tile: tests pin the tile width
+int choose_bn(int mode, bool b_mn, int M, int N, int total_kb, bool plain, int* splits_out) {
+  auto allowed = [&](int bn) {
+    if (mode == kF32x3) return bn == 128;
+    if (mode == kBf16 && b_mn) return bn == 128 || bn == 256;
+    return true;
+  };
+  auto slots_of = [&](int bn) { return (mode == kF32x3 || bn > 160) ? 1 : 2; };
+  if (g_force_bn && allowed(g_force_bn)) {
+    const int tiles = ((N + g_force_bn - 1) / g_force_bn) * ((M + BM - 1) / BM);
+    *splits_out = splits_for(tiles, total_kb, slots_of(g_force_bn), plain);
+    return g_force_bn;
+  }
+  const int cands[4] = {128, 160, 224, 256};
+  double best = 1e300;
+  int best_bn = 128;
+  *splits_out = 1;
+  for (int bn : cands) {
+    if (!allowed(bn)) continue;
+    const int tiles = ((N + bn - 1) / bn) * ((M + BM - 1) / BM);
+    const int splits = splits_for(tiles, total_kb, slots_of(bn), plain);
+    const int kb_local = (total_kb + splits - 1) / splits;
+    const double waves = std::ceil((double)tiles * splits / 148.0);
+    const double cost = waves * ((double)(128 + bn) * kb_local + (bn <= 160 ? 1.0 : 3.0) * bn);
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_bn = bn;
+      *splits_out = splits;
+    }
+  }
+  return best_bn;
+}
+
+int gemm_impl(void* stream_, int mode, int a_mn_major, int b_mn_major, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+              void* C, int ldc, int c_bf16, const float* bias, int act, int accumulate, const void* aux, int ld_aux, int aux_bf16,
+              int aux_mode, float aux_scale, float dropout_p, unsigned long long seed, bool allow_overlap) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (mode != kTf32 && mode != kF32x3 && mode != kBf16) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: unknown operand kind");
+  if (M <= 0 || N <= 0 || K <= 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: M, N, K must be positive");
+  if (!A || !B || !C) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: null pointer");
+  if (act < 0 || act > 1) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: act must be 0 (none) or 1 (relu)");
+  if (aux_mode < 0 || aux_mode > 2 || (aux_mode != 0 && (!aux || ld_aux < N)))
+    return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: bad aux mask arguments");
+  if (dropout_p < 0.f || dropout_p >= 1.f) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: dropout_p must be in [0, 1)");
+  if (dropout_p > 0.f && N % 4 != 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: dropout needs N % 4 == 0 (one Philox block per 4 columns)");
+  const int row_align = mode == kBf16 ? 8 : 4;  // elements per 16 bytes
+  if ((lda % row_align) || (ldb % row_align) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
+    return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: operand rows must be 16-byte aligned (ld % 4 == 0 for fp32, ld % 8 == 0 for bf16)");
+  if (ldc < N || (!allow_overlap && (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K))))
+    return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: leading dimension smaller than the row length");
+  if (lda <= 0 || ldb <= 0) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: non-positive leading dimension");
+  if (c_bf16 && accumulate) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: accumulation needs an fp32 C");
+  const int bke = kRowBytes / (mode == kBf16 ? 2 : 4);
+  const int total_kb = (K + bke - 1) / bke;
+  const bool plain = act == 0 && aux_mode == 0 && dropout_p == 0.f && bias == nullptr && !c_bf16;
+  int splits = 1;
+  const int BN = choose_bn(mode, b_mn_major != 0, M, N, total_kb, plain, &splits);
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a_mn_major)
+    rc = make_map(&ma, mode, A, M, K, lda, BM, false);   // [M][K]: box {128 B of k, 128 m}
+  else
+    rc = make_map(&ma, mode, A, K, M, lda, bke, true);   // [K][M]: box {128 B of m, bke k}
+  if (rc) return rc;
+  if (!b_mn_major)
+    rc = make_map(&mb, mode, B, N, K, ldb, BN, false);
+  else
+    rc = make_map(&mb, mode, B, K, N, ldb, bke, true);
+  if (rc) return rc;
+  if (splits > 1 && !accumulate) W2L_CUDA_CHECK(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, stream));
+  GemmParams p{M, N, K, ldc, act, C, bias, accumulate, aux_mode, ld_aux, aux, aux_scale, dropout_p, seed, splits, c_bf16, aux_bf16};
+  if (mode == kBf16) return launch<kBf16>(stream, a_mn_major, b_mn_major, BN, ma, mb, p);
+  if (mode == kF32x3) return launch<kF32x3>(stream, a_mn_major, b_mn_major, BN, ma, mb, p);
+  return launch<kTf32>(stream, a_mn_major, b_mn_major, BN, ma, mb, p);
+}
+
+// fp32-operand entry points follow the thread's precision setting
+int f32_kind() { return current_precision() == W2L_PRECISION_F32 ? kF32x3 : kTf32; }
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(long long n4, const float4* __restrict__ x, uint2* __restrict__ y, long long n,
+                                                        const float* __restrict__ xs, __nv_bfloat16* __restrict__ ys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 v = x[i];
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    y[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+  if (i < n - 4 * n4) ys[4 * n4 + i] = __float2bfloat16_rn(xs[4 * n4 + i]);
+}
+// rows of `cols` floats (row stride ld_in) -> rows of cols_p bf16 (row stride cols_p), zero-padded columns
+__global__ void __launch_bounds__(256) cast_bf16_rows_kernel(long long rows, int cols, int ld_in, int cols_p, const float* __restrict__ x,
+                                                             __nv_bfloat16* __restrict__ y) {
+  const long long total = rows * cols_p;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_p;
+    const int c = (int)(i % cols_p);
+    y[i] = c < cols ? __float2bfloat16_rn(x[r * ld_in + c]) : __float2bfloat16_rn(0.f);
+  }
+}
+
+}  // namespace
+}  // namespace w2l
+
+using namespace w2l;
+
+extern "C" int w2l_gemm_set_tile(int bn) {
+  if (bn != 0 && bn != 128 && bn != 160 && bn != 224 && bn != 256) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: tile width must be 0 (auto), 128, 160, 224 or 256");
+  g_force_bn = bn;
+  return W2L_OK;
+}
+
+extern "C" int w2l_gemm(void* stream, int kind, int a_mn_major, int b_mn_major, int M, int N, int K, const void* A, int lda, const void* B,
+                        int ldb, void* C, int ldc, int c_bf16, const float* bias, int act, int accumulate, const void* aux, int ld_aux,
+                        int aux_bf16, int aux_mode, float aux_scale, float dropout_p, unsigned long long seed, int allow_overlap) {
+  return gemm_impl(stream, kind, a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, c_bf16, bias, act, accumulate, aux, ld_aux, aux_bf16,
+                   aux_mode, aux_scale, dropout_p, seed, allow_overlap != 0);
+}
+
+extern "C" int w2l_gemm_tf32_ex(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                                const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate,
+                                const float* aux, int ld_aux, int aux_mode, float aux_scale, float dropout_p,
+                                unsigned long long seed) {
+  return gemm_impl(stream_, f32_kind(), a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, 0, bias, act, accumulate, aux, ld_aux, 0, aux_mode,
+                   aux_scale, dropout_p, seed, false);
+}
+
+extern "C" int w2l_gemm_tf32(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                             const float* B, int ldb, float* C, int ldc, const float* bias, int act) {
+  return w2l_gemm_tf32_ex(stream_, a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, bias, act, 0, nullptr, 0, 0, 1.f, 0.f, 0ull);
+}
+
+// Same contraction with OVERLAPPING operand rows allowed (lda / ldb smaller than the row length): the TMA tensor map
+// takes any 16-byte-multiple row stride, so the im2col matrix of a time convolution over [T][Cin] activations —
+// row t = frames t .. t+kw-1, i.e. kw*Cin contiguous floats starting at frame t, row stride Cin — is a zero-copy view.
+extern "C" int w2l_gemm_tf32_view(void* stream_, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
+                                  const float* B, int ldb, float* C, int ldc, const float* bias, int act, int accumulate) {
+  return gemm_impl(stream_, f32_kind(), a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, 0, bias, act, accumulate, nullptr, 0, 0, 0, 1.f, 0.f,
+                   0ull, true);
+}
+
+extern "C" int w2l_cast_bf16(void* stream_, long long n, const float* x, void* y) {
+  if (n <= 0) return W2L_OK;
+  if (!x || !y) return fail(W2L_ERR_INVALID_ARGUMENT, "cast_bf16: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 7) == 0);
+  const long long n4 = vec ? n / 4 : 0;
+  const long long threads = std::max<long long>(n4, n - 4 * n4);
+  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n4, reinterpret_cast<const float4*>(x), static_cast<uint2*>(y), n, x,
+                                                                         static_cast<__nv_bfloat16*>(y));
+  W2L_LAUNCH_CHECK("cast_bf16_kernel");
+  return W2L_OK;
+}
+extern "C" int w2l_cast_bf16_rows(void* stream_, long long rows, int cols, int ld_in, int cols_padded, const float* x, void* y) {
+  if (rows <= 0 || cols <= 0) return W2L_OK;
+  if (!x || !y || cols_padded < cols || ld_in < cols) return fail(W2L_ERR_INVALID_ARGUMENT, "cast_bf16_rows: bad arguments");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long total = rows * cols_padded;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  cast_bf16_rows_kernel<<<grid, 256, 0, stream>>>(rows, cols, ld_in, cols_padded, x, static_cast<__nv_bfloat16*>(y));
+  W2L_LAUNCH_CHECK("cast_bf16_rows_kernel");
+  return W2L_OK;
+}

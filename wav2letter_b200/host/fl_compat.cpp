@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -49,6 +52,8 @@ size_t dtypeSize(DType t) {
       return 4;
     case DType::f64:
       return 8;
+    case DType::bf16:
+      return 2;
     default:
       return 1;
   }
@@ -66,7 +71,9 @@ struct Storage {
   cudaStream_t stream = nullptr;
   bool owner = true;
   ~Storage() {
-    if (ptr && owner) cudaFreeAsync(ptr, stream);
+    // stream-ordered free on the stream the thread is working on NOW (every C-ABI call sets it): that orders the free
+    // after the buffer's last use even when a cached buffer (workspaces, arenas) was allocated under another stream
+    if (ptr && owner) cudaFreeAsync(ptr, g_stream ? g_stream : stream);
   }
 };
 
@@ -269,6 +276,13 @@ void Variable::backward(const Variable& g, bool retainGraph) {
     order.push_back(v);
   };
   dfs(*this);
+  // the overlapped reducer launches a bucket when every gradient CONTRIBUTION of its parameters has landed: a parameter
+  // consumed by several graph nodes (shared / tied module, a module applied twice) is counted once per consumer
+  if (g_active_reducer)
+    for (const Variable& v : order)
+      if (v.impl_->gradFunc)
+        for (const Variable& in : v.impl_->inputs)
+          if (in.impl_ && !in.impl_->boundGrad.isEmpty()) g_active_reducer->expectContribution(in.impl_.get());
   for (auto it = order.rbegin(); it != order.rend(); ++it) {
     Variable& v = *it;
     if (v.impl_->gradFunc && v.isGradAvailable()) v.impl_->gradFunc(v.impl_->inputs, v.grad());
@@ -372,6 +386,53 @@ af::array workspaceFor(af::array& cache, size_t bytes) {
   return cache;
 }
 thread_local af::array g_conv_ws;
+
+// ---- precision of the dense contractions (w2l_set_precision) ----------------------------------
+bool bf16Mode() { return w2l_get_precision() == W2L_PRECISION_BF16; }
+int gemmKind() { return bf16Mode() ? W2L_GEMM_BF16 : (w2l_get_precision() == W2L_PRECISION_F32 ? W2L_GEMM_F32X3 : W2L_GEMM_TF32); }
+// operand rows are TMA rows: 16-byte multiples = 4 floats or 8 bf16; channel counts are carried padded to that
+int chanPad() { return bf16Mode() ? 8 : 4; }
+long long padUp(long long n, long long a) { return (n + a - 1) / a * a; }
+// rows of `cols` floats (row stride ld) -> [rows][colsP], zero-padded columns: fp32 copy, or bf16 in BF16 mode
+af::array padRowsF32(const float* x, long long rows, int cols, int ld, int colsP) {
+  af::array out = af::array::zeros(af::dim4(colsP, rows));
+  w2l::copyRows(out.f32(), sizeof(float) * (size_t)colsP, x, sizeof(float) * (size_t)ld, sizeof(float) * (size_t)cols, (size_t)rows);
+  return out;
+}
+af::array castRowsBf16(const float* x, long long rows, int cols, int ld, int colsP) {
+  af::array out = af::array::empty(af::dim4(colsP, rows), DType::bf16);
+  if (cols == colsP && ld == cols)
+    check(w2l_cast_bf16(currentStream(), rows * cols, x, out.ptr()));
+  else
+    check(w2l_cast_bf16_rows(currentStream(), rows, cols, ld, colsP, x, out.ptr()));
+  return out;
+}
+// GEMM operand in the thread's precision: the fp32 rows themselves when they are already TMA rows (TF32 / F32X3), a
+// zero-padded fp32 copy when not, a (padded) bf16 copy in BF16 mode.  `ld` out = row stride in elements.
+struct GemmOperand {
+  af::array a;
+  int ld = 0;
+};
+GemmOperand gemmOperand(const af::array& x, long long rows, int cols, int ld) {
+  GemmOperand op;
+  if (bf16Mode()) {
+    op.ld = (int)padUp(cols, 8);
+    op.a = castRowsBf16(x.f32(), rows, cols, ld, op.ld);
+  } else if (ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x.ptr()) & 15) == 0) {
+    op.a = x;
+    op.ld = ld;
+  } else {
+    op.ld = (int)padUp(cols, 4);
+    op.a = padRowsF32(x.f32(), rows, cols, ld, op.ld);
+  }
+  return op;
+}
+int gemmP(int a_mn, int b_mn, int M, int N, int K, const GemmOperand& A, const GemmOperand& B, float* C, int ldc, const float* bias, int act,
+          int accumulate, const float* aux = nullptr, int ld_aux = 0, int aux_mode = 0, float aux_scale = 1.f, float dropP = 0.f,
+          unsigned long long seed = 0, int allowOverlap = 0) {
+  return w2l_gemm(currentStream(), gemmKind(), a_mn, b_mn, M, N, K, A.a.ptr(), A.ld, B.a.ptr(), B.ld, C, ldc, 0, bias, act, accumulate, aux, ld_aux, 0,
+                  aux_mode, aux_scale, dropP, seed, allowOverlap);
+}
 }  // namespace
 
 // ================================================================================================
@@ -388,7 +449,7 @@ Variable View::forward(const Variable& in) {
   // head of a conv_glu arch: `V -1 1 NFEAT 0` -> [T,1,F,B]: the features are CHANNELS (W = 1); same transposition
   if (dims_[1] == 1 && dims_[0] == -1 && dims_[2] > 1 && in.dims(2) == 1 && in.dims(1) == dims_[2]) {
     const long long T = in.dims(0), F = in.dims(1), B = in.dims(3);
-    if (F % 4) throw std::invalid_argument("View: the channel-major head needs a feature count that is a multiple of 4");
+    if (F % chanPad()) throw std::invalid_argument("View: the channel-major head needs a feature count that is a multiple of 4 (8 in bf16 mode)");
     af::array out = af::array::empty(af::dim4(1, F, T, B));
     check(w2l_transpose_input(currentStream(), (int)B, (int)F, (int)T, in.array().f32(), out.f32()));
     return Variable(out, in.isCalcGrad());
@@ -428,7 +489,7 @@ Variable Conv2D::forwardWith(const Variable& in, const Variable& weight, const V
   requireInternal(in, "Conv2D");
   const int W = (int)in.dims(0), Cin = (int)in.dims(1), T = (int)in.dims(2), B = (int)in.dims(3);
   // W = 1 (`V -1 1 NFEAT 0` archs: features are channels): the large-channel GEMM path
-  if (W == 1 && Cin == (nIn + 3) / 4 * 4) return forwardGemm(in, weight, biasVar);
+  if (W == 1 && (Cin == padUp(nIn, 4) || Cin == padUp(nIn, 8))) return forwardGemm(in, weight, biasVar);
   if (Cin != nIn) throw std::invalid_argument("Conv2D: input has " + std::to_string(Cin) + " channels, expected " + std::to_string(nIn));
   int pl, pr;
   if (explicitPad_) {
@@ -511,6 +572,8 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
   // shrinks by kw-1 per layer and travels with the variable (validFrames); fl::Reorder drops the slack at the end.
   if (stride != 1) throw std::invalid_argument("Conv2D: the large-channel path covers stride 1 only");
   const int Cp = (int)in.dims(1), TsIn = (int)in.dims(2), B = (int)in.dims(3);
+  const int align = chanPad();
+  if (Cp % align) throw std::invalid_argument("Conv2D: the activation's channel padding does not match the precision mode (bf16 rows are multiples of 8 channels)");
   const int TvIn = in.validFrames() >= 0 ? (int)in.validFrames() : TsIn;
   int pl, pr;
   if (explicitPad_) {
@@ -528,7 +591,7 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
   if (Tout <= 0) throw std::invalid_argument("Conv2D: input shorter than the kernel");
   const bool glu = gluSplit_;
   if (glu && (nOut % 2)) throw std::invalid_argument("Conv2D: a GLU needs an even channel count");
-  const int CoutP = glu ? 2 * ((nOut / 2 + 3) / 4 * 4) : (nOut + 3) / 4 * 4;
+  const int CoutP = glu ? 2 * (int)padUp(nOut / 2, align) : (int)padUp(nOut, align);
   const int cin = nIn, cout = nOut, k = kw;
   const bool hasBias = hasBias_, relu = relu_;
   af::array fwdW = af::array::empty(af::dim4((long long)k * Cp, CoutP));
@@ -543,10 +606,13 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
   }
   const long long rowsAll = (long long)B * Ts, M = rowsAll - k + 1;  // output rows that have a full window in the buffer
   if (rowsAll > 0x7fffffffLL / 2) throw std::invalid_argument("Conv2D: batch too long for one GEMM");
+  // operands in the thread's precision (bf16 copies in BF16 mode; the fp32 buffers themselves otherwise)
+  const GemmOperand xop = gemmOperand(xp, rowsAll, Cp, Cp);
+  const GemmOperand fwdOp = gemmOperand(fwdW, CoutP, k * Cp, k * Cp);
+  const GemmOperand flipOp = gemmOperand(flipW, Cp, k * CoutP, k * CoutP);
   af::array y = af::array::empty(af::dim4(1, CoutP, Ts, B));
   cudaMemsetAsync(y.f32() + (size_t)M * CoutP, 0, sizeof(float) * (size_t)(k - 1) * CoutP, static_cast<cudaStream_t>(currentStream()));
-  check(w2l_gemm_tf32_view(currentStream(), 0, 0, (int)M, CoutP, k * Cp, xp.f32(), Cp, fwdW.f32(), k * Cp, y.f32(), CoutP, biasP.f32(),
-                           relu ? 1 : 0, 0));
+  check(gemmP(0, 0, (int)M, CoutP, k * Cp, xop, fwdOp, y.f32(), CoutP, biasP.f32(), relu ? 1 : 0, 0, nullptr, 0, 0, 1.f, 0.f, 0ull, 1));
   std::vector<Variable> inputs{in, weight};
   if (hasBias) inputs.push_back(biasVar);
   Variable out(y, inputs, [=](std::vector<Variable>& ins, const Variable& gout) {
@@ -559,7 +625,8 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
     }
     if (ins[1].isCalcGrad()) {
       af::array dWarr = af::array::empty(af::dim4((long long)k * Cp, CoutP));
-      check(w2l_gemm_tf32_view(currentStream(), 1, 1, CoutP, k * Cp, (int)M, dy.f32(), CoutP, xp.f32(), Cp, dWarr.f32(), k * Cp, nullptr, 0, 0));
+      const GemmOperand dyop = gemmOperand(dy, rowsAll, CoutP, CoutP);
+      check(gemmP(1, 1, CoutP, k * Cp, (int)M, dyop, xop, dWarr.f32(), k * Cp, nullptr, 0, 0, nullptr, 0, 0, 1.f, 0.f, 0ull, 1));
       af::array dw = ins[1].gradStorage();
       if (dw.isEmpty()) dw = af::array::zeros(ins[1].dims());
       af::array db;
@@ -575,13 +642,20 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
     if (ins[0].isCalcGrad()) {
       // dXp[m][ci] = sum_j dY[m - (kw-1) + j][..] Wflip: a copy of dY with kw-1 zero rows in front gives the view its
       // left context; a sample's first frames see the previous sample's slack rows, which are zero
-      af::array dyp = af::array::empty(af::dim4(CoutP, rowsAll + k - 1));
-      cudaMemsetAsync(dyp.f32(), 0, sizeof(float) * (size_t)(k - 1) * CoutP, static_cast<cudaStream_t>(currentStream()));
-      w2l::copyRows(dyp.f32() + (size_t)(k - 1) * CoutP, sizeof(float) * (size_t)rowsAll * CoutP, dy.f32(), sizeof(float) * (size_t)rowsAll * CoutP,
-                    sizeof(float) * (size_t)rowsAll * CoutP, 1);
+      GemmOperand dypOp;
+      dypOp.ld = CoutP;
+      if (bf16Mode()) {
+        dypOp.a = af::array::empty(af::dim4(CoutP, rowsAll + k - 1), DType::bf16);
+        cudaMemsetAsync(dypOp.a.ptr(), 0, 2 * (size_t)(k - 1) * CoutP, static_cast<cudaStream_t>(currentStream()));
+        check(w2l_cast_bf16(currentStream(), rowsAll * CoutP, dy.f32(), static_cast<char*>(dypOp.a.ptr()) + 2 * (size_t)(k - 1) * CoutP));
+      } else {
+        dypOp.a = af::array::empty(af::dim4(CoutP, rowsAll + k - 1));
+        cudaMemsetAsync(dypOp.a.ptr(), 0, sizeof(float) * (size_t)(k - 1) * CoutP, static_cast<cudaStream_t>(currentStream()));
+        w2l::copyRows(dypOp.a.f32() + (size_t)(k - 1) * CoutP, sizeof(float) * (size_t)rowsAll * CoutP, dy.f32(), sizeof(float) * (size_t)rowsAll * CoutP,
+                      sizeof(float) * (size_t)rowsAll * CoutP, 1);
+      }
       af::array dxp = af::array::empty(af::dim4(1, Cp, Ts, B));
-      check(w2l_gemm_tf32_view(currentStream(), 0, 0, (int)rowsAll, Cp, k * CoutP, dyp.f32(), CoutP, flipW.f32(), k * CoutP, dxp.f32(), Cp,
-                               nullptr, 0, 0));
+      check(gemmP(0, 0, (int)rowsAll, Cp, k * CoutP, dypOp, flipOp, dxp.f32(), Cp, nullptr, 0, 0, nullptr, 0, 0, 1.f, 0.f, 0ull, 1));
       if (Tv < Ts)  // gradients of slack input frames must not reach the previous layer
         cudaMemset2DAsync(dxp.f32() + (size_t)Tv * Cp, sizeof(float) * (size_t)Ts * Cp, 0, sizeof(float) * (size_t)(Ts - Tv) * Cp, (size_t)B,
                           static_cast<cudaStream_t>(currentStream()));
@@ -723,6 +797,50 @@ Variable Dropout::forward(const Variable& in) {
 std::string Dropout::prettyString() const { return "Dropout (" + std::to_string(p_) + ")"; }
 
 // ================================================================================================
+// SpecAugment (arch opcode SAUG): frequency / time masking of the filterbank input, training mode only
+// (upstream fl/contrib/modules/SpecAugment: nFMask bands of width U[0, fMaskF) at U[0, F - f); nTMask bands of width
+// U[0, min(tMaskT, T * tMaskP)) at U[0, T - t); `seq(f0, f0 + f)` is inclusive upstream, so a band covers f + 1 bins;
+// the same bands for the whole batch; time warping (tWarpW) is accepted and unused, as upstream)
+// ================================================================================================
+SpecAugment::SpecAugment(int tWarpW, int fMaskF, int nFMask, int tMaskT, double tMaskP, int nTMask)
+    : tWarpW_(tWarpW), fMaskF_(fMaskF), nFMask_(nFMask), tMaskT_(tMaskT), nTMask_(nTMask), tMaskP_(tMaskP), rng_(nextSeed()) {
+  if (nFMask > 0 && fMaskF <= 0) throw std::invalid_argument("invalid arguments for frequency masking.");
+  if (nTMask > 0 && tMaskT <= 0) throw std::invalid_argument("invalid arguments for time masking.");
+  if (nTMask > 0 && (tMaskP <= 0 || tMaskP > 1.0)) throw std::invalid_argument("invalid arguments for time masking.");
+  if (nFMask > 8 || nTMask > 8) throw std::invalid_argument("SpecAugment: at most 8 masks per axis are covered");
+}
+std::string SpecAugment::prettyString() const {
+  std::ostringstream o;
+  o << "SpecAugment ( W: " << tWarpW_ << ", F: " << fMaskF_ << ", mF: " << nFMask_ << ", T: " << tMaskT_ << ", p: " << tMaskP_ << ", mT: " << nTMask_ << " )";
+  return o.str();
+}
+Variable SpecAugment::forward(const Variable& in) {
+  if (!train_) return in;
+  requireInternal(in, "SpecAugment");
+  const int W = (int)in.dims(0), C = (int)in.dims(1), T = (int)in.dims(2), B = (int)in.dims(3);  // W = frequency bins
+  if (W < fMaskF_) throw std::runtime_error("Invalid input frequency channels");
+  auto randInt = [&](int low, int high) {  // uniform in [low, high - 1]
+    return high - 1 <= low ? low : std::uniform_int_distribution<int>(low, high - 1)(rng_);
+  };
+  int f0[8], f1[8], t0[8], t1[8], nt = 0;
+  for (int i = 0; i < nFMask_; ++i) {
+    const int f = randInt(0, fMaskF_);
+    f0[i] = randInt(0, W - f);
+    f1[i] = std::min(W, f0[i] + f + 1);
+  }
+  const int Tm = std::min(tMaskT_, (int)(T * tMaskP_));
+  if (Tm > 0)
+    for (; nt < nTMask_; ++nt) {
+      const int t = randInt(0, Tm);
+      t0[nt] = randInt(0, T - t);
+      t1[nt] = std::min(T, t0[nt] + t + 1);
+    }
+  af::array y = af::array::empty(in.dims());
+  check(w2l_mask_bands(currentStream(), B, T, C, W, in.array().f32(), y.f32(), nFMask_, f0, f1, nt, t0, t1, 0.0f));
+  return Variable(y, false);  // data augmentation: detached, like upstream
+}
+
+// ================================================================================================
 // LayerNorm over the whole sample, scalar affine
 // ================================================================================================
 LayerNorm::LayerNorm(const std::vector<int>& axes, double eps, bool affine) : axes_(axes), eps_(eps) {
@@ -795,9 +913,8 @@ Variable LayerNorm::forwardResidual(const Variable& a, const Variable& r, int br
 // ================================================================================================
 Linear::Linear(int nIn_, int nOut_, bool bias) : nIn(nIn_), nOut(nOut_), hasBias_(bias) {
   if (nIn <= 0 || nOut <= 0) throw std::invalid_argument("Linear: non-positive size");
-  // the input rows are TMA operands (16-byte row stride); an output size that is not a multiple of 4 (e.g. ~30 letter
-  // classes) is handled in backward by a zero-padded copy of the incoming gradient
-  if (nIn % 4) throw std::invalid_argument("Linear: the input size must be a multiple of 4 (16-byte rows for the TMA loads)");
+  // GEMM operand rows are TMA rows (16-byte multiples); sizes that are not (e.g. `WN 0 L 375 1000` of
+  // recipes/conv_glu/wsj/network.arch:48, or ~30 letter classes on the output side) go through zero-padded operand copies
   const double bound = std::sqrt(1.0 / (double)nIn);
   // memory [nOut][nIn] (nIn fastest) == column-major dims [nIn, nOut]: the K-major B operand of the forward
   // GEMM.  Upstream stores the transpose ([out, in] column-major); INTEGRATION.md lists the conversion.
@@ -816,11 +933,17 @@ Variable Linear::forwardWith(const Variable& in, const Variable& weight, const V
   requireInternal(in, "Linear");
   if (in.validFrames() >= 0 && in.validFrames() != in.dims(2))
     throw std::invalid_argument("Linear: the input carries slack frames (large-channel convolutions); a Reorder must come first");
+  // input rows: nIn features, or nIn features followed by the zero channels the large-channel convolutions carry
+  // (channel counts padded to 4 floats / 8 bf16)
+  auto isPadded = [&](long long c) { return c == nIn || (c > nIn && (c == padUp(nIn, 4) || c == padUp(nIn, 8))); };
   long long T, B;
-  if (in.dims(0) == nIn) {  // flattened [K, T, B]
+  int inCols;
+  if (isPadded(in.dims(0))) {  // flattened [K, T, B]
+    inCols = (int)in.dims(0);
     T = in.dims(1);
     B = in.dims(2) * in.dims(3);
   } else if (in.dims(0) * in.dims(1) == nIn) {  // activation [W, C, T, B]
+    inCols = nIn;
     T = in.dims(2);
     B = in.dims(3);
   } else {
@@ -831,9 +954,21 @@ Variable Linear::forwardWith(const Variable& in, const Variable& weight, const V
   Variable wv = weight;
   Variable bv = hasBias_ ? bias : Variable();
   const float dp = (train_ && dropP > 0) ? dropP : 0.f;
-  // NOTE: the weight is stored [nOut][nIn] row-major (K-major B operand)
-  check(w2l_gemm_tf32_ex(currentStream(), 0, 0, M, nOut, nIn, in.array().f32(), nIn, wv.array().f32(), nIn, y.f32(), nOut,
-                         hasBias_ ? bv.array().f32() : nullptr, relu ? 1 : 0, 0, nullptr, 0, 0, 1.f, dp, nextSeed()));
+  // operands in the thread's precision; K = the operand row length Kp >= inCols >= nIn (extra columns are zero)
+  const GemmOperand xop = gemmOperand(in.array(), M, inCols, inCols);
+  const int Kp = xop.ld;
+  GemmOperand wop;
+  if (bf16Mode()) {
+    wop.ld = Kp;
+    wop.a = castRowsBf16(wv.array().f32(), nOut, nIn, nIn, Kp);
+  } else if (Kp == nIn) {
+    wop.a = wv.array();  // NOTE: the weight is stored [nOut][nIn] row-major (K-major B operand)
+    wop.ld = nIn;
+  } else {
+    wop.ld = Kp;
+    wop.a = padRowsF32(wv.array().f32(), nOut, nIn, nIn, Kp);
+  }
+  check(gemmP(0, 0, M, nOut, Kp, xop, wop, y.f32(), nOut, hasBias_ ? bv.array().f32() : nullptr, relu ? 1 : 0, 0, nullptr, 0, 0, 1.f, dp, nextSeed()));
   const int nin = nIn, nout = nOut;
   const bool hasBias = hasBias_;
   std::vector<Variable> inputs{in, wv};
@@ -845,33 +980,47 @@ Variable Linear::forwardWith(const Variable& in, const Variable& weight, const V
       check(w2l_mask_mul(currentStream(), y.elements(), dy.f32(), y.f32(), relu ? 1 : 2, dp > 0.f ? 1.0f / (1.0f - dp) : 1.0f, m.f32()));
       dy = m;
     }
-    int ldy = nout;  // row stride of dy as a TMA operand
-    if (nout % 4) {  // pad the rows to a multiple of 4 floats (zero columns)
-      ldy = (nout + 3) / 4 * 4;
-      af::array dyp = af::array::zeros(af::dim4(ldy, M));
-      w2l::copyRows(dyp.f32(), sizeof(float) * ldy, dy.f32(), sizeof(float) * nout, sizeof(float) * nout, (size_t)M);
-      dy = dyp;
-    }
-    if (ins[1].isCalcGrad()) {  // dW[nout][nin] = dy^T x  (both operands MN-major, no transposition pass)
-      af::array dw = ins[1].gradStorage();
-      const int accumulate = dw.isEmpty() ? 0 : 1;  // arena slot (zeroed by zeroGrad): C += in the GEMM epilogue
-      if (!accumulate) dw = af::array::empty(ins[1].dims());
-      check(w2l_gemm_tf32_ex(currentStream(), 1, 1, nout, nin, M, dy.f32(), ldy, ins[0].array().f32(), nin, dw.f32(), nin, nullptr, 0,
-                             accumulate, nullptr, 0, 0, 1.f, 0.f, 0ull));
-      ins[1].addGrad(Variable(dw, false));
+    const GemmOperand dyop = gemmOperand(dy, M, nout, nout);  // zero-padded columns when nout is not a TMA row length
+    if (ins[1].isCalcGrad()) {  // dW[nout][Kp] = dy^T x  (both operands MN-major, no transposition pass)
+      if (Kp == nin) {
+        af::array dw = ins[1].gradStorage();
+        const int accumulate = dw.isEmpty() ? 0 : 1;  // arena slot (zeroed by zeroGrad): C += in the GEMM epilogue
+        if (!accumulate) dw = af::array::empty(ins[1].dims());
+        check(gemmP(1, 1, nout, nin, M, dyop, xop, dw.f32(), nin, nullptr, 0, accumulate));
+        ins[1].addGrad(Variable(dw, false));
+      } else {  // padded K: the gradient of the zero columns is dropped
+        af::array dwp = af::array::empty(af::dim4(Kp, nout));
+        check(gemmP(1, 1, nout, Kp, M, dyop, xop, dwp.f32(), Kp, nullptr, 0, 0));
+        af::array dw = af::array::empty(ins[1].dims());
+        w2l::copyRows(dw.f32(), sizeof(float) * (size_t)nin, dwp.f32(), sizeof(float) * (size_t)Kp, sizeof(float) * (size_t)nin, (size_t)nout);
+        ins[1].addGrad(Variable(dw, false));
+      }
       if (hasBias) {
         af::array db = ins[2].gradStorage();
         if (db.isEmpty()) db = af::array::zeros(ins[2].dims());
-        check(w2l_colsum_accumulate(currentStream(), M, nout, dy.f32(), ldy, db.f32()));
+        check(w2l_colsum_accumulate(currentStream(), M, nout, dy.f32(), nout, db.f32()));
         ins[2].addGrad(Variable(db, false));
       }
     }
-    if (ins[0].isCalcGrad()) {  // dx[M][nin] = dy W  (B = W MN-major)
-      af::array acc = ins[0].accumulableGrad();  // e.g. LN2's residual gradient: C += in the GEMM epilogue
-      af::array dx = acc.isEmpty() ? af::array::empty(ins[0].dims()) : acc;
-      check(w2l_gemm_tf32_ex(currentStream(), 0, 1, M, nin, nout, dy.f32(), ldy, ins[1].array().f32(), nin, dx.f32(), nin, nullptr, 0,
-                             acc.isEmpty() ? 0 : 1, inMaskMode ? ins[0].array().f32() : nullptr, nin, inMaskMode, inMaskScale, 0.f, 0ull));
-      if (acc.isEmpty()) ins[0].addGrad(Variable(dx, false), true);
+    if (ins[0].isCalcGrad()) {  // dx[M][Kp] = dy W  (B = W MN-major)
+      if (Kp == inCols) {
+        af::array acc = ins[0].accumulableGrad();  // e.g. LN2's residual gradient: C += in the GEMM epilogue
+        af::array dx = acc.isEmpty() ? af::array::empty(ins[0].dims()) : acc;
+        check(gemmP(0, 1, M, Kp, nout, dyop, wop, dx.f32(), Kp, nullptr, 0, acc.isEmpty() ? 0 : 1, inMaskMode ? ins[0].array().f32() : nullptr, Kp,
+                    inMaskMode, inMaskScale));
+        if (acc.isEmpty()) ins[0].addGrad(Variable(dx, false), true);
+      } else {  // the input rows were padded for the GEMM: drop the pad columns again
+        af::array dxp = af::array::empty(af::dim4(Kp, M));
+        check(gemmP(0, 1, M, Kp, nout, dyop, wop, dxp.f32(), Kp, nullptr, 0, 0));
+        af::array dx = af::array::empty(ins[0].dims());
+        w2l::copyRows(dx.f32(), sizeof(float) * (size_t)inCols, dxp.f32(), sizeof(float) * (size_t)Kp, sizeof(float) * (size_t)inCols, (size_t)M);
+        if (inMaskMode) {
+          af::array m = af::array::empty(dx.dims());
+          check(w2l_mask_mul(currentStream(), dx.elements(), dx.f32(), ins[0].array().f32(), inMaskMode, inMaskScale, m.f32()));
+          dx = m;
+        }
+        ins[0].addGrad(Variable(dx, false), true);
+      }
     }
   });
 }
@@ -954,8 +1103,8 @@ void FirstOrderOptimizer::zeroGrad() {
   for (auto& p : parameters_) p.zeroGrad();
 }
 SGDOptimizer::SGDOptimizer(const std::vector<Variable>& params, double lr, double momentum, double weightDecay, bool useNesterov)
-    : FirstOrderOptimizer(params, lr), mu_(momentum), wd_(weightDecay) {
-  if (useNesterov) throw std::invalid_argument("SGDOptimizer: Nesterov momentum is not covered");
+    : FirstOrderOptimizer(params, lr), mu_(momentum), wd_(weightDecay), nesterov_(useNesterov) {
+  if (useNesterov && momentum <= 0) throw std::invalid_argument("SGDOptimizer: Nesterov momentum needs momentum > 0");
   if (mu_ != 0)
     for (auto& p : parameters_) velocities_.push_back(af::array::zeros(p.dims()));
 }
@@ -963,13 +1112,13 @@ void SGDOptimizer::step() {
   for (size_t i = 0; i < parameters_.size(); ++i) {
     auto& p = parameters_[i];
     if (!p.isGradAvailable()) continue;
-    check(w2l_sgd_step(currentStream(), p.elements(), p.array().f32(), p.grad().array().f32(), mu_ != 0 ? velocities_[i].f32() : nullptr,
-                       (float)lr_, (float)mu_, (float)wd_, 1.0f, 0.f, nullptr));
+    check(w2l_sgd_step_ex(currentStream(), p.elements(), p.array().f32(), p.grad().array().f32(), mu_ != 0 ? velocities_[i].f32() : nullptr,
+                          (float)lr_, (float)mu_, (float)wd_, 1.0f, 0.f, nullptr, nesterov_ ? 1 : 0, nullptr));
   }
 }
 std::string SGDOptimizer::prettyString() const {
   std::ostringstream o;
-  o << "SGD" << (mu_ != 0 ? " (momentum=" + std::to_string(mu_) + ")" : "") << (wd_ != 0 ? " (weight decay=" + std::to_string(wd_) + ")" : "");
+  o << "SGD" << (mu_ != 0 ? std::string(nesterov_ ? " (Nesterov momentum=" : " (momentum=") + std::to_string(mu_) + ")" : "") << (wd_ != 0 ? " (weight decay=" + std::to_string(wd_) + ")" : "");
   return o.str();
 }
 double clipGradNorm(const std::vector<Variable>& params, double maxNorm) {
@@ -1100,6 +1249,7 @@ OverlappedArenaReducer::OverlappedArenaReducer(const std::vector<Variable>& para
   if (open) bucket_.push_back(cur);
   std::sort(owner_.begin(), owner_.end());
   seen_.assign(owner_.size(), 0);
+  expected_.assign(owner_.size(), 0);
   cudaStream_t cs;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -1127,6 +1277,7 @@ void OverlappedArenaReducer::arm() {
     b.launched = false;
   }
   std::fill(seen_.begin(), seen_.end(), 0);
+  std::fill(expected_.begin(), expected_.end(), 0);
   armed_ = true;
   g_active_reducer = this;
 }
@@ -1140,15 +1291,24 @@ void OverlappedArenaReducer::launch(Bucket& b) {
   float* ptr = grads_.f32() + b.offset;
   ncclCheck(ncclAllReduce(ptr, ptr, b.count, ncclFloat32, ncclSum, g_comm, comm), "ncclAllReduce (bucket)");
 }
+void OverlappedArenaReducer::expectContribution(const void* id) {
+  if (!armed_) return;
+  auto it = std::lower_bound(owner_.begin(), owner_.end(), std::make_pair(id, -1));
+  if (it == owner_.end() || it->first != id) return;
+  ++expected_[(size_t)(it - owner_.begin())];
+}
 void OverlappedArenaReducer::onGradReady(const void* id) {
   if (!armed_) return;
   auto it = std::lower_bound(owner_.begin(), owner_.end(), std::make_pair(id, -1));
   if (it == owner_.end() || it->first != id) return;
   const size_t k = (size_t)(it - owner_.begin());
-  if (seen_[k]) return;  // only the first arrival of a step counts (a shared parameter would arrive again)
-  seen_[k] = 1;
   Bucket& b = bucket_[(size_t)it->second];
-  if (--b.remaining == 0 && !b.launched) launch(b);
+  if (b.launched)  // a contribution nobody announced (expectContribution) after the bucket went out: the sum would be wrong
+    throw std::logic_error("OverlappedArenaReducer: a gradient arrived after its bucket was reduced");
+  ++seen_[k];
+  // the parameter is complete when all announced consumers have contributed (an unannounced parameter: the first arrival)
+  if (seen_[k] != std::max(1, expected_[k])) return;
+  if (--b.remaining == 0) launch(b);
 }
 void OverlappedArenaReducer::finalize() {
   if (!armed_) return;
@@ -1180,6 +1340,48 @@ void initDistributed(int worldRank, int worldSize, const void* id128) {
   g_world = worldSize;
 }
 
+// the reference's own signature (recipes/slimIPL/src/Train.cpp:189-193): file-system rendezvous — rank 0 publishes the
+// NCCL id under rndvFilepath, the other ranks wait for it; the device is worldRank % maxDevicesPerNode as upstream
+void initDistributed(int worldRank, int worldSize, int maxDevicesPerNode, const std::string& rndvFilepath) {
+  if (g_comm) return;
+  if (worldSize < 1 || worldRank < 0 || worldRank >= worldSize) throw std::invalid_argument("initDistributed: bad rank / size");
+  if (maxDevicesPerNode > 0) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) cudaSetDevice(worldRank % std::min(maxDevicesPerNode, ndev));
+  }
+  if (worldSize == 1) {
+    unsigned char id[128];
+    createUniqueId(id);
+    initDistributed(0, 1, id);
+    return;
+  }
+  if (rndvFilepath.empty()) throw std::invalid_argument("initDistributed: a rendezvous path is needed for more than one process");
+  const std::string path = rndvFilepath + "/w2l_b200_nccl_id." + std::to_string(worldSize);
+  unsigned char id[128];
+  if (worldRank == 0) {
+    createUniqueId(id);
+    const std::string tmp = path + ".tmp";
+    {
+      std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+      if (!f) throw std::runtime_error("initDistributed: cannot write " + tmp);
+      f.write(reinterpret_cast<const char*>(id), 128);
+    }
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("initDistributed: cannot publish " + path);
+  } else {
+    bool ok = false;
+    for (int tries = 0; tries < 6000 && !ok; ++tries) {  // up to ~10 minutes
+      std::ifstream f(path, std::ios::binary);
+      if (f && f.read(reinterpret_cast<char*>(id), 128) && f.gcount() == 128) ok = true;
+      else std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    }
+    if (!ok) throw std::runtime_error("initDistributed: rendezvous file " + path + " did not appear");
+  }
+  initDistributed(worldRank, worldSize, id);
+  if (worldRank == 0) {  // every rank has joined once ncclCommInitRank returns: retire the file so a later run cannot read a stale id
+    std::remove(path.c_str());
+  }
+}
+
 // ---- arch DSL (cpc/SequentialBuilder.cpp:29-57 for the file walk, :92-626 for the opcodes) ------------
 namespace {
 std::vector<std::string> splitWs(const std::string& line) {
@@ -1203,10 +1405,12 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
   auto net = std::make_shared<Sequential>();
   std::istringstream in(archText);
   std::string line;
-  std::shared_ptr<Conv2D> lastConv;  // candidate for ReLU / Dropout fusion
+  // epilogue-fusion candidates: each is valid only for the opcode IMMEDIATELY after the module that set it (plus the
+  // R -> DO chain), so an intervening opcode can never reorder operations relative to SequentialBuilder's semantics
+  std::shared_ptr<Conv2D> lastConv;           // `C2` conv: a following R / DO is fused into its epilogue
   std::shared_ptr<Conv2D> lastBigConv;        // `C` conv that a following GLU splits
-  std::shared_ptr<GatedLinearUnit> lastGlu;   // candidate for Dropout fusion
-  int pendingPadL = -1, pendingPadR = -1;
+  std::shared_ptr<GatedLinearUnit> lastGlu;   // GLU: a following DO is fused
+  int pendingPadL = -1, pendingPadR = -1;     // `PD`: must be consumed by the very next line (a C2)
   int lineNo = 0;
   while (std::getline(in, line)) {
     ++lineNo;
@@ -1222,14 +1426,19 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
       return std::stoi(p[i]);
     };
     const std::string& op = p[0];
+    if (pendingPadL >= 0 && op != "C2") throw bad("PD must be followed by the C2 convolution it pads");
+    // candidates taken over by this line; everything else is dropped
+    std::shared_ptr<Conv2D> conv0 = std::move(lastConv), big0 = std::move(lastBigConv);
+    std::shared_ptr<GatedLinearUnit> glu0 = std::move(lastGlu);
+    lastConv.reset();
+    lastBigConv.reset();
+    lastGlu.reset();
     if (op == "V") {
       if (p.size() != 5) throw bad("V expects 4 dims");
       net->add(std::make_shared<View>(af::dim4(num(1), num(2), num(3), num(4))));
-      lastConv.reset();
     } else if (op == "RO") {
       if (p.size() != 5) throw bad("RO expects 4 dims");
       net->add(std::make_shared<Reorder>(num(1), num(2), num(3), num(4)));
-      lastConv.reset();
     } else if (op == "PD") {
       // `PD val l0 r0 [l1 r1 ...]`: the archs pad time (dim 0) only, before a C2 (streaming TDS)
       if (p.size() < 4 || std::stod(p[1]) != 0.0) throw bad("only zero padding of the time axis is covered");
@@ -1237,6 +1446,7 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
         if (num(i) != 0) throw bad("only the time axis may be padded");
       pendingPadL = num(2);
       pendingPadR = num(3);
+      if (pendingPadL < 0 || pendingPadR < 0) throw bad("negative padding");
     } else if (op == "C2") {
       if (p.size() < 7) throw bad("C2 expects cin cout kw kh sx sy [px py dx dy]");
       const int px = p.size() > 7 ? num(7) : 0, py = p.size() > 8 ? num(8) : 0;
@@ -1276,55 +1486,49 @@ std::shared_ptr<Sequential> buildSequentialModule(const std::string& archText, i
       }
       if (wnDim >= 0) layer = std::make_shared<WeightNorm>(layer, wnDim);
       net->add(layer);
-      lastConv.reset();
       lastBigConv = conv;
-      lastGlu.reset();
     } else if (op == "GLU") {
       if (p.size() != 2) throw bad("GLU expects the axis");
       auto glu = std::make_shared<GatedLinearUnit>(num(1));
-      if (lastBigConv) lastBigConv->setGluSplit(true);  // the conv pads its two channel halves separately
+      if (big0) big0->setGluSplit(true);  // the conv pads its two channel halves separately
       net->add(glu);
-      lastConv.reset();
-      lastBigConv.reset();
       lastGlu = glu;
-    } else if (op == "DO" && lastGlu) {
-      if (p.size() != 2) throw bad("DO expects the probability");
-      lastGlu->fuseDropout((float)std::stod(p[1]));
-      lastGlu.reset();
     } else if (op == "R") {
-      if (lastConv)
-        lastConv->fuseRelu();  // fused into the convolution's epilogue
-      else
+      if (conv0) {
+        conv0->fuseRelu();  // fused into the convolution's epilogue
+        lastConv = conv0;   // a DO right after the R still belongs to this convolution
+      } else {
         net->add(std::make_shared<ReLU>());
+      }
     } else if (op == "DO") {
       if (p.size() != 2) throw bad("DO expects a probability");
-      if (lastConv)
-        lastConv->fuseDropout(std::stof(p[1]));
+      if (glu0)
+        glu0->fuseDropout((float)std::stod(p[1]));
+      else if (conv0)
+        conv0->fuseDropout(std::stof(p[1]));
       else
         net->add(std::make_shared<Dropout>(std::stod(p[1])));
-      lastConv.reset();
     } else if (op == "LN") {
       std::vector<int> axes;
       for (size_t i = 1; i < p.size(); ++i) axes.push_back(num(i));
       if (axes.empty()) throw bad("LN expects axes");
       net->add(std::make_shared<LayerNorm>(axes));
-      lastConv.reset();
     } else if (op == "TDS") {
       if (p.size() < 4) throw bad("TDS expects c kw w [dropout] [inner] [rPad] [lnIncludeTime]");
       net->add(std::make_shared<TDSBlock>(num(1), num(2), num(3), p.size() > 4 ? std::stod(p[4]) : 0.0, p.size() > 5 ? num(5) : 0,
                                           p.size() > 6 ? num(6) : -1, p.size() > 7 ? num(7) != 0 : true));
-      lastConv.reset();
     } else if (op == "L") {
       if (p.size() < 3) throw bad("L expects in out [bias]");
       net->add(std::make_shared<Linear>(num(1), num(2), p.size() > 3 ? num(3) != 0 : true));
-      lastConv.reset();
     } else if (op == "SAUG") {
-      // SpecAugment is data augmentation ahead of the hot path: identity here
-      lastConv.reset();
+      // `SAUG tWarpW fMaskF nFMask tMaskT tMaskP nTMask` (cpc/SequentialBuilder.cpp:602-613)
+      if (p.size() != 7) throw bad("SAUG expects tWarpW fMaskF nFMask tMaskT tMaskP nTMask");
+      net->add(std::make_shared<SpecAugment>(num(1), num(2), num(3), num(4), std::stod(p[5]), num(6)));
     } else {
       throw bad("opcode '" + op + "' is outside the hot-path subset (V RO PD C C2 WN GLU R DO LN TDS L SAUG)");
     }
   }
+  if (pendingPadL >= 0) throw std::invalid_argument("arch: trailing PD without a convolution");
   return net;
 }
 ModulePlugin::ModulePlugin(const std::string& path) : path_(path) {
@@ -1379,7 +1583,7 @@ AutoSegmentationCriterion::AutoSegmentationCriterion(int N, CriterionScaleMode s
 std::string AutoSegmentationCriterion::prettyString() const { return "AutoSegmentationCriterion"; }
 
 namespace {
-// shared by ASG (terms = FCC|FAC) and LinSeg (terms = FAC on the stretched target)
+// shared by ASG and LinSeg (ASG on the linearly stretched target)
 std::vector<Variable> asgForward(int terms, int N, CriterionScaleMode mode, bool train, Variable trans, af::array& wsCache,
                                  const Variable& emis, const af::array& target) {
   const int T = (int)emis.dims(1), B = (int)emis.dims(2), L = (int)target.dims(0);
@@ -1474,7 +1678,9 @@ std::vector<Variable> LinearSegmentationCriterion::forward(const std::vector<Var
   const int T = (int)inputs[0].dims(1), B = (int)inputs[0].dims(2), L = (int)inputs[1].dims(0);
   af::array stretched = af::array::empty(af::dim4(T, B), DType::i32);
   check(w2l_linseg_target(currentStream(), B, T, L, inputs[1].array().i32(), stretched.i32()));
-  return asgForward(W2L_TERM_FAC, N_, scaleMode_, train_, params_[0], ws_, inputs[0], stretched);
+  // upstream LinearSegmentationCriterion derives from AutoSegmentationCriterion and only replaces the target by its
+  // linear stretch before calling ASG::forward: loss = FCC - FAC(stretched target), gradients with ASG's signs
+  return asgForward(W2L_TERM_ASG, N_, scaleMode_, train_, params_[0], ws_, inputs[0], stretched);
 }
 af::array LinearSegmentationCriterion::viterbiPath(const af::array& input, const af::array&) {
   const int N = (int)input.dims(0), T = (int)input.dims(1), B = (int)input.dims(2);

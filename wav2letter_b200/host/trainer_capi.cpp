@@ -32,9 +32,17 @@ struct Trainer {
   std::shared_ptr<SequenceCriterion> crit;
   ParameterArena netArena, critArena;
   af::array sqnorm;
+  af::array guard;  // int32[2]: [0] this step had a non-finite loss / gradient (update skipped), [1] count of such steps
+  int precision = W2L_PRECISION_TF32;
   float lr, lrcrit, momentum, maxgradnorm;
   int nFeat, nLabel;
   bool isCtc;
+};
+
+struct PrecisionScope {  // the trainer's precision for the duration of one call; the thread's own setting is restored
+  int saved;
+  explicit PrecisionScope(int p) : saved(w2l_get_precision()) { w2l_set_precision(p); }
+  ~PrecisionScope() { w2l_set_precision(saved); }
 };
 
 template <typename F>
@@ -78,6 +86,8 @@ W2L_API void* w2l_trainer_create(void* stream, const char* arch_text, int n_feat
     tr->netArena = flattenParameters({tr->net});
     if (!tr->crit->params().empty()) tr->critArena = flattenParameters({tr->crit});
     tr->sqnorm = af::array::zeros(af::dim4(1), w2l::DType::f64);
+    tr->guard = af::array::zeros(af::dim4(2), w2l::DType::i32);
+    tr->precision = w2l_get_precision();  // the creating thread's setting; w2l_trainer_set_precision changes it
     tr->lr = lr;
     tr->lrcrit = lrcrit;
     tr->momentum = momentum;
@@ -134,6 +144,7 @@ W2L_API int w2l_trainer_step(void* h, void* stream, int B, int T, const float* f
   return guarded([&] {
     w2l::setCurrentStream(stream);
     auto* t = static_cast<Trainer*>(h);
+    PrecisionScope scope(t->precision);
     if (train) {
       t->net->train();
       t->crit->train();
@@ -163,21 +174,39 @@ W2L_API int w2l_trainer_step(void* h, void* stream, int B, int T, const float* f
     loss.backward();
     if (t->reducer) t->reducer->finalize();
     if (fl::isDistributedInit() && t->critArena.elements) fl::allReduce(t->critArena.grads);
-    // [opt]  grads /= totalBatch (Train.cpp:1752,1783), clipGradNorm(net U crit) (:1791-1798), step (:1801-1802)
+    // [opt]  grads /= totalBatch (Train.cpp:1752,1783), clipGradNorm(net U crit) (:1791-1798), step (:1801-1802).
+    // The reference's numerical guards — LOG(FATAL) on a NaN / Inf loss (:1686-1698), skip-and-retry on non-finite
+    // gradients under mixed precision (:1753-1771) — run on the device: the squared gradient norm is computed anyway, a
+    // one-CTA kernel turns "loss or norm not finite" into a flag, and both SGD kernels return early when it is set.
+    // w2l_trainer_status reads the count of skipped steps whenever the caller wants it (no sync inside the step).
     const float gscale = 1.0f / total_batch;
-    const double* sq = nullptr;
-    if (t->maxgradnorm > 0) {
-      t->sqnorm.zero();
-      w2l::check(w2l_sq_norm_accumulate(stream, t->netArena.elements, t->netArena.grads.f32(), t->sqnorm.f64()));
-      if (t->critArena.elements)
-        w2l::check(w2l_sq_norm_accumulate(stream, t->critArena.elements, t->critArena.grads.f32(), t->sqnorm.f64()));
-      sq = t->sqnorm.f64();
-    }
+    t->sqnorm.zero();
+    w2l::check(w2l_sq_norm_accumulate(stream, t->netArena.elements, t->netArena.grads.f32(), t->sqnorm.f64()));
     if (t->critArena.elements)
-      w2l::check(w2l_sgd_step(stream, t->critArena.elements, t->critArena.values.f32(), t->critArena.grads.f32(), t->critArena.velocity.f32(),
-                              t->lrcrit, 0.f, 0.f, gscale, t->maxgradnorm, sq));
-    w2l::check(w2l_sgd_step(stream, t->netArena.elements, t->netArena.values.f32(), t->netArena.grads.f32(), t->netArena.velocity.f32(), t->lr,
-                            t->momentum, 0.f, gscale, t->maxgradnorm, sq));
+      w2l::check(w2l_sq_norm_accumulate(stream, t->critArena.elements, t->critArena.grads.f32(), t->sqnorm.f64()));
+    w2l::check(w2l_finite_guard(stream, B, loss.array().f32(), t->sqnorm.f64(), t->guard.i32()));
+    const double* sq = t->maxgradnorm > 0 ? t->sqnorm.f64() : nullptr;
+    if (t->critArena.elements)
+      w2l::check(w2l_sgd_step_ex(stream, t->critArena.elements, t->critArena.values.f32(), t->critArena.grads.f32(), t->critArena.velocity.f32(),
+                                 t->lrcrit, 0.f, 0.f, gscale, t->maxgradnorm, sq, 0, t->guard.i32()));
+    w2l::check(w2l_sgd_step_ex(stream, t->netArena.elements, t->netArena.values.f32(), t->netArena.grads.f32(), t->netArena.velocity.f32(), t->lr,
+                               t->momentum, 0.f, gscale, t->maxgradnorm, sq, 0, t->guard.i32()));
+  });
+}
+
+W2L_API int w2l_trainer_set_precision(void* h, int precision) {
+  if (precision != W2L_PRECISION_TF32 && precision != W2L_PRECISION_F32 && precision != W2L_PRECISION_BF16)
+    return w2l::fail(W2L_ERR_INVALID_ARGUMENT, "trainer_set_precision: unknown precision");
+  static_cast<Trainer*>(h)->precision = precision;
+  return W2L_OK;
+}
+// number of steps whose update was skipped because the loss or a gradient was NaN / Inf (synchronises the stream)
+W2L_API int w2l_trainer_status(void* h, void* stream, long long* skipped_steps) {
+  return guarded([&] {
+    w2l::setCurrentStream(stream);
+    auto* t = static_cast<Trainer*>(h);
+    const std::vector<int32_t> g = t->guard.host<int32_t>();
+    if (skipped_steps) *skipped_steps = g[1];
   });
 }
 
@@ -187,6 +216,7 @@ W2L_API int w2l_trainer_forward(void* h, void* stream, int B, int T, const float
   return guarded([&] {
     w2l::setCurrentStream(stream);
     auto* t = static_cast<Trainer*>(h);
+    PrecisionScope scope(t->precision);
     t->net->eval();
     Variable out = t->net->forward(std::vector<Variable>{fl::input(af::array::wrap(const_cast<float*>(features), af::dim4(T, t->nFeat, 1, B)))}).front();
     if (out.elements() > capacity) throw std::invalid_argument("trainer_forward: output buffer too small");

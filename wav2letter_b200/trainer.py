@@ -17,7 +17,8 @@ from .capi import _check, _ptr, _stream, lib
 class Trainer:
     def __init__(self, arch_text: str, n_feat: int, n_label: int, criterion: str = "ctc", scale_mode="none",
                  transdiag: float = 0.0, lr: float = 0.05, lrcrit: float = 0.0, momentum: float = 0.0,
-                 maxgradnorm: float = 0.0):
+                 maxgradnorm: float = 0.0, precision: str | None = None):
+        """precision: None (the thread's w2l_set_precision), "tf32", "f32" (fp32-accurate) or "bf16"."""
         mode = capi.SCALE_MODES[scale_mode] if isinstance(scale_mode, str) else int(scale_mode)
         self.h = lib.w2l_trainer_create(_stream(), arch_text.encode(), n_feat, n_label, criterion.encode(), mode,
                                         transdiag, lr, lrcrit, momentum, maxgradnorm)
@@ -25,6 +26,17 @@ class Trainer:
             raise capi.W2LError(1, lib.w2l_last_error().decode())
         self.h = ctypes.c_void_p(self.h)
         self.n_feat, self.n_label, self.criterion = n_feat, n_label, criterion
+        if precision is not None:
+            self.set_precision(precision)
+
+    def set_precision(self, precision):
+        _check(lib.w2l_trainer_set_precision(self.h, capi.PRECISIONS[precision] if isinstance(precision, str) else int(precision)))
+
+    def skipped_steps(self) -> int:
+        """steps whose update the device-side guard skipped (NaN / Inf loss or gradient); synchronises"""
+        n = ctypes.c_longlong(0)
+        _check(lib.w2l_trainer_status(self.h, _stream(), ctypes.byref(n)))
+        return int(n.value)
 
     def close(self):
         if getattr(self, "h", None):
