@@ -31,11 +31,25 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+def build_native() -> str:
+    """-march=native build for the host it is called on (bench.py's CPU legs)"""
+    so = os.path.join(_HERE, "libw2l_oracle_native.so")
+    subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])
+    return so
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        build()
-        _lib = ctypes.CDLL(_SO)
+        so = _SO
+        if os.environ.get("W2L_ORACLE_NATIVE") == "1":  # set by bench.py only
+            try:
+                so = build_native()
+            except Exception:
+                so = _SO
+        if so == _SO:
+            build()
+        _lib = ctypes.CDLL(so)
         _lib.oracle_scale.restype = ctypes.c_double
         _lib.oracle_scale.argtypes = [ctypes.c_int] * 3
     return _lib

@@ -106,11 +106,17 @@ class TorchConvGlu:
         return wn_lin(x, 8, self.p[-1].numel())
 
 
-def test_conv_glu_train_step_matches_torch_reference():
+PREC_TOL = {"f32": dict(emis=3e-4, per_param=5e-3, floor=1e-3, overall=1e-3), "tf32": dict(emis=5e-3, per_param=0.05, floor=1e-2, overall=2e-2),
+            "bf16": dict(emis=3e-2, per_param=0.3, floor=1e-2, overall=1e-1)}
+
+
+@pytest.mark.parametrize("precision", ["f32", "tf32", "bf16"])
+def test_conv_glu_train_step_matches_torch_reference(precision):
     from wav2letter_b200.trainer import Trainer
 
     B, T, L, N = 3, 50, 5, 6
-    tr = Trainer(ARCH, 40, N, "asg", "target_sz_sqrt", transdiag=1.0, lr=0.0, lrcrit=0.0)
+    tol = PREC_TOL[precision]
+    tr = Trainer(ARCH, 40, N, "asg", "target_sz_sqrt", transdiag=1.0, lr=0.0, lrcrit=0.0, precision=precision)
     g = torch.Generator(device="cuda").manual_seed(2)
     feat = torch.randn((B, 1, 40, T), device="cuda", generator=g)
     tgt = torch.randint(0, N, (B, L), device="cuda", generator=g, dtype=torch.int32)
@@ -123,19 +129,19 @@ def test_conv_glu_train_step_matches_torch_reference():
     logits = ref.forward(feat)
     assert logits.shape == (B, T - 3, N)
     got = tr.forward(feat)
-    assert rel(got, logits) < 5e-3, rel(got, logits)
+    assert rel(got, logits) < tol["emis"], rel(got, logits)
     trans = tr.get_flat(1, 0).view(N, N).cpu().numpy()
     ol, ode, odt = oracle.asg(logits.detach().float().cpu().numpy(), tgt.cpu().numpy(), trans, "target_sz_sqrt")
-    assert rel(loss, torch.from_numpy(ol).cuda()) < 5e-3
+    assert rel(loss, torch.from_numpy(ol).cuda()) < tol["emis"]
     logits.backward(torch.from_numpy(ode).double().cuda())
     full = torch.cat([p.grad.flatten() for p in ref.p])
     mine = torch.cat([grads[off:off + n] for off, n, _ in tr.layout(0)])
     gscale = float(full.abs().max())
     for (off, n, dims), p in zip(tr.layout(0), ref.p):
-        denom = max(float(p.grad.abs().max()), 1e-2 * gscale)
+        denom = max(float(p.grad.abs().max()), tol["floor"] * gscale)
         gerr = float((grads[off:off + n].double() - p.grad.flatten()).abs().max()) / denom
-        assert gerr < 0.05, f"param at {off} dims {dims}: grad rel err {gerr}"
-    assert rel(mine, full) < 2e-2, rel(mine, full)
+        assert gerr < tol["per_param"], f"{precision}: param at {off} dims {dims}: grad rel err {gerr}"
+    assert rel(mine, full) < tol["overall"], rel(mine, full)
 
 
 def test_conv_glu_training_reduces_loss_with_dropout():

@@ -133,3 +133,92 @@ def test_gemm_view_data_gradient(T, Cin, Cout, kw):
     y.backward(dyp[kw - 1:kw - 1 + Tout].double().t().unsqueeze(0))
     ref = x64.grad[0].t()
     assert float((dx.double() - ref).abs().max()) < 3e-3 * float(ref.abs().max()) + 1e-3
+
+
+# ---- operand kinds: fp32-accurate 3xTF32 split and bf16 (csrc/gemm_umma.cu) -----------------------------------------
+def _operands(M, N, K, a_mn, b_mn, seed, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g)
+    B = torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g)
+    return A.to(dtype), B.to(dtype)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (200, 136, 100), (76, 52, 36), (1000, 800, 1440), (360, 360, 9600)])
+def test_gemm_f32x3_is_fp32_accurate(M, N, K, a_mn, b_mn):
+    """error-compensated 3xTF32: |C - ref| <= 4e-6 * (|A| |B|^T) element-wise — 350x tighter than the TF32 bound, the
+    accuracy class of an fp32 SGEMM (the reference's af::matmul -> cublasSgemm)"""
+    import wav2letter_b200 as w
+
+    A, B = _operands(M, N, K, a_mn, b_mn, seed=M + K)
+    C = w.capi.gemm(A, B, "f32x3", a_mn, b_mn)
+    torch.cuda.synchronize()
+    A64, B64 = (A.t() if a_mn else A).double(), (B.t() if b_mn else B).double()
+    ref = A64 @ B64.t()
+    bound = 4e-6 * (A64.abs() @ B64.abs().t()) + 1e-6
+    ratio = float(((C.double() - ref).abs() / bound).max())
+    assert ratio <= 1.0, f"f32x3 M={M} N={N} K={K}: err/bound {ratio}"
+
+
+def test_precision_switch_routes_fp32_entry_points():
+    import wav2letter_b200 as w
+
+    A, B = _operands(512, 320, 800, False, False, seed=3)
+    ref = A.double() @ B.double().t()
+    w.capi.set_precision("f32")
+    try:
+        C = w.capi.gemm_tf32(A, B)
+    finally:
+        w.capi.set_precision("tf32")
+    C2 = w.capi.gemm_tf32(A, B)
+    e1, e2 = float((C.double() - ref).abs().max()), float((C2.double() - ref).abs().max())
+    assert e1 < 2e-4 and e2 > 10 * e1, (e1, e2)  # fp32-accurate vs TF32 rounding
+
+
+@pytest.mark.parametrize("out_bf16", [False, True])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 128), (200, 136, 104), (76, 56, 40), (4000, 800, 800),
+                                   (1000, 2000, 1440), (1120, 1120, 4800)])
+def test_gemm_bf16_kind(M, N, K, a_mn, b_mn, out_bf16):
+    """bf16 operands are exact inputs here (the reference is computed from the same bf16 values), so the only error is
+    fp32 accumulation (+ the bf16 rounding of C when out_bf16)"""
+    import wav2letter_b200 as w
+
+    A, B = _operands(M, N, K, a_mn, b_mn, seed=N + K, dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    C = w.capi.gemm(A, B, "bf16", a_mn, b_mn, bias=bias, act=1, out_bf16=out_bf16)
+    torch.cuda.synchronize()
+    assert C.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
+    A64, B64 = (A.t() if a_mn else A).double(), (B.t() if b_mn else B).double()
+    ref = (A64 @ B64.t() + bias.double()).clamp_min(0)
+    bound = 2e-6 * (A64.abs() @ B64.abs().t()) + 1e-5 + (ref.abs() * 2.0 ** -8 if out_bf16 else 0)
+    ratio = float(((C.double() - ref).abs() / bound).max())
+    assert ratio <= 1.0, f"bf16 M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn}: err/bound {ratio}"
+
+
+def test_gemm_bf16_mask_accumulate_and_view():
+    import wav2letter_b200 as w
+
+    # data-gradient shape with the activation mask read from a bf16 tensor and an fp32 accumulate
+    A, B = _operands(300, 256, 160, False, True, seed=11, dtype=torch.bfloat16)
+    aux = torch.randn(300, 256, device="cuda").to(torch.bfloat16)
+    C0 = torch.randn(300, 256, device="cuda")
+    C = C0.clone()
+    w.capi.gemm(A, B, "bf16", False, True, out=C, accumulate=True, aux=aux, aux_mode=1, aux_scale=1.25)
+    ref = C0.double() + (A.double() @ B.double()) * (aux.double() > 0) * 1.25
+    assert float((C.double() - ref).abs().max()) < 1e-3
+    # im2col view: rows of kw*Cin bf16 with row stride Cin
+    T, Cin, Cout, kw = 300, 64, 96, 5
+    x = torch.randn(T + kw - 1, Cin, device="cuda").to(torch.bfloat16)
+    wt = torch.randn(Cout, kw * Cin, device="cuda").to(torch.bfloat16)
+    y = torch.empty(T, Cout, device="cuda")
+    w.capi.gemm(x, wt, "bf16", out=y, M=T, N=Cout, K=kw * Cin, lda=Cin, ldb=kw * Cin, allow_overlap=True)
+    cols = torch.stack([x[t:t + kw].reshape(-1) for t in range(T)]).double()
+    assert float((y.double() - cols @ wt.double().t()).abs().max()) < 2e-3
+
+
+def test_cast_bf16_matches_torch():
+    import wav2letter_b200 as w
+
+    x = torch.randn(1003, 37, device="cuda") * 5
+    assert torch.equal(w.capi.cast_bf16(x.reshape(-1)), x.reshape(-1).to(torch.bfloat16))

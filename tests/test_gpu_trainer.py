@@ -161,13 +161,22 @@ def make_batch(B, T, N, L, seed, blank):
     return feat, tgt
 
 
+# precision "f32" (fp32-accurate contractions) pins the arithmetic: every parameter within 5e-3 of its own gradient scale
+# (floor: 1e-3 of the net's largest gradient entry).  "tf32" is the same graph with 10-bit operand mantissas: its
+# per-parameter deviation is rounding only (the exact path is pinned by "f32") and is bounded loosely.
+PREC_TOL = {"f32": dict(emis=3e-4, per_param=5e-3, floor=1e-3, overall=1e-3), "tf32": dict(emis=5e-3, per_param=0.25, floor=1e-2, overall=2e-2)}
+
+
+@pytest.mark.parametrize("precision", ["f32", "tf32"])
 @pytest.mark.parametrize("criterion,N,arch_name", [("ctc", 12, "tds"), ("asg", 8, "tds"), ("ctc", 12, "streaming")])
-def test_train_step_matches_torch_reference(criterion, N, arch_name):
+def test_train_step_matches_torch_reference(criterion, N, arch_name, precision):
     from wav2letter_b200.trainer import Trainer
 
     B, T, L = 3, 64, 5
+    tol = PREC_TOL[precision]
     arch_text, ref_cls = (ARCH, TorchTDS) if arch_name == "tds" else (STREAMING_ARCH, TorchStreamingTDS)
-    tr = Trainer(arch_text, 80, N, criterion, "target_sz" if criterion == "ctc" else "none", transdiag=1.0, lr=0.0, lrcrit=0.0)
+    tr = Trainer(arch_text, 80, N, criterion, "target_sz" if criterion == "ctc" else "none", transdiag=1.0, lr=0.0, lrcrit=0.0,
+                 precision=precision)
     feat, tgt = make_batch(B, T, N, L, 1, criterion == "ctc")
     flat0 = tr.get_flat(0, 0).clone()
     loss = tr.step(feat, tgt, train=True)
@@ -186,8 +195,8 @@ def test_train_step_matches_torch_reference(criterion, N, arch_name):
         assert rel(tr.get_flat(1, 1), torch.from_numpy(odt).flatten().cuda()) < 5e-3
     # emissions and loss
     got = tr.forward(feat)
-    assert rel(got, logits) < 5e-3, rel(got, logits)
-    assert rel(loss, torch.from_numpy(ol).cuda()) < 5e-3, (loss, ol)
+    assert rel(got, logits) < tol["emis"], rel(got, logits)
+    assert rel(loss, torch.from_numpy(ol).cuda()) < tol["emis"], (loss, ol)
     # gradients of every parameter: chain the oracle's d_emis through the float64 torch graph
     logits.backward(torch.from_numpy(ode).double().cuda())
     full = torch.cat([p.grad.flatten() for p in ref.p])
@@ -196,10 +205,10 @@ def test_train_step_matches_torch_reference(criterion, N, arch_name):
     for (off, n, dims), p in zip(tr.layout(0), ref.p):
         # scalar LayerNorm gains/biases are sums with heavy cancellation: measure against the larger of the
         # parameter's own gradient scale and 1% of the global one
-        denom = max(float(p.grad.abs().max()), 1e-2 * gscale)
+        denom = max(float(p.grad.abs().max()), tol["floor"] * gscale)
         gerr = float((grads[off:off + n].double() - p.grad.flatten()).abs().max()) / denom
-        assert gerr < 0.25, f"param at {off} dims {dims}: grad rel err {gerr}"
-    assert rel(mine, full) < 2e-2, rel(mine, full)
+        assert gerr < tol["per_param"], f"{precision}: param at {off} dims {dims}: grad rel err {gerr}"
+    assert rel(mine, full) < tol["overall"], rel(mine, full)
 
 
 def test_training_reduces_loss_and_dropout_runs():
@@ -222,4 +231,5 @@ def test_arch_errors():
     with pytest.raises(W2LError):
         Trainer("TR 4 4 8 2 100\n", 80, 12)  # transformer blocks are outside the hot-path subset
     with pytest.raises(W2LError):
-        Trainer("V -1 NFEAT 1 0\nL 78 12\n", 78, 12)  # Linear input rows must be multiples of 4 floats (TMA)
+        Trainer("V -1 NFEAT 1 0\nPD 0 3 1\nR\n", 80, 12)  # PD must be followed by the convolution it pads
+    Trainer("V -1 NFEAT 1 0\nL 78 12\n", 78, 12).close()  # Linear rows that are not TMA rows go through padded copies

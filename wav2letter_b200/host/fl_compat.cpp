@@ -454,6 +454,15 @@ Variable View::forward(const Variable& in) {
     check(w2l_transpose_input(currentStream(), (int)B, (int)F, (int)T, in.array().f32(), out.f32()));
     return Variable(out, in.isCalcGrad());
   }
+  // `V 0 W' C' 0` on a [T,W,C,B] activation: regroup the W*C features of every frame into C' channels of width W'
+  // (feature index c*W + w is the internal memory order, so this is a relabelling too)
+  if (dims_[2] > 1 && dims_[1] > 0 && (dims_[0] == 0 || dims_[0] == -1 || dims_[0] == in.dims(2)) && (dims_[3] == 0 || dims_[3] == in.dims(3)) &&
+      dims_[1] * dims_[2] == in.dims(0) * in.dims(1) && (dims_[1] != in.dims(0) || dims_[2] != in.dims(1))) {
+    af::array y = in.array().reshaped(af::dim4(dims_[1], dims_[2], in.dims(2), in.dims(3)));
+    Variable out(y, {in}, [](std::vector<Variable>& ins, const Variable& g) { ins[0].addGrad(Variable(g.array().reshaped(ins[0].dims()), false)); });
+    out.setValidFrames(in.validFrames());
+    return out;
+  }
   return in;  // [T,W,C,B] <-> [C*W,T,B] <-> [N,T,B] are the same memory in the internal layout
 }
 std::string View::prettyString() const { return "View (" + dims_.str() + ")"; }

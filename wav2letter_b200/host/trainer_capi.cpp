@@ -80,8 +80,15 @@ W2L_API void* w2l_trainer_create(void* stream, const char* arch_text, int n_feat
     } else if (c == "asg") {
       tr->crit = std::make_shared<ASGLoss>(n_label, mode, transdiag);
       tr->isCtc = false;
+    } else if (c == "linseg") {
+      // the --linseg warm start (Train.cpp:589-617, :1867-1883): LinSegCriterion sharing the ASG transition matrix
+      auto asg = std::make_shared<ASGLoss>(n_label, mode, transdiag);
+      auto lin = std::make_shared<LinSegCriterion>(n_label, mode);
+      lin->setParams(asg->param(0), 0);
+      tr->crit = lin;
+      tr->isCtc = false;
     } else {
-      throw std::invalid_argument("criterion must be 'ctc' or 'asg'");
+      throw std::invalid_argument("criterion must be 'ctc', 'asg' or 'linseg'");
     }
     tr->netArena = flattenParameters({tr->net});
     if (!tr->crit->params().empty()) tr->critArena = flattenParameters({tr->crit});
@@ -221,7 +228,7 @@ W2L_API int w2l_trainer_forward(void* h, void* stream, int B, int T, const float
     Variable out = t->net->forward(std::vector<Variable>{fl::input(af::array::wrap(const_cast<float*>(features), af::dim4(T, t->nFeat, 1, B)))}).front();
     if (out.elements() > capacity) throw std::invalid_argument("trainer_forward: output buffer too small");
     af::array::wrap(emissions_out, out.dims()).copyFrom(out.array());
-    if (t_out) *t_out = (int)out.dims(1);
+    if (t_out) *t_out = (int)(out.elements() / ((long long)B * t->nLabel));  // frames of nLabel values per sample
   });
 }
 

@@ -105,50 +105,13 @@ def init_distributed(rank: int, world: int, uid: bytes):
     _check(lib.w2l_init_distributed(rank, world, ctypes.c_char_p(uid)))
 
 
-SEQ2SEQ_TDS_CTC_ARCH = """# recipes/seq2seq_tds/librispeech/network.arch with the CTC head BASELINE.json configs[1] asks for
+from . import archs  # noqa: E402
+
+# recipes/seq2seq_tds/librispeech/network.arch with the CTC head BASELINE.json configs[1] asks for
 # (last line `L 1440 NLABEL` instead of the seq2seq encoder's `L 1440 1024`)
-V -1 NFEAT 1 0
-C2 1 10 21 1 2 1 -1 -1
-R
-DO 0.2
-LN 3
-TDS 10 21 80 0.2
-TDS 10 21 80 0.2
-C2 10 14 21 1 2 1 -1 -1
-R
-DO 0.2
-LN 3
-TDS 14 21 80 0.2
-TDS 14 21 80 0.2
-TDS 14 21 80 0.2
-C2 14 18 21 1 2 1 -1 -1
-R
-DO 0.2
-LN 3
-TDS 18 21 80 0.2
-TDS 18 21 80 0.2
-TDS 18 21 80 0.2
-TDS 18 21 80 0.2
-TDS 18 21 80 0.2
-TDS 18 21 80 0.2
-V 0 1440 1 0
-RO 1 0 3 2
-L 1440 NLABEL
-"""
+SEQ2SEQ_TDS_CTC_ARCH = archs.seq2seq_tds(ctc_head=True)
 
 
 def conv_glu_librispeech_arch() -> str:
-    """The 17-layer Conv1D+GLU acoustic model of recipes/conv_glu/librispeech/network.arch (WeightNorm everywhere, one
-    170-frame padding up front, `valid` convolutions after it, two WeightNorm Linear layers at the end) as arch text —
-    the (cin, cout, kw, dropout) table is that file's."""
-    layers = [("NFEAT", 400, 13, 0.2), (200, 440, 14, 0.214), (220, 484, 15, 0.22898), (242, 532, 16, 0.2450086),
-              (266, 584, 17, 0.262159202), (292, 642, 18, 0.28051034614), (321, 706, 19, 0.30014607037),
-              (353, 776, 20, 0.321156295296), (388, 852, 21, 0.343637235966), (426, 936, 22, 0.367691842484),
-              (468, 1028, 23, 0.393430271458), (514, 1130, 24, 0.42097039046), (565, 1242, 25, 0.450438317792),
-              (621, 1366, 26, 0.481969000038), (683, 1502, 27, 0.51570683004), (751, 1652, 28, 0.551806308143),
-              (826, 1816, 29, 0.590432749713)]
-    out = ["V -1 1 NFEAT 0"]
-    for i, (cin, cout, kw, do) in enumerate(layers):
-        out += [f"WN 3 C {cin} {cout} {kw} 1 {170 if i == 0 else 0}", "GLU 2", f"DO {do}"]
-    out += ["RO 2 0 3 1", "WN 0 L 908 1816", "GLU 0", "DO 0.590432749713", "WN 0 L 908 NLABEL"]
-    return "\n".join(out) + "\n"
+    """recipes/conv_glu/librispeech/network.arch (17 WeightNorm Conv1D+GLU layers, two WeightNorm Linear layers)"""
+    return archs.conv_glu_librispeech()
