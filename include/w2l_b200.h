@@ -315,9 +315,40 @@ W2L_API int w2l_trainer_get_flat(void* trainer, void* stream, int which, int wha
 W2L_API int w2l_trainer_set_flat(void* trainer, void* stream, int which, const float* in);
 W2L_API int w2l_trainer_sync_parameters(void* trainer, void* stream);   /* fl::allReduceParameters, Train.cpp:1078-1079 */
 W2L_API const char* w2l_trainer_describe(void* trainer);
+/* Checkpoints (the role of Serializer::save / load in Train.cpp:747-800): own little-endian container with
+ * the constructor arguments + parameter / momentum arenas of network and criterion; load rebuilds the trainer. */
+W2L_API int w2l_trainer_save(void* trainer, void* stream, const char* path);
+W2L_API void* w2l_trainer_load(void* stream, const char* path);
+/* Export for the in-tree streaming inference stack, following the conversions of
+ * recipes/streaming_convnets/tools/StreamingTDSModelConverter.cpp:46-136,203-283: every layer's arrays in the inference
+ * library's layouts (acoustic_model.json + acoustic_model.bin), transitions.bin (ASG; the cereal std::vector<float> the
+ * inference examples read, :310-326) and tokens.txt (tokens_text nullable).  Streaming TDS archs only (LN 1 2), like the converter. */
+W2L_API int w2l_trainer_export_streaming(void* trainer, void* stream, const char* outdir, const char* tokens_text);
 /* data-parallel rendezvous: rank 0 creates the 128-byte NCCL id, the launcher ships it to every rank */
 W2L_API int w2l_nccl_unique_id(void* out128);
 W2L_API int w2l_init_distributed(int rank, int world, const void* id128);
+
+/* ----------------------------------------------------------------------------------------
+ * Token / target pipeline either side of the criterion (host code, no GPU work):
+ *   w2l_text_create     Dictionary(tokens) + "<1>".."<replabel>" + the CTC blank appended last (Train.cpp:236-254), the
+ *                       lexicon (loadWords), and the flags --criterion --surround --usewordpiece --wordseparator
+ *   w2l_text_encode     the dataset's target transform (targetFeatures, Train.cpp:296-316): words -> lexicon spelling or
+ *                       letter fallback -> indices -> surround -> replabel packing -> ASG dedup
+ *   w2l_text_prediction2ltr / target2ltr / ltr2wrd / w2l_edit_distance   evalOutput (Train.cpp:829-872): Viterbi path ->
+ *                       uniq -> drop blanks -> unpack replabels -> trim surround / silence -> letters -> words -> Levenshtein
+ * Strings are UTF-8; token sequences are space-joined.  Functions returning long long give the element / byte count needed
+ * (call with a zero capacity to size) or -1 on error (w2l_last_error).
+ * ---------------------------------------------------------------------------------------- */
+W2L_API void* w2l_text_create(const char* tokens_text, const char* lexicon_text, const char* criterion, int replabel,
+                              const char* surround, int usewordpiece, const char* wordsep);
+W2L_API void w2l_text_destroy(void* text);
+W2L_API int w2l_text_num_classes(void* text);
+W2L_API long long w2l_text_encode(void* text, const char* transcript, int32_t* out, long long cap);
+W2L_API long long w2l_text_prediction2ltr(void* text, const int32_t* path, int n, char* out, long long cap);
+W2L_API long long w2l_text_target2ltr(void* text, const int32_t* target, int len, char* out, long long cap);
+W2L_API long long w2l_text_ltr2wrd(void* text, const char* letters, char* out, long long cap);
+/* out4 += {reference length, deletions, insertions, substitutions} of one (hypothesis, reference) pair */
+W2L_API int w2l_edit_distance(const char* hyp, const char* ref, long long* out4);
 
 #ifdef __cplusplus
 }

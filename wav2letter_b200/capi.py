@@ -25,7 +25,9 @@ EXPORTS = [
     "w2l_fac_viterbi_workspace_size", "w2l_fac_viterbi",
     "w2l_ctc_workspace_size", "w2l_ctc_forward_backward", "w2l_argmax_path", "w2l_linseg_target",
     "w2l_set_precision", "w2l_get_precision", "w2l_gemm", "w2l_cast_bf16", "w2l_cast_bf16_rows", "w2l_sgd_step_ex", "w2l_finite_guard",
-    "w2l_mask_bands", "w2l_trainer_set_precision", "w2l_trainer_status",
+    "w2l_mask_bands", "w2l_trainer_set_precision", "w2l_trainer_status", "w2l_trainer_save", "w2l_trainer_load", "w2l_trainer_export_streaming",
+    "w2l_text_create", "w2l_text_destroy", "w2l_text_num_classes", "w2l_text_encode", "w2l_text_prediction2ltr", "w2l_text_target2ltr",
+    "w2l_text_ltr2wrd", "w2l_edit_distance",
     "w2l_gemm_set_tile", "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_gemm_tf32_view", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
     "w2l_conv_time_wgrad", "w2l_layernorm_fwd", "w2l_layernorm_bwd", "w2l_colsum_accumulate", "w2l_sq_norm_accumulate",
     "w2l_sgd_step", "w2l_weightnorm_fwd", "w2l_weightnorm_bwd", "w2l_conv1d_arrange", "w2l_conv1d_unarrange_grad",
@@ -102,6 +104,23 @@ def _load() -> ctypes.CDLL:
     lib.w2l_mask_bands.argtypes = [vp, i, i, i, i, vp, vp, i, vp, vp, i, vp, vp, f32]
     lib.w2l_trainer_set_precision.argtypes = [vp, i]
     lib.w2l_trainer_status.argtypes = [vp, vp, vp]
+    cp = ctypes.c_char_p
+    lib.w2l_trainer_save.argtypes = [vp, vp, cp]
+    lib.w2l_trainer_load.restype = vp
+    lib.w2l_trainer_load.argtypes = [vp, cp]
+    lib.w2l_trainer_export_streaming.argtypes = [vp, vp, cp, cp]
+    lib.w2l_text_create.restype = vp
+    lib.w2l_text_create.argtypes = [cp, cp, cp, i, cp, i, cp]
+    lib.w2l_text_destroy.argtypes = [vp]
+    lib.w2l_text_destroy.restype = None
+    lib.w2l_text_num_classes.argtypes = [vp]
+    for fn in (lib.w2l_text_encode, lib.w2l_text_prediction2ltr, lib.w2l_text_target2ltr, lib.w2l_text_ltr2wrd):
+        fn.restype = ll
+    lib.w2l_text_encode.argtypes = [vp, cp, vp, ll]
+    lib.w2l_text_prediction2ltr.argtypes = [vp, vp, i, vp, ll]
+    lib.w2l_text_target2ltr.argtypes = [vp, vp, i, vp, ll]
+    lib.w2l_text_ltr2wrd.argtypes = [vp, cp, vp, ll]
+    lib.w2l_edit_distance.argtypes = [cp, cp, vp]
     lib.w2l_trainer_create.restype = vp
     lib.w2l_trainer_create.argtypes = [vp, ctypes.c_char_p, i, i, ctypes.c_char_p, i, f32, f32, f32, f32, f32]
     lib.w2l_trainer_destroy.argtypes = [vp]

@@ -8,8 +8,12 @@
 // The Python harness (bench.py, tests) drives it with device pointers; no arithmetic happens on the host.
 #include <cuda_runtime.h>
 
+#include <sys/stat.h>
+
 #include <cstring>
+#include <fstream>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -37,6 +41,11 @@ struct Trainer {
   float lr, lrcrit, momentum, maxgradnorm;
   int nFeat, nLabel;
   bool isCtc;
+  // what w2l_trainer_save needs to rebuild the trainer (the reference checkpoints config + network + criterion + both
+  // optimizers, Train.cpp:747-800)
+  std::string archText, critName;
+  int scaleMode = 0;
+  float transdiag = 0.f;
 };
 
 struct PrecisionScope {  // the trainer's precision for the duration of one call; the thread's own setting is restored
@@ -56,6 +65,48 @@ int guarded(F&& f) {
     return w2l::fail(W2L_ERR_CUDA, e.what());
   }
 }
+}  // namespace
+
+namespace {
+template <typename T>
+void put(std::ostream& o, const T& v) { o.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <typename T>
+T get(std::istream& i) {
+  T v;
+  i.read(reinterpret_cast<char*>(&v), sizeof(T));
+  if (!i) throw std::runtime_error("checkpoint: truncated file");
+  return v;
+}
+void putStr(std::ostream& o, const std::string& s) {
+  put<uint64_t>(o, s.size());
+  o.write(s.data(), (std::streamsize)s.size());
+}
+std::string getStr(std::istream& i) {
+  const uint64_t n = get<uint64_t>(i);
+  if (n > (1ull << 28)) throw std::runtime_error("checkpoint: implausible string length");
+  std::string s(n, '\0');
+  i.read(&s[0], (std::streamsize)n);
+  if (!i) throw std::runtime_error("checkpoint: truncated file");
+  return s;
+}
+void putArena(std::ostream& o, const af::array& a, long long n) {
+  put<uint64_t>(o, (uint64_t)n);
+  if (n == 0) return;
+  std::vector<float> h = a.host<float>();
+  o.write(reinterpret_cast<const char*>(h.data()), (std::streamsize)(sizeof(float) * (size_t)n));
+}
+void getArena(std::istream& i, const af::array& a, long long n, void* stream) {
+  const uint64_t m = get<uint64_t>(i);
+  if ((long long)m != n) throw std::runtime_error("checkpoint: arena size does not match the architecture");
+  if (n == 0) return;
+  std::vector<float> h((size_t)n);
+  i.read(reinterpret_cast<char*>(h.data()), (std::streamsize)(sizeof(float) * (size_t)n));
+  if (!i) throw std::runtime_error("checkpoint: truncated file");
+  if (cudaMemcpyAsync(a.ptr(), h.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess ||
+      cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    throw std::runtime_error("checkpoint: upload failed");
+}
+constexpr char kMagic[8] = {'W', '2', 'L', 'B', '2', '0', '0', '\0'};
 }  // namespace
 
 extern "C" {
@@ -101,6 +152,10 @@ W2L_API void* w2l_trainer_create(void* stream, const char* arch_text, int n_feat
     tr->maxgradnorm = maxgradnorm;
     tr->nFeat = n_feat;
     tr->nLabel = n_label;
+    tr->archText = arch;
+    tr->critName = c;
+    tr->scaleMode = scale_mode;
+    tr->transdiag = transdiag;
     t = tr.release();
   });
   return rc == W2L_OK ? t : nullptr;
@@ -247,6 +302,231 @@ W2L_API int w2l_trainer_sync_parameters(void* h, void* stream) {  // fl::allRedu
     if (t->critArena.elements) fl::allReduce(t->critArena.values, 1.0 / fl::getWorldSize());
   });
 }
+// ---- checkpoints -------------------------------------------------------------------------
+// Own container, little endian: "W2LB200\0", u32 version, the constructor arguments (so load rebuilds the modules), then
+// the flat arenas: network values + momentum, criterion values + momentum, the NaN-guard counters.  Plays the role of
+// Serializer::save(path, version, config, network, criterion, netoptim, critoptim) (Train.cpp:747-800).
+
+W2L_API int w2l_trainer_save(void* h, void* stream, const char* path) {
+  return guarded([&] {
+    w2l::setCurrentStream(stream);
+    auto* t = static_cast<Trainer*>(h);
+    const std::string tmp = std::string(path) + ".tmp";
+    {
+      std::ofstream o(tmp, std::ios::binary | std::ios::trunc);
+      if (!o) throw std::runtime_error(std::string("checkpoint: cannot write ") + tmp);
+      o.write(kMagic, 8);
+      put<uint32_t>(o, 1);
+      put<int32_t>(o, t->nFeat);
+      put<int32_t>(o, t->nLabel);
+      put<int32_t>(o, t->scaleMode);
+      put<int32_t>(o, t->precision);
+      put<float>(o, t->transdiag);
+      put<float>(o, t->lr);
+      put<float>(o, t->lrcrit);
+      put<float>(o, t->momentum);
+      put<float>(o, t->maxgradnorm);
+      putStr(o, t->critName);
+      putStr(o, t->archText);
+      putArena(o, t->netArena.values, t->netArena.elements);
+      putArena(o, t->netArena.velocity, t->netArena.elements);
+      putArena(o, t->critArena.values, t->critArena.elements);
+      putArena(o, t->critArena.velocity, t->critArena.elements);
+      const std::vector<int32_t> g = t->guard.host<int32_t>();
+      put<int32_t>(o, g[0]);
+      put<int32_t>(o, g[1]);
+      if (!o) throw std::runtime_error(std::string("checkpoint: write failed: ") + tmp);
+    }
+    if (std::rename(tmp.c_str(), path) != 0) throw std::runtime_error(std::string("checkpoint: cannot move into place: ") + path);
+  });
+}
+
+W2L_API void* w2l_trainer_load(void* stream, const char* path) {
+  void* out = nullptr;
+  guarded([&] {
+    std::ifstream i(path, std::ios::binary);
+    if (!i) throw std::invalid_argument(std::string("checkpoint: cannot open ") + path);
+    char magic[8];
+    i.read(magic, 8);
+    if (!i || std::memcmp(magic, kMagic, 8) != 0) throw std::invalid_argument("checkpoint: not a w2l_b200 checkpoint");
+    if (get<uint32_t>(i) != 1) throw std::invalid_argument("checkpoint: unsupported version");
+    const int nFeat = get<int32_t>(i), nLabel = get<int32_t>(i), scaleMode = get<int32_t>(i), precision = get<int32_t>(i);
+    const float transdiag = get<float>(i), lr = get<float>(i), lrcrit = get<float>(i), momentum = get<float>(i), maxgradnorm = get<float>(i);
+    const std::string crit = getStr(i), arch = getStr(i);
+    void* h = w2l_trainer_create(stream, arch.c_str(), nFeat, nLabel, crit.c_str(), scaleMode, transdiag, lr, lrcrit, momentum, maxgradnorm);
+    if (!h) throw std::invalid_argument(std::string("checkpoint: cannot rebuild the trainer: ") + w2l_last_error());
+    std::unique_ptr<Trainer> t(static_cast<Trainer*>(h));
+    t->precision = precision;
+    w2l::setCurrentStream(stream);
+    getArena(i, t->netArena.values, t->netArena.elements, stream);
+    getArena(i, t->netArena.velocity, t->netArena.elements, stream);
+    getArena(i, t->critArena.values, t->critArena.elements, stream);
+    getArena(i, t->critArena.velocity, t->critArena.elements, stream);
+    int32_t g[2] = {get<int32_t>(i), get<int32_t>(i)};
+    if (cudaMemcpyAsync(t->guard.ptr(), g, sizeof(g), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess ||
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess)
+      throw std::runtime_error("checkpoint: upload failed");
+    out = t.release();
+  });
+  return out;
+}
+
+// ---- export for the in-tree streaming inference stack --------------------------------------------------------
+// The contract of recipes/streaming_convnets/tools/StreamingTDSModelConverter.cpp: walk the arch (C2 [after PD], R, LN 1 2,
+// TDS, L; V / RO / DO / SAUG skipped, :203-283) consuming the parameters in order and hand every layer its arrays in the
+// INFERENCE layouts — activations per frame [groups = nFeat][channels] (feature w*C + c), Conv1d weights
+// fl::reorder(wt, 2, 1, 0) = [cout/g][kw][cin/g] shared by all groups (:58-90), Linear weights W[i*nOut + o] (:92-101),
+// LayerNorm as two scalars (:46-56), TDS = conv, LN, Linear, Linear, LN from its 10 parameters (:103-136) — plus
+// transitions.bin for ASG as a cereal binary std::vector<float> (u64 count + floats; :310-326, read back by
+// inference/examples/SimpleStreamingASRExample.cpp:206-217) and tokens.txt.  This library's Linear layers index features
+// c*W + w (its [B][T][C][W] activation layout), upstream's c + C*w: the export permutes the feature side of every Linear.
+// Files: <outdir>/acoustic_model.json (layer list with offsets), acoustic_model.bin (fp32 blob), transitions.bin, tokens.txt.
+W2L_API int w2l_trainer_export_streaming(void* h, void* stream, const char* outdir, const char* tokens_text) {
+  return guarded([&] {
+    w2l::setCurrentStream(stream);
+    auto* t = static_cast<Trainer*>(h);
+    const std::string dir = outdir;
+    ::mkdir(dir.c_str(), 0755);
+    // host copies of the parameters in module order
+    std::vector<std::vector<float>> params;
+    for (auto& p : t->net->params()) params.push_back(p.array().host<float>());
+    std::vector<float> blob;
+    std::ostringstream js;
+    js << "{\"n_feat\": " << t->nFeat << ", \"n_label\": " << t->nLabel << ", \"layers\": [";
+    bool first = true;
+    auto emit = [&](const std::string& obj) {
+      js << (first ? "" : ", ") << obj;
+      first = false;
+    };
+    auto push = [&](const std::vector<float>& v) {
+      const size_t off = blob.size();
+      blob.insert(blob.end(), v.begin(), v.end());
+      return off;
+    };
+    size_t pi = 0;
+    auto next = [&]() -> const std::vector<float>& {
+      if (pi >= params.size()) throw std::runtime_error("export: not enough parameters for the arch");
+      return params[pi++];
+    };
+    const int W = t->nFeat;  // groups of every layer = the filterbank count (converter: groups = nFeat)
+    // ours [cout][cin][kw] -> inference [cout][kw][cin]
+    auto convLayout = [](const std::vector<float>& w, int cout, int cin, int kw) {
+      std::vector<float> o(w.size());
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int k = 0; k < kw; ++k) o[((size_t)co * kw + k) * cin + ci] = w[((size_t)co * cin + ci) * kw + k];
+      return o;
+    };
+    // ours W[o][i] (feature f_int = c*W + w where the side is a [C][W] frame) -> inference W[i*nOut + o] (feature w*C + c)
+    auto linLayout = [&](const std::vector<float>& w, int nin, int nout, int cIn /*0: not a frame*/, int cOut) {
+      auto up = [&](int f, int c) { return c ? (f % W) * c + f / W : f; };  // internal index -> upstream index
+      std::vector<float> o(w.size());
+      for (int oo = 0; oo < nout; ++oo)
+        for (int ii = 0; ii < nin; ++ii) o[(size_t)up(ii, cIn) * nout + up(oo, cOut)] = w[(size_t)oo * nin + ii];
+      return o;
+    };
+    auto vecLayout = [&](const std::vector<float>& b, int c) {
+      std::vector<float> o(b.size());
+      for (size_t f = 0; f < b.size(); ++f) o[c ? ((int)f % W) * c + (int)f / W : f] = b[f];
+      return o;
+    };
+    std::istringstream in(t->archText);
+    std::string line;
+    int curC = 1, padL = -1, padR = -1;
+    while (std::getline(in, line)) {
+      const auto hash = line.find('#');
+      if (hash != std::string::npos) line = line.substr(0, hash);
+      for (const char* key : {"NFEAT", "NLABEL"}) {
+        size_t pos;
+        const std::string val = std::to_string(std::string(key) == "NFEAT" ? t->nFeat : t->nLabel);
+        while ((pos = line.find(key)) != std::string::npos) line.replace(pos, std::strlen(key), val);
+      }
+      std::istringstream ls(line);
+      std::vector<std::string> c;
+      std::string tok;
+      while (ls >> tok) c.push_back(tok);
+      if (c.empty()) continue;
+      const std::string& op = c[0];
+      std::ostringstream o;
+      if (op == "PD") {
+        if (c.size() != 4) throw std::invalid_argument("export: padding is supported only along the time axis");
+        padL = std::stoi(c[2]);
+        padR = std::stoi(c[3]);
+      } else if (op == "C2") {
+        if (c.size() < 8) throw std::invalid_argument("export: invalid arch specified for C2");
+        const int cin = std::stoi(c[1]), cout = std::stoi(c[2]), kw = std::stoi(c[3]), dw = std::stoi(c[5]);
+        int pl = padL, pr = padR;
+        if (pl == -1 && pr == -1) pl = pr = (kw - dw + 1) / 2;
+        const size_t wo = push(convLayout(next(), cout, cin, kw)), bo = push(next());
+        o << "{\"type\": \"conv1d\", \"cin\": " << cin * W << ", \"cout\": " << cout * W << ", \"kw\": " << kw << ", \"stride\": " << dw
+          << ", \"pad_left\": " << pl << ", \"pad_right\": " << pr << ", \"groups\": " << W << ", \"weight\": " << wo << ", \"bias\": " << bo << "}";
+        emit(o.str());
+        padL = padR = -1;
+        curC = cout;
+      } else if (op == "R") {
+        emit("{\"type\": \"relu\"}");
+      } else if (op == "LN") {
+        if (c.size() != 3 || c[1] != "1" || c[2] != "2") throw std::invalid_argument("export: unsupported LayerNorm axis: must be {1, 2} for streaming");
+        const float g = next()[0], b = next()[0];
+        o << "{\"type\": \"layernorm\", \"feat\": " << curC * W << ", \"gain\": " << g << ", \"bias\": " << b << "}";
+        emit(o.str());
+      } else if (op == "L") {
+        const int nin = std::stoi(c[1]), nout = std::stoi(c[2]);
+        if (nin != curC * W) throw std::invalid_argument("export: the Linear head does not take a whole frame");
+        const size_t wo = push(linLayout(next(), nin, nout, curC, 0));
+        const size_t bo = push(next());
+        o << "{\"type\": \"linear\", \"nin\": " << nin << ", \"nout\": " << nout << ", \"weight\": " << wo << ", \"bias\": " << bo << "}";
+        emit(o.str());
+      } else if (op == "TDS") {
+        const int ch = std::stoi(c[1]), kw = std::stoi(c[2]), w = std::stoi(c[3]);
+        const int inner = c.size() > 5 && std::stoi(c[5]) > 0 ? std::stoi(c[5]) : ch * w;
+        const int rpad = c.size() > 6 ? std::stoi(c[6]) : -1;
+        if (w != W) throw std::invalid_argument("export: the TDS width must be the filterbank count");
+        if (c.size() > 7 && std::stoi(c[7]) != 0) throw std::invalid_argument("export: streaming TDS blocks normalise per frame (lNormIncludeTime = 0)");
+        const int pr = rpad >= 0 ? rpad : (kw - 1 + 1) / 2, pl = rpad >= 0 ? kw - 1 - rpad : (kw - 1 + 1) / 2;
+        const size_t cw = push(convLayout(next(), ch, ch, kw)), cb = push(next());
+        const float g1 = next()[0], b1 = next()[0];
+        const size_t w1 = push(linLayout(next(), ch * w, inner, ch, 0)), bb1 = push(next());
+        const size_t w2 = push(linLayout(next(), inner, ch * w, 0, ch));
+        const size_t bb2 = push(vecLayout(next(), ch));
+        const float g2 = next()[0], b2 = next()[0];
+        o << "{\"type\": \"tds\", \"channels\": " << ch << ", \"kw\": " << kw << ", \"feat\": " << ch * w << ", \"inner\": " << inner
+          << ", \"pad_left\": " << pl << ", \"pad_right\": " << pr << ", \"groups\": " << W << ", \"conv_weight\": " << cw << ", \"conv_bias\": " << cb
+          << ", \"ln1\": [" << g1 << ", " << b1 << "], \"lin1_weight\": " << w1 << ", \"lin1_bias\": " << bb1 << ", \"lin2_weight\": " << w2
+          << ", \"lin2_bias\": " << bb2 << ", \"ln2\": [" << g2 << ", " << b2 << "]}";
+        emit(o.str());
+        curC = ch;
+      } else if (op == "V" || op == "RO" || op == "DO" || op == "SAUG") {
+        // skipped, as the converter does
+      } else {
+        throw std::logic_error("export: unrecognized/unparsable line " + line);
+      }
+    }
+    if (pi != params.size()) throw std::runtime_error("export: parameters left over after walking the arch");
+    js << "], \"blob_floats\": " << blob.size() << "}\n";
+    {
+      std::ofstream f(dir + "/acoustic_model.json");
+      f << js.str();
+      std::ofstream b(dir + "/acoustic_model.bin", std::ios::binary);
+      b.write(reinterpret_cast<const char*>(blob.data()), (std::streamsize)(blob.size() * sizeof(float)));
+      if (!f || !b) throw std::runtime_error("export: cannot write under " + dir);
+    }
+    if (tokens_text) {
+      std::ofstream f(dir + "/tokens.txt");
+      f << tokens_text;
+    }
+    if (!t->isCtc) {  // transitions.bin: cereal::BinaryOutputArchive of std::vector<float> = u64 size tag + raw data
+      auto cp = t->crit->params();
+      if (cp.empty() || cp[0].elements() != (long long)t->nLabel * t->nLabel) throw std::runtime_error("Invalid criterion parameters for ASG");
+      const std::vector<float> tr = cp[0].array().host<float>();
+      std::ofstream f(dir + "/transitions.bin", std::ios::binary);
+      put<uint64_t>(f, tr.size());
+      f.write(reinterpret_cast<const char*>(tr.data()), (std::streamsize)(tr.size() * sizeof(float)));
+      if (!f) throw std::runtime_error("export: cannot write transitions.bin");
+    }
+  });
+}
+
 W2L_API const char* w2l_trainer_describe(void* h) {
   static thread_local std::string s;
   auto* t = static_cast<Trainer*>(h);

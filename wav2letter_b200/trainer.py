@@ -38,6 +38,25 @@ class Trainer:
         _check(lib.w2l_trainer_status(self.h, _stream(), ctypes.byref(n)))
         return int(n.value)
 
+    def save(self, path: str):
+        """own-format checkpoint: constructor arguments + parameter / momentum arenas (Train.cpp:747-800)"""
+        _check(lib.w2l_trainer_save(self.h, _stream(), path.encode()))
+
+    @classmethod
+    def load(cls, path: str) -> "Trainer":
+        h = lib.w2l_trainer_load(_stream(), path.encode())
+        if not h:
+            raise capi.W2LError(1, lib.w2l_last_error().decode())
+        self = cls.__new__(cls)
+        self.h = ctypes.c_void_p(h)
+        self.n_feat = self.n_label = self.criterion = None
+        return self
+
+    def export_streaming(self, outdir: str, tokens_text: str | None = None):
+        """arrays of every layer in the layouts of the in-tree streaming inference library + transitions.bin / tokens.txt
+        (the conversions of recipes/streaming_convnets/tools/StreamingTDSModelConverter.cpp)"""
+        _check(lib.w2l_trainer_export_streaming(self.h, _stream(), outdir.encode(), None if tokens_text is None else tokens_text.encode()))
+
     def close(self):
         if getattr(self, "h", None):
             lib.w2l_trainer_destroy(self.h)
