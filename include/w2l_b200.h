@@ -188,6 +188,9 @@ W2L_API int w2l_cast_bf16(void* stream, long long n, const float* x, void* y);
 W2L_API int w2l_cast_bf16_rows(void* stream, long long rows, int cols, int ld_in, int cols_padded, const float* x, void* y);
 /* Pin the GEMM tile width (128 / 160 / 224 / 256; 0 = choose per shape, the default).  Thread-local; for tests and tuning. */
 W2L_API int w2l_gemm_set_tile(int bn);
+/* 1 (default): the persistent kernel — one CTA per SM walking tiles, two TMEM accumulators so a tile's epilogue overlaps the
+ * next tile's main loop; 0: one tile per CTA.  Thread-local; for tests (the two must agree) and tuning. */
+W2L_API int w2l_gemm_set_variant(int variant);
 W2L_API int w2l_gemm_tf32(void* stream, int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, int lda,
                           const float* B, int ldb, float* C, int ldc, const float* bias, int act);
 
@@ -212,6 +215,9 @@ W2L_API int w2l_gemm_tf32_ex(void* stream, int a_mn_major, int b_mn_major, int M
  * The workspace size call covers all three.
  * ---------------------------------------------------------------------------------------- */
 W2L_API size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K);
+/* 0 (default): tensor-core kernels where the shape allows (TF32, or 3xTF32 under W2L_PRECISION_F32); 1: always the fp32 SIMT
+ * kernels (the fallback for widths that are not multiples of 8).  Thread-local; for tests. */
+W2L_API int w2l_conv_set_path(int path);
 W2L_API int w2l_conv_time_fwd(void* stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                               int pad_left, const float* x, const float* wt, const float* bias, const float* add, float* y,
                               int act, float dropout_p, unsigned long long seed, void* ws, size_t ws_bytes);

@@ -9,9 +9,11 @@ reference tree).  Dropout probabilities are set to 0 and SpecAugment's mask coun
 compared across implementations; both are covered by their own tests.
 
 Tolerances.  precision "f32" (fp32-accurate contractions: 3xTF32 split GEMMs, fp32 SIMT time convolutions):
-emissions 2e-4 of the largest emission, per-sample loss 2e-4, every single parameter's gradient 5e-3 of
-max(its own largest entry, 1e-3 of the largest gradient entry of the net) — a wrong LayerNorm gain / bias / WeightNorm
-gradient fails this by orders of magnitude.  "tf32" / "bf16" run the same graph with 10- / 8-bit operand mantissas; they
+emissions 2e-4 of the largest emission, per-sample loss 2e-4, every single parameter's gradient within 5e-3 of
+max(its own largest entry, 1e-3 of the largest gradient entry of the net) OR within 4x of the error stock fp32 torch (TF32
+off) makes on that same parameter against float64 — the scalar LayerNorm gains / biases of the TDS archs are sums with
+heavy cancellation whose fp32 noise floor is percent-level for ANY fp32 implementation; everything else sits at 1e-4..1e-3.
+A wrong LayerNorm gain / bias / WeightNorm gradient fails this by orders of magnitude.  "tf32" / "bf16" run the same graph with 10- / 8-bit operand mantissas; they
 are checked for gross correctness only (overall gradient error 4e-2 / 1.5e-1), the exact arithmetic being pinned by f32."""
 import json
 import os
@@ -72,18 +74,35 @@ def run_case(name, precision):
         ol, ode, _ = oracle.asg(e_np, y, trans, mode)
     e64.backward(torch.from_numpy(ode).to(e64.device).double())
     g64 = ref.grads_flat(layout, flat.numel())
+    # what stock fp32 torch (TF32 off) makes of the same graph: scalar LayerNorm gains / biases are sums with heavy
+    # cancellation (a shift of a tensor that is re-normalised right after), their fp32 noise floor is far above 1e-3
+    t32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref32 = am_ref.RefNet(arch, F, N, flat, layout, dtype=torch.float32)
+        e32 = ref32.forward(feat)
+        e32.backward(torch.from_numpy(ode).to(e32.device))
+        g32 = ref32.grads_flat(layout, flat.numel()).double()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = t32
     emis_err = float((emis.double() - e64.detach()).abs().max() / e64.detach().abs().max())
     loss_err = float(np.abs(loss.cpu().numpy() - ol).max() / max(1e-6, np.abs(ol).max()))
     gmax = float(g64.abs().max())
     overall = float((grads - g64).abs().max() / gmax)
-    per = []
+    per, excess = [], 0.0
     for i, (o, n, dims) in enumerate(layout):
         own = float(g64[o:o + n].abs().max())
         err = float((grads[o:o + n] - g64[o:o + n]).abs().max())
-        per.append((err / max(own, 1e-3 * gmax), i, dims, own))
+        err32 = float((g32[o:o + n] - g64[o:o + n]).abs().max())
+        denom = max(own, 1e-3 * gmax)
+        per.append((err / denom, i, dims, own / gmax, err32 / denom))
+        # the f32 criterion: within 5e-3 of the parameter's scale, or within 4x of stock fp32 torch's own error on it
+        excess = max(excess, err / max(5e-3 * denom, 4.0 * err32))
     per.sort(reverse=True)
     rec = {"arch": name, "precision": precision, "emis_err": emis_err, "loss_err": loss_err, "grad_overall": overall,
            "grad_worst_param": per[0][0], "worst_param_index": per[0][1], "worst_param_dims": list(per[0][2]),
+           "worst5": [{"rel": round(q[0], 6), "index": q[1], "dims": list(q[2]), "own_over_gmax": round(q[3], 6), "torch_fp32_rel": round(q[4], 6)} for q in per[:5]],
+           "f32_criterion_excess": excess, "torch_fp32_overall": float((g32 - g64).abs().max() / gmax),
            "params": len(layout), "n_param_elements": int(flat.numel()), "loss": [float(v) for v in loss.cpu().numpy()]}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "arch_parity.jsonl"), "a") as f:
@@ -100,8 +119,10 @@ def test_arch_file_parity_fp32_accurate(name):
     assert np.isfinite(rec["loss"]).all()
     assert rec["emis_err"] <= t["emis"], rec
     assert rec["loss_err"] <= t["loss"], rec
-    assert rec["grad_overall"] <= t["overall"], rec
-    assert rec["grad_worst_param"] <= t["per_param"], rec
+    # overall: within 1e-3 of the largest gradient entry, or 4x stock fp32 torch's own overall error
+    assert rec["grad_overall"] <= max(t["overall"], 4 * rec["torch_fp32_overall"]), rec
+    # every parameter: within 5e-3 of its own scale, or within 4x of stock fp32 torch's error on that parameter
+    assert rec["f32_criterion_excess"] <= 1.0, rec
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])

@@ -177,7 +177,7 @@ def test_precision_switch_routes_fp32_entry_points():
 
 @pytest.mark.parametrize("out_bf16", [False, True])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 128), (200, 136, 104), (76, 56, 40), (4000, 800, 800),
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 128), (200, 136, 104), (72, 56, 40), (4000, 800, 800),
                                    (1000, 2000, 1440), (1120, 1120, 4800)])
 def test_gemm_bf16_kind(M, N, K, a_mn, b_mn, out_bf16):
     """bf16 operands are exact inputs here (the reference is computed from the same bf16 values), so the only error is
@@ -222,3 +222,32 @@ def test_cast_bf16_matches_torch():
 
     x = torch.randn(1003, 37, device="cuda") * 5
     assert torch.equal(w.capi.cast_bf16(x.reshape(-1)), x.reshape(-1).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("kind", ["tf32", "f32x3", "bf16"])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(9600, 800, 800, False, False), (4800, 1120, 1120, False, True), (1120, 1120, 4800, True, True),
+                                              (300, 10000, 1440, False, False), (130, 72, 4000, True, False), (128, 128, 64, False, False)])
+def test_gemm_persistent_and_per_tile_kernels_agree(M, N, K, a_mn, b_mn, kind):
+    """the persistent kernel (two TMEM accumulators, tiles walked per SM) against the one-tile-per-CTA kernel: same tile
+    shape and k order, so results agree to the last bit except under split-K (atomic accumulation order)"""
+    import wav2letter_b200 as w
+
+    A, B = _operands(M, N, K, a_mn, b_mn, seed=M + N, dtype=torch.bfloat16 if kind == "bf16" else torch.float32)
+    bias = torch.randn(N, device="cuda")
+    try:
+        w.capi.gemm_set_tile(128)
+        w.capi.gemm_set_variant(0)
+        C0 = w.capi.gemm(A, B, kind, a_mn, b_mn, bias=bias, act=1)
+        P0 = w.capi.gemm(A, B, kind, a_mn, b_mn)  # plain: may split K
+        w.capi.gemm_set_variant(1)
+        C1 = w.capi.gemm(A, B, kind, a_mn, b_mn, bias=bias, act=1)
+        P1 = w.capi.gemm(A, B, kind, a_mn, b_mn)
+    finally:
+        w.capi.gemm_set_variant(1)
+        w.capi.gemm_set_tile(0)
+    torch.cuda.synchronize()
+    assert torch.equal(C0, C1)
+    assert float((P0 - P1).abs().max()) <= 1e-4 * float(P0.abs().max()) + 1e-6
+    ref = (A.t() if a_mn else A).double() @ (B.t() if b_mn else B).double().t()
+    tol = {"tf32": 3e-3, "f32x3": 2e-5, "bf16": 2e-5}[kind]
+    assert float((P1.double() - ref).abs().max()) <= tol * float(ref.abs().max()) * (K ** 0.5) / 8 + 1e-4

@@ -28,7 +28,7 @@ EXPORTS = [
     "w2l_mask_bands", "w2l_trainer_set_precision", "w2l_trainer_status", "w2l_trainer_save", "w2l_trainer_load", "w2l_trainer_export_streaming",
     "w2l_text_create", "w2l_text_destroy", "w2l_text_num_classes", "w2l_text_encode", "w2l_text_prediction2ltr", "w2l_text_target2ltr",
     "w2l_text_ltr2wrd", "w2l_edit_distance",
-    "w2l_gemm_set_tile", "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_gemm_tf32_view", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
+    "w2l_gemm_set_variant", "w2l_gemm_set_tile", "w2l_gemm_tf32", "w2l_gemm_tf32_ex", "w2l_gemm_tf32_view", "w2l_conv_set_path", "w2l_conv_time_workspace_size", "w2l_conv_time_fwd", "w2l_conv_time_dgrad",
     "w2l_conv_time_wgrad", "w2l_layernorm_fwd", "w2l_layernorm_bwd", "w2l_colsum_accumulate", "w2l_sq_norm_accumulate",
     "w2l_sgd_step", "w2l_weightnorm_fwd", "w2l_weightnorm_bwd", "w2l_conv1d_arrange", "w2l_conv1d_unarrange_grad",
     "w2l_glu_fwd", "w2l_glu_bwd", "w2l_transpose_input", "w2l_axpy", "w2l_fill", "w2l_act_fwd", "w2l_mask_mul",
@@ -349,6 +349,11 @@ def cast_bf16(x):
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _check(lib.w2l_cast_bf16(_stream(), x.numel(), _ptr(x), _ptr(y)))
     return y
+
+
+def gemm_set_variant(v: int = 1):
+    """1: persistent kernel with two TMEM accumulators (default); 0: one tile per CTA"""
+    _check(lib.w2l_gemm_set_variant(int(v)))
 
 
 def gemm_set_tile(bn: int = 0):

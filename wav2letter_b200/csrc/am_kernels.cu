@@ -14,15 +14,17 @@
 // the dense contractions live in gemm_umma.cu.
 #include <cuda_runtime.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace w2l {
 // tensor-core path (conv_mma.cu)
 bool conv_mma_supported(int W, int Cin, int Cout, int K, int stride);
-// the TF32 tensor-core path, unless the thread asked for fp32-accurate contractions (w2l_set_precision): then the fp32 SIMT kernels
-static bool use_conv_mma(int W, int Cin, int Cout, int K, int stride) {
-  return current_precision() != W2L_PRECISION_F32 && conv_mma_supported(W, Cin, Cout, K, stride);
-}
+// the tensor-core path (TF32 products; under W2L_PRECISION_F32 the same kernels run error-compensated 3xTF32); shapes it
+// does not cover fall back to the fp32 SIMT kernels below
+static thread_local int g_conv_path = 0;  // w2l_conv_set_path: 0 auto, 1 force the fp32 SIMT kernels (tests)
+static bool use_conv_mma(int W, int Cin, int Cout, int K, int stride) { return g_conv_path == 0 && conv_mma_supported(W, Cin, Cout, K, stride); }
 size_t conv_mma_arranged_floats(int Cin, int Cout, int K);
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                  const float* x, const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y,
@@ -412,6 +414,93 @@ __global__ void __launch_bounds__(256) ln_apply_kernel(long long R, int vec, flo
       const float v = ab[i] + (rb ? rb[i] : 0.f);
       yb[i] = (v - mu) * sc + bi;
     }
+  }
+}
+
+// ---- single-launch forward (cooperative): every CTA owns one contiguous chunk of one sample and KEEPS what it reads in
+// shared memory; the grid meets once (the per-sample statistics need every chunk), then the normalised values are
+// written straight from shared memory.  HBM traffic = read a (+ r) once, write y once — the two-kernel version above
+// reads the inputs twice.  2 CTAs of 512 threads and ~110 KB per SM: the 33 MB of shared memory of the chip hold a whole
+// TDS activation tensor (30.7 MB at B = 16 x 600 frames x 800 features).  Used by the forward pass only: a cooperative
+// grid must be co-resident, which the backward pass cannot promise while NCCL kernels share the SMs.
+constexpr int kLnFusedThreads = 512;
+constexpr int kLnFusedSmem = 110 * 1024;
+__global__ void __launch_bounds__(kLnFusedThreads, 2) ln_fused_fwd_kernel(long long R, long long chunk, int keep, float eps,
+                                                                           const float* __restrict__ a, const float* __restrict__ r,
+                                                                           const float* __restrict__ gain, const float* __restrict__ bias,
+                                                                           float* __restrict__ y, float* __restrict__ mean_rstd,
+                                                                           double* __restrict__ scratch) {
+  extern __shared__ __align__(16) float ln_sv[];
+  __shared__ double red[2][kLnFusedThreads / 32];
+  __shared__ double tot[2];
+  const int b = blockIdx.y, parts = gridDim.x;
+  const long long lo = (long long)blockIdx.x * chunk, hi = min(R, lo + chunk);
+  const float* ab = a + (size_t)b * R;
+  const float* rb = r ? r + (size_t)b * R : nullptr;
+  float* yb = y + (size_t)b * R;
+  double s = 0.0, q = 0.0;
+#pragma unroll 4
+  for (long long i = lo + 4 * threadIdx.x; i < hi; i += 4 * kLnFusedThreads) {
+    float4 v = ld4(ab, i);
+    if (rb) v = add4(v, ld4(rb, i));
+    const long long k = i - lo;
+    if (k < keep) *reinterpret_cast<float4*>(ln_sv + k) = v;
+    s += (double)((v.x + v.y) + (v.z + v.w));
+    q += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0, Q = 0;
+    for (int w = 0; w < kLnFusedThreads / 32; ++w) {
+      S += red[0][w];
+      Q += red[1][w];
+    }
+    scratch[2 * ((size_t)b * parts + blockIdx.x)] = S;
+    scratch[2 * ((size_t)b * parts + blockIdx.x) + 1] = Q;
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  if (threadIdx.x < 32) {  // fixed-order sum of the sample's partials: deterministic
+    double S = 0.0, Q = 0.0;
+    const double* pp = scratch + 2 * (size_t)b * parts;
+    for (int i = threadIdx.x; i < parts; i += 32) {
+      S += pp[2 * i];
+      Q += pp[2 * i + 1];
+    }
+    S = warp_sum(S);
+    Q = warp_sum(Q);
+    if (threadIdx.x == 0) {
+      tot[0] = S;
+      tot[1] = Q;
+    }
+  }
+  __syncthreads();
+  const double mean = tot[0] / (double)R;
+  const double var = fmax(tot[1] / (double)R - mean * mean, 0.0);
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float mu = (float)mean, g = gain ? *gain : 1.f, bi = bias ? *bias : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    mean_rstd[2 * b] = mu;
+    mean_rstd[2 * b + 1] = rstd;
+  }
+  const float sc = rstd * g;
+#pragma unroll 2
+  for (long long i = lo + 4 * threadIdx.x; i < hi; i += 4 * kLnFusedThreads) {
+    const long long k = i - lo;
+    float4 v;
+    if (k < keep) {
+      v = *reinterpret_cast<const float4*>(ln_sv + k);
+    } else {  // the tail that did not fit in shared memory: L2
+      v = ld4(ab, i);
+      if (rb) v = add4(v, ld4(rb, i));
+    }
+    *reinterpret_cast<float4*>(yb + i) = make_float4((v.x - mu) * sc + bi, (v.y - mu) * sc + bi, (v.z - mu) * sc + bi, (v.w - mu) * sc + bi);
   }
 }
 
@@ -832,6 +921,11 @@ static size_t conv_ws_partial_bytes(int B, int Tout, int Cin, int Cout, int K) {
   const size_t mma = conv_mma_wgrad_parts(B, Tout, 0, Cin, Cout, K, 1, nullptr, nullptr);  // W unknown here: ten slices
   return align_up(std::max(simt, std::max(mma, (size_t)B * (size_t)std::max(Tout, 16))) * per, 256);
 }
+extern "C" int w2l_conv_set_path(int path) {
+  if (path != 0 && path != 1) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_set_path: 0 (auto) or 1 (fp32 SIMT kernels)");
+  g_conv_path = path;
+  return W2L_OK;
+}
 extern "C" size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K) {
   const size_t arranged = std::max((size_t)std::max(Cin, Cout) * K * co_pad(std::max(Cin, Cout)), conv_mma_arranged_floats(Cin, Cout, K)) * sizeof(float);
   return conv_ws_partial_bytes(B, Tout, Cin, Cout, K) + align_up(arranged, 256);
@@ -986,6 +1080,35 @@ extern "C" int w2l_layernorm_fwd(void* stream_, int B, long long R, float eps, c
     return W2L_OK;
   }
   if (B > 65535) return fail(W2L_ERR_UNSUPPORTED, "layernorm_fwd: more than 65535 long groups");
+  {  // single cooperative launch when the grid can be co-resident (2 CTAs per SM) and the rows are vectorisable
+    static int capacity = -1;  // co-resident CTAs of ln_fused_fwd_kernel on this device
+    if (capacity < 0) {
+      int per_sm = 0, dev = 0, sms = 0, coop = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      if (coop && cudaFuncSetAttribute(ln_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnFusedSmem) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ln_fused_fwd_kernel, kLnFusedThreads, kLnFusedSmem) == cudaSuccess)
+        capacity = per_sm * sms;
+      else
+        capacity = 0;
+      cudaGetLastError();
+    }
+    const int parts = (int)std::min<long long>(std::min<long long>(capacity / B, W2L_LN_MAX_PARTS), (R + 4095) / 4096);
+    if (vec && parts >= 1 && R >= 16384) {
+      long long chunk = ((R + parts - 1) / parts + 3) / 4 * 4;
+      int keep = (int)std::min<long long>(chunk, kLnFusedSmem / 4);
+      float epsv = eps;
+      void* args[] = {&R, &chunk, &keep, &epsv, (void*)&a, (void*)&r, (void*)&gain, (void*)&bias, (void*)&y, (void*)&mean_rstd, (void*)&scratch};
+      const cudaError_t e = cudaLaunchCooperativeKernel((const void*)ln_fused_fwd_kernel, dim3((unsigned)parts, (unsigned)B), dim3(kLnFusedThreads), args,
+                                                        (size_t)kLnFusedSmem, stream);
+      if (e == cudaSuccess) {
+        W2L_LAUNCH_CHECK("ln_fused_fwd_kernel");
+        return W2L_OK;
+      }
+      cudaGetLastError();  // (e.g. the stream is being captured): fall through to the two-kernel path
+    }
+  }
   // whole multiples of the 148 SMs at full occupancy (8 CTAs of 256 threads per SM) when the samples are long enough;
   // at most W2L_LN_MAX_PARTS CTAs per sample (the scratch holds one partial pair per CTA)
   dim3 grid(std::max(1, std::min(std::min(blocks_for(R, 256 * 4 * 4), W2L_LN_MAX_PARTS), 148 * 8 / std::max(1, std::min(B, 148 * 8)))), B);

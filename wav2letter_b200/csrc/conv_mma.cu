@@ -28,6 +28,14 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// fp32-accurate mode (W2L_PRECISION_F32): operands stay raw fp32 in shared memory and are split at fragment load into
+// hi = tf32(x) and lo = tf32(x - hi) (round-to-nearest by integer arithmetic: add half an ulp of the 13 dropped bits, clear
+// them — full-rate ALU ops); the tensor core accumulates lo*hi + hi*lo + hi*hi: error-compensated 3xTF32
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - hi);
+}
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -39,7 +47,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], con
 // memory, TF32-rounded, 16-byte stores.  Activations are [t][c][W], so the window rows (t, c) of a sample are
 // consecutive global rows: smem row r <- global row r + row_base, zero when outside [0, rows_total).
 // Lanes: 2 WT float4 per row, 32 / (2 WT) rows per warp pass — divisions by compile-time constants only.
-template <int WT>
+template <int WT, bool kRaw = false>
 __device__ __forceinline__ void stage_rows(float* dst, int pitch, const float* __restrict__ src, int W, int row_base,
                                            int rows_total, int nrows, int zero_rows) {
   constexpr int q = 2 * WT, RPW = 32 / q, kWarps = kMmaThreads / 32;
@@ -51,7 +59,7 @@ __device__ __forceinline__ void stage_rows(float* dst, int pitch, const float* _
       const int gr = r + row_base;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gr >= 0 && gr < rows_total) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * W) + c4);
-      *reinterpret_cast<float4*>(dst + (size_t)r * pitch + 4 * c4) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      *reinterpret_cast<float4*>(dst + (size_t)r * pitch + 4 * c4) = kRaw ? v : make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
     }
   }
   // rows read by the zero-padded tail of K must be finite
@@ -69,7 +77,7 @@ __host__ __device__ constexpr int wg_pitch(int WT) { return 8 * WT + 4; }
 // slices of 40: 58-81 KB per CTA for every TDS shape -> 2-3 CTAs per SM).  Weight fragments come straight from
 // global memory (L1-resident, 50 KB at most), prefetched one k-step ahead.
 // ------------------------------------------------------------------------------------------
-template <int MT, int UPW, int WT>  // m tiles of 16 output channels (1 or 2); frames per warp; 8-column tiles per slice
+template <int MT, int UPW, int WT, bool kX3>  // m tiles of 16 output channels (1 or 2); frames per warp; 8-column tiles per slice; 3xTF32
 __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                                                                        int pad_left, int Kpad, int apitch,
                                                                        const float* __restrict__ x, const float* __restrict__ wa,
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[u][m][j][q] = 0.f;
   const int nframes = (nto - 1) * stride + K;
-  stage_rows<WT>(xs, kPitch, x + (size_t)b * T * Cin * W + w_off, W, (to0 * stride - pad_left) * Cin, T * Cin, nframes * Cin, 8);
+  stage_rows<WT, kX3>(xs, kPitch, x + (size_t)b * T * Cin * W + w_off, W, (to0 * stride - pad_left) * Cin, T * Cin, nframes * Cin, 8);
   __syncthreads();
   // frames past the end of the sample recompute the last valid one (their result is not stored): no divergent
   // branch around the MMAs
@@ -122,6 +130,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
       an[m][2] = __ldg(ap + (size_t)16 * m * apitch + kn + 4);
       an[m][3] = __ldg(ap + (size_t)(16 * m + 8) * apitch + kn + 4);
     }
+    float ah[MT][4], al[MT][4];
+    if (kX3) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_tf32(a[m][q], ah[m][q], al[m][q]);
+    }
 #pragma unroll
     for (int u = 0; u < UPW; ++u) {
       const float* bq = bp[u] + (size_t)k0 * kPitch;
@@ -130,8 +145,20 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
         float bf[2];
         bf[0] = bq[8 * j];
         bf[1] = bq[4 * kPitch + 8 * j];
+        if (kX3) {
+          float bh[2], bl[2];
+          split_tf32(bf[0], bh[0], bl[0]);
+          split_tf32(bf[1], bh[1], bl[1]);
 #pragma unroll
-        for (int m = 0; m < MT; ++m) mma_tf32(acc[u][m][j], a[m], bf);
+          for (int m = 0; m < MT; ++m) {
+            mma_tf32(acc[u][m][j], al[m], bh);
+            mma_tf32(acc[u][m][j], ah[m], bl);
+            mma_tf32(acc[u][m][j], ah[m], bh);
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_tf32(acc[u][m][j], a[m], bf);
+        }
       }
     }
 #pragma unroll
@@ -212,7 +239,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_fwd_kernel(int T, int
 // flip != 0 builds a data-gradient operator: wa[ci][dk'*Cout + co] = wt[co][ci][tap_off + tap_step*(K-1-dk')] — all
 // taps reversed for stride 1 (tap_step 1), or the taps of one phase of a strided convolution (K = taps of the phase)
 __global__ void conv_mma_arrange_kernel(int Cin, int Cout, int Kfull, int K, int tap_step, int tap_off, int rows, int apitch,
-                                        const float* __restrict__ wt, float* __restrict__ wa, int flip) {
+                                        const float* __restrict__ wt, float* __restrict__ wa, int flip, int raw) {
   const int kin = flip ? Cout : Cin;  // channel count that plays "input" in the arranged operator
   const int mout = flip ? Cin : Cout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * apitch; i += gridDim.x * blockDim.x) {
@@ -222,7 +249,7 @@ __global__ void conv_mma_arrange_kernel(int Cin, int Cout, int Kfull, int K, int
       const int dk = k / kin, c = k % kin;
       v = flip ? wt[((size_t)c * Cin + m) * Kfull + tap_off + tap_step * (K - 1 - dk)] : wt[((size_t)m * Cin + c) * Kfull + dk];
     }
-    wa[i] = to_tf32(v);
+    wa[i] = raw ? v : to_tf32(v);
   }
 }
 
@@ -233,7 +260,7 @@ __global__ void conv_mma_arrange_kernel(int Cin, int Cout, int Kfull, int K, int
 // ------------------------------------------------------------------------------------------
 constexpr int kWgMaxNt = 8;  // k tiles per warp (Kc <= 8 * 8 * 8 = 512)
 
-template <int MT, int WT>
+template <int MT, int WT, bool kX3>
 __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_wgrad_kernel(int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                                                                          int pad_left, int TC, int NT, const float* __restrict__ x,
                                                                          const float* __restrict__ dy, float* __restrict__ partial) {
@@ -262,8 +289,8 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_wgrad_kernel(int T, i
     const int nto = min(TC, Tout - to0);
     const int nframes = (nto - 1) * stride + K;
     __syncthreads();  // the previous chunk's reads are done
-    stage_rows<WT>(xs, kPitch, x + (size_t)b * T * Cin * W + w_off, W, (to0 * stride - pad_left) * Cin, T * Cin, nframes * Cin, 8);
-    stage_rows<WT>(ds, kPitch, dy + (size_t)b * Tout * Cout * W + w_off, W, to0 * Cout, Tout * Cout, nto * Cout, 0);
+    stage_rows<WT, kX3>(xs, kPitch, x + (size_t)b * T * Cin * W + w_off, W, (to0 * stride - pad_left) * Cin, T * Cin, nframes * Cin, 8);
+    stage_rows<WT, kX3>(ds, kPitch, dy + (size_t)b * Tout * Cout * W + w_off, W, to0 * Cout, Tout * Cout, nto * Cout, 0);
     if (to0 == blockIdx.x * TC)
       for (int i = threadIdx.x; i < kPitch; i += blockDim.x) ds[(size_t)TC * Cout * kPitch + i] = 0.f;
     __syncthreads();
@@ -286,6 +313,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_wgrad_kernel(int T, i
           a[m][2] = ar[m][0][8 * wt + 4];
           a[m][3] = ar[m][1][8 * wt + 4];
         }
+        float ah[MT][4], al[MT][4];
+        if (kX3) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_tf32(a[m][q], ah[m][q], al[m][q]);
+        }
 #pragma unroll
         for (int j = 0; j < kWgMaxNt; ++j) {
           if (j < NT) {  // NT is a kernel argument: warp-uniform
@@ -293,8 +327,20 @@ __global__ void __launch_bounds__(kMmaThreads, 2) conv_mma_wgrad_kernel(int T, i
             float bf[2];
             bf[0] = bp[0];
             bf[1] = bp[4];
+            if (kX3) {
+              float bh[2], bl[2];
+              split_tf32(bf[0], bh[0], bl[0]);
+              split_tf32(bf[1], bh[1], bl[1]);
 #pragma unroll
-            for (int m = 0; m < MT; ++m) mma_tf32(acc[m][j], a[m], bf);
+              for (int m = 0; m < MT; ++m) {
+                mma_tf32(acc[m][j], al[m], bh);
+                mma_tf32(acc[m][j], ah[m], bl);
+                mma_tf32(acc[m][j], ah[m], bh);
+              }
+            } else {
+#pragma unroll
+              for (int m = 0; m < MT; ++m) mma_tf32(acc[m][j], a[m], bf);
+            }
           }
         }
       }
@@ -393,14 +439,14 @@ static int slice_tiles(int W) {
 }
 constexpr size_t kConvSmemTarget = 112 * 1024;  // two CTAs per SM
 
-template <int MT, int UPW, int WT>
+template <int MT, int UPW, int WT, bool kX3>
 static int launch_fwd(cudaStream_t stream, dim3 grid, size_t smem, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                       int pad_left, int Kpad, int apitch, const float* x, const float* arranged, const float* bias,
                       const float* add, float* y, int act, float drop_p, unsigned long long seed, int out_fstride, int out_foff,
                       int out_frames) {
   if (smem > 48 * 1024)
-    W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<MT, UPW, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv_mma_fwd_kernel<MT, UPW, WT><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x,
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_fwd_kernel<MT, UPW, WT, kX3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_mma_fwd_kernel<MT, UPW, WT, kX3><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x,
                                                                         arranged, bias, add, y, act, drop_p, seed, out_fstride, out_foff,
                                                                         out_frames);
   return W2L_OK;
@@ -416,7 +462,8 @@ int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, in
   const int MT = (Cout + 15) / 16;
   const int Kpad = (K * Cin + 7) / 8 * 8;
   const int apitch = apitch_for(Kpad);
-  conv_mma_arrange_kernel<<<16, 256, 0, stream>>>(wt_cin, wt_cout, Kfull, K, tap_step, tap_off, 16 * MT, apitch, wt, arranged, flip);
+  const bool x3 = current_precision() == W2L_PRECISION_F32;  // fp32-accurate contractions: 3xTF32 split at fragment load
+  conv_mma_arrange_kernel<<<16, 256, 0, stream>>>(wt_cin, wt_cout, Kfull, K, tap_step, tap_off, 16 * MT, apitch, wt, arranged, flip, x3 ? 1 : 0);
   W2L_LAUNCH_CHECK("conv_mma_arrange_kernel");
   const int WT = slice_tiles(W);
   auto bytes_for = [&](int tb) { return ((size_t)((tb - 1) * stride + K) * Cin + 8) * fwd_pitch(WT) * 4; };
@@ -429,8 +476,10 @@ int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, in
   int rc = W2L_OK;
 #define W2L_FWD_CASE(MT_, UPW_, WT_)                                                                                  \
   if (MT == MT_ && UPW == UPW_ && WT == WT_)                                                                         \
-    rc = launch_fwd<MT_, UPW_, WT_>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged, \
-                                    bias, add, y, act, drop_p, seed, out_fstride, out_foff, out_frames);
+    rc = x3 ? launch_fwd<MT_, UPW_, WT_, true>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged, \
+                                               bias, add, y, act, drop_p, seed, out_fstride, out_foff, out_frames)             \
+            : launch_fwd<MT_, UPW_, WT_, false>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, Kpad, apitch, x, arranged, \
+                                                bias, add, y, act, drop_p, seed, out_fstride, out_foff, out_frames);
 #define W2L_FWD_WT(WT_) W2L_FWD_CASE(1, 1, WT_) W2L_FWD_CASE(1, 2, WT_) W2L_FWD_CASE(2, 1, WT_)
   W2L_FWD_WT(1) W2L_FWD_WT(2) W2L_FWD_WT(3) W2L_FWD_WT(4) W2L_FWD_WT(5)
 #undef W2L_FWD_WT
@@ -471,12 +520,12 @@ size_t conv_mma_wgrad_parts(int B, int Tout, int W, int Cin, int Cout, int K, in
   return (size_t)B * nslices * per_sample;
 }
 
-template <int MT, int WT>
+template <int MT, int WT, bool kX3>
 static int launch_wgrad(cudaStream_t stream, dim3 grid, size_t smem, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                         int pad_left, int TC, int NT, const float* x, const float* dy, float* partial) {
   if (smem > 48 * 1024)
-    W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_wgrad_kernel<MT, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv_mma_wgrad_kernel<MT, WT><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TC, NT, x, dy, partial);
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(conv_mma_wgrad_kernel<MT, WT, kX3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_mma_wgrad_kernel<MT, WT, kX3><<<grid, kMmaThreads, smem, stream>>>(T, Tout, W, Cin, Cout, K, stride, pad_left, TC, NT, x, dy, partial);
   return W2L_OK;
 }
 
@@ -492,8 +541,11 @@ int conv_mma_wgrad(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, 
   if (NT > kWgMaxNt) return fail(W2L_ERR_UNSUPPORTED, "conv_mma_wgrad: filter too large for the register tiles");
   dim3 grid((unsigned)per_sample, W / (8 * WT), B);
   int rc = W2L_OK;
-#define W2L_WG_CASE(MT_, WT_) \
-  if (MT == MT_ && WT == WT_) rc = launch_wgrad<MT_, WT_>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, TC, NT, x, dy, partial);
+  const bool x3 = current_precision() == W2L_PRECISION_F32;
+#define W2L_WG_CASE(MT_, WT_)                                                                                                              \
+  if (MT == MT_ && WT == WT_)                                                                                                              \
+    rc = x3 ? launch_wgrad<MT_, WT_, true>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, TC, NT, x, dy, partial)          \
+            : launch_wgrad<MT_, WT_, false>(stream, grid, smem, T, Tout, W, Cin, Cout, K, stride, pad_left, TC, NT, x, dy, partial);
 #define W2L_WG_WT(WT_) W2L_WG_CASE(1, WT_) W2L_WG_CASE(2, WT_)
   W2L_WG_WT(1) W2L_WG_WT(2) W2L_WG_WT(3) W2L_WG_WT(4) W2L_WG_WT(5)
 #undef W2L_WG_WT

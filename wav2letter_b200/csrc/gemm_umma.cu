@@ -175,6 +175,145 @@ __device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t
   return make_uint4(c0, c1, c2, c3);
 }
 
+// ---- epilogue of one 128 x BN accumulator tile (warps 0..3; TMEM lanes 32*warp .. +31) -------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per chunk).  Bias, ReLU and the dropout mask
+// (one Philox block per 4 consecutive columns) are applied in that layout; the chunk is then transposed through shared
+// memory (tbuf: 4 x 32 x 33 floats, conflict-free both ways) so that every global access of the rest — mask read, C read
+// for accumulation, store / red — is one row x 32 consecutive columns per warp instruction: 128 B coalesced.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, float* tbuf_all, const float* sbias, int m0, int n0,
+                                              int warp, int lane, bool have_work) {
+  float* tbuf = tbuf_all + warp * (32 * 33);
+  const int row_own = m0 + warp * 32 + lane;
+  const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+  const bool rd_aux = p.aux_mode != 0, rd_c = p.accumulate && p.k_splits == 1;
+  float* Cf = static_cast<float*>(p.C);
+  __nv_bfloat16* Ch = static_cast<__nv_bfloat16*>(p.C);
+  if (have_work) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= p.N) break;  // warp-uniform
+      const int col = nb + lane;
+      const bool col_ok = col < p.N;
+      const int rows_here = min(32, p.M - (m0 + warp * 32));  // warp-uniform; may be <= 0
+      uint32_t v[32];
+      const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (p.bias != nullptr) x += sbias[c * 32 + j];  // broadcast read
+        if (p.act == 1) x = fmaxf(x, 0.f);
+        o[j] = x;
+      }
+      if (p.drop_p > 0.f) {
+        // element index row * N + n; nb % 4 == 0, and N % 4 == 0 is required for dropout (checked by the host), so one
+        // Philox block covers the 4 consecutive columns j .. j+3
+        const unsigned long long base_idx = (unsigned long long)row_own * (unsigned long long)p.N + (unsigned long long)nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const unsigned long long idx = base_idx + j;
+          const uint4 r = philox4x32_g((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+          o[j] *= ((float)(r.x >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+          o[j + 1] *= ((float)(r.y >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+          o[j + 2] *= ((float)(r.z >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+          o[j + 3] *= ((float)(r.w >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+        }
+      }
+      __syncwarp();  // the previous chunk's transposed reads are done
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = o[j];
+      // the chunk's mask (or, without a mask, its C values to accumulate onto) in the coalesced layout (lane = column,
+      // one row per instruction); the lines were prefetched into L2 during the main loop
+      float pre[32];
+      if (rd_aux) {
+        if (p.aux_bf16) {
+          const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(p.aux) + (size_t)(m0 + warp * 32) * p.ld_aux + col;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? __bfloat162float(src[(size_t)rr * p.ld_aux]) : 0.f;
+        } else {
+          const float* src = static_cast<const float*>(p.aux) + (size_t)(m0 + warp * 32) * p.ld_aux + col;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? src[(size_t)rr * p.ld_aux] : 0.f;
+        }
+      } else if (rd_c) {
+        const float* src = Cf + (size_t)(m0 + warp * 32) * p.ldc + col;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? src[(size_t)rr * p.ldc] : 0.f;
+      }
+      __syncwarp();
+      if (p.c_bf16 && rd_aux) {  // bf16 C behind a mask: column layout (the mask was fetched in it), 2-byte stores
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < rows_here && col_ok) {
+            float x = tbuf[rr * 33 + lane];
+            x *= (p.aux_mode == 1 ? pre[rr] > 0.f : pre[rr] != 0.f) ? p.aux_scale : 0.f;
+            Ch[(size_t)(m0 + warp * 32 + rr) * p.ldc + col] = __float2bfloat16_rn(x);
+          }
+        }
+      } else if (p.c_bf16) {  // bf16 C (no accumulate / split-K: checked by the host): a lane stores two adjacent columns
+        const int sub = lane >> 4, cp = (lane & 15) * 2;
+        const bool pair_ok = nb + cp + 1 < p.N, one_ok = nb + cp < p.N;
+#pragma unroll 8
+        for (int r2 = 0; r2 < 16; ++r2) {
+          const int rr = 2 * r2 + sub;
+          if (rr < rows_here && one_ok) {
+            const float x0 = tbuf[rr * 33 + cp], x1 = tbuf[rr * 33 + cp + 1];
+            __nv_bfloat16* dst = Ch + (size_t)(m0 + warp * 32 + rr) * p.ldc + nb + cp;
+            if (pair_ok && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+              *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(x0, x1);
+            } else {
+              dst[0] = __float2bfloat16_rn(x0);
+              if (pair_ok) dst[1] = __float2bfloat16_rn(x1);
+            }
+          }
+        }
+      } else if (!rd_aux && !rd_c) {  // no global reads: stream the rows out
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < rows_here && col_ok) {
+            float* dst = Cf + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
+            const float x = tbuf[rr * 33 + lane];
+            if (p.k_splits > 1)
+              atomicAdd(dst, x);  // split-K: C was zeroed (or holds the value to accumulate onto) by the host wrapper
+            else
+              *dst = x;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < rows_here && col_ok) {
+            float* dst = Cf + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
+            float x = tbuf[rr * 33 + lane];
+            if (rd_aux) {
+              x *= (p.aux_mode == 1 ? pre[rr] > 0.f : pre[rr] != 0.f) ? p.aux_scale : 0.f;
+              if (rd_c) x += *dst;  // mask and accumulation together (not on the TDS path): C is read here
+            } else {
+              x += pre[rr];
+            }
+            if (p.k_splits > 1)
+              atomicAdd(dst, x);
+            else
+              *dst = x;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int kMode, bool kAMn, bool kBMn, int BN>
 __global__ void __launch_bounds__(kGemmThreads, (kMode == kF32x3 || BN > 160) ? 1 : 2)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
@@ -347,137 +486,248 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* tbuf = reinterpret_cast<float*>(smem_a) + warp * (32 * 33);  // all TMA writes / UMMA reads of the ring are complete
-    const int row_own = m0 + warp * 32 + lane;
-    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-    const bool rd_aux = p.aux_mode != 0, rd_c = p.accumulate && p.k_splits == 1;
-    float* Cf = static_cast<float*>(p.C);
-    __nv_bfloat16* Ch = static_cast<__nv_bfloat16*>(p.C);
-    if (num_kb > 0 || p.k_splits == 1) {
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int nb = n0 + c * 32;
-        if (nb >= p.N) break;  // warp-uniform
-        const int col = nb + lane;
-        const bool col_ok = col < p.N;
-        const int rows_here = min(32, p.M - (m0 + warp * 32));  // warp-uniform; may be <= 0
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float o[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (p.bias != nullptr) x += sbias[c * 32 + j];  // broadcast read
-          if (p.act == 1) x = fmaxf(x, 0.f);
-          o[j] = x;
-        }
-        if (p.drop_p > 0.f) {
-          // element index row * N + n; nb % 4 == 0, and N % 4 == 0 is required for dropout (checked by the host), so one
-          // Philox block covers the 4 consecutive columns j .. j+3
-          const unsigned long long base_idx = (unsigned long long)row_own * (unsigned long long)p.N + (unsigned long long)nb;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const unsigned long long idx = base_idx + j;
-            const uint4 r = philox4x32_g((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-            o[j] *= ((float)(r.x >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-            o[j + 1] *= ((float)(r.y >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-            o[j + 2] *= ((float)(r.z >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-            o[j + 3] *= ((float)(r.w >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-          }
-        }
-        __syncwarp();  // the previous chunk's transposed reads are done
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = o[j];
-        // the chunk's mask (or, without a mask, its C values to accumulate onto) in the coalesced layout (lane = column,
-        // one row per instruction); the lines were prefetched into L2 during the main loop
-        float pre[32];
-        if (rd_aux) {
-          if (p.aux_bf16) {
-            const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(p.aux) + (size_t)(m0 + warp * 32) * p.ld_aux + col;
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? __bfloat162float(src[(size_t)rr * p.ld_aux]) : 0.f;
+    epilogue_tile<BN>(p, tmem_base, reinterpret_cast<float*>(smem_a), sbias, m0, n0, warp, lane, num_kb > 0 || p.k_splits == 1);  // the ring is idle by now
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ================================================================================================
+// Persistent variant (the default): ONE CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so the
+// CTAs running together share their A rows in L2).  What it removes from the one-tile-per-CTA kernel above:
+//   * the per-tile prologue (barrier init, TMEM allocation, descriptor fetch, cold first loads): paid once per SM;
+//   * the exposed epilogue: TWO accumulators live in TMEM (2 x BN columns); while warps 0..3 drain accumulator i
+//     (tcgen05.ld -> bias / ReLU / dropout -> transposition -> coalesced stores), the MMA thread already accumulates the
+//     next tile into accumulator i ^ 1 and the TMA warp keeps the operand ring full across the tile boundary.
+// Roles: warps 0..3 epilogue, warp 4 TMA producer, warp 5 MMA issuer + TMEM owner, (F32X3 only) warps 6..9 operand split.
+// Barriers: full / empty (/ ready) per ring stage with a k-block counter that runs across tiles; acc_full / acc_empty per
+// accumulator with the tile counter's parity.
+// ================================================================================================
+__host__ __device__ constexpr int pstages_for(int mode, int bn) { return mode == kF32x3 ? 3 : (bn <= 160 ? 5 : 4); }
+__host__ __device__ constexpr int pthreads_for(int mode) { return mode == kF32x3 ? 320 : 192; }
+__host__ __device__ constexpr int acc_stride_for(int bn) { return bn <= 128 ? 128 : 256; }
+constexpr int kTbufBytes = 4 * 32 * 33 * 4;
+__host__ __device__ constexpr size_t psmem_for(int mode, int bn) {
+  return pstages_for(mode, bn) * stage_bytes(mode, bn) + kTbufBytes + 256 + 2 * 1024 + 1024;  // ring + transposition + barriers + 2 bias rows + slack
+}
+
+template <int kMode, bool kAMn, bool kBMn, int BN>
+__global__ void __launch_bounds__(pthreads_for(kMode), 1)
+gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p, int tiles_m,
+                            int tiles_n) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool kIsBf16 = kMode == kBf16, kSplit = kMode == kF32x3;
+  constexpr int ES = kIsBf16 ? 2 : 4;
+  constexpr int BKE = kRowBytes / ES;
+  constexpr int kMnAtom = kRowBytes / ES;
+  constexpr int kMnBoxBytes = BKE * kRowBytes;
+  constexpr int kMnStep = kIsBf16 ? 2048 : 1024;
+  constexpr int kMnSbo = kIsBf16 ? 1024 : 512;
+  constexpr int kMnLayout = kIsBf16 ? 2 : 1;
+  constexpr int kStages = pstages_for(kMode, BN), kTileBytesB = BN * kRowBytes;
+  constexpr int kOperandBytes = kTileBytes + kTileBytesB;
+  constexpr int kAccStride = acc_stride_for(BN), kTmemCols = 2 * kAccStride;
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + kStages * kTileBytes;
+  unsigned char* smem_lo = smem + kStages * kOperandBytes;  // F32X3: [stage][A lo | B lo]
+  unsigned char* tail = smem + kStages * stage_bytes(kMode, BN);
+  float* tbuf = reinterpret_cast<float*>(tail);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kTbufBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* ready = bars + 2 * kStages;
+  uint64_t* acc_full = bars + 3 * kStages;       // [2]
+  uint64_t* acc_empty = bars + 3 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+  float* sbias_all = reinterpret_cast<float*>(tail + kTbufBytes + 256);  // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_kb = (p.K + BKE - 1) / BKE;
+  const int kb_per = (total_kb + p.k_splits - 1) / p.k_splits;
+  const int tiles_mn = tiles_m * tiles_n, total_tiles = tiles_mn * p.k_splits;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&ready[s], 128);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // every role walks the same tile sequence with the same k-block counts, so the ring / accumulator phases agree
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kb_begin, int& num_kb) {
+    const int z = t / tiles_mn, r = t - z * tiles_mn;
+    m0 = (r / tiles_n) * BM;
+    n0 = (r % tiles_n) * BN;
+    kb_begin = z * kb_per;
+    num_kb = max(0, min(total_kb, kb_begin + kb_per) - kb_begin);
+  };
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb_begin, num_kb;
+        tile_coords(t, m0, n0, kb_begin, num_kb);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], kOperandBytes);
+          unsigned char* sa = smem_a + s * kTileBytes;
+          unsigned char* sb = smem_b + s * kTileBytesB;
+          const int k0 = (kb_begin + kb) * BKE;
+          if (!kAMn) {
+            tma_load_2d(&map_a, &full[s], sa, k0, m0);
           } else {
-            const float* src = static_cast<const float*>(p.aux) + (size_t)(m0 + warp * 32) * p.ld_aux + col;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? src[(size_t)rr * p.ld_aux] : 0.f;
+            for (int j = 0; j < BM / kMnAtom; ++j) tma_load_2d(&map_a, &full[s], sa + j * kMnBoxBytes, m0 + kMnAtom * j, k0);
           }
-        } else if (rd_c) {
-          const float* src = Cf + (size_t)(m0 + warp * 32) * p.ldc + col;
+          if (!kBMn) {
+            tma_load_2d(&map_b, &full[s], sb, k0, n0);
+          } else {
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) pre[rr] = (rr < rows_here && col_ok) ? src[(size_t)rr * p.ldc] : 0.f;
-        }
-        __syncwarp();
-        if (p.c_bf16 && rd_aux) {  // bf16 C behind a mask: column layout (the mask was fetched in it), 2-byte stores
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr < rows_here && col_ok) {
-              float x = tbuf[rr * 33 + lane];
-              x *= (p.aux_mode == 1 ? pre[rr] > 0.f : pre[rr] != 0.f) ? p.aux_scale : 0.f;
-              Ch[(size_t)(m0 + warp * 32 + rr) * p.ldc + col] = __float2bfloat16_rn(x);
-            }
-          }
-        } else if (p.c_bf16) {  // bf16 C (no accumulate / split-K: checked by the host): a lane stores two adjacent columns
-          const int sub = lane >> 4, cp = (lane & 15) * 2;
-          const bool pair_ok = nb + cp + 1 < p.N, one_ok = nb + cp < p.N;
-#pragma unroll 8
-          for (int r2 = 0; r2 < 16; ++r2) {
-            const int rr = 2 * r2 + sub;
-            if (rr < rows_here && one_ok) {
-              const float x0 = tbuf[rr * 33 + cp], x1 = tbuf[rr * 33 + cp + 1];
-              __nv_bfloat16* dst = Ch + (size_t)(m0 + warp * 32 + rr) * p.ldc + nb + cp;
-              if (pair_ok && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
-                *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(x0, x1);
-              } else {
-                dst[0] = __float2bfloat16_rn(x0);
-                if (pair_ok) dst[1] = __float2bfloat16_rn(x1);
-              }
-            }
-          }
-        } else if (!rd_aux && !rd_c) {  // no global reads: stream the rows out
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr < rows_here && col_ok) {
-              float* dst = Cf + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
-              const float x = tbuf[rr * 33 + lane];
-              if (p.k_splits > 1)
-                atomicAdd(dst, x);  // split-K: C was zeroed (or holds the value to accumulate onto) by the host wrapper
-              else
-                *dst = x;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr < rows_here && col_ok) {
-              float* dst = Cf + (size_t)(m0 + warp * 32 + rr) * p.ldc + col;
-              float x = tbuf[rr * 33 + lane];
-              if (rd_aux) {
-                x *= (p.aux_mode == 1 ? pre[rr] > 0.f : pre[rr] != 0.f) ? p.aux_scale : 0.f;
-                if (rd_c) x += *dst;  // mask and accumulation together (not on the TDS path): C is read here
-              } else {
-                x += pre[rr];
-              }
-              if (p.k_splits > 1)
-                atomicAdd(dst, x);
-              else
-                *dst = x;
-            }
+            for (int j = 0; j < BN / kMnAtom; ++j) tma_load_2d(&map_b, &full[s], sb + j * kMnBoxBytes, n0 + kMnAtom * j, k0);
           }
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kIsBf16, BM, BN, kAMn, kBMn);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        int m0, n0, kb_begin, num_kb;
+        tile_coords(t, m0, n0, kb_begin, num_kb);
+        const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(&acc_empty[acc], aph ^ 1);  // the epilogue has drained this accumulator (first use: passes)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(kSplit ? &ready[s] : &full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem_a + s * kTileBytes);
+          const uint32_t sb = smem_u32(smem_b + s * kTileBytesB);
+          const uint32_t la = smem_u32(smem_lo + s * kOperandBytes), lb = la + kTileBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            auto adesc = [&](uint32_t base) { return kAMn ? make_smem_desc(base + k * kMnStep, kMnBoxBytes, kMnSbo, kMnLayout) : make_smem_desc(base + k * 32, 16, 1024, 2); };
+            auto bdesc = [&](uint32_t base) { return kBMn ? make_smem_desc(base + k * kMnStep, kMnBoxBytes, kMnSbo, kMnLayout) : make_smem_desc(base + k * 32, 16, 1024, 2); };
+            if (kSplit) {
+              umma<false>(tmem_acc, adesc(la), bdesc(sb), idesc, (kb | k) != 0);  // Al * Bh
+              umma<false>(tmem_acc, adesc(sa), bdesc(lb), idesc, 1);              // Ah * Bl
+              umma<false>(tmem_acc, adesc(sa), bdesc(sb), idesc, 1);              // Ah * Bh
+            } else {
+              umma<kIsBf16>(tmem_acc, adesc(sa), bdesc(sb), idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[acc]);  // all MMAs of this tile done -> the epilogue may read the accumulator
+      }
+    }
+  } else if (warp < 4) {
+    // ===== epilogue =====
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      int m0, n0, kb_begin, num_kb;
+      tile_coords(t, m0, n0, kb_begin, num_kb);
+      const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+      float* sbias = sbias_all + acc * BN;
+      if (p.bias != nullptr)
+        for (int j = threadIdx.x; j < BN; j += 128) sbias[j] = n0 + j < p.N ? __ldg(p.bias + n0 + j) : 0.f;
+      // pull the tile's mask / C lines into L2 while its main loop runs
+      if (p.aux_mode != 0 || (p.accumulate && p.k_splits == 1)) {
+        const int lines = (BN * 4 + 127) / 128;
+        for (int i = threadIdx.x; i < BM * lines; i += 128) {
+          const int r = m0 + i / lines, cc = n0 + (i % lines) * 32;
+          if (r < p.M && cc < p.N) {
+            if (p.aux_mode != 0) {
+              if (p.aux_bf16) {
+                if (((i % lines) & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const __nv_bfloat16*>(p.aux) + (size_t)r * p.ld_aux + cc));
+              } else {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const float*>(p.aux) + (size_t)r * p.ld_aux + cc));
+              }
+            }
+            if (p.accumulate && p.k_splits == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const float*>(p.C) + (size_t)r * p.ldc + cc));
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias row staged; every warp is past the previous tile's reads of the other row
+      mbar_wait(&acc_full[acc], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      epilogue_tile<BN>(p, tmem_base + acc * kAccStride, tbuf, sbias, m0, n0, warp, lane, num_kb > 0 || p.k_splits == 1);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&acc_empty[acc]);  // this thread's TMEM reads of the accumulator are complete
+    }
+  } else if (kSplit) {
+    // ===== F32X3 operand split (warps 6..9): x = hi + lo, hi = tf32(x) written back in place, lo = tf32(x - hi) in the
+    // second tile of the stage; round-to-nearest by integer arithmetic (add half an ulp of the 13 dropped bits, clear them):
+    // full-rate ALU ops instead of quarter-rate cvt.rna
+    const int tid = threadIdx.x - 192;
+    constexpr int kVecA = kTileBytes / 16 / 128, kVecB = kTileBytesB / 16 / 128;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int m0, n0, kb_begin, num_kb;
+      tile_coords(t, m0, n0, kb_begin, num_kb);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        uint4* ta = reinterpret_cast<uint4*>(smem_a + s * kTileBytes);
+        uint4* tb = reinterpret_cast<uint4*>(smem_b + s * kTileBytesB);
+        uint4* la = reinterpret_cast<uint4*>(smem_lo + s * kOperandBytes);
+        uint4* lb = reinterpret_cast<uint4*>(smem_lo + s * kOperandBytes + kTileBytes);
+        auto rn = [](uint32_t x) { return (x + 0x1000u) & 0xffffe000u; };
+        auto split = [&](uint4* hi, uint4* lo, int i) {
+          const uint4 v = hi[i];
+          uint4 h, l;
+          h.x = rn(v.x);
+          h.y = rn(v.y);
+          h.z = rn(v.z);
+          h.w = rn(v.w);
+          l.x = rn(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)));
+          l.y = rn(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)));
+          l.z = rn(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)));
+          l.w = rn(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
+          hi[i] = h;
+          lo[i] = l;
+        };
+#pragma unroll
+        for (int i = 0; i < kVecA; ++i) split(ta, la, i * 128 + tid);
+#pragma unroll
+        for (int i = 0; i < kVecB; ++i) split(tb, lb, i * 128 + tid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&ready[s]);
+      }
+    }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 5) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -541,8 +791,50 @@ int launch_bn(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb,
   W2L_LAUNCH_CHECK(kernel_name(kMode));
   return W2L_OK;
 }
+thread_local int g_variant = 1;  // 1: persistent kernel (default), 0: one tile per CTA (w2l_gemm_set_variant; tests compare the two)
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+template <int kMode, bool kAMn, bool kBMn, int BN>
+int launch_persistent_bn(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  constexpr size_t smem = psmem_for(kMode, BN);
+  static_assert(smem <= 227 * 1024, "gemm (persistent): shared-memory budget");
+  static bool configured = false;
+  if (!configured) {
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<kMode, kAMn, kBMn, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int total = tiles_m * tiles_n * p.k_splits;
+  profile_kind(1);
+  profile_start(stream);
+  gemm_umma_persistent_kernel<kMode, kAMn, kBMn, BN><<<std::min(total, sm_count()), pthreads_for(kMode), smem, stream>>>(ma, mb, p, tiles_m, tiles_n);
+  profile_stop(stream);
+  W2L_LAUNCH_CHECK(kernel_name(kMode));
+  return W2L_OK;
+}
 template <int kMode, bool kAMn, bool kBMn>
 int launch_mode(cudaStream_t stream, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
+  if (g_variant == 1) {
+    if constexpr (kMode == kF32x3) {
+      return launch_persistent_bn<kMode, kAMn, kBMn, 128>(stream, ma, mb, p);
+    } else if constexpr (kMode == kBf16 && kBMn) {
+      return bn <= 128 ? launch_persistent_bn<kMode, kAMn, kBMn, 128>(stream, ma, mb, p) : launch_persistent_bn<kMode, kAMn, kBMn, 256>(stream, ma, mb, p);
+    } else {
+      switch (bn) {
+        case 128: return launch_persistent_bn<kMode, kAMn, kBMn, 128>(stream, ma, mb, p);
+        case 160: return launch_persistent_bn<kMode, kAMn, kBMn, 160>(stream, ma, mb, p);
+        case 224: return launch_persistent_bn<kMode, kAMn, kBMn, 224>(stream, ma, mb, p);
+        default: return launch_persistent_bn<kMode, kAMn, kBMn, 256>(stream, ma, mb, p);
+      }
+    }
+  }
   if constexpr (kMode == kF32x3) {
     return launch_bn<kMode, kAMn, kBMn, 128>(stream, ma, mb, p);
   } else if constexpr (kMode == kBf16 && kBMn) {  // 64-wide MN-major boxes: BN a multiple of 64
@@ -579,7 +871,7 @@ int choose_bn(int mode, bool b_mn, int M, int N, int total_kb, bool plain, int* 
     if (mode == kBf16 && b_mn) return bn == 128 || bn == 256;
     return true;
   };
-  auto slots_of = [&](int bn) { return (mode == kF32x3 || bn > 160) ? 1 : 2; };
+  auto slots_of = [&](int bn) { return (g_variant == 1 || mode == kF32x3 || bn > 160) ? 1 : 2; };
   if (g_force_bn && allowed(g_force_bn)) {
     const int tiles = ((N + g_force_bn - 1) / g_force_bn) * ((M + BM - 1) / BM);
     *splits_out = splits_for(tiles, total_kb, slots_of(g_force_bn), plain);
@@ -676,6 +968,12 @@ __global__ void __launch_bounds__(256) cast_bf16_rows_kernel(long long rows, int
 }  // namespace w2l
 
 using namespace w2l;
+
+extern "C" int w2l_gemm_set_variant(int variant) {
+  if (variant != 0 && variant != 1) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: variant must be 0 (one tile per CTA) or 1 (persistent)");
+  g_variant = variant;
+  return W2L_OK;
+}
 
 extern "C" int w2l_gemm_set_tile(int bn) {
   if (bn != 0 && bn != 128 && bn != 160 && bn != 224 && bn != 256) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: tile width must be 0 (auto), 128, 160, 224 or 256");

@@ -947,7 +947,11 @@ Variable Linear::forwardWith(const Variable& in, const Variable& weight, const V
   auto isPadded = [&](long long c) { return c == nIn || (c > nIn && (c == padUp(nIn, 4) || c == padUp(nIn, 8))); };
   long long T, B;
   int inCols;
-  if (isPadded(in.dims(0))) {  // flattened [K, T, B]
+  if (in.dims(0) == 1 && isPadded(in.dims(1))) {  // [1, C(+pad), T, B]: the large-channel convolutions' activations
+    inCols = (int)in.dims(1);
+    T = in.dims(2);
+    B = in.dims(3);
+  } else if (isPadded(in.dims(0))) {  // flattened [K, T, B]
     inCols = (int)in.dims(0);
     T = in.dims(1);
     B = in.dims(2) * in.dims(3);
