@@ -440,6 +440,8 @@ class OverlappedArenaReducer {
   void arm();       // call after zeroGrad, before loss.backward()
   void finalize();  // call after backward
   int buckets() const { return (int)bucket_.size(); }
+  // device double that receives sum(g^2) of every bucket right after its reduction (on the communication stream)
+  void setNormAccumulator(double* acc) { norm_acc_ = acc; }
   void onGradReady(const void* id);  // called by Variable::addGrad for arena-bound parameters
   void expectContribution(const void* id);  // called by Variable::backward once per graph node that consumes the parameter
 
@@ -458,6 +460,7 @@ class OverlappedArenaReducer {
   void* comm_stream_ = nullptr;
   void* done_ = nullptr;
   bool armed_ = false;
+  double* norm_acc_ = nullptr;
 };
 
 class Reducer {

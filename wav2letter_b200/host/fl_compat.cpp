@@ -1254,7 +1254,12 @@ OverlappedArenaReducer::OverlappedArenaReducer(const std::vector<Variable>& para
     cur.count = (off + g.bytes()) / 4 - cur.offset;
     cur.params += 1;
     owner_.emplace_back(p.id(), (int)bucket_.size());
-    if (cur.count * 4 >= bucketBytes) {
+    // Backward fills the arena back to front, so the FIRST buckets complete last and their all-reduce is the exposed
+    // tail of the step: they are kept small (bucketBytes / 8, / 4, / 2, then full size) — the big buckets of the later
+    // layers are reduced while backward is still running
+    const size_t k = bucket_.size();
+    const size_t limit = k == 0 ? bucketBytes / 8 : (k == 1 ? bucketBytes / 4 : (k == 2 ? bucketBytes / 2 : bucketBytes));
+    if (cur.count * 4 >= limit) {
       bucket_.push_back(cur);
       open = false;
     }
@@ -1303,6 +1308,8 @@ void OverlappedArenaReducer::launch(Bucket& b) {
     throw std::runtime_error("OverlappedArenaReducer: event record/wait failed");
   float* ptr = grads_.f32() + b.offset;
   ncclCheck(ncclAllReduce(ptr, ptr, b.count, ncclFloat32, ncclSum, g_comm, comm), "ncclAllReduce (bucket)");
+  // the squared norm of the reduced bucket (clipGradNorm's input) right behind its all-reduce, off the critical path
+  if (norm_acc_) check(w2l_sq_norm_accumulate(comm, (long long)b.count, ptr, norm_acc_));
 }
 void OverlappedArenaReducer::expectContribution(const void* id) {
   if (!armed_) return;
@@ -1348,7 +1355,13 @@ void initDistributed(int worldRank, int worldSize, const void* id128) {
   if (g_comm) return;
   ncclUniqueId id;
   std::memcpy(&id, id128, 128);
-  ncclCheck(ncclCommInitRank(&g_comm, worldSize, id, worldRank), "ncclCommInitRank");
+  // the all-reduce runs UNDER the backward pass: cap its CTAs so it does not take SMs from the GEMMs it overlaps
+  // (W2L_NCCL_MAX_CTAS overrides; NVLink5 / NVSwitch needs few CTAs to saturate)
+  ncclConfig_t config = NCCL_CONFIG_INITIALIZER;
+  int maxCtas = 8;
+  if (const char* e = std::getenv("W2L_NCCL_MAX_CTAS")) maxCtas = std::atoi(e);
+  if (maxCtas > 0) config.maxCTAs = maxCtas;
+  ncclCheck(ncclCommInitRankConfig(&g_comm, worldSize, id, worldRank, &config), "ncclCommInitRankConfig");
   g_rank = worldRank;
   g_world = worldSize;
 }

@@ -231,7 +231,11 @@ W2L_API int w2l_trainer_step(void* h, void* stream, int B, int T, const float* f
     }
     // reducer: Train.cpp:1721-1735 adds every gradient after backward; here the network's gradient arena is reduced in
     // buckets WHILE backward runs (the callback pattern of cpc/Train.cpp:972-976), on a separate stream
-    if (fl::isDistributedInit() && !t->reducer) t->reducer = std::make_unique<fl::OverlappedArenaReducer>(t->net->params(), t->netArena.grads);
+    if (fl::isDistributedInit() && !t->reducer) {
+      t->reducer = std::make_unique<fl::OverlappedArenaReducer>(t->net->params(), t->netArena.grads);
+      t->reducer->setNormAccumulator(t->sqnorm.f64());  // per-bucket sum(g^2) behind each all-reduce, off the critical path
+    }
+    t->sqnorm.zero();  // before any bucket can be launched
     if (t->reducer) t->reducer->arm();
     loss.backward();
     if (t->reducer) t->reducer->finalize();
@@ -242,8 +246,8 @@ W2L_API int w2l_trainer_step(void* h, void* stream, int B, int T, const float* f
     // one-CTA kernel turns "loss or norm not finite" into a flag, and both SGD kernels return early when it is set.
     // w2l_trainer_status reads the count of skipped steps whenever the caller wants it (no sync inside the step).
     const float gscale = 1.0f / total_batch;
-    t->sqnorm.zero();
-    w2l::check(w2l_sq_norm_accumulate(stream, t->netArena.elements, t->netArena.grads.f32(), t->sqnorm.f64()));
+    if (!t->reducer)  // (with a reducer the network's norm was accumulated bucket by bucket on the communication stream)
+      w2l::check(w2l_sq_norm_accumulate(stream, t->netArena.elements, t->netArena.grads.f32(), t->sqnorm.f64()));
     if (t->critArena.elements)
       w2l::check(w2l_sq_norm_accumulate(stream, t->critArena.elements, t->critArena.grads.f32(), t->sqnorm.f64()));
     w2l::check(w2l_finite_guard(stream, B, loss.array().f32(), t->sqnorm.f64(), t->guard.i32()));
