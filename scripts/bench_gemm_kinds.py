@@ -42,6 +42,23 @@ def main():
                 us = time_one(kind, M, N, K, a_mn, b_mn)
                 rec[kind + "_us"] = round(us, 2)
                 rec[kind + "_tflops"] = round(2.0 * M * N * K / us / 1e6, 1)
+            # F32X3 experiment: rely on the tensor core ignoring the 13 low mantissa bits of the hi operand
+            w.capi.gemm_set_variant(3)
+            rec["f32x3_trust_us"] = round(time_one("f32x3", M, N, K, a_mn, b_mn), 2)
+            A = torch.randn((K, M) if a_mn else (M, K), device="cuda")
+            Bm = torch.randn((K, N) if b_mn else (N, K), device="cuda")
+            C3 = w.capi.gemm(A, Bm, "f32x3", a_mn, b_mn)
+            w.capi.gemm_set_variant(1)
+            C1 = w.capi.gemm(A, Bm, "f32x3", a_mn, b_mn)
+            A64, B64 = (A.t() if a_mn else A).double(), (Bm.t() if b_mn else Bm).double()
+            ref = A64 @ B64.t()
+            bound = A64.abs() @ B64.abs().t()
+            rec["f32x3_err_over_absprod"] = float(((C1.double() - ref).abs() / bound).max())
+            rec["f32x3_trust_err_over_absprod"] = float(((C3.double() - ref).abs() / bound).max())
+            w.capi.gemm_set_variant(0)
+            rec["tf32_per_tile_us"] = round(time_one("tf32", M, N, K, a_mn, b_mn), 2)
+            rec["bf16_per_tile_us"] = round(time_one("bf16", M, N, K, a_mn, b_mn), 2)
+            w.capi.gemm_set_variant(1)
             out.append(rec)
             print(json.dumps(rec), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

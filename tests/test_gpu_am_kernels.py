@@ -176,14 +176,15 @@ def test_colsum_sqnorm_sgd():
     assert rel(v, ve) < 1e-5 and rel(p, p0 - lr * ve) < 1e-5
 
 
-@pytest.mark.parametrize("path", ["tf32", "x3", "simt"])
+@pytest.mark.parametrize("path", ["tf32", "mma", "x3", "simt"])
 @pytest.mark.parametrize("B,T,Cin,Cout,K,stride,pl,pr", [
     (2, 40, 23, 23, 11, 1, 10, 0), (2, 40, 15, 15, 9, 1, 7, 1), (2, 46, 19, 23, 12, 2, 9, 1), (2, 40, 23, 27, 11, 1, 10, 0),
     (2, 52, 1, 15, 10, 2, 5, 3), (2, 36, 27, 27, 11, 1, 10, 0), (1, 24, 18, 18, 21, 1, 10, 10),
 ])
 def test_conv_time_streaming_shapes_all_paths(B, T, Cin, Cout, K, stride, pl, pr, path):
     """the asymmetric paddings of the streaming TDS arch (PD l r + C2, TDS with rightPadding) on the three arithmetic paths:
-    TF32 tensor-core kernels, the same kernels in error-compensated 3xTF32 (W2L_PRECISION_F32), and the fp32 SIMT fallback"""
+    the tcgen05 / TMA kernel (forward, stride-1 data gradient), the mma.sync TF32 kernels, the same in error-compensated
+    3xTF32 (W2L_PRECISION_F32), and the fp32 SIMT fallback"""
     from wav2letter_b200 import capi
 
     W = 80
@@ -198,14 +199,14 @@ def test_conv_time_streaming_shapes_all_paths(B, T, Cin, Cout, K, stride, pl, pr
     pre.backward(dy.double())
     try:
         capi.set_precision("f32" if path == "x3" else "tf32")
-        capi._check(capi.lib.w2l_conv_set_path(1 if path == "simt" else 0))
+        capi._check(capi.lib.w2l_conv_set_path({"simt": 1, "mma": 2}.get(path, 0)))  # tf32: auto = the tcgen05 kernel
         y = capi.conv_time_fwd(x, wt, bias, Tout, stride, pl)
         dx = capi.conv_time_dgrad(dy, wt, T, stride, pl)
         dwt, dbias = capi.conv_time_wgrad(x, dy, K, stride, pl)
     finally:
         capi.set_precision("tf32")
         capi._check(capi.lib.w2l_conv_set_path(0))
-    tol = 3e-3 if path == "tf32" else 2e-5
+    tol = 3e-3 if path in ("tf32", "mma") else 2e-5
     assert rel(y, pre) < tol, (path, rel(y, pre))
     assert rel(dx, x64.grad) < tol, (path, rel(dx, x64.grad))
     assert rel(dwt, w64.grad) < tol, (path, rel(dwt, w64.grad))

@@ -21,10 +21,19 @@
 namespace w2l {
 // tensor-core path (conv_mma.cu)
 bool conv_mma_supported(int W, int Cin, int Cout, int K, int stride);
+bool conv_umma_supported(int W, int Cin, int Cout, int K, int stride);
+size_t conv_umma_arranged_floats(int Cin, int Cout, int K);
+int conv_umma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left, const float* x,
+                  const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y, int act, float drop_p,
+                  unsigned long long seed, float* arranged);
 // the tensor-core path (TF32 products; under W2L_PRECISION_F32 the same kernels run error-compensated 3xTF32); shapes it
 // does not cover fall back to the fp32 SIMT kernels below
-static thread_local int g_conv_path = 0;  // w2l_conv_set_path: 0 auto, 1 force the fp32 SIMT kernels (tests)
-static bool use_conv_mma(int W, int Cin, int Cout, int K, int stride) { return g_conv_path == 0 && conv_mma_supported(W, Cin, Cout, K, stride); }
+static thread_local int g_conv_path = 0;  // w2l_conv_set_path: 0 auto, 1 force the fp32 SIMT kernels, 2 mma.sync kernels (no tcgen05) — tests
+static bool use_conv_mma(int W, int Cin, int Cout, int K, int stride) { return g_conv_path != 1 && conv_mma_supported(W, Cin, Cout, K, stride); }
+// tcgen05 / TMA forward and stride-1 data gradient (conv_umma.cu); W2L_PRECISION_F32 keeps the 3xTF32 mma.sync kernels
+static bool use_conv_umma(int W, int Cin, int Cout, int K, int stride) {
+  return g_conv_path == 0 && current_precision() != W2L_PRECISION_F32 && conv_umma_supported(W, Cin, Cout, K, stride);
+}
 size_t conv_mma_arranged_floats(int Cin, int Cout, int K);
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
                  const float* x, const float* wt, int wt_cin, int wt_cout, int flip, const float* bias, const float* add, float* y,
@@ -922,12 +931,13 @@ static size_t conv_ws_partial_bytes(int B, int Tout, int Cin, int Cout, int K) {
   return align_up(std::max(simt, std::max(mma, (size_t)B * (size_t)std::max(Tout, 16))) * per, 256);
 }
 extern "C" int w2l_conv_set_path(int path) {
-  if (path != 0 && path != 1) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_set_path: 0 (auto) or 1 (fp32 SIMT kernels)");
+  if (path < 0 || path > 2) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_set_path: 0 (auto), 1 (fp32 SIMT kernels) or 2 (mma.sync kernels)");
   g_conv_path = path;
   return W2L_OK;
 }
 extern "C" size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K) {
-  const size_t arranged = std::max((size_t)std::max(Cin, Cout) * K * co_pad(std::max(Cin, Cout)), conv_mma_arranged_floats(Cin, Cout, K)) * sizeof(float);
+  const size_t arranged = std::max(std::max((size_t)std::max(Cin, Cout) * K * co_pad(std::max(Cin, Cout)), conv_mma_arranged_floats(Cin, Cout, K)),
+                                   conv_umma_arranged_floats(Cin, Cout, K)) * sizeof(float);
   return conv_ws_partial_bytes(B, Tout, Cin, Cout, K) + align_up(arranged, 256);
 }
 
@@ -961,6 +971,8 @@ extern "C" int w2l_conv_time_fwd(void* stream_, int B, int T, int Tout, int W, i
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_fwd: workspace too small");
   const int CO = co_pad(Cout);
   float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
+  if (use_conv_umma(W, Cin, Cout, K, stride))
+    return conv_umma_fwd(stream, B, T, Tout, W, Cin, Cout, K, stride, pad_left, x, wt, Cin, Cout, 0, bias, add, y, act, dropout_p, seed, arranged);
   if (use_conv_mma(W, Cin, Cout, K, stride))
     return conv_mma_fwd(stream, B, T, Tout, W, Cin, Cout, K, stride, pad_left, x, wt, Cin, Cout, 0, bias, add, y, act, dropout_p, seed,
                         arranged, K, 1, 0, 1, 0, Tout);
@@ -986,6 +998,11 @@ extern "C" int w2l_conv_time_dgrad(void* stream_, int B, int T, int Tout, int W,
   if (int rc = conv_check(B, T, Tout, W, Cin, Cout, K, stride)) return rc;
   if (!dy || !wt || !dx || !ws) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_time_dgrad: null pointer");
   if (ws_bytes < w2l_conv_time_workspace_size(B, Tout, Cin, Cout, K)) return fail(W2L_ERR_WORKSPACE, "conv_time_dgrad: workspace too small");
+  if (stride == 1 && use_conv_umma(W, Cout, Cin, K, 1)) {
+    // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped — tcgen05 path
+    float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));
+    return conv_umma_fwd(stream, B, Tout, T, W, Cout, Cin, K, 1, K - 1 - pad_left, dy, wt, Cin, Cout, 1, nullptr, add, dx, 0, 0.f, 0ull, arranged);
+  }
   if (stride == 1 && use_conv_mma(W, Cout, Cin, K, 1)) {
     // dx = conv(dy, flipped weights) with pad_left' = K-1-pad_left, channel roles swapped — on the tensor-core path
     float* arranged = reinterpret_cast<float*>(static_cast<char*>(ws) + conv_ws_partial_bytes(B, Tout, Cin, Cout, K));

@@ -45,9 +45,11 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace w2l {
 namespace {
+using namespace umma;
 
 constexpr int BM = 128;                     // tile rows
 constexpr int kRowBytes = 128;              // one swizzle row of k: 32 fp32 or 64 bf16
@@ -66,49 +68,6 @@ __host__ __device__ constexpr int tmem_cols_for(int bn) { return bn <= 128 ? 128
 __host__ __device__ constexpr size_t stage_bytes(int mode, int bn) { return (size_t)(mode == kF32x3 ? 2 : 1) * (kTileBytes + bn * kRowBytes); }
 __host__ __device__ constexpr size_t smem_for(int mode, int bn) { return stages_for(mode, bn) * stage_bytes(mode, bn) + 128 + 1024 + 1024; }  // ring + barriers + bias row + alignment slack
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem_dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// layout_type: 2 = SWIZZLE_128B (K-major operands; MN-major 16-bit operands), 1 = SWIZZLE_128B_BASE32B (the only
-// layout the tensor core accepts for MN-major 32-bit operands: Swizzle<2,5,2>, atoms of 4 k-rows x 128 B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
 // instruction descriptor: D = f32; A = B = tf32 (format 2, kind::tf32) or bf16 (format 1, kind::f16); M x N; majors
 __host__ __device__ constexpr uint32_t make_idesc(bool bf16, int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -136,9 +95,6 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t 
         : "memory");
   }
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -156,6 +112,7 @@ struct GemmParams {
   unsigned long long seed;
   int k_splits;  // > 1: blockIdx.z owns a slice of the k blocks and the epilogue adds atomically (few tiles, long K: wgrad)
   int c_bf16, aux_bf16;
+  int trust_trunc;  // F32X3 experiment: rely on the tensor core ignoring the 13 low mantissa bits (hi is not written back)
 };
 
 __device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
@@ -183,7 +140,13 @@ __device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, float* tbuf_all, const float* sbias, int m0, int n0,
                                               int warp, int lane, bool have_work) {
-  float* tbuf = tbuf_all + warp * (32 * 33);
+  float* tbuf = tbuf_all + warp * (32 * 36);
+  const uint32_t tb_sa = smem_u32(tbuf), sbias_sa = smem_u32(sbias);
+  // vector fast path (interior chunks of 16-byte aligned rows): the 32 x 32 chunk goes through shared memory as float4 and
+  // every global access is 128 bits — 8 LDS.128 + 8 STG.128 per chunk instead of 32 + 32 scalar ones with per-row address
+  // arithmetic and bounds checks (the scalar epilogue was the persistent kernel's bottleneck: 1800 instructions per chunk)
+  const bool vec_tile = p.k_splits == 1 && (p.ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                        (p.aux_mode == 0 || ((p.ld_aux % 4) == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0));
   const int row_own = m0 + warp * 32 + lane;
   const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
   const bool rd_aux = p.aux_mode != 0, rd_c = p.accumulate && p.k_splits == 1;
@@ -210,12 +173,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       float o[32];
+      if (p.bias != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (p.bias != nullptr) x += sbias[c * 32 + j];  // broadcast read
-        if (p.act == 1) x = fmaxf(x, 0.f);
-        o[j] = x;
+        for (int j = 0; j < 32; j += 4) {
+          float4 b4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias_sa + (uint32_t)(c * 32 + j) * 4));
+          o[j] = __uint_as_float(v[j]) + b4.x;
+          o[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+          o[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+          o[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
       }
       if (p.drop_p > 0.f) {
         // element index row * N + n; nb % 4 == 0, and N % 4 == 0 is required for dropout (checked by the host), so one
@@ -232,6 +206,60 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         }
       }
       __syncwarp();  // the previous chunk's transposed reads are done
+      if (vec_tile && rows_here >= 32 && nb + 32 <= p.N) {  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tb_sa + (uint32_t)(lane * 36 + 4 * j) * 4), "f"(o[4 * j]), "f"(o[4 * j + 1]),
+                       "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+        const int rsub = lane >> 3, c4 = lane & 7;  // this lane: rows rsub, rsub + 4, ..., columns 4 c4 .. 4 c4 + 3 of the chunk
+        const size_t row0 = (size_t)(m0 + warp * 32 + rsub);
+        const int colv = nb + 4 * c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(tb_sa + (uint32_t)((rsub + 4 * i) * 36 + 4 * c4) * 4));
+          const size_t row = row0 + 4 * i;
+          if (rd_aux) {
+            float4 m;
+            if (p.aux_bf16) {
+              const uint2 mb = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.aux) + row * p.ld_aux + colv);
+              const float2 m01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mb.x)), m23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mb.y));
+              m = make_float4(m01.x, m01.y, m23.x, m23.y);
+            } else {
+              m = *reinterpret_cast<const float4*>(static_cast<const float*>(p.aux) + row * p.ld_aux + colv);
+            }
+            const float sc = p.aux_scale;
+            if (p.aux_mode == 1) {
+              x.x *= m.x > 0.f ? sc : 0.f;
+              x.y *= m.y > 0.f ? sc : 0.f;
+              x.z *= m.z > 0.f ? sc : 0.f;
+              x.w *= m.w > 0.f ? sc : 0.f;
+            } else {
+              x.x *= m.x != 0.f ? sc : 0.f;
+              x.y *= m.y != 0.f ? sc : 0.f;
+              x.z *= m.z != 0.f ? sc : 0.f;
+              x.w *= m.w != 0.f ? sc : 0.f;
+            }
+          }
+          if (p.c_bf16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+            *reinterpret_cast<uint2*>(Ch + row * p.ldc + colv) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(Cf + row * p.ldc + colv);
+            if (rd_c) {
+              const float4 cv = *dst;
+              x.x += cv.x;
+              x.y += cv.y;
+              x.z += cv.z;
+              x.w += cv.w;
+            }
+            *dst = x;
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = o[j];
       // the chunk's mask (or, without a mask, its C values to accumulate onto) in the coalesced layout (lane = column,
@@ -510,7 +538,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 __host__ __device__ constexpr int pstages_for(int mode, int bn) { return mode == kF32x3 ? 3 : (bn <= 160 ? 5 : 4); }
 __host__ __device__ constexpr int pthreads_for(int mode) { return mode == kF32x3 ? 320 : 192; }
 __host__ __device__ constexpr int acc_stride_for(int bn) { return bn <= 128 ? 128 : 256; }
-constexpr int kTbufBytes = 4 * 32 * 33 * 4;
+constexpr int kTbufBytes = 4 * 32 * 36 * 4;  // per warp [32][36] floats: 128-bit conflict-free both ways (the scalar path uses a 33 pitch)
 __host__ __device__ constexpr size_t psmem_for(int mode, int bn) {
   return pstages_for(mode, bn) * stage_bytes(mode, bn) + kTbufBytes + 256 + 2 * 1024 + 1024;  // ring + transposition + barriers + 2 bias rows + slack
 }
@@ -707,6 +735,14 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         auto split = [&](uint4* hi, uint4* lo, int i) {
           const uint4 v = hi[i];
           uint4 h, l;
+          if (p.trust_trunc) {  // hi = the raw value as the hardware truncates it; only lo is written
+            l.x = rn(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u)));
+            l.y = rn(__float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u)));
+            l.z = rn(__float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u)));
+            l.w = rn(__float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u)));
+            lo[i] = l;
+            return;
+          }
           h.x = rn(v.x);
           h.y = rn(v.y);
           h.z = rn(v.z);
@@ -791,6 +827,7 @@ int launch_bn(cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb,
   W2L_LAUNCH_CHECK(kernel_name(kMode));
   return W2L_OK;
 }
+thread_local int g_trust_trunc = 0;
 thread_local int g_variant = 1;  // 1: persistent kernel (default), 0: one tile per CTA (w2l_gemm_set_variant; tests compare the two)
 int sm_count() {
   static int sms = 0;
@@ -934,7 +971,7 @@ int gemm_impl(void* stream_, int mode, int a_mn_major, int b_mn_major, int M, in
     rc = make_map(&mb, mode, B, K, N, ldb, bke, true);
   if (rc) return rc;
   if (splits > 1 && !accumulate) W2L_CUDA_CHECK(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, stream));
-  GemmParams p{M, N, K, ldc, act, C, bias, accumulate, aux_mode, ld_aux, aux, aux_scale, dropout_p, seed, splits, c_bf16, aux_bf16};
+  GemmParams p{M, N, K, ldc, act, C, bias, accumulate, aux_mode, ld_aux, aux, aux_scale, dropout_p, seed, splits, c_bf16, aux_bf16, g_trust_trunc};
   if (mode == kBf16) return launch<kBf16>(stream, a_mn_major, b_mn_major, BN, ma, mb, p);
   if (mode == kF32x3) return launch<kF32x3>(stream, a_mn_major, b_mn_major, BN, ma, mb, p);
   return launch<kTf32>(stream, a_mn_major, b_mn_major, BN, ma, mb, p);
@@ -970,8 +1007,9 @@ __global__ void __launch_bounds__(256) cast_bf16_rows_kernel(long long rows, int
 using namespace w2l;
 
 extern "C" int w2l_gemm_set_variant(int variant) {
-  if (variant != 0 && variant != 1) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: variant must be 0 (one tile per CTA) or 1 (persistent)");
-  g_variant = variant;
+  if (variant < 0 || variant > 3) return fail(W2L_ERR_INVALID_ARGUMENT, "gemm: variant must be 0 (one tile per CTA) or 1 (persistent); +2: F32X3 trusts hardware truncation");
+  g_variant = variant & 1;
+  g_trust_trunc = (variant >> 1) & 1;
   return W2L_OK;
 }
 

@@ -104,7 +104,7 @@ class Trainer:
 
     def forward(self, features: torch.Tensor) -> torch.Tensor:
         B, _, F, T = features.shape
-        cap = B * T * self.n_label
+        cap = B * (2 * T + 64) * self.n_label  # SAME-padded even kernels grow the frame count by one each
         out = torch.empty(cap, dtype=torch.float32, device=features.device)
         tout = ctypes.c_int(0)
         _check(lib.w2l_trainer_forward(self.h, _stream(), B, T, _ptr(features), _ptr(out), cap, ctypes.byref(tout)))
