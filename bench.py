@@ -15,7 +15,7 @@ the gradient all-reduce is the only collective — SURVEY.md §8e):
                      B=8 x T=1000 x 80 per GPU, 10 000 word pieces (train_am_500ms_future_context.cfg: batchsize 8).
   asg                configs[4] point: fused ASG forward+backward at T=1500, N=30, B=64 per GPU (no train step).
   asg_sweep          configs[4]: T in {100,500,1500,4000} x B in {1,16,64,256} per GPU, oracle parity on every point.
---precision: f32 (fp32-accurate 3xTF32 tcgen05 GEMMs + fp32 SIMT time convolutions), tf32, bf16 (bf16 GEMM operands,
+--precision: f32 (fp32-accurate: error-compensated 3xTF32 tcgen05 GEMMs and time convolutions), tf32, bf16 (bf16 GEMM operands,
 fp32 accumulation / LayerNorm / criterion / optimizer); default = the precision the workload's BASELINE config states.
 
 One JSON line on rank 0.  `value` = frames/s with the batch resident in HBM; `e2e` = the same step through the C ABI
@@ -74,7 +74,7 @@ WORKLOADS = {
 }
 DTYPE_NOTE = {
     "f32": "f32 storage and fp32-ACCURATE contractions: the tcgen05 GEMMs split every staged operand tile into tf32 hi + lo parts and "
-           "accumulate Al*Bh + Ah*Bl + Ah*Bh in fp32 TMEM (products good to ~2^-21); time convolutions on the fp32 SIMT kernels; "
+           "accumulate Al*Bh + Ah*Bl + Ah*Bh in fp32 TMEM (products good to ~2^-21); time convolutions on the mma.sync kernels with the same 3xTF32 split in registers; "
            "criterion / LayerNorm / optimizer in f32/f64",
     "tf32": "f32 storage; dense contractions multiply TF32 operands on the tensor cores with f32 accumulation (cuDNN / cuBLAS default for "
             "fp32 tensors); criterion, LayerNorm, optimizer in f32/f64",
@@ -229,8 +229,8 @@ class CpuArm:
 
     def pick_threads(self, feat, tgt):
         """all host threads — unless fewer are faster (oneDNN + OpenMP thrash on many-core hosts): one timed step of a
-        B=2 sample per candidate, the sweep is reported"""
-        cands = sorted({c for c in (self.ncpu, 64, 32, 16) if c <= self.ncpu}, reverse=True)
+        B=2 sample per candidate, smallest first, stopping as soon as more threads stop helping; the sweep is reported"""
+        cands = sorted({c for c in (16, 32, 64, self.ncpu) if c <= self.ncpu} | {min(self.ncpu, 16)})
         sweep, best = {}, None
         for c in cands:
             self.oracle.set_num_threads(c)
@@ -241,7 +241,7 @@ class CpuArm:
             sweep[c] = round(time.perf_counter() - t0, 3)
             if best is None or sweep[c] < sweep[best]:
                 best = c
-            if sweep[c] > 30:  # a candidate this slow ends the sweep
+            elif sweep[c] > 1.5 * sweep[best]:  # clearly past the optimum
                 break
         return best, sweep
 

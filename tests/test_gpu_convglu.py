@@ -138,8 +138,8 @@ def test_conv_glu_train_step_matches_torch_reference(precision):
     mine = torch.cat([grads[off:off + n] for off, n, _ in tr.layout(0)])
     gscale = float(full.abs().max())
     for (off, n, dims), p in zip(tr.layout(0), ref.p):
-        denom = max(float(p.grad.abs().max()), tol["floor"] * gscale)
-        gerr = float((grads[off:off + n].double() - p.grad.flatten()).abs().max()) / denom
+        denom = max(float(p.grad.norm()), tol["floor"] * gscale * n ** 0.5)
+        gerr = float((grads[off:off + n].double() - p.grad.flatten()).norm()) / denom
         assert gerr < tol["per_param"], f"{precision}: param at {off} dims {dims}: grad rel err {gerr}"
     assert rel(mine, full) < tol["overall"], rel(mine, full)
 

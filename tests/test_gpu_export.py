@@ -87,11 +87,11 @@ def test_checkpoint_round_trip_continues_training_identically(tmp_path):
     tr.save(path)
     tr2 = Trainer.load(path)
     assert torch.equal(tr.get_flat(0, 0), tr2.get_flat(0, 0)) and torch.equal(tr.get_flat(1, 0), tr2.get_flat(1, 0))
-    for _ in range(3):  # momentum state travelled too: the next steps are bit-identical (dropout is 0)
+    for _ in range(3):  # momentum state travelled too: the next steps agree (not bitwise: split-K weight gradients add atomically)
         l1 = tr.step(feat, tgt, True).clone()
         l2 = tr2.step(feat, tgt, True).clone()
-        assert torch.equal(l1, l2)
-    assert torch.equal(tr.get_flat(0, 0), tr2.get_flat(0, 0))
+        assert torch.allclose(l1, l2, rtol=2e-4, atol=1e-5), (l1, l2)
+    assert torch.allclose(tr.get_flat(0, 0), tr2.get_flat(0, 0), rtol=1e-3, atol=1e-5)
     tr.close()
     tr2.close()
     with pytest.raises(Exception):

@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(kCuThreads) conv_umma_fwd_kernel(const __grid_
   const int kblocks = p.Kp / 32;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)kblocks * NP * 128);
   uint64_t* ld_full = bars;      // window + weights landed
-  uint64_t* acc_full = bars + 1; // all MMAs done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  float* sbias = reinterpret_cast<float*>(bars + 4);  // [NP]
+  uint64_t* acc_full = bars + 1; // [4]: the MMAs of accumulator a are done (its epilogue overlaps the next one's MMAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* sbias = reinterpret_cast<float*>(bars + 6);  // [NP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, w0 = blockIdx.y * 32, to0 = blockIdx.x * p.F;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kCuThreads) conv_umma_fwd_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     mbar_init(ld_full, 1);
-    mbar_init(acc_full, 1);
+    for (int a = 0; a < 4; ++a) mbar_init(&acc_full[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
@@ -140,20 +140,27 @@ __global__ void __launch_bounds__(kCuThreads) conv_umma_fwd_kernel(const __grid_
             accumulate = 1;
           }
         }
+        umma_commit(&acc_full[a]);
       }
-      umma_commit(acc_full);
     }
   } else {
     // ===== epilogue: warp = frame within the accumulator's group of four, lane = column =====
-    mbar_wait(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // Dropout: the backward pass reads the mask back from the stored activation (nothing is regenerated), so this kernel
+    // is free to draw it its own way: ONE Philox block per thread and 8 output channels, 16 random bits per element
+    // (keep iff bits >= p * 65536) — the block is keyed by (seed, element index of the first of the 8 channels).
     const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const uint32_t thresh = (uint32_t)(p.drop_p * 65536.0f);
     const int w = w0 + lane;
+    const size_t cw = (size_t)p.W;
     for (int a = 0; a < n_acc; ++a) {
+      mbar_wait(&acc_full[a], 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int to = to0 + 4 * a + warp;
       const bool live = to < p.Tout && w < p.W;
+      const size_t base = (((size_t)b * p.Tout + (size_t)(live ? to : 0)) * p.Cout) * cw + (live ? w : 0);
 #pragma unroll
       for (int c0 = 0; c0 < NP; c0 += 16) {
+        if (c0 >= p.Cout) break;  // warp-uniform
         uint32_t v[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * NP + c0);
         asm volatile(
@@ -162,17 +169,25 @@ __global__ void __launch_bounds__(kCuThreads) conv_umma_fwd_kernel(const __grid_
               "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t rnd[8];  // 16 x 16 random bits
+        if (p.drop_p > 0.f) {
+          const unsigned long long i0 = (unsigned long long)(base + (size_t)c0 * cw), i1 = (unsigned long long)(base + (size_t)(c0 + 8) * cw);
+          const uint4 r0 = philox4x32((uint32_t)i0, (uint32_t)(i0 >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+          const uint4 r1 = philox4x32((uint32_t)i1, (uint32_t)(i1 >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+          rnd[0] = r0.x; rnd[1] = r0.y; rnd[2] = r0.z; rnd[3] = r0.w;
+          rnd[4] = r1.x; rnd[5] = r1.y; rnd[6] = r1.z; rnd[7] = r1.w;
+        }
+        float* yp = p.y + base + (size_t)c0 * cw;
+        const float* ap = p.add != nullptr ? p.add + base + (size_t)c0 * cw : nullptr;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int co = c0 + j;
-          if (co < p.Cout) {  // warp-uniform
-            float x = __uint_as_float(v[j]) + sbias[co];
+          if (c0 + j < p.Cout) {  // warp-uniform
+            float x = __uint_as_float(v[j]) + sbias[c0 + j];
             if (p.act == 1) x = fmaxf(x, 0.f);
-            const size_t idx = (((size_t)b * p.Tout + (size_t)(live ? to : 0)) * p.Cout + co) * p.W + (live ? w : 0);
-            if (p.drop_p > 0.f) x *= dropout_scale(p.seed, idx, p.drop_p, inv_keep);
+            if (p.drop_p > 0.f) x *= ((rnd[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= thresh ? inv_keep : 0.f;
             if (live) {
-              if (p.add != nullptr) x += p.add[idx];  // add may alias y (in-place accumulation): same element, same thread
-              p.y[idx] = x;
+              if (ap != nullptr) x += ap[(size_t)j * cw];  // add may alias y (in-place accumulation): same element, same thread
+              yp[(size_t)j * cw] = x;
             }
           }
         }
@@ -260,7 +275,7 @@ int conv_umma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, i
   // output frames per CTA: 16 (4 accumulators) when window + weights leave room for two CTAs per SM, else 8, else 4
   auto smem_for = [&](int F) {
     const size_t win = ((size_t)((F - 1) * stride + K) * p.Cp * 128 + 1023) / 1024 * 1024;
-    return win + (size_t)(p.Kp / 32) * p.Np * 128 + 64 + p.Np * 4 + 1024;
+    return win + (size_t)(p.Kp / 32) * p.Np * 128 + 96 + p.Np * 4 + 1024;
   };
   int F = 16;
   if (smem_for(16) > 110 * 1024) F = 8;
