@@ -626,7 +626,8 @@ def run_train(args, rank, world, local_rank):
                      "frac": achieved / peak, "traffic": traffic,
                      "peak_source": src + " bf16_tflops_sustained (tf32 / f32x3 math has 1/2 / 1/6 of the bf16 hardware ceiling)",
                      "gemm_ms_per_step": gemm_ms_per_step, "gemm_launches_per_step": len(kern) / max(1, prof_steps),
-                     "algorithmic_flops_per_step": gemm_flops, "gemm_share_of_step": gemm_ms_per_step / (ms / args.steps)},
+                     "algorithmic_flops_per_step": gemm_flops, "gemm_share_of_step": gemm_ms_per_step / (ms / args.steps),
+                     "gemm_launch_us_first_step": [round(1e3 * t, 1) for t in kern[:int(len(kern) / max(1, prof_steps))]]},
         "step_breakdown": {"method": "one extra traced step after the timed region, a CUDA event after every launch",
                            "traced_ms": round(tr_total, 3), "kernels": dict(list(breakdown.items())[:16])},
         "cpu_baseline": cpu,

@@ -215,8 +215,9 @@ W2L_API int w2l_gemm_tf32_ex(void* stream, int a_mn_major, int b_mn_major, int M
  * The workspace size call covers all three.
  * ---------------------------------------------------------------------------------------- */
 W2L_API size_t w2l_conv_time_workspace_size(int B, int Tout, int Cin, int Cout, int K);
-/* 0 (default): tensor-core kernels where the shape allows (TF32, or 3xTF32 under W2L_PRECISION_F32); 1: always the fp32 SIMT
- * kernels (the fallback for widths that are not multiples of 8).  Thread-local; for tests. */
+/* 0 (default): the mma.sync tensor-core kernels where the shape allows (TF32, or 3xTF32 under W2L_PRECISION_F32); 1: always the
+ * fp32 SIMT kernels (the fallback for widths that are not multiples of 8); 2: mma.sync; 3: the tcgen05 / TMA kernel of
+ * conv_umma.cu for forward and stride-1 data gradients (parity-green, measured slower at kw = 21: see DESIGN.md).  Thread-local. */
 W2L_API int w2l_conv_set_path(int path);
 W2L_API int w2l_conv_time_fwd(void* stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride,
                               int pad_left, const float* x, const float* wt, const float* bias, const float* add, float* y,
@@ -245,6 +246,9 @@ W2L_API int w2l_weightnorm_bwd(void* stream, int rows, int len, const float* v, 
                                const float* dw, float* dv, float* dg);
 W2L_API int w2l_conv1d_arrange(void* stream, int cin, int cout, int kw, int cin_p, int cout_p, int glu_split, const float* w,
                                const float* bias, float* fwd, float* flip, float* bias_p);
+/* the same with bf16 destination operands (out_bf16 != 0; W2L_PRECISION_BF16): fwd / flip are written as bf16 directly */
+W2L_API int w2l_conv1d_arrange_ex(void* stream, int cin, int cout, int kw, int cin_p, int cout_p, int glu_split, const float* w,
+                                  const float* bias, void* fwd, void* flip, float* bias_p, int out_bf16);
 W2L_API int w2l_conv1d_unarrange_grad(void* stream, int cin, int cout, int kw, int cin_p, int cout_p, int glu_split,
                                       const float* dfwd, float* dw, long long rows, const float* dy, float* dbias);
 W2L_API int w2l_glu_fwd(void* stream, long long rows, int half, const float* x, float* y, float dropout_p,

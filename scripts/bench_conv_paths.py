@@ -33,7 +33,7 @@ for (B, T, C, K, pl) in [(16, 600, 10, 21, 10), (16, 300, 14, 21, 10), (16, 150,
     bias = torch.randn(C, device="cuda")
     rec = {"B": B, "T": T, "C": C, "K": K, "MB": round(2 * x.numel() * 4 / 1e6, 1)}
     for p in (0.0, 0.2):
-        rec[f"umma_us_p{p}"] = round(time_fwd(x, wt, bias, T, pl, p, 0), 1)
+        rec[f"umma_us_p{p}"] = round(time_fwd(x, wt, bias, T, pl, p, 3), 1)
         rec[f"mma_us_p{p}"] = round(time_fwd(x, wt, bias, T, pl, p, 2), 1)
     rec["umma_GBps"] = round(rec["MB"] * 1e3 / rec["umma_us_p0.2"], 1)
     rec["mma_GBps"] = round(rec["MB"] * 1e3 / rec["mma_us_p0.2"], 1)

@@ -83,7 +83,7 @@ for (B_, T, C, K, pl) in [(2, 20, 18, 21, 10), (2, 40, 14, 21, 10), (2, 80, 10, 
     pre = ref_conv(x64, w64, b64, 1, pl, Tout)
     dy = torch.randn(B_, Tout, C, 80, device="cuda")
     pre.backward(dy.double())
-    for path, prec, cp in [("umma", "tf32", 0), ("mma", "tf32", 2), ("x3", "f32", 0), ("simt", "tf32", 1)]:
+    for path, prec, cp in [("umma", "tf32", 3), ("mma", "tf32", 2), ("x3", "f32", 0), ("simt", "tf32", 1)]:
         try:
             capi.set_precision(prec)
             capi._check(capi.lib.w2l_conv_set_path(cp))

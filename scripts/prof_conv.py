@@ -7,6 +7,7 @@ import torch
 sys.path.insert(0, ".")
 from wav2letter_b200 import capi  # noqa: E402
 
+capi._check(capi.lib.w2l_conv_set_path(3))
 for (B, T, C, K) in [(16, 600, 10, 21), (16, 300, 14, 21), (16, 150, 18, 21)]:
     x = torch.randn(B, T, C, 80, device="cuda")
     wt = torch.randn(C, C, K, device="cuda") * 0.1

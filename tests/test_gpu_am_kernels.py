@@ -199,7 +199,7 @@ def test_conv_time_streaming_shapes_all_paths(B, T, Cin, Cout, K, stride, pl, pr
     pre.backward(dy.double())
     try:
         capi.set_precision("f32" if path == "x3" else "tf32")
-        capi._check(capi.lib.w2l_conv_set_path({"simt": 1, "mma": 2}.get(path, 0)))  # tf32: auto = the tcgen05 kernel
+        capi._check(capi.lib.w2l_conv_set_path({"simt": 1, "mma": 2, "tf32": 3}.get(path, 0)))  # "tf32" = the tcgen05 kernel
         y = capi.conv_time_fwd(x, wt, bias, Tout, stride, pl)
         dx = capi.conv_time_dgrad(dy, wt, T, stride, pl)
         dwt, dbias = capi.conv_time_wgrad(x, dy, K, stride, pl)

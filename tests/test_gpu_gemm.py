@@ -246,7 +246,10 @@ def test_gemm_persistent_and_per_tile_kernels_agree(M, N, K, a_mn, b_mn, kind):
         w.capi.gemm_set_variant(1)
         w.capi.gemm_set_tile(0)
     torch.cuda.synchronize()
-    assert torch.equal(C0, C1)
+    if kind == "f32x3":  # the two kernels round the hi / lo split differently (cvt.rna vs integer round-to-nearest)
+        assert float((C0 - C1).abs().max()) <= 2e-5 * float(C0.abs().max())
+    else:
+        assert torch.equal(C0, C1)
     assert float((P0 - P1).abs().max()) <= 1e-4 * float(P0.abs().max()) + 1e-6
     ref = (A.t() if a_mn else A).double() @ (B.t() if b_mn else B).double().t()
     tol = {"tf32": 3e-3, "f32x3": 2e-5, "bf16": 2e-5}[kind]

@@ -28,11 +28,14 @@ int conv_umma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, i
                   unsigned long long seed, float* arranged);
 // the tensor-core path (TF32 products; under W2L_PRECISION_F32 the same kernels run error-compensated 3xTF32); shapes it
 // does not cover fall back to the fp32 SIMT kernels below
-static thread_local int g_conv_path = 0;  // w2l_conv_set_path: 0 auto, 1 force the fp32 SIMT kernels, 2 mma.sync kernels (no tcgen05) — tests
+static thread_local int g_conv_path = 0;  // w2l_conv_set_path: 0 auto (= mma.sync where the shape allows), 1 fp32 SIMT kernels, 2 mma.sync, 3 tcgen05 — tests / tuning
 static bool use_conv_mma(int W, int Cin, int Cout, int K, int stride) { return g_conv_path != 1 && conv_mma_supported(W, Cin, Cout, K, stride); }
-// tcgen05 / TMA forward and stride-1 data gradient (conv_umma.cu); W2L_PRECISION_F32 keeps the 3xTF32 mma.sync kernels
+// tcgen05 / TMA forward and stride-1 data gradient (conv_umma.cu): parity-green but MEASURED SLOWER than the mma.sync kernel
+// at kw = 21 (138 vs 56 us on the stage-1 shape, profiles/conv_paths_r2.json): with 10-27 channels every tcgen05.mma is a
+// 128 x 16 x 8 sliver and a window needs kw * Cp/8 of them per 128 positions — the tensor pipe is issue-bound at 5 % use.
+// Kept selectable (w2l_conv_set_path(3)) and tested; the default stays on the mma.sync kernels.
 static bool use_conv_umma(int W, int Cin, int Cout, int K, int stride) {
-  return g_conv_path == 0 && current_precision() != W2L_PRECISION_F32 && conv_umma_supported(W, Cin, Cout, K, stride);
+  return g_conv_path == 3 && current_precision() != W2L_PRECISION_F32 && conv_umma_supported(W, Cin, Cout, K, stride);
 }
 size_t conv_mma_arranged_floats(int Cin, int Cout, int K);
 int conv_mma_fwd(cudaStream_t stream, int B, int T, int Tout, int W, int Cin, int Cout, int K, int stride, int pad_left,
@@ -931,7 +934,7 @@ static size_t conv_ws_partial_bytes(int B, int Tout, int Cin, int Cout, int K) {
   return align_up(std::max(simt, std::max(mma, (size_t)B * (size_t)std::max(Tout, 16))) * per, 256);
 }
 extern "C" int w2l_conv_set_path(int path) {
-  if (path < 0 || path > 2) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_set_path: 0 (auto), 1 (fp32 SIMT kernels) or 2 (mma.sync kernels)");
+  if (path < 0 || path > 3) return fail(W2L_ERR_INVALID_ARGUMENT, "conv_set_path: 0 (auto), 1 (fp32 SIMT kernels), 2 (mma.sync kernels) or 3 (tcgen05 kernel)");
   g_conv_path = path;
   return W2L_OK;
 }

@@ -603,11 +603,16 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
   const int CoutP = glu ? 2 * (int)padUp(nOut / 2, align) : (int)padUp(nOut, align);
   const int cin = nIn, cout = nOut, k = kw;
   const bool hasBias = hasBias_, relu = relu_;
-  af::array fwdW = af::array::empty(af::dim4((long long)k * Cp, CoutP));
-  af::array flipW = af::array::empty(af::dim4((long long)k * CoutP, Cp));
+  // GEMM operands of the weights, arranged once per step in the thread's precision (bf16 operands are written directly)
+  const DType wtype = bf16Mode() ? DType::bf16 : DType::f32;
+  GemmOperand fwdOp, flipOp;
+  fwdOp.a = af::array::empty(af::dim4((long long)k * Cp, CoutP), wtype);
+  fwdOp.ld = k * Cp;
+  flipOp.a = af::array::empty(af::dim4((long long)k * CoutP, Cp), wtype);
+  flipOp.ld = k * CoutP;
   af::array biasP = af::array::empty(af::dim4(CoutP));
-  check(w2l_conv1d_arrange(currentStream(), cin, cout, k, Cp, CoutP, glu ? 1 : 0, weight.array().f32(),
-                           hasBias ? biasVar.array().f32() : nullptr, fwdW.f32(), flipW.f32(), biasP.f32()));
+  check(w2l_conv1d_arrange_ex(currentStream(), cin, cout, k, Cp, CoutP, glu ? 1 : 0, weight.array().f32(),
+                              hasBias ? biasVar.array().f32() : nullptr, fwdOp.a.ptr(), flipOp.a.ptr(), biasP.f32(), bf16Mode() ? 1 : 0));
   af::array xp = in.array();
   if (padded) {
     xp = af::array::zeros(af::dim4(1, Cp, Ts, B));
@@ -617,8 +622,6 @@ Variable Conv2D::forwardGemm(const Variable& in, const Variable& weight, const V
   if (rowsAll > 0x7fffffffLL / 2) throw std::invalid_argument("Conv2D: batch too long for one GEMM");
   // operands in the thread's precision (bf16 copies in BF16 mode; the fp32 buffers themselves otherwise)
   const GemmOperand xop = gemmOperand(xp, rowsAll, Cp, Cp);
-  const GemmOperand fwdOp = gemmOperand(fwdW, CoutP, k * Cp, k * Cp);
-  const GemmOperand flipOp = gemmOperand(flipW, Cp, k * CoutP, k * CoutP);
   af::array y = af::array::empty(af::dim4(1, CoutP, Ts, B));
   cudaMemsetAsync(y.f32() + (size_t)M * CoutP, 0, sizeof(float) * (size_t)(k - 1) * CoutP, static_cast<cudaStream_t>(currentStream()));
   check(gemmP(0, 0, (int)M, CoutP, k * Cp, xop, fwdOp, y.f32(), CoutP, biasP.f32(), relu ? 1 : 0, 0, nullptr, 0, 0, 1.f, 0.f, 0ull, 1));
