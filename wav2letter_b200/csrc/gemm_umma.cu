@@ -115,23 +115,6 @@ struct GemmParams {
   int trust_trunc;  // F32X3 experiment: rely on the tensor core ignoring the 13 low mantissa bits (hi is not written back)
 };
 
-__device__ __forceinline__ uint4 philox4x32_g(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
-  uint32_t c2 = 0, c3 = 0;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0;
-    c1 = lo1;
-    c2 = n2;
-    c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-
 // ---- epilogue of one 128 x BN accumulator tile (warps 0..3; TMEM lanes 32*warp .. +31) -------------------------------
 // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per chunk).  Bias, ReLU and the dropout mask
 // (one Philox block per 4 consecutive columns) are applied in that layout; the chunk is then transposed through shared
@@ -192,17 +175,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
       }
       if (p.drop_p > 0.f) {
-        // element index row * N + n; nb % 4 == 0, and N % 4 == 0 is required for dropout (checked by the host), so one
-        // Philox block covers the 4 consecutive columns j .. j+3
-        const unsigned long long base_idx = (unsigned long long)row_own * (unsigned long long)p.N + (unsigned long long)nb;
+        // Dropout mask: the backward pass reads it back from the stored activation (nothing is regenerated), so the generator
+        // only has to be a good hash of (seed, element index): one 32-bit murmur3-style finaliser per PAIR of columns, 16 bits
+        // per element, keep iff bits >= p * 65536.  (Philox4x32-10 per 4 columns was 480 of the ~600 instructions of a chunk.)
+        const uint32_t thresh = (uint32_t)(p.drop_p * 65536.0f);
+        const uint32_t s0 = (uint32_t)p.seed, s1 = (uint32_t)(p.seed >> 32);
+        const unsigned long long base_idx = ((unsigned long long)row_own * (unsigned long long)p.N + (unsigned long long)nb) >> 1;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const unsigned long long idx = base_idx + j;
-          const uint4 r = philox4x32_g((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-          o[j] *= ((float)(r.x >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-          o[j + 1] *= ((float)(r.y >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-          o[j + 2] *= ((float)(r.z >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
-          o[j + 3] *= ((float)(r.w >> 8) * (1.0f / 16777216.0f)) >= p.drop_p ? inv_keep : 0.f;
+        for (int j = 0; j < 32; j += 2) {
+          const unsigned long long idx = base_idx + (j >> 1);
+          uint32_t h = ((uint32_t)idx ^ s0) * 0x9E3779B1u + ((uint32_t)(idx >> 32) ^ s1);
+          h ^= h >> 15;
+          h *= 0x85EBCA77u;
+          h ^= h >> 13;
+          h *= 0xC2B2AE3Du;
+          h ^= h >> 16;
+          o[j] *= (h & 0xffffu) >= thresh ? inv_keep : 0.f;
+          o[j + 1] *= (h >> 16) >= thresh ? inv_keep : 0.f;
         }
       }
       __syncwarp();  // the previous chunk's transposed reads are done
