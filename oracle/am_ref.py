@@ -113,14 +113,32 @@ class RefNet:
             dev = device or flat.device
             self.params = [flat[o:o + n].detach().to(dev).to(dtype).clone().requires_grad_(True) for o, n, _ in layout]
 
-    # ---- pieces ------------------------------------------------------------------------------------------
-    @staticmethod
-    def _ln_whole(x, g, b):
-        return F.layer_norm(x, x.shape[1:], eps=1e-5) * g + b
+        # conditioning of the scalar LayerNorm parameters, filled by backward(): parameter index -> sum of the ABSOLUTE
+        # contributions to its gradient (gain: sum |dy * xhat|, bias: sum |dy|).  These gradients are sums with heavy
+        # cancellation; a backward-error bound compares their error with this scale, not with the (tiny) result.
+        self.cond = {}
+        self._pidx = 0
 
-    @staticmethod
-    def _ln_frame(x, g, b):  # x [B,T,C,W]: normalise every frame over (C, W)
-        return F.layer_norm(x, x.shape[2:], eps=1e-5) * g + b
+    # ---- pieces ------------------------------------------------------------------------------------------
+    def _ln(self, x, g, b, dims):
+        n = F.layer_norm(x, dims, eps=1e-5)
+        out = n * g + b
+        ig, ib = self._pidx - 2, self._pidx - 1  # gain and bias were the last two parameters drawn
+        if out.requires_grad:
+            nd = n.detach()
+
+            def note(gr, nd=nd, ig=ig, ib=ib):
+                self.cond[ig] = float((gr * nd).abs().sum())
+                self.cond[ib] = float(gr.abs().sum())
+
+            out.register_hook(note)
+        return out
+
+    def _ln_whole(self, x, g, b):
+        return self._ln(x, g, b, x.shape[1:])
+
+    def _ln_frame(self, x, g, b):  # x [B,T,C,W]: normalise every frame over (C, W)
+        return self._ln(x, g, b, x.shape[2:])
 
     @staticmethod
     def _conv_time(x, w, b, stride, pl, pr):
@@ -131,7 +149,12 @@ class RefNet:
     def forward(self, feat: torch.Tensor) -> torch.Tensor:
         """feat [B,1,F,T] (== ArrayFire [T,F,1,B]) -> emissions [B,T',N]"""
         it = iter(self.params)
-        P = lambda: next(it)  # noqa: E731
+        self._pidx = 0
+
+        def P():
+            self._pidx += 1
+            return next(it)
+
         x = feat.to(self.dtype)
         mode = None  # "tds": [B,T,C,W]; "glu": [B,T,C]; "flat": [B,T,K]
         pend_pad = None
@@ -189,18 +212,18 @@ class RefNet:
                 ln_time = (int(p[7]) != 0) if len(p) > 7 else True
                 ln = self._ln_whole if ln_time else self._ln_frame
                 cw, cb = P().view(c, c, k), P().view(c)
-                g1, b1 = P(), P()
-                W1, bb1, W2, bb2 = P().view(inner, c * w_), P(), P().view(c * w_, inner), P()
-                g2, b2 = P(), P()
                 if rpad < 0:
                     pl = pr = same_pad_strided(x.shape[1], k, 1)
                 else:
                     pl, pr = k - 1 - rpad, rpad
                 y1 = self._conv_time(x, cw, cb, 1, pl, pr).clamp_min(0)
-                z = ln(x + y1, g1, b1)
+                g1, b1 = P(), P()
+                z = ln(x + y1, g1, b1)  # (called right after its two parameters are drawn: _ln notes their indices)
+                W1, bb1, W2, bb2 = P().view(inner, c * w_), P(), P().view(c * w_, inner), P()
                 B, T = z.shape[:2]
                 f = z.reshape(B, T, c * w_)
                 u = F.linear(F.linear(f, W1, bb1).clamp_min(0), W2, bb2)
+                g2, b2 = P(), P()
                 x = ln(z + u.view(B, T, c, w_), g2, b2)
             elif op == "L":
                 nin, nout = int(p[1]), int(p[2])

@@ -41,6 +41,7 @@ CASES = {
     "conv_glu_librispeech": (40, 30, 2, 48, 10, "target_sz_sqrt", 4.0),
     "streaming_tds_ctc": (80, 2000, 2, 160, 6, "none", 0.0),
 }
+COND_TOL = 1e-4  # backward-error bound of the scalar LayerNorm gradients in the fp32-accurate mode (see run_case)
 TOL = {"f32": dict(emis=2e-4, loss=2e-4, overall=1e-2, per_param=5e-2),
        "tf32": dict(emis=2e-2, loss=2e-2, overall=4e-2, per_param=None),
        "bf16": dict(emis=6e-2, loss=6e-2, overall=1.5e-1, per_param=None)}
@@ -94,7 +95,7 @@ def run_case(name, precision):
     loss_err = float(np.abs(loss.cpu().numpy() - ol).max() / max(1e-6, np.abs(ol).max()))
     gmax = float(g64.abs().max())
     overall = float((grads - g64).abs().max() / gmax)
-    per, excess = [], 0.0
+    per, excess, cond_worst = [], 0.0, 0.0
     for i, (o, n, dims) in enumerate(layout):
         own = float(g64[o:o + n].abs().max())
         err = float((grads[o:o + n] - g64[o:o + n]).abs().max())
@@ -107,13 +108,20 @@ def run_case(name, precision):
         l2_32 = float((g32[o:o + n] - g64[o:o + n]).norm())
         denom = max(own, 1e-3 * gmax)
         per.append((l2 / l2ref, i, dims, own / gmax, l2_32 / l2ref, err / denom))
-        # the f32 criterion: relative L2 error within 1e-2, or within 4x of stock fp32 torch's own error on that parameter
+        if n == 1 and i in ref.cond:
+            # scalar LayerNorm gain / bias: the gradient is ONE sum over every activation of the layer, with heavy
+            # cancellation (a constant shift of a tensor that the next LayerNorm removes again) — its value can sit orders of
+            # magnitude below the sum of the absolute contributions, so a relative criterion on the VALUE measures the
+            # conditioning of the sum, not the kernels.  Backward-error bound instead: |error| <= COND_TOL * sum |contribution|
+            cond_worst = max(cond_worst, err / max(ref.cond[i], 1e-30))
+            continue
+        # the f32 criterion: relative L2 error within 5e-2, or within 8x of stock fp32 torch's own error on that parameter
         excess = max(excess, l2 / max(5e-2 * l2ref, 8.0 * l2_32))
     per.sort(reverse=True)
     rec = {"arch": name, "precision": precision, "emis_err": emis_err, "loss_err": loss_err, "grad_overall": overall,
            "grad_worst_param": per[0][0], "worst_param_index": per[0][1], "worst_param_dims": list(per[0][2]),
            "worst5": [{"rel": round(q[0], 6), "index": q[1], "dims": list(q[2]), "own_over_gmax": round(q[3], 6), "torch_fp32_rel": round(q[4], 6), "max_abs_rel": round(q[5], 6)} for q in per[:5]],
-           "f32_criterion_excess": excess, "torch_fp32_overall": float((g32 - g64).abs().max() / gmax),
+           "f32_criterion_excess": excess, "scalar_ln_backward_error": cond_worst, "torch_fp32_overall": float((g32 - g64).abs().max() / gmax),
            "params": len(layout), "n_param_elements": int(flat.numel()), "loss": [float(v) for v in loss.cpu().numpy()]}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "arch_parity.jsonl"), "a") as f:
@@ -134,6 +142,8 @@ def test_arch_file_parity_fp32_accurate(name):
     assert rec["grad_overall"] <= max(t["overall"], 8 * rec["torch_fp32_overall"]), rec
     # every parameter: relative L2 error within 5e-2 (floor 1e-2 of the largest entry), or within 8x of stock fp32 torch's error
     assert rec["f32_criterion_excess"] <= 1.0, rec
+    # scalar LayerNorm parameters: backward error (|error| / sum of absolute contributions) at the fp32 level
+    assert rec["scalar_ln_backward_error"] <= COND_TOL, rec
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])

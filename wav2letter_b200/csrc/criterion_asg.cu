@@ -3,30 +3,37 @@
 // {FullConnectionCriterion,ForceAlignmentCriterion}.cu as reached from
 // recipes/slimIPL/src/Train.cpp:408-410 (construction), :1675 (forward), :1720 (backward).
 //
-// Pipeline (4 launches, all on the caller's stream):
-//   1. asg_prep_kernel    HBM-bound, parallel over frames: m_t = max_i e_t[i],
-//                         X_t[i] = exp(e_t[i]-m_t) (padded to 32 lanes); per-sample target
-//                         size, validity, scale*dloss.
-//   2. asg_chains_kernel  latency-bound, one CTA per (sample, criterion):
-//        FCC CTA: warp 0 walks alpha (t = 0..T-1), warp 1 walks beta (t = T-1..0) at the same
-//                 time, in the LINEAR domain: a_t = X_t .* (M' a_{t-1}) * 2^-k with M' =
-//                 exp(trans - max trans) held in registers (row i in lane i), the vector
-//                 exchanged through shared memory (1 STS + 8 broadcast LDS.128), 16 FFMA2 per
-//                 step, X streamed into a shared-memory ring by cp.async 16 frames ahead, and a
-//                 power-of-two rescale taken from the exponent bits of a lagged maximum (no
-//                 reduction on the dependent chain; exact; damped — see pow2_rescale).
-//        FAC CTA: 128 threads walk alpha from t=0 and 128 walk beta from t=T-1 in the LOG
-//                 domain (the left-to-right band has unbounded dynamic range, a linear-domain
-//                 form is not safe there), re-centred every step by the band maximum; they
-//                 meet at h = T/2, the partition function is taken at the junction, and each
-//                 group finishes its walk reading the other group's stored half lattice to
-//                 emit occupancies (gamma = xi_stay + xi_adv) and transition statistics.
-//                 Every global read of the walk (emission frames, stored rows, offsets) is
-//                 issued 8 steps ahead with cp.async into shared-memory rings.
-//   3. asg_grad_kernel    parallel over (sample, frame chunk): gamma_fcc = a.*b / sum,
-//                         d_emis = coef*(gamma_fcc - gamma_fac), per-CTA partial of
-//                         d_trans = M' .* sum_t w_t a_{t-1}^T.
-//   4. asg_dtrans_reduce_kernel  deterministic sum of the d_trans partials (no atomics).
+// Round-2 design ("lean chains + parallel gradient").  The only sequential part of the
+// criterion is four first-order recursions per utterance (FCC alpha / beta, FAC alpha / beta), T
+// dependent steps each.  Everything else (posteriors, transition statistics, emission gradients) is
+// parallel over frames once the recursions' values are known.  So:
+//
+//   1. asg_prep_kernel     HBM-bound, parallel over frames: m_t = max_i e_t[i],
+//                          Z_t[i] = (e_t[i]-m_t)*log2(e) padded to 32 lanes; per-sample target size,
+//                          validity, scale*dloss; label-sorted index of the target positions.
+//   2. asg_chains_kernel   latency-/issue-bound.  ONE WARP PER RECURSION, one 32-thread CTA per warp,
+//                          no inter-warp communication at all.
+//        FCC chains: linear domain, a_t = X_t .* (M' a_{t-1}) * 2^-k, M' = exp(trans - max) in
+//                    registers (row i / column j in lane i / j), the state vector exchanged through
+//                    128 bytes of shared memory (1 STS + 8 broadcast LDS.128), 16 FFMA2 per step,
+//                    power-of-two rescale from the exponent bits of a lagged maximum (one CREDUX,
+//                    exact, off the dependent chain, damped — see pow2_rescale), Z prefetched one
+//                    16-frame block ahead into registers; every a-hat / b-hat vector is stored
+//                    (128 B per frame and direction — the size of the emissions).
+//        FAC chains: log2 domain (the left-to-right band has unbounded dynamic range), lane j owns
+//                    the P = Lp/32 CONSECUTIVE target positions P*j .. P*j+P-1 in registers, so the
+//                    l-1 neighbour is a register except for one SHFL per step; 2 MUFU per state
+//                    (ex2 + lg2), the adds packed two states per instruction (FADD2/FFMA2);
+//                    emissions gathered from an 8-frame shared-memory tile; re-centred every 4
+//                    frames (offset carried in double); the row is stored only every 8 frames (a
+//                    checkpoint: a full FAC lattice would be Lp/32 times the size of the emissions).
+//   3. asg_fac_grad_kernel parallel over (sample, 8-frame segment): recomputes the FAC beta rows
+//                          of the segment backwards from the checkpoint into shared memory, then
+//                          the alpha rows forwards, emitting per-frame normalised occupancies per
+//                          label (through the label-sorted index) and transition statistics.
+//   4. asg_fcc_grad_kernel parallel over frames, from the stored FCC vectors:
+//                          d_emis = coef*(gamma_fcc - gamma_fac), d_trans partials.
+//   5. asg_parts_reduce_kernel (x2)  deterministic tree sum of the d_trans partials (no atomics).
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -35,18 +42,23 @@ namespace w2l {
 namespace {
 
 constexpr int kW = 32;            // padded FCC state width (one lane per state)
-constexpr int kChainThreads = 320;    // FAC: 4 + 4 compute warps + 2 flush warps; FCC uses warps 0-2
-constexpr int kGroup = 128;       // threads per FAC direction
-constexpr int kXDepth = 16;       // frames of X in flight ahead of the FCC walks
-constexpr int kXRing = 32;        // ring slots (power of two > kXDepth)
-constexpr int kFDepth = 8;        // steps in flight ahead of the FAC walks
-constexpr int kFRing = 16;        // ring slots (power of two > kFDepth)
-constexpr int kGradWarps = 8;     // warps per CTA in the grad kernel
-constexpr int kGradChunk = 32;    // frames per warp in the grad kernel
-constexpr float kFix = 268435456.0f;  // 2^28 fixed point for the integer REDUX frame sums
+constexpr int kBlk = 16;          // frames per register-prefetch block of the FCC chains
+constexpr int kSeg = 8;           // frames per FAC checkpoint segment (= shared-memory tile of the FAC chains)
+constexpr int kRc = 4;            // FAC chains re-centre every kRc frames
+constexpr float kNeg = -1.0e30f;  // "log zero": finite, absorbing under fp32 addition of ordinary scores
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr double kLn2 = 0.6931471805599453;
+constexpr int kFccGradWarps = 8;  // warps per CTA in the FCC grad kernel
+constexpr int kFccGradFrames = 16;  // frames per warp in the FCC grad kernel
+constexpr int kFlushRegs = 16;    // positions per label kept in registers by the label-sum
+constexpr int kRedGroup = 32;     // partials summed per thread in the first stage of the d_trans reduction
+
+enum Role { kRoleFacAlpha = 0, kRoleFacBeta = 1, kRoleFccAlpha = 2, kRoleFccBeta = 3, kRoleMsum = 4 };
 
 struct AsgParams {
-  int B, T, N, L, Lp, scale_mode, terms, h, need_grad, oring, n_grad_parts;
+  int B, T, N, L, Lp, P, nC, scale_mode, terms, need_grad;
+  int n_roles, roles[5];
+  int n_fcc_parts, n_fac_parts, fac_grad_warps;
   const float* emis;
   const int32_t* target;
   const float* trans;
@@ -55,72 +67,44 @@ struct AsgParams {
   float* d_emis;
   float* d_trans;
   // workspace
-  float* X;       // [B][T][32]
-  float* mrow;    // [B][T]
-  float* A;       // [B][T][32] FCC alpha-hat
-  float* Bh;      // [B][T][32] FCC beta-hat
-  float* sA;      // [B][T] power-of-two scale applied at step t of the alpha walk
-  float* G;       // [B][T][32] FAC occupancy per label (unnormalised; the grad kernel normalises)
-  float* facA;    // [B][h][Lp]    stored alpha-tilde rows, t < h
-  float* facB;    // [B][T-h][Lp]  stored beta-tilde rows,  t >= h
-  double* cA;     // [B][T] re-centring offsets of the FAC alpha walk
-  double* cB;     // [B][T]
-  double* fccLogZ;  // [B]
-  double* facLogZ;  // [B]
-  float* parts;   // [n_grad_parts + B][32*32] d_trans partial sums
-  int* tsz;       // [B]
-  int* valid;     // [B]
-  float* scale;   // [B]
-  float* coef;    // [B] scale * dloss
+  float* Z;         // [B][T][32]  (e - m_t) * log2(e); lanes >= N hold kNeg
+  float* mrow;      // [B][T]
+  float* A;         // [B][T][32] FCC alpha-hat
+  float* Bh;        // [B][T][32] FCC beta-hat
+  float* sA;        // [B][T] power-of-two scale applied at step t of the alpha chain
+  float* ckAa;      // [B][nC][Lp] FAC alpha-tilde row of frame c*kSeg-1 (c >= 1), log2 units
+  float* ckBa;      // [B][nC][Lp] FAC beta-tilde  row of frame (c+1)*kSeg (when < T)
+  double* ckCA;     // [B][nC] offset of the stored alpha row (true = tilde + C + t * tmax2)
+  double* ckCB;     // [B][nC]
+  float* G;         // [B][T][32] FAC occupancy per label, normalised per frame
+  double* fccLogZ;  // [B] natural log, without sum_t m_t
+  double* facLogZ2; // [B] log2 units, without sum_t m_t and without (T-1) * tmax * log2e (what the grad kernel subtracts)
+  double* facLogZ;  // [B] natural log, without sum_t m_t
+  double* msum;     // [B] sum_t m_t
+  float* parts;     // [n_fcc_parts + n_fac_parts][32*32] d_trans partial sums
+  float* parts2;    // [ceil(parts / kRedGroup)][32*32]
+  int* order;       // [B][Lp] target positions sorted by label (stable)
+  int* start;       // [B][36] first index of label n in `order` (start[32] = tsz)
+  int* tsz;         // [B]
+  int* valid;       // [B]
+  float* scale;     // [B]
+  float* coef;      // [B] scale * dloss
 };
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
-}
-// 32-bit shared-window addresses: the FAC step loop addresses ~15 shared locations per step; through generic pointers the
-// compiler re-derived every one of them from the layout arithmetic (and a generic->shared conversion for each cp.async).
-// (the value is laundered through an empty asm so that ptxas keeps it in a register instead of re-deriving it from the
-// thread index and the layout constants inside the loop)
-__device__ __forceinline__ uint32_t sa_of(const void* smem_ptr) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
-  asm volatile("" : "+r"(a));
-  return a;
-}
-__device__ __forceinline__ int opaque_i(int v) {
-  asm volatile("" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ float lds_f(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ double lds_d(uint32_t a) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ void cp_async4_sa(uint32_t dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8_sa(uint32_t dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+// log2(2^a + 2^b) for finite a, b (kNeg stands for log zero): 2 MUFU, no branches
+__device__ __forceinline__ float lse2_log2(float a, float b) {
+  const float mx = fmaxf(a, b), mn = fminf(a, b);
+  return mx + lg2f(1.0f + ex2f(mn - mx));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -128,49 +112,79 @@ __device__ __forceinline__ void cp_async8_sa(uint32_t dst, const void* gsrc) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) asg_prep_kernel(AsgParams p, int frame_blocks) {
   const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
   if ((int)blockIdx.x < frame_blocks) {
-    if (!(p.terms & W2L_TERM_FCC)) return;
     const long long nframes = (long long)p.B * p.T;
-    const long long warps = (long long)frame_blocks * (blockDim.x >> 5);
-    for (long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < nframes; f += warps) {
-      float e = lane < p.N ? __ldg(p.emis + f * p.N + lane) : kNegInf;
+    const long long warps = (long long)frame_blocks * wpb;
+    for (long long f = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); f < nframes; f += warps) {
+      const float e = lane < p.N ? __ldg(p.emis + f * p.N + lane) : kNegInf;
       float m = warp_max(e);
-      float x = lane < p.N ? __expf(e - m) : 0.0f;
-      p.X[f * kW + lane] = x;
+      if (__any_sync(0xffffffffu, e != e)) m = NAN;  // a NaN emission poisons the frame maximum -> the loss
+      float z = lane < p.N ? fmaxf((e - m) * kLog2e, kNeg) : kNeg;  // fmaxf drops NaN: the chains stay finite
+      p.Z[f * kW + lane] = z;
       if (lane == 0) p.mrow[f] = m;
     }
     return;
   }
-  // per-sample metadata
-  int b = ((int)blockIdx.x - frame_blocks) * blockDim.x + threadIdx.x;
+  // per-sample metadata: one warp per sample
+  const int b = ((int)blockIdx.x - frame_blocks) * wpb + (threadIdx.x >> 5);
   if (b >= p.B) return;
   int tsz = 0, ok = 1;
+  const int32_t* y = nullptr;
   if (p.target != nullptr && p.L > 0) {
-    const int32_t* y = p.target + (size_t)b * p.L;
-    tsz = target_size(y, p.L, p.T);
+    y = p.target + (size_t)b * p.L;
+    // index of the last non-negative entry + 1, clamped to T (upstream CriterionUtils::batchTargetSize)
+    int last = 0;
+    for (int l = lane; l < p.L; l += 32)
+      if (__ldg(y + l) >= 0) last = l + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    tsz = min(last, p.T);
     if (p.terms & W2L_TERM_FAC) {
-      if (tsz <= 0) ok = 0;
-      for (int l = 0; l < tsz; ++l)
-        if (y[l] < 0 || y[l] >= p.N) ok = 0;
+      int bad = tsz <= 0;
+      for (int l = lane; l < tsz; l += 32) {
+        const int v = __ldg(y + l);
+        if (v < 0 || v >= p.N) bad = 1;
+      }
+      if (__any_sync(0xffffffffu, bad)) ok = 0;
     }
   } else if (p.terms & W2L_TERM_FAC) {
     ok = 0;
   }
-  float sc = scale_of(p.scale_mode, p.T, tsz);
-  p.tsz[b] = tsz;
-  p.valid[b] = ok;
-  p.scale[b] = sc;
-  p.coef[b] = ok ? sc * (p.dloss ? p.dloss[b] : 1.0f) : 0.0f;
+  const float sc = scale_of(p.scale_mode, p.T, tsz);
+  if (lane == 0) {
+    p.tsz[b] = tsz;
+    p.valid[b] = ok;
+    p.scale[b] = sc;
+    p.coef[b] = ok ? sc * (p.dloss ? p.dloss[b] : 1.0f) : 0.0f;
+  }
+  // label-sorted index of the target positions (stable): lane n lists the positions with y_l == n
+  if ((p.terms & W2L_TERM_FAC) && p.need_grad && ok) {
+    int cnt = 0;
+    for (int l = 0; l < tsz; ++l) cnt += (__ldg(y + l) == lane);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    int w0 = pre - cnt;
+    int* st = p.start + (size_t)b * 36;
+    int* od = p.order + (size_t)b * p.Lp;
+    st[lane] = w0;
+    if (lane == 31) st[32] = pre;
+    for (int l = 0; l < tsz; ++l)
+      if (__ldg(y + l) == lane) od[w0++] = l;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // 2a. FCC chains (linear domain)
 // ------------------------------------------------------------------------------------------
-// acc = sum_j M[j] * v[j] over the 32 shared-memory entries (broadcast LDS.128), mx = max_j v[j].
+// acc = sum_j M[j] * v[j] over the 32 shared-memory entries (broadcast LDS.128).
 // The eight loads are issued back to back through volatile asm: left to itself ptxas reuses one
-// register quad for successive loads, which serialises them into dependent ~30-cycle rounds
-// (41% short-scoreboard stalls in profiles/asg_chains_r1.md).
-__device__ __forceinline__ void matvec32(const float (&M)[kW], const float* vsm, float& acc, float& mx) {
+// register quad for successive loads, which serialises them into dependent ~30-cycle rounds.
+__device__ __forceinline__ float matvec32(const float (&M)[kW], const float* vsm) {
   const unsigned base = (unsigned)__cvta_generic_to_shared(vsm);
   float4 v[kW / 4];
 #pragma unroll
@@ -179,7 +193,6 @@ __device__ __forceinline__ void matvec32(const float (&M)[kW], const float* vsm,
                  : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
                  : "r"(base + 16u * q));
   float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-  float m0 = 0.f, m1 = 0.f;
 #pragma unroll
   for (int q = 0; q < kW / 4; ++q) {
     float2 lo = make_float2(v[q].x, v[q].y), hi = make_float2(v[q].z, v[q].w);
@@ -191,22 +204,19 @@ __device__ __forceinline__ void matvec32(const float (&M)[kW], const float* vsm,
       a0 = __ffma2_rn(mlo, lo, a0);
       a1 = __ffma2_rn(mhi, hi, a1);
     }
-    m0 = fmaxf(fmaxf(m0, v[q].x), v[q].y);
-    m1 = fmaxf(fmaxf(m1, v[q].z), v[q].w);
   }
   float2 s = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
-  acc = s.x + s.y;
-  mx = fmaxf(m0, m1);
+  return s.x + s.y;
 }
 
 // 2^-k with k = (unbiased exponent of mx) >> kDamp; returns k through kout.  Exact.
-// kDamp = 1 for the alpha walk: its rescale acts with a lag of two steps (A_t = A_{t-1} + rho_t
+// kDamp = 1 for the alpha chain: its rescale acts with a lag of two steps (A_t = A_{t-1} + rho_t
 // - k(A_{t-2})), and the undamped feedback has its characteristic roots ON the unit circle, so the
 // exponent random-walks out of fp32 range within ~1000 frames; halving the correction puts the
-// roots at |lambda| = 0.71 (exponent stays within ~[-14, +3]; tests/test_kernel_math.py).  The
-// beta walk's rescale has lag one (dead-beat) and uses kDamp = 0.  mx >= 0, so the exponent
-// field is the top bits; for kDamp = 1, k lies in [-64, 64] and 127 - k is always a valid
-// exponent field; kDamp = 0 clamps.
+// roots at |lambda| = 0.71 (exponent stays within ~[-14, +3]; tests/test_kernel_math.py).  A
+// rescale with lag one (dead-beat) uses kDamp = 0.  mx >= 0, so the exponent field is the top
+// bits; for kDamp = 1, k lies in [-64, 64] and 127 - k is always a valid exponent field;
+// kDamp = 0 clamps.
 template <int kDamp>
 __device__ __forceinline__ float pow2_rescale(float mx, int& kout) {
   int k = (__float_as_int(mx) >> 23) - 127;
@@ -218,788 +228,728 @@ __device__ __forceinline__ float pow2_rescale(float mx, int& kout) {
   return __int_as_float((127 - k) << 23);
 }
 
-template <bool kGrad>
-__device__ void fcc_role(const AsgParams& p, int b) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ __align__(16) float vec[2][2][kW];
-  __shared__ float xring[2][kXRing][kW];
-  __shared__ double msum_s;
-  const int T = p.T, N = p.N;
-  if (warp == 2) {  // sum of the per-frame maxima, off the chains
-    double s = 0.0;
-    for (int t = lane; t < T; t += 32) s += (double)p.mrow[(size_t)b * T + t];
-    s = warp_sum(s);
-    if (lane == 0) msum_s = s;
-    __threadfence_block();
-    asm volatile("bar.arrive 1, 64;" ::: "memory");
-    return;
-  }
-  if (warp > 2 || (warp == 1 && !kGrad)) return;
-
-  // transitions: global max, then M' row (alpha walk) or column (beta walk) into registers
+__device__ __forceinline__ float trans_max(const float* trans, int N, int lane) {
   float tmax = kNegInf;
-  for (int j = 0; j < N; ++j) {
-    float v = lane < N ? __ldg(p.trans + lane * N + j) : kNegInf;
-    tmax = fmaxf(tmax, v);
-  }
-  tmax = warp_max(tmax);
+  for (int k = lane; k < N * N; k += 32) tmax = fmaxf(tmax, __ldg(trans + k));
+  return warp_max(tmax);
+}
+
+// alpha chain: a_t = (X_t * s_t) .* (M' a_{t-1})
+__device__ void fcc_alpha_chain(const AsgParams& p, int b, float* vec /* [2][32] shared */) {
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, N = p.N;
+  const float tmax = trans_max(p.trans, N, lane);
   float M[kW];
 #pragma unroll
-  for (int j = 0; j < kW; ++j) {
-    float v = 0.f;
-    if (lane < N && j < N) v = __expf(__ldg(p.trans + (warp == 0 ? lane * N + j : j * N + lane)) - tmax);
-    M[j] = v;
-  }
-  const float* Xl = p.X + (size_t)b * T * kW + lane;  // this lane's column of X
-  float* xr = &xring[warp][0][lane];
-
-  if (warp == 0) {
-    // ---- alpha walk: a_t = (X_t * s_t) .* (M' a_{t-1}) ----------------------------------------
-    float* Al = p.A + (size_t)b * T * kW + lane;
-    float* sAb = p.sA + (size_t)b * T;
-    float a = __ldg(Xl);
-    if (kGrad) {
-      Al[0] = a;
-      if (lane == 0) sAb[0] = 1.0f;
+  for (int j = 0; j < kW; ++j) M[j] = (lane < N && j < N) ? __expf(__ldg(p.trans + lane * N + j) - tmax) : 0.f;
+  const float* Zl = p.Z + (size_t)b * T * kW + lane;
+  float* Al = p.A + (size_t)b * T * kW + lane;
+  float* sAb = p.sA + (size_t)b * T;
+  const bool store = p.need_grad != 0;
+  const int nblk = (T + kBlk - 1) / kBlk;
+  float zn[kBlk];
+#pragma unroll
+  for (int k = 0; k < kBlk; ++k) zn[k] = k < T ? __ldg(Zl + (size_t)k * kW) : 0.f;
+  float a = 0.f, s = 1.0f;
+  int ksum = 0, kcur = 0;
+  for (int c = 0; c < nblk; ++c) {
+    float zc[kBlk];
+    const int tb = c * kBlk;
+#pragma unroll
+    for (int k = 0; k < kBlk; ++k) {
+      zc[k] = zn[k];
+      const int tn = tb + kBlk + k;
+      zn[k] = tn < T ? __ldg(Zl + (size_t)tn * kW) : 0.f;
     }
-    for (int q = 1; q <= kXDepth; ++q) {  // group g (0-based) carries frame g + 1
-      if (q < T) cp_async4(xr + (q & (kXRing - 1)) * kW, Xl + (size_t)q * kW);
-      cp_async_commit();
-    }
-    float s = 1.0f;
-    int ksum = 0, kcur = 0;
-    for (int t = 1; t < T; ++t) {
-      float* vb = vec[0][t & 1];
+#pragma unroll
+    for (int k = 0; k < kBlk; ++k) {
+      const int t = tb + k;
+      if (t >= T) break;
+      const float x = ex2f(zc[k]);
+      if (t == 0) {
+        a = x;
+        if (store) {
+          Al[0] = a;
+          if (lane == 0) sAb[0] = 1.0f;
+        }
+        continue;
+      }
+      const float xs = x * s;
+      float* vb = vec + (k & 1) * kW;
       vb[lane] = a;
-      if (t + kXDepth < T) cp_async4(xr + ((t + kXDepth) & (kXRing - 1)) * kW, Xl + (size_t)(t + kXDepth) * kW);
-      cp_async_commit();
-      cp_async_wait<kXDepth>();  // the group carrying frame t has landed (own lane's element)
-      const float xs = xr[(t & (kXRing - 1)) * kW] * s;
+      const float mx = warp_max(a);  // max_j a_{t-1}[j]: one CREDUX, off the dependent chain
       __syncwarp();
-      float acc, mx;
-      matvec32(M, vb, acc, mx);
-      a = xs * acc;
+      a = xs * matvec32(M, vb);
       ksum += kcur;
-      if (kGrad) {
+      if (store) {
         Al[(size_t)t * kW] = a;
         if (lane == 0) sAb[t] = s;
       }
       s = pow2_rescale<1>(mx, kcur);  // applied at t+1 from |a_{t-1}| (lag two): damped
     }
-    const float tot = warp_sum(a);
-    asm volatile("bar.sync 1, 64;" ::: "memory");
-    if (lane == 0) {
-      p.fccLogZ[b] = msum_s + (double)(T - 1) * (double)tmax + 0.6931471805599453 * (double)ksum +
-                     log((double)tot);
+  }
+  const float tot = warp_sum(a);
+  if (lane == 0) p.fccLogZ[b] = (double)(T - 1) * (double)tmax + kLn2 * (double)ksum + log((double)tot);
+}
+
+// beta chain: b_t = M'^T (X_{t+1} .* b_{t+1} * s)
+__device__ void fcc_beta_chain(const AsgParams& p, int b, float* vec) {
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, N = p.N;
+  const float tmax = trans_max(p.trans, N, lane);
+  float M[kW];
+#pragma unroll
+  for (int i = 0; i < kW; ++i) M[i] = (lane < N && i < N) ? __expf(__ldg(p.trans + i * N + lane) - tmax) : 0.f;
+  const float* Zl = p.Z + (size_t)b * T * kW + lane;
+  float* Bl = p.Bh + (size_t)b * T * kW + lane;
+  float bh = lane < N ? 1.0f : 0.0f;  // b_{T-1}
+  Bl[(size_t)(T - 1) * kW] = bh;
+  if (T < 2) return;
+  // step t (T-2 .. 0) consumes X_{t+1}; block c covers t in [c*kBlk, c*kBlk + kBlk) and reads frames t+1
+  const int ctop = (T - 2) / kBlk;
+  float zn[kBlk];
+#pragma unroll
+  for (int k = 0; k < kBlk; ++k) {
+    const int f = ctop * kBlk + k + 1;
+    zn[k] = f < T ? __ldg(Zl + (size_t)f * kW) : 0.f;
+  }
+  float s = 1.0f;
+  int kdummy;
+  for (int c = ctop; c >= 0; --c) {
+    float zc[kBlk];
+    const int tb = c * kBlk;
+#pragma unroll
+    for (int k = 0; k < kBlk; ++k) {
+      zc[k] = zn[k];
+      const int f = tb - kBlk + k + 1;
+      zn[k] = f >= 1 ? __ldg(Zl + (size_t)f * kW) : 0.f;
     }
-  } else {
-    // ---- beta walk: b_t = M'^T (X_{t+1} .* b_{t+1} * s) -----------------------------------------
-    float* Bl = p.Bh + (size_t)b * T * kW + lane;
-    float bh = lane < N ? 1.0f : 0.0f;
-    Bl[(size_t)(T - 1) * kW] = bh;
-    // step t (T-2 .. 0) consumes X_{t+1}; group g (0-based) carries frame T-1-g
-    for (int q = 0; q < kXDepth; ++q) {
-      const int f = T - 1 - q;
-      if (f >= 1) cp_async4(xr + (f & (kXRing - 1)) * kW, Xl + (size_t)f * kW);
-      cp_async_commit();
-    }
-    float s = 1.0f;
-    int kdummy;
-    for (int t = T - 2; t >= 0; --t) {
-      float* vb = vec[1][t & 1];
-      const int f = t + 1 - kXDepth;  // frame needed kXDepth steps from now
-      if (f >= 1) cp_async4(xr + (f & (kXRing - 1)) * kW, Xl + (size_t)f * kW);
-      cp_async_commit();
-      cp_async_wait<kXDepth>();
-      const float u = bh * (xr[((t + 1) & (kXRing - 1)) * kW] * s);  // uses X_{t+1}
+#pragma unroll
+    for (int k = kBlk - 1; k >= 0; --k) {
+      const int t = tb + k;
+      if (t > T - 2) continue;
+      const float u = bh * (ex2f(zc[k]) * s);
+      float* vb = vec + (k & 1) * kW;
       vb[lane] = u;
+      const float mx = warp_max(u);
       __syncwarp();
-      float acc, mx;
-      matvec32(M, vb, acc, mx);
-      bh = acc;
+      bh = matvec32(M, vb);
       Bl[(size_t)t * kW] = bh;
       s = pow2_rescale<0>(mx, kdummy);
     }
   }
-  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------
-// 2b. FAC chains (log domain, meet in the middle)
+// 2b. FAC chains (log2 domain).  Lane j owns positions P*j .. P*j+P-1.
 //
-// CTA = 10 warps: warps 0-3 walk alpha (group 0), warps 4-7 walk beta (group 1), warp 8 / 9 are
-// the groups' FLUSH warps.  A compute thread owns target positions l = gt + 128 k (k < KMAX) and
-// keeps their label, transition scores and transition-gradient accumulators in registers; the
-// rows live in shared memory (neighbour exchange) and every global read is prefetched kFDepth
-// steps ahead with cp.async.  In phase 2 a compute thread writes its state occupancy to a
-// shared-memory row; the flush warp sums it per label through a label-sorted index (no atomics:
-// shared-memory fp32 atomics are CAS spin loops on sm_100) while the compute warps already run
-// the next step, and publishes the frame's normaliser (integer REDUX on a 2^28 fixed-point
-// image) that rescales the transition statistics two steps later.
+// Scores are normalised so that nothing drifts: emissions by the frame maximum (Z <= 0) and transitions by the
+// global transition maximum (s1, s2 <= 0); the recursion then computes alpha_t - t * tmax2 (beta: - (T-1-t) * tmax2),
+// which only moves by the log-count of merging paths, and is re-centred every kRc frames (offset in double).
 // ------------------------------------------------------------------------------------------
-struct FacLayout {  // offsets in 4-byte words from the start of dynamic shared memory
-  int cring, red, wmax, rnorm, ering, dtr, y, order, start, rows, gam, oring, total;
+template <int P>
+struct FacState {
+  float v[P];    // alpha-tilde / beta-tilde of the owned positions
+  float s1[P];   // (self-transition score - tmax) * log2e
+  float s2[P];   // alpha: transition (l-1 -> l); beta: transition (l -> l+1); kNeg where there is none
+  int y4[P];     // 4 * label (byte offset into a frame of the Z tile)
 };
-__host__ __device__ inline FacLayout fac_layout(int Lp, int oring) {
-  FacLayout f;
-  int o = 0;
-  f.cring = o;  o += 2 * (2 * kFRing + 4);       // doubles: [2][kFRing] (+4 spare)
-  f.red = o;    o += 16;
-  f.wmax = o;   o += 16;                         // [2 groups][2 bufs][4 warps]
-  f.rnorm = o;  o += 16;                         // [2 groups][2]
-  f.ering = o;  o += 2 * kFRing * 32;            // [2 groups][kFRing][32]
-  f.dtr = o;    o += kW * kW;
-  f.y = o;      o += Lp + 4;
-  f.order = o;  o += Lp;
-  f.start = o;  o += 36;
-  f.rows = o;   o += 4 * (Lp + 4);               // rowA[2], rowB[2], each with 2 pad slots on both sides
-  f.gam = o;    o += 4 * Lp;                     // [2 groups][2 bufs][Lp]
-  f.oring = o;  o += oring ? 2 * kFRing * Lp : 0;
-  f.total = o;
-  return f;
+
+template <int P>
+__device__ __forceinline__ void fac_load_target(FacState<P>& st, const AsgParams& p, int b, int L, int lane, bool beta, float tmax) {
+  const int32_t* yg = p.target + (size_t)b * p.L;
+  const int N = p.N;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int l = lane * P + k;
+    const int yl = l < L ? __ldg(yg + l) : 0;
+    st.y4[k] = 4 * yl;
+    st.s1[k] = l < L ? (__ldg(p.trans + yl * N + yl) - tmax) * kLog2e : 0.f;
+    float s2 = kNeg;
+    if (!beta) {
+      if (l < L && l > 0) s2 = (__ldg(p.trans + yl * N + __ldg(yg + l - 1)) - tmax) * kLog2e;
+    } else {
+      if (l + 1 < L) s2 = (__ldg(p.trans + __ldg(yg + l + 1) * N + yl) - tmax) * kLog2e;
+    }
+    st.s2[k] = s2;
+    st.v[k] = kNeg;
+  }
 }
-__host__ __device__ inline size_t fac_smem_bytes(int Lp, int oring) { return (size_t)fac_layout(Lp, oring).total * 4; }
-
-
-// State of one group's walk; every method is force-inlined so the fields live in registers.
-// Everything a step addresses is carried as a running pointer / ring slot that advances by a constant per step
-// (the walks visit consecutive frames): the step loop was issue-bound with ~60 % integer address arithmetic.
-template <int KMAX>
-struct FacWalk {
-  const AsgParams& p;
-  int b, grp, gt, gw, lane, T, N, L, Lp, dir, p2_lo, p2_hi, cur;
-  bool use_oring, p2_open;
-  const float* eb;
-  float *rowbase, *wmax, *ering, *oring, *gam, *rnorm;
-  double* cring;
-  const float* other_base;
-  const double* other_c;
-  double C;
-  int yk[KMAX];
-  float s1k[KMAX], s2k[KMAX], ds1k[KMAX], ds2k[KMAX];
-  // running state of the copy pipeline: `it` is the next frame to issue
-  int it, islot;
-  const float* e_it;    // eb + it*N + gt
-  const float* o_it;    // other group's stored row of frame `it` (valid once phase 2 is open)
-  const double* oc_it;  // other_c + it
-  // running state of the walk itself: frame of the NEXT step
-  int slot;             // frame & (kFRing-1)
-  float* srow_run;      // half-lattice row the next mode-1 step stores
-  double* c_run;        // offset slot the next mode-1 step stores
-  const float* o_cur;   // other group's row of the next step's frame (direct path, no ring)
-  // shared-window byte addresses (set by bind_shared): rows / warp maxima ping-pong between two fixed addresses
-  uint32_t rp_sa, rn_sa, wm_cur_sa, wm_nxt_sa, ering_sa, oring_sa, cring_sa, gam_cur_sa, gam_oth_sa, rno_cur_sa, rno_oth_sa;
-  uint32_t gt4;         // 4 * gt
-  int Lp4;              // 4 * Lp
-  int yk4[KMAX];        // 4 * label
-
-  __device__ __forceinline__ explicit FacWalk(const AsgParams& p_) : p(p_) {}
-  __device__ __forceinline__ const float* other_row(int t) const {
-    return other_base + (size_t)(grp == 0 ? t - p.h : t) * Lp;
-  }
-  __device__ __forceinline__ float* row(int k) const { return rowbase + k * (Lp + 4); }
-  // call once the pointer fields, cur (= 0) and yk are set
-  __device__ __forceinline__ void bind_shared() {
-    rp_sa = sa_of(row(0));
-    rn_sa = sa_of(row(1));
-    wm_cur_sa = sa_of(wmax);
-    wm_nxt_sa = sa_of(wmax + 4);
-    ering_sa = sa_of(ering);
-    oring_sa = sa_of(oring);
-    cring_sa = sa_of(cring);
-    gam_cur_sa = gam_oth_sa = sa_of(gam);
-    rno_cur_sa = rno_oth_sa = sa_of(rnorm);
-    gt4 = (uint32_t)opaque_i(4 * gt);
-    Lp4 = opaque_i(4 * Lp);
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+// two states at once: (va, na) / (vb, nb) = (own value, neighbour value) of states a / b; returns the new values.
+// 6 packed adds + 4 FMNMX + 4 MUFU for the pair.
+__device__ __forceinline__ float2 fac_pair(float va, float na, float s1a, float s2a, float za, float vb, float nb, float s1b,
+                                           float s2b, float zb) {
+  const float2 a = __fadd2_rn(make_float2(va, na), make_float2(s1a, s2a));
+  const float2 b = __fadd2_rn(make_float2(vb, nb), make_float2(s1b, s2b));
+  const float2 mx = make_float2(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+  const float2 mn = make_float2(fminf(a.x, a.y), fminf(b.x, b.y));
+  const float2 d = __ffma2_rn(mx, make_float2(-1.f, -1.f), mn);  // mn - mx (exact)
+  const float2 q = __fadd2_rn(make_float2(ex2f(d.x), ex2f(d.y)), make_float2(1.f, 1.f));
+  const float2 base = __fadd2_rn(make_float2(za, zb), mx);
+  return __fadd2_rn(base, make_float2(lg2f(q.x), lg2f(q.y)));
+}
+// one alpha step: row_t[l] = z_t[y_l] + lse(row[l] + s1, row[l-1] + s2); zrow = shared byte address of frame t's Z row
+template <int P>
+__device__ __forceinline__ void fac_alpha_step(FacState<P>& st, uint32_t zrow, int lane) {
+  const float (&s2)[P] = st.s2;
+  float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1);
+  if (lane == 0) up = kNeg;
+  if constexpr (P == 1) {
+    st.v[0] = lds_f(zrow + st.y4[0]) + lse2_log2(st.v[0] + st.s1[0], up + s2[0]);
+  } else {
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) yk4[k] = 4 * yk[k];
+    for (int k = P - 2; k >= 0; k -= 2) {  // pairs in descending order: v[k-1], v[k] are still the previous frame's values
+      const float2 nv = fac_pair(st.v[k], k ? st.v[k - 1] : up, st.s1[k], s2[k], lds_f(zrow + st.y4[k]),  //
+                                 st.v[k + 1], st.v[k], st.s1[k + 1], s2[k + 1], lds_f(zrow + st.y4[k + 1]));
+      st.v[k] = nv.x;
+      st.v[k + 1] = nv.y;
+    }
   }
-  // start the copy pipeline at frame t0 and the walk at frame t0 + dir
-  __device__ __forceinline__ void prime(int t0) {
-    it = t0;
-    islot = t0 & (kFRing - 1);
-    e_it = eb + (size_t)t0 * N + gt;
-    o_it = nullptr;
-    oc_it = nullptr;
-    const int t1 = t0 + dir;
-    slot = t1 & (kFRing - 1);
-    srow_run = grp == 0 ? p.facA + ((size_t)b * p.h + t1) * Lp : p.facB + ((size_t)b * (T - p.h) + (t1 - p.h)) * Lp;
-    c_run = (grp == 0 ? p.cA : p.cB) + (size_t)b * T + t1;
-    o_cur = nullptr;
-  }
-  // the other group's half lattice is complete: phase 2 may read it (t_next = frame of the next step)
-  __device__ __forceinline__ void open_phase2(int t_next) {
-    p2_open = true;
-    o_it = other_row(it);
-    oc_it = other_c + it;
-    o_cur = other_row(t_next);
-    const uint32_t g0 = sa_of(gam), r0 = sa_of(rnorm);
-    const int par = t_next & 1;
-    gam_cur_sa = (uint32_t)opaque_i((int)(g0 + par * Lp4));
-    gam_oth_sa = (uint32_t)opaque_i((int)(g0 + (par ^ 1) * Lp4));
-    rno_cur_sa = (uint32_t)opaque_i((int)(r0 + par * 4));
-    rno_oth_sa = (uint32_t)opaque_i((int)(r0 + (par ^ 1) * 4));
-  }
-  __device__ __forceinline__ void issue_other(int t) {  // explicit frame (catch-up at the junction only)
-    if (t >= p2_lo && t <= p2_hi) {
-      if (use_oring) {
-        const float* src = other_row(t);
-        float* dst = oring + (size_t)(t & (kFRing - 1)) * Lp;
+}
+// one beta step: row_t[l] = z_t[y_l] + lse(row[l] + s1, row[l+1] + s2)
+template <int P>
+__device__ __forceinline__ void fac_beta_step(FacState<P>& st, const float (&s2)[P], uint32_t zrow, int lane) {
+  float dn = __shfl_down_sync(0xffffffffu, st.v[0], 1);
+  if (lane == 31) dn = kNeg;
+  if constexpr (P == 1) {
+    st.v[0] = lds_f(zrow + st.y4[0]) + lse2_log2(st.v[0] + st.s1[0], dn + s2[0]);
+  } else {
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int l = gt + k * kGroup;
-          if (l < L) cp_async4(dst + l, src + l);
-        }
+    for (int k = 0; k < P; k += 2) {  // pairs in ascending order: v[k+1], v[k+2] are still the next frame's values
+      const float2 nv = fac_pair(st.v[k], st.v[k + 1], st.s1[k], s2[k], lds_f(zrow + st.y4[k]),  //
+                                 st.v[k + 1], k + 2 < P ? st.v[k + 2] : dn, st.s1[k + 1], s2[k + 1], lds_f(zrow + st.y4[k + 1]));
+      st.v[k] = nv.x;
+      st.v[k + 1] = nv.y;
+    }
+  }
+}
+// subtract the row maximum (exact bookkeeping in C); rows that are entirely "zero" stay put
+template <int P>
+__device__ __forceinline__ void fac_recentre(FacState<P>& st, double& C) {
+  float m = kNeg;
+#pragma unroll
+  for (int k = 0; k < P; ++k) m = fmaxf(m, st.v[k]);
+  m = warp_max(m);
+  if (m > -1.0e29f) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) st.v[k] -= m;
+    C += (double)m;
+  }
+}
+template <int P>
+__device__ __forceinline__ void fac_store_row(const FacState<P>& st, float* row, int lane) {
+  if constexpr (P >= 4) {
+#pragma unroll
+    for (int k = 0; k < P; k += 4)
+      *reinterpret_cast<float4*>(row + lane * P + k) = make_float4(st.v[k], st.v[k + 1], st.v[k + 2], st.v[k + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) row[lane * P + k] = st.v[k];
+  }
+}
+template <int P>
+__device__ __forceinline__ void fac_load_row(FacState<P>& st, const float* row, int lane) {
+  if constexpr (P >= 4) {
+#pragma unroll
+    for (int k = 0; k < P; k += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(row + lane * P + k);
+      st.v[k] = q.x;
+      st.v[k + 1] = q.y;
+      st.v[k + 2] = q.z;
+      st.v[k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) st.v[k] = row[lane * P + k];
+  }
+}
+
+template <int P>
+__device__ void fac_alpha_chain(const AsgParams& p, int b, float* ztile /* [kSeg][32] shared */) {
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, L = p.tsz[b];
+  const float tmax = trans_max(p.trans, p.N, lane);
+  FacState<P> st;
+  fac_load_target<P>(st, p, b, L, lane, false, tmax);
+  const float* Zl = p.Z + (size_t)b * T * kW + lane;
+  const uint32_t zt = (uint32_t)__cvta_generic_to_shared(ztile);
+  const bool store = p.need_grad != 0;
+  float zn[kSeg];
+#pragma unroll
+  for (int k = 0; k < kSeg; ++k) zn[k] = k < T ? __ldg(Zl + (size_t)k * kW) : 0.f;
+  double C = 0.0;
+  for (int c = 0; c < p.nC; ++c) {
+    const int tb = c * kSeg;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kSeg; ++k) {
+      ztile[k * kW + lane] = zn[k];
+      const int tn = tb + kSeg + k;
+      zn[k] = tn < T ? __ldg(Zl + (size_t)tn * kW) : 0.f;
+    }
+    __syncwarp();
+    int k0 = 0;
+    if (c == 0) {  // alpha_0: position 0 carries the first frame's score
+      if (lane == 0) st.v[0] = ztile[st.y4[0] >> 2];
+      k0 = 1;
+    }
+    const int kend = min(kSeg, T - tb);
+    if (k0 == 0 && kend == kSeg) {  // the common case, fully unrolled
+#pragma unroll
+      for (int k = 0; k < kSeg; ++k) {
+        fac_alpha_step<P>(st, zt + k * (4 * kW), lane);
+        if ((k + 1) % kRc == 0) fac_recentre<P>(st, C);
       }
-      if (gt == 0) cp_async8(cring + (t & (kFRing - 1)), other_c + t);
-    }
-  }
-  // issue (one commit group) the asynchronous copies of the next frame in walk order
-  __device__ __forceinline__ void issue_next() {
-    if (it >= 0 && it < T) {
-      if (gt < N) cp_async4_sa(ering_sa + islot * 128 + gt4, e_it);
-      if (p2_open && it >= p2_lo && it <= p2_hi) {
-        if (use_oring) {
-          const uint32_t dst = oring_sa + islot * Lp4 + gt4;
-#pragma unroll
-          for (int k = 0; k < KMAX; ++k) {
-            const int l = gt + k * kGroup;
-            if (l < L) cp_async4_sa(dst + k * (4 * kGroup), o_it + l);
-          }
-        }
-        if (gt == 0) cp_async8_sa(cring_sa + islot * 8, oc_it);
-      }
-    }
-    cp_async_commit();
-    it += dir;
-    islot = (islot + dir) & (kFRing - 1);
-    e_it += dir * N;
-    o_it += dir * Lp;   // only dereferenced while phase 2 is open (re-based by open_phase2)
-    oc_it += dir;
-  }
-  // One step of this group's walk at frame t: computes row[cur^1] from row[cur] (re-centred by
-  // the previous row's maximum).  kMode 0: plain; 1: also store the row to the half lattice;
-  // 2: phase 2 — also emit occupancies / transition statistics from the other group's row.
-  template <int kMode>
-  __device__ __forceinline__ void step(int t, double logZ) {
-    const float4 w4 = lds_f4(wm_cur_sa);
-    const float dmx = fmaxf(fmaxf(w4.x, w4.y), fmaxf(w4.z, w4.w));
-    const float delta = (dmx > -1e30f) ? dmx : 0.0f;
-    issue_next();
-    const int lo = max(0, L - (T - t)), hi = min(t, L - 1);
-    const uint32_t fr_sa = ering_sa + slot * 128;
-    float Kd = 0.f, rn_lag = 1.f;
-    uint32_t orow_sa = 0;
-    if (kMode == 2) {
-      // K = C_prev + C_other(t) - logZ ; xi = exp(a + o + K + delta) with a already re-centred
-      Kd = (float)(C + lds_d(cring_sa + slot * 8) - logZ) + delta;
-      orow_sa = oring_sa + slot * Lp4 + gt4;
-      rn_lag = lds_f(rno_cur_sa);  // normaliser of two steps ago (written by the flush warp)
-    }
-    C += (double)delta;
-    float lmax = kNegInf;
-    const uint32_t rp_l = rp_sa + gt4, rn_l = rn_sa + gt4, gm_l = gam_cur_sa + gt4;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int l = gt + k * kGroup;
-      constexpr int kb = 4 * kGroup;  // byte distance between this thread's consecutive labels
-      if (l < L) {
-        const float a0 = lds_f(rp_l + k * kb) + (s1k[k] - delta);
-        const float a1 = lds_f(rp_l + k * kb - 4 * dir) + (s2k[k] - delta);  // pads and missing transitions are -inf
-        float val = kNegInf;
-        if (l >= lo && l <= hi) val = lds_f(fr_sa + yk4[k]) + lse2f(a0, a1);
-        sts_f(rn_l + k * kb, val);
-        lmax = fmaxf(lmax, val);
-        if (kMode == 1) srow_run[l] = val;
-        if (kMode == 2) {
-          const float o = (use_oring ? lds_f(orow_sa + k * kb) : o_cur[l]) + Kd;
-          const float xs = __expf(a0 + o);
-          const float xa = __expf(a1 + o);
-          ds1k[k] = fmaf(xs, rn_lag, ds1k[k]);
-          ds2k[k] = fmaf(xa, rn_lag, ds2k[k]);
-          sts_f(gm_l + k * kb, xs + xa);
-        }
+    } else {
+      for (int h = 0; h < kSeg; h += kRc) {
+        const int lo = max(k0, h), hi = min(kend, h + kRc);
+        for (int k = lo; k < hi; ++k) fac_alpha_step<P>(st, zt + k * (4 * kW), lane);
+        if (hi > lo) fac_recentre<P>(st, C);
       }
     }
-    const float wm = warp_max(lmax);
-    if (lane == 0) sts_f(wm_nxt_sa + 4 * gw, wm);
-    if (kMode == 1 && gt == 0) *c_run = C;
-    cur ^= 1;
-    {
-      uint32_t x = rp_sa;
-      rp_sa = rn_sa;
-      rn_sa = x;
-      x = wm_cur_sa;
-      wm_cur_sa = wm_nxt_sa;
-      wm_nxt_sa = x;
-      if (kMode == 2) {
-        x = gam_cur_sa;
-        gam_cur_sa = gam_oth_sa;
-        gam_oth_sa = x;
-        x = rno_cur_sa;
-        rno_cur_sa = rno_oth_sa;
-        rno_oth_sa = x;
+    if (store && c + 1 < p.nC) {  // (a full segment: the row was re-centred right above)
+      fac_store_row<P>(st, p.ckAa + ((size_t)b * p.nC + c + 1) * p.Lp, lane);
+      if (lane == 0) p.ckCA[(size_t)b * p.nC + c + 1] = C;
+    }
+  }
+  // log2 partition function: the last position at the last frame
+  float last = kNeg;
+#pragma unroll
+  for (int k = 0; k < P; ++k)
+    if (lane * P + k == L - 1) last = st.v[k];
+  last = warp_max(last);
+  if (lane == 0) {
+    p.facLogZ2[b] = (double)last + C;
+    p.facLogZ[b] = ((double)last + C) * kLn2 + (double)(T - 1) * (double)tmax;
+  }
+}
+
+template <int P>
+__device__ void fac_beta_chain(const AsgParams& p, int b, float* ztile) {
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, L = p.tsz[b];
+  const float tmax = trans_max(p.trans, p.N, lane);
+  FacState<P> st;
+  fac_load_target<P>(st, p, b, L, lane, true, tmax);
+  const float* Zl = p.Z + (size_t)b * T * kW + lane;
+  const uint32_t zt = (uint32_t)__cvta_generic_to_shared(ztile);
+  // segment c covers frames [c*kSeg, c*kSeg + kSeg), walked downwards; the first one holds frame T-1 (initial row)
+  const int ctop = (T - 1) / kSeg;
+  float zn[kSeg];
+#pragma unroll
+  for (int k = 0; k < kSeg; ++k) {
+    const int f = ctop * kSeg + k;
+    zn[k] = f < T ? __ldg(Zl + (size_t)f * kW) : 0.f;
+  }
+  double C = 0.0;
+  for (int c = ctop; c >= 0; --c) {
+    const int tb = c * kSeg;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kSeg; ++k) {
+      ztile[k * kW + lane] = zn[k];
+      const int f = tb - kSeg + k;
+      zn[k] = f >= 0 ? __ldg(Zl + (size_t)f * kW) : 0.f;
+    }
+    __syncwarp();
+    int khi = kSeg - 1;
+    if (c == ctop) {  // beta_{T-1}: the last position carries the last frame's score
+      const int kl = T - 1 - tb;
+#pragma unroll
+      for (int k = 0; k < P; ++k)
+        if (lane * P + k == L - 1) st.v[k] = ztile[kl * kW + (st.y4[k] >> 2)];
+      khi = kl - 1;
+    }
+    if (khi == kSeg - 1) {  // the common case, fully unrolled
+#pragma unroll
+      for (int k = kSeg - 1; k >= 0; --k) {
+        fac_beta_step<P>(st, st.s2, zt + k * (4 * kW), lane);
+        if (k % kRc == 0) fac_recentre<P>(st, C);
+      }
+    } else {
+      for (int h = kSeg - kRc; h >= 0; h -= kRc) {
+        const int hi = min(khi, h + kRc - 1);
+        for (int k = hi; k >= h; --k) fac_beta_step<P>(st, st.s2, zt + k * (4 * kW), lane);
+        if (hi >= h || h == 0) fac_recentre<P>(st, C);
       }
     }
-    slot = (slot + dir) & (kFRing - 1);
-    srow_run += dir * Lp;
-    c_run += dir;
-    o_cur += dir * Lp;
-    cp_async_wait<kFDepth - 1>();  // everything the next step needs has landed (this thread's copies)
-    if (kMode == 2)
-      named_barrier_sync(4 + grp, kGroup + 32);  // compute warps + flush warp
-    else
-      named_barrier_sync(2 + grp, kGroup);
+    if (c >= 1) {  // row of frame c*kSeg = checkpoint c-1 (re-centred right above)
+      fac_store_row<P>(st, p.ckBa + ((size_t)b * p.nC + c - 1) * p.Lp, lane);
+      if (lane == 0) p.ckCB[(size_t)b * p.nC + c - 1] = C;
+    }
   }
-};
+}
 
-// flush warp: occupancy of frame t per label from the group's gamma row, through the label-sorted index.  The index is
-// loop-invariant, so each lane keeps the first kFlushRegs positions of its label in registers: the per-frame work is then
-// up to kFlushRegs INDEPENDENT shared-memory loads instead of a chain of dependent (order[i] -> gamma[order[i]]) pairs —
-// that chain (8 positions per label on average for L = 250, N = 30) used to set the length of every phase-2 step.
-constexpr int kFlushRegs = 16;
+template <int P>
+__global__ void __launch_bounds__(32) asg_chains_kernel(AsgParams p) {
+  __shared__ __align__(16) float sm[kSeg * kW];
+  const int role = p.roles[blockIdx.x / p.B];
+  const int b = blockIdx.x % p.B;
+  const int lane = threadIdx.x;
+  if (role == kRoleMsum) {  // sum of the per-frame maxima, in double
+    double s = 0.0;
+    for (int t = lane; t < p.T; t += 32) s += (double)p.mrow[(size_t)b * p.T + t];
+    s = warp_sum(s);
+    if (lane == 0) p.msum[b] = s;
+    return;
+  }
+  if (!p.valid[b]) return;
+  if (role == kRoleFacAlpha)
+    fac_alpha_chain<P>(p, b, sm);
+  else if (role == kRoleFacBeta)
+    fac_beta_chain<P>(p, b, sm);
+  else if (role == kRoleFccAlpha)
+    fcc_alpha_chain(p, b, sm);
+  else
+    fcc_beta_chain(p, b, sm);
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. FAC gradient: one warp per kSeg-frame segment, all warps of a CTA on the same sample
+// ------------------------------------------------------------------------------------------
+// label-sum: occupancy of one frame per label from the frame's per-position row, through the label-sorted
+// index.  The index is loop-invariant, so each lane keeps the first kFlushRegs positions of its label in
+// registers: up to kFlushRegs INDEPENDENT shared-memory loads instead of a chain of dependent pairs.
 struct FlushIndex {
   int rest0, rest1;
-  int pos[kFlushRegs];     // j-th position of this lane's label inside a gamma row (0 past the count)
-  float use[kFlushRegs];   // 1 for a real position, 0 past the count (the load then reads slot 0 and is multiplied away)
-  __device__ __forceinline__ void load(const int* order, const int* start, int lane) {
+  int pos[kFlushRegs];     // byte offset of the j-th position of this lane's label inside a row (past the count: the zero slot behind the row)
+  __device__ __forceinline__ void load(const int* order, const int* start, int lane, int Lp) {
     const int i0 = start[lane], i1 = start[lane + 1];
     const int cnt = min(kFlushRegs, i1 - i0);
     rest0 = i0 + kFlushRegs;
     rest1 = i1;
 #pragma unroll
     for (int j = 0; j < kFlushRegs; ++j) {
-      pos[j] = j < cnt ? order[i0 + j] : 0;
-      use[j] = j < cnt ? 1.f : 0.f;
+      pos[j] = j < cnt ? 4 * order[i0 + j] : 4 * Lp;
     }
   }
 };
-__device__ __forceinline__ void fac_flush(const float* gm, const int* order, const FlushIndex& fx, int lane, float* Grow,
-                                          float* rnorm_slot) {
+__device__ __forceinline__ float label_sum(uint32_t row_sa, const float* row, const int* order, const FlushIndex& fx) {
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int j = 0; j < kFlushRegs; j += 2) {
-    s0 = fmaf(fx.use[j], gm[fx.pos[j]], s0);
-    s1 = fmaf(fx.use[j + 1], gm[fx.pos[j + 1]], s1);
+    s0 += lds_f(row_sa + fx.pos[j]);
+    s1 += lds_f(row_sa + fx.pos[j + 1]);
   }
 #pragma unroll 1
-  for (int i = fx.rest0; i < fx.rest1; ++i) s0 += gm[order[i]];  // labels with more than kFlushRegs positions
-  const float s = s0 + s1;
-  const int tot_i = __reduce_add_sync(0xffffffffu, __float2int_rn(s * kFix));
-  Grow[lane] = s;
-  if (lane == 0) *rnorm_slot = tot_i > 0 ? __fdividef(kFix, (float)tot_i) : 0.f;
+  for (int i = fx.rest0; i < fx.rest1; ++i) s0 += row[order[i]];  // labels with more than kFlushRegs positions
+  return s0 + s1;
 }
 
-template <bool kGrad, int KMAX>
-__device__ void fac_role(const AsgParams& p, int b, float* smem) {
-  const int tid = threadIdx.x;
-  const int T = p.T, N = p.N, Lp = p.Lp;
+// dynamic shared memory of the FAC grad kernel (4-byte words)
+struct FacGradLayout {
+  int order, start, y, ztile, brow, grow, dsum, dtr, per_warp, total;
+};
+__host__ __device__ inline FacGradLayout fac_grad_layout(int Lp, int warps) {
+  FacGradLayout f;
+  int o = 0;
+  f.order = o;  o += Lp;
+  f.start = o;  o += 36;
+  f.y = o;      o += Lp;
+  f.dsum = o;   o += 2 * Lp;
+  f.dtr = o;    o += kW * (kW + 1);
+  o = (o + 3) & ~3;
+  f.per_warp = kSeg * kW + kSeg * Lp + Lp + 4;  // Z tile, beta rows, gamma row (+ a zero slot behind it)
+  f.ztile = o;
+  f.brow = o + kSeg * kW;
+  f.grow = f.brow + kSeg * Lp;
+  f.total = o + warps * f.per_warp;
+  return f;
+}
+
+// forward step of the gradient pass for the pair of states (a, b): transition posteriors (unnormalised) and new values
+__device__ __forceinline__ float2 fac_grad_pair(float va, float na, float s1a, float s2a, float za, float oa,  //
+                                                float vb, float nb, float s1b, float s2b, float zb, float ob,  //
+                                                float2& xsa /* (stay, advance) of a */, float2& xsb) {
+  const float2 a = __fadd2_rn(make_float2(va, na), make_float2(s1a, s2a));
+  const float2 b = __fadd2_rn(make_float2(vb, nb), make_float2(s1b, s2b));
+  const float2 ea = __fadd2_rn(a, make_float2(oa, oa));
+  const float2 eb = __fadd2_rn(b, make_float2(ob, ob));
+  xsa = make_float2(ex2f(ea.x), ex2f(ea.y));
+  xsb = make_float2(ex2f(eb.x), ex2f(eb.y));
+  const float2 mx = make_float2(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+  const float2 mn = make_float2(fminf(a.x, a.y), fminf(b.x, b.y));
+  const float2 d = __ffma2_rn(mx, make_float2(-1.f, -1.f), mn);
+  const float2 q = __fadd2_rn(make_float2(ex2f(d.x), ex2f(d.y)), make_float2(1.f, 1.f));
+  const float2 base = __fadd2_rn(make_float2(za, zb), mx);
+  return __fadd2_rn(base, make_float2(lg2f(q.x), lg2f(q.y)));
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int b = blockIdx.y;
+  const int T = p.T, Lp = p.Lp;
+  const FacGradLayout lay = fac_grad_layout(Lp, nw);
+  float* part = p.parts + ((size_t)p.n_fcc_parts + (size_t)b * gridDim.x + blockIdx.x) * (kW * kW);
+  if (!p.valid[b]) {
+    for (int k = threadIdx.x; k < kW * kW; k += blockDim.x) part[k] = 0.f;
+    return;  // the FCC grad kernel writes the zero gradient rows
+  }
   const int L = p.tsz[b];
-  const FacLayout lay = fac_layout(Lp, p.oring);
-  int* y_s = reinterpret_cast<int*>(smem + lay.y);
   int* order_s = reinterpret_cast<int*>(smem + lay.order);
   int* start_s = reinterpret_cast<int*>(smem + lay.start);
+  int* y_s = reinterpret_cast<int*>(smem + lay.y);
+  float* dsum_s = smem + lay.dsum;
   float* dtr_s = smem + lay.dtr;
-  float* red_s = smem + lay.red;
-  const bool is_flush = tid >= 2 * kGroup;
-  const int grp = is_flush ? (tid - 2 * kGroup) >> 5 : tid / kGroup;  // 0: alpha walk, 1: beta walk
-  const int gt = is_flush ? 0 : tid % kGroup;
-  const int gw = gt >> 5, lane = tid & 31;
-  const float* eb = p.emis + (size_t)b * T * N;
-  float* Gb = p.G + (size_t)b * T * kW;
-  float* part = p.parts ? p.parts + (size_t)(p.n_grad_parts + b) * (kW * kW) : nullptr;
-
-  if (!p.valid[b]) {
-    if (tid == 0) p.facLogZ[b] = (double)NAN;
-    if (kGrad && part)
-      for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = 0.f;
-    return;  // whole CTA (uniform)
+  for (int l = threadIdx.x; l < Lp; l += blockDim.x) {
+    order_s[l] = l < L ? p.order[(size_t)b * Lp + l] : 0;
+    y_s[l] = l < L ? __ldg(p.target + (size_t)b * p.L + l) : 0;
+    dsum_s[l] = 0.f;
+    dsum_s[Lp + l] = 0.f;
   }
-  const int32_t* yg = p.target + (size_t)b * p.L;
-  for (int l = tid; l < Lp + 4; l += kChainThreads) y_s[l] = l < L ? yg[l] : 0;
-  for (int l = tid; l < 4 * (Lp + 4); l += kChainThreads) smem[lay.rows + l] = kNegInf;
-  if (kGrad)
-    for (int k = tid; k < kW * kW; k += kChainThreads) dtr_s[k] = 0.f;
-  if (tid < 16) smem[lay.rnorm + tid] = 1.0f;
-  __syncthreads();  // S1
+  for (int k = threadIdx.x; k < 33; k += blockDim.x) start_s[k] = p.start[(size_t)b * 36 + k];
+  for (int k = threadIdx.x; k < kW * (kW + 1); k += blockDim.x) dtr_s[k] = 0.f;
+  __syncthreads();
 
-  if (T == 1) {  // single frame: the only alignment is (0,0); L was clamped to 1
-    if (tid == 0) p.facLogZ[b] = (double)eb[y_s[0]];
-    if (kGrad && tid < kW) Gb[tid] = (tid == y_s[0]) ? 1.0f : 0.0f;
-    if (kGrad && part)
-      for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = 0.f;
-    return;
-  }
-  if (kGrad) {
-    // label-sorted index of the target positions (stable, deterministic): lane k lists y_l == k
-    if (tid < 32) {
-      int cnt = 0;
-      for (int l = 0; l < L; ++l) cnt += (y_s[l] == tid);
-      int pre = cnt;  // inclusive scan over the 32 labels
+  float ds1[P], ds2[P];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, pre, o);
-        if (tid >= o) pre += v;
-      }
-      int w0 = pre - cnt;
-      start_s[tid] = w0;
-      if (tid == 31) start_s[32] = pre;
-      for (int l = 0; l < L; ++l)
-        if (y_s[l] == tid) order_s[w0++] = l;
-    }
-    __syncthreads();  // S1b
-  } else if (is_flush || grp == 1) {
-    return;  // forward only: the alpha group walks the whole sequence alone
-  }
-
-  const int h = kGrad ? p.h : T;
-  float* ering_g = smem + lay.ering + grp * kFRing * 32;
-  float* gam_g = smem + lay.gam + grp * 2 * Lp;
-  float* rnorm_g = smem + lay.rnorm + grp * 2;
-
-  if (is_flush) {
-    // ---- flush warp: sleeps on the phase-2 barrier of its group, one frame per release ----------
-    __syncthreads();  // S2 (mid-point)
-    __syncthreads();  // S3
-    __syncthreads();  // S4 (phase 2 open)
+  for (int k = 0; k < P; ++k) ds1[k] = ds2[k] = 0.f;
+  {
+    float* ztile = smem + lay.ztile + warp * lay.per_warp;
+    float* brow = smem + lay.brow + warp * lay.per_warp;
+    float* grow = smem + lay.grow + warp * lay.per_warp;
+    const uint32_t zt = (uint32_t)__cvta_generic_to_shared(ztile);
+    const uint32_t grow_sa = (uint32_t)__cvta_generic_to_shared(grow);
+    const float tmax = trans_max(p.trans, p.N, lane);
+    const float* Zb = p.Z + (size_t)b * T * kW;
+    float* Gb = p.G + (size_t)b * T * kW;
+    const double logZ2 = p.facLogZ2[b];
+    FacState<P> st;  // s2 = the alpha walk's advance scores; the beta walk's live in s2b
+    float s2b[P];
+    fac_load_target<P>(st, p, b, L, lane, true, tmax);
+#pragma unroll
+    for (int k = 0; k < P; ++k) s2b[k] = st.s2[k];
+    fac_load_target<P>(st, p, b, L, lane, false, tmax);
     FlushIndex fx;
-    fx.load(order_s, start_s, lane);
-    if (grp == 0) {
-      for (int t = h; t < T; ++t) {
-        named_barrier_sync(4, kGroup + 32);
-        fac_flush(gam_g + (t & 1) * Lp, order_s, fx, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
+    fx.load(order_s, start_s, lane, Lp);
+    if (lane == 0) grow[Lp] = 0.f;
+    // segments are dealt round-robin to the warps of the sample's CTAs
+    for (int c = blockIdx.x * nw + warp; c < p.nC; c += gridDim.x * nw) {
+      const int t0 = c * kSeg, t1 = min(T, t0 + kSeg);
+      __syncwarp();
+      for (int k = 0; k < t1 - t0; ++k) ztile[k * kW + lane] = __ldg(Zb + (size_t)(t0 + k) * kW + lane);
+      __syncwarp();
+      // ---- backwards: beta-tilde rows of frames t1-1 .. t0 into shared memory --------------------
+      double CB = 0.0;
+      int tstart;
+      if (t1 >= T) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) st.v[k] = (lane * P + k == L - 1) ? ztile[(T - 1 - t0) * kW + (st.y4[k] >> 2)] : kNeg;
+        fac_store_row<P>(st, brow + (size_t)(T - 1 - t0) * Lp, lane);
+        tstart = T - 2;
+      } else {
+        fac_load_row<P>(st, p.ckBa + ((size_t)b * p.nC + c) * Lp, lane);
+        CB = p.ckCB[(size_t)b * p.nC + c];
+        tstart = t1 - 1;
       }
-    } else {
-      for (int t = h - 1; t >= 0; --t) {
-        named_barrier_sync(5, kGroup + 32);
-        fac_flush(gam_g + (t & 1) * Lp, order_s, fx, lane, Gb + (size_t)t * kW, rnorm_g + (t & 1));
+      for (int t = tstart; t >= t0; --t) {
+        fac_beta_step<P>(st, s2b, zt + (t - t0) * (4 * kW), lane);
+        fac_store_row<P>(st, brow + (size_t)(t - t0) * Lp, lane);
       }
-    }
-    __syncthreads();  // S5
-    __syncthreads();  // S6
-    if (part != nullptr)
-      for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = dtr_s[k];
-    return;
-  }
-
-  // ---- compute warps ------------------------------------------------------------------------------
-  FacWalk<KMAX> w(p);
-  w.b = b;
-  w.grp = grp;
-  w.gt = gt;
-  w.gw = gw;
-  w.lane = lane;
-  w.T = T;
-  w.N = N;
-  w.L = L;
-  w.Lp = Lp;
-  w.eb = eb;
-  w.rowbase = smem + lay.rows + grp * 2 * (Lp + 4) + 2;
-  w.wmax = smem + lay.wmax + grp * 8;
-  w.ering = ering_g;
-  w.cring = reinterpret_cast<double*>(smem + lay.cring) + grp * kFRing;
-  w.oring = smem + lay.oring + (size_t)grp * kFRing * Lp;
-  w.gam = gam_g;
-  w.rnorm = rnorm_g;
-  w.dir = grp == 0 ? 1 : -1;
-  w.use_oring = p.oring != 0;
-  // phase-2 sources: the OTHER group's stored half lattice and offsets
-  w.other_base = grp == 0 ? p.facB + (size_t)b * (T - p.h) * Lp : p.facA + (size_t)b * p.h * Lp;
-  w.other_c = (grp == 0 ? p.cB : p.cA) + (size_t)b * T;
-  w.p2_lo = grp == 0 ? p.h + 1 : 0;
-  w.p2_hi = grp == 0 ? T - 1 : p.h - 1;
-  w.p2_open = false;  // the other group's rows exist only after the mid-point barrier
-  w.C = 0.0;          // re-centring offset of the current row (uniform across the group)
-  w.cur = 0;
+      // ---- forwards: alpha-tilde, occupancies, transition statistics -----------------------------
+      double CA = 0.0;
+      int tfirst = t0;
+      if (t0 == 0) {
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    const int l = gt + k * kGroup;
-    const int yl = l < L ? y_s[l] : 0;
-    w.yk[k] = yl;
-    w.s1k[k] = l < L ? __ldg(p.trans + yl * N + yl) : 0.f;
-    float s2 = kNegInf;
-    if (grp == 0) {
-      if (l < L && l > 0) s2 = __ldg(p.trans + yl * N + y_s[l - 1]);  // transition l-1 -> l
-    } else {
-      if (l + 1 < L) s2 = __ldg(p.trans + y_s[l + 1] * N + yl);       // transition l -> l+1
-    }
-    w.s2k[k] = s2;
-    w.ds1k[k] = 0.f;
-    w.ds2k[k] = 0.f;
-  }
-  w.bind_shared();
-  const int bar_c = 2 + grp, dir = w.dir;
-  const int t_first = grp == 0 ? 0 : T - 1;
-  // group g (0-based) carries the frame at walk offset g; offsets 0..kFDepth are issued here,
-  // step at offset q issues offset q + kFDepth and, before its barrier, waits until at most
-  // kFDepth-1 groups are pending, i.e. offset q+1 has landed.
-  w.prime(t_first);
-  for (int q = 0; q <= kFDepth; ++q) w.issue_next();
-  cp_async_wait<kFDepth - 1>();
-  named_barrier_sync(bar_c, kGroup);
-
-  // ---- initial row ------------------------------------------------------------------------
-  {
-    float lmax = kNegInf;
-    float* r0 = w.row(0);
-    if (grp == 0) {
-      const float v = ering_g[(0 & (kFRing - 1)) * 32 + y_s[0]];
-      if (gt == 0) {
-        r0[0] = v;
-        lmax = v;
-        if (kGrad) p.cA[(size_t)b * T] = 0.0;
+        for (int k = 0; k < P; ++k) st.v[k] = kNeg;
+        if (lane == 0) st.v[0] = ztile[st.y4[0] >> 2];
+        Gb[lane] = (lane == y_s[0]) ? 1.0f : 0.0f;  // frame 0 sits at position 0 with probability one
+        tfirst = 1;
+      } else {
+        fac_load_row<P>(st, p.ckAa + ((size_t)b * p.nC + c) * Lp, lane);
+        CA = p.ckCA[(size_t)b * p.nC + c];
       }
-      if (kGrad)
-        for (int l = gt; l < L; l += kGroup) p.facA[((size_t)b * p.h + 0) * Lp + l] = (l == 0) ? v : kNegInf;
-    } else {
-      const float v = ering_g[((T - 1) & (kFRing - 1)) * 32 + y_s[L - 1]];
-      if (gt == 0) {
-        r0[L - 1] = v;
-        lmax = v;
-        p.cB[(size_t)b * T + T - 1] = 0.0;
-      }
-      for (int l = gt; l < L; l += kGroup)
-        p.facB[((size_t)b * (T - p.h) + (T - 1 - p.h)) * Lp + l] = (l == L - 1) ? v : kNegInf;
-    }
-    float wm = warp_max(lmax);
-    if (lane == 0) w.wmax[0 * 4 + gw] = wm;
-    named_barrier_sync(bar_c, kGroup);
-  }
-
-  // ---- phase 1: walk to the middle, storing the half lattices ---------------------------------
-  if (grp == 0) {
-    if (kGrad) {
-      for (int t = 1; t < h; ++t) w.template step<1>(t, 0.0);
-    } else {
-      for (int t = 1; t < h; ++t) w.template step<0>(t, 0.0);
-    }
-  } else {
-    for (int t = T - 2; t >= h; --t) w.template step<1>(t, 0.0);
-  }
-  if (!kGrad) {
-    if (gt == 0) p.facLogZ[b] = (double)w.row(w.cur)[L - 1] + w.C;
-    cp_async_wait<0>();
-    return;
-  }
-  __syncthreads();  // S2
-
-  // ---- junction at t = h: alpha group computes alpha_h; partition function from alpha_h + beta_h
-  __shared__ int curB_s;
-  __shared__ double CB_h_s, logZ_s;
-  if (grp == 1 && gt == 0) {
-    curB_s = w.cur;
-    CB_h_s = w.C;
-  }
-  __syncthreads();  // S3
-  if (grp == 0) {
-    const float* rb = smem + lay.rows + (2 + curB_s) * (Lp + 4) + 2;
-    w.template step<0>(h, 0.0);  // row[cur] = alpha-tilde_h, offset C
-    const float* ra = w.row(w.cur);
-    const float* fr = ering_g + (h & (kFRing - 1)) * 32;
-    float qk[KMAX];
-    float qmax = kNegInf;
+      // alpha_{t-1}[l] + s + beta_t[l] - log2 Z  =  tilde values + (CA + CB - facLogZ2): the t * tmax terms cancel
+      const float K = (float)(CA + CB - logZ2);
+      __syncwarp();
+      for (int t = tfirst; t < t1; ++t) {
+        const uint32_t zrow = zt + (t - t0) * (4 * kW);
+        const float* br = brow + (size_t)(t - t0) * Lp + lane * P;
+        float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1);
+        if (lane == 0) up = kNeg;
+        float xs[P], xa[P];
+        float gs;
+        if constexpr (P == 1) {
+          const float a0 = st.v[0] + st.s1[0], a1 = up + st.s2[0];
+          const float o = br[0] + K;
+          xs[0] = ex2f(a0 + o);
+          xa[0] = ex2f(a1 + o);
+          gs = xs[0] + xa[0];
+          st.v[0] = lds_f(zrow + st.y4[0]) + lse2_log2(a0, a1);
+        } else {
+          float2 g2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int l = gt + k * kGroup;
-      qk[k] = l < L ? ra[l] + rb[l] - fr[w.yk[k]] : kNegInf;
-      qmax = fmaxf(qmax, qk[k]);
-    }
-    qmax = warp_max(qmax);
-    if (lane == 0) red_s[gw] = qmax;
-    named_barrier_sync(bar_c, kGroup);
-    qmax = fmaxf(fmaxf(red_s[0], red_s[1]), fmaxf(red_s[2], red_s[3]));
-    float part_sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      qk[k] = (qk[k] == kNegInf) ? 0.f : __expf(qk[k] - qmax);
-      part_sum += qk[k];
-    }
-    part_sum = warp_sum(part_sum);
-    if (lane == 0) red_s[4 + gw] = part_sum;
-    named_barrier_sync(bar_c, kGroup);
-    const float tot = red_s[4] + red_s[5] + red_s[6] + red_s[7];
-    if (gt == 0) {
-      double lz = w.C + CB_h_s + (double)qmax + log((double)tot);
-      logZ_s = lz;
-      p.facLogZ[b] = lz;
-    }
-    // occupancy of frame h -> gamma row; the flush warp takes it at the first phase-2 barrier
-    float* gm = gam_g + (h & 1) * Lp;
-    const float inv = 1.0f / tot;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int l = gt + k * kGroup;
-      if (l < L) gm[l] = qk[k] * inv;
-    }
-  }
-  // Open phase 2: the half lattices are complete (barrier above); catch up on the other group's
-  // rows for the first kFDepth steps (their frame copies are already in flight), one extra
-  // commit group, drained before the walks resume.
-  {
-    const int t_next = grp == 0 ? h + 1 : h - 1;
-    w.open_phase2(t_next);
-    for (int q = 0; q < kFDepth; ++q) w.issue_other(t_next + dir * q);
-    cp_async_commit();
-    cp_async_wait<0>();
-  }
-  __syncthreads();  // S4
-  const double logZ = logZ_s;
-
-  // ---- phase 2: finish the walks, emitting occupancies and transition statistics --------------
-  // alpha group: t = h+1 .. T-1, transitions (t-1 -> t), reads stored beta-tilde_t
-  // beta  group: t = h-1 .. 0,   transitions (t -> t+1), reads stored alpha-tilde_t
-  if (grp == 0) {
-    named_barrier_sync(4, kGroup + 32);  // releases the flush of frame h
-    for (int t = h + 1; t < T; ++t) w.template step<2>(t, logZ);
-  } else {
-    for (int t = h - 1; t >= 0; --t) w.template step<2>(t, logZ);
-  }
-  cp_async_wait<0>();
-  __syncthreads();  // S5
-  // transition-gradient partial of this CTA: FAC enters ASG with a minus sign
-  if (part != nullptr) {
-    const float sgn = (p.terms & W2L_TERM_FCC) ? -1.0f : 1.0f;
-    const float c = sgn * p.coef[b];
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int l = gt + k * kGroup;
-      if (l < L) {
-        const int yl = w.yk[k];
-        if (w.ds1k[k] != 0.f) atomicAdd(&dtr_s[yl * kW + yl], c * w.ds1k[k]);
-        if (w.ds2k[k] != 0.f) {
-          if (grp == 0) {
-            if (l > 0) atomicAdd(&dtr_s[yl * kW + y_s[l - 1]], c * w.ds2k[k]);
-          } else {
-            if (l + 1 < L) atomicAdd(&dtr_s[y_s[l + 1] * kW + yl], c * w.ds2k[k]);
+          for (int k = P - 2; k >= 0; k -= 2) {  // pairs, descending: v[k-1], v[k] are still alpha_{t-1}
+            float2 xsa, xsb;
+            const float2 brk = *reinterpret_cast<const float2*>(br + k);
+            const float2 nv = fac_grad_pair(st.v[k], k ? st.v[k - 1] : up, st.s1[k], st.s2[k], lds_f(zrow + st.y4[k]), brk.x + K,  //
+                                            st.v[k + 1], st.v[k], st.s1[k + 1], st.s2[k + 1], lds_f(zrow + st.y4[k + 1]), brk.y + K, xsa, xsb);
+            xs[k] = xsa.x;
+            xa[k] = xsa.y;
+            xs[k + 1] = xsb.x;
+            xa[k + 1] = xsb.y;
+            g2 = __fadd2_rn(g2, __fadd2_rn(xsa, xsb));
+            st.v[k] = nv.x;
+            st.v[k + 1] = nv.y;
           }
+          gs = g2.x + g2.y;
         }
+        const float tot = warp_sum(gs);
+        const float inv = tot > 0.f ? __fdividef(1.0f, tot) : 0.f;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          ds1[k] = fmaf(xs[k], inv, ds1[k]);
+          ds2[k] = fmaf(xa[k], inv, ds2[k]);
+          grow[lane * P + k] = (xs[k] + xa[k]) * inv;
+        }
+        __syncwarp();
+        Gb[(size_t)t * kW + lane] = label_sum(grow_sa, grow, order_s, fx);
+        __syncwarp();
       }
     }
   }
-  __syncthreads();  // S6
-  if (part != nullptr)
-    for (int k = tid; k < kW * kW; k += kChainThreads) part[k] = dtr_s[k];
-}
-
-template <bool kGrad, int KMAX>
-__global__ void __launch_bounds__(kChainThreads) asg_chains_kernel(AsgParams p, int n_fac) {
-  extern __shared__ __align__(16) float smem_dyn[];
-  if ((int)blockIdx.x < n_fac) {
-    fac_role<kGrad, KMAX>(p, blockIdx.x, smem_dyn);
-  } else {
-    fcc_role<kGrad>(p, blockIdx.x - n_fac);
+  // ---- CTA partial of the transition gradient (fixed order: deterministic) ----------------------
+  for (int w = 0; w < nw; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        dsum_s[lane * P + k] += ds1[k];
+        dsum_s[Lp + lane * P + k] += ds2[k];
+      }
+    }
+    __syncthreads();
   }
+  if (warp == 0) {  // lane n owns row n of the partial: positions with label n, in sorted order
+    float* row = dtr_s + lane * (kW + 1);
+    for (int i = start_s[lane]; i < start_s[lane + 1]; ++i) {
+      const int l = order_s[i];
+      row[lane] += dsum_s[l];
+      if (l > 0) row[y_s[l - 1]] += dsum_s[Lp + l];
+    }
+  }
+  __syncthreads();
+  const float sgn = (p.terms & W2L_TERM_FCC) ? -1.0f : 1.0f;  // FAC enters ASG with a minus sign
+  const float cf = sgn * p.coef[b];
+  for (int k = threadIdx.x; k < kW * kW; k += blockDim.x) part[k] = cf * dtr_s[(k / kW) * (kW + 1) + (k % kW)];
 }
 
 // ------------------------------------------------------------------------------------------
-// 3. gradient assembly (parallel) — one CTA = kGradWarps warps x kGradChunk frames of one sample
+// 4. FCC gradient + emission gradient, from the stored a-hat / b-hat vectors: no dependence between frames
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGradWarps * 32) asg_grad_kernel(AsgParams p) {
+__global__ void __launch_bounds__(kFccGradWarps * 32) asg_fcc_grad_kernel(AsgParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int chunk = blockIdx.x * kGradWarps + warp;
+  const int chunk = blockIdx.x * kFccGradWarps + warp;
   const int T = p.T, N = p.N;
-  const int t0 = chunk * kGradChunk, t1 = min(T, t0 + kGradChunk);
   const bool has_fcc = p.terms & W2L_TERM_FCC, has_fac = p.terms & W2L_TERM_FAC;
-  const bool want_dtr = has_fcc && p.parts != nullptr;
   const int ok = p.valid[b];
-  __shared__ __align__(16) float aprev_s[kGradWarps][kW];
-  __shared__ float acc_s[kGradWarps][kW][kW + 1];
+  __shared__ float red_s[kW][kW + 1];
   if (chunk == 0 && lane == 0) {
     float l = NAN;
     if (ok) {
       double v = 0.0;
-      if (has_fcc) v += p.fccLogZ[b];
-      if (has_fac) v += (has_fcc ? -1.0 : 1.0) * p.facLogZ[b];
+      if (has_fcc) v += p.fccLogZ[b] + p.msum[b];
+      if (has_fac) v += (has_fcc ? -1.0 : 1.0) * (p.facLogZ[b] + p.msum[b]);
       l = (float)((double)p.scale[b] * v);
     }
     p.loss[b] = l;
   }
-  float acc[kW];
+  const int t0 = chunk * kFccGradFrames, t1 = min(T, t0 + kFccGradFrames);
+  float2 acc[kW / 2];
 #pragma unroll
-  for (int j = 0; j < kW; ++j) acc[j] = 0.f;
-  if (t0 < T && p.d_emis != nullptr) {
+  for (int j = 0; j < kW / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+  if (t0 < T) {
     float* de = p.d_emis + (size_t)b * T * N;
+    const float* Gb = p.G + (size_t)b * T * kW;
     if (!ok) {
       for (int t = t0; t < t1; ++t)
         if (lane < N) de[(size_t)t * N + lane] = 0.f;
+    } else if (!has_fcc) {
+      const float coef = p.coef[b];
+      for (int t = t0; t < t1; ++t)
+        if (lane < N) de[(size_t)t * N + lane] = coef * Gb[(size_t)t * kW + lane];
     } else {
       const float coef = p.coef[b];
-      const float sG = has_fac ? (has_fcc ? -1.f : 1.f) : 0.f;
       const float* Ab = p.A + (size_t)b * T * kW;
       const float* Bb = p.Bh + (size_t)b * T * kW;
-      const float* Xb = p.X + (size_t)b * T * kW;
-      const float* Gb = p.G + (size_t)b * T * kW;
+      const float* Zb = p.Z + (size_t)b * T * kW;
+      const float* sAb = p.sA + (size_t)b * T;
+#pragma unroll 4
       for (int t = t0; t < t1; ++t) {
-        float gam = 0.f;
-        if (has_fcc) {
-          const float a = Ab[(size_t)t * kW + lane];
-          const float bh = Bb[(size_t)t * kW + lane];
-          const float g = a * bh;
-          const float gs = warp_sum(g);
-          gam = g / gs;
-          if (t >= 1 && want_dtr) {
-            const float w = Xb[(size_t)t * kW + lane] * bh * (p.sA[(size_t)b * T + t] / gs);
-            aprev_s[warp][lane] = Ab[(size_t)(t - 1) * kW + lane];
-            __syncwarp();
-            const float4* v4 = reinterpret_cast<const float4*>(aprev_s[warp]);
+        const float a = __ldg(Ab + (size_t)t * kW + lane);
+        const float bh = __ldg(Bb + (size_t)t * kW + lane);
+        const float gf = has_fac ? __ldg(Gb + (size_t)t * kW + lane) : 0.f;
+        const float g = a * bh;
+        const float inv = __fdividef(1.0f, warp_sum(g));
+        if (lane < N) de[(size_t)t * N + lane] = coef * (g * inv - gf);
+        if (t >= 1) {
+          // xi_t(i, j) = w_i * a_{t-1}[j] * M'[i][j],  w_i = X_t[i] * s_t * b_t[i] / sum_i a_t[i] b_t[i]
+          const float w = ex2f(__ldg(Zb + (size_t)t * kW + lane)) * bh * (__ldg(sAb + t) * inv);
+          const float4* ap = reinterpret_cast<const float4*>(Ab + (size_t)(t - 1) * kW);
+          const float2 w2 = make_float2(w, w);
 #pragma unroll
-            for (int q = 0; q < kW / 4; ++q) {
-              float4 v = v4[q];
-              acc[4 * q + 0] = fmaf(w, v.x, acc[4 * q + 0]);
-              acc[4 * q + 1] = fmaf(w, v.y, acc[4 * q + 1]);
-              acc[4 * q + 2] = fmaf(w, v.z, acc[4 * q + 2]);
-              acc[4 * q + 3] = fmaf(w, v.w, acc[4 * q + 3]);
-            }
-            __syncwarp();
+          for (int q = 0; q < kW / 4; ++q) {
+            const float4 v = __ldg(ap + q);  // every lane reads the same 16 bytes: one broadcast transaction
+            acc[2 * q] = __ffma2_rn(w2, make_float2(v.x, v.y), acc[2 * q]);
+            acc[2 * q + 1] = __ffma2_rn(w2, make_float2(v.z, v.w), acc[2 * q + 1]);
           }
         }
-        float gf = 0.f;
-        if (has_fac) {
-          gf = Gb[(size_t)t * kW + lane];
-          const float tot = warp_sum(gf);  // FAC occupancies are stored unnormalised
-          gf = tot > 0.f ? gf / tot : 0.f;
-        }
-        if (lane < N) de[(size_t)t * N + lane] = coef * (gam + sG * gf);
       }
     }
   }
-  if (!want_dtr) return;
-  // CTA partial of the FCC transition gradient: sum the warps' accumulators, apply coef * M'
-#pragma unroll
-  for (int j = 0; j < kW; ++j) acc_s[warp][lane][j] = acc[j];
+  if (!has_fcc) return;
+  // CTA partial of the FCC transition gradient: sum the warps' accumulators in a fixed order, apply coef * M'
+  for (int k = threadIdx.x; k < kW * (kW + 1); k += blockDim.x) (&red_s[0][0])[k] = 0.f;
   __syncthreads();
-  float tmax = kNegInf;
-  for (int k = lane; k < N * N; k += 32) tmax = fmaxf(tmax, __ldg(p.trans + k));
-  tmax = warp_max(tmax);
+  for (int w = 0; w < kFccGradWarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < kW / 2; ++j) {
+        red_s[lane][2 * j] += acc[j].x;
+        red_s[lane][2 * j + 1] += acc[j].y;
+      }
+    }
+    __syncthreads();
+  }
+  const float tmax = trans_max(p.trans, N, lane);
   const float coef = ok ? p.coef[b] : 0.f;
   float* part = p.parts + ((size_t)b * gridDim.x + blockIdx.x) * (kW * kW);
-  for (int k = threadIdx.x; k < kW * kW; k += kGradWarps * 32) {
+  for (int k = threadIdx.x; k < kW * kW; k += blockDim.x) {
     const int i = k / kW, j = k % kW;
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < kGradWarps; ++w) s += acc_s[w][i][j];
     const float m = (i < N && j < N) ? __expf(__ldg(p.trans + i * N + j) - tmax) : 0.f;
-    part[k] = coef * s * m;
+    part[k] = coef * red_s[i][j] * m;
   }
 }
 
-// 4. d_trans[i][j] = sum over partials (FCC grad CTAs, then FAC CTAs) — fixed order, no atomics
-__global__ void __launch_bounds__(256) asg_dtrans_reduce_kernel(AsgParams p, int n_parts) {
+// 5. out[g][k] = sum of the partials q in [g*group, (g+1)*group) — fixed order, no atomics.  final_N > 0: the single
+// group is written as d_trans [N][N].
+__global__ void __launch_bounds__(256) asg_parts_reduce_kernel(const float* in, int n_in, int group, float* out, int final_N) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= kW * kW) return;
-  const int i = k / kW, j = k % kW;
-  if (i >= p.N || j >= p.N) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int q = 0;
-  for (; q + 3 < n_parts; q += 4) {
-    s0 += p.parts[(size_t)q * (kW * kW) + k];
-    s1 += p.parts[(size_t)(q + 1) * (kW * kW) + k];
-    s2 += p.parts[(size_t)(q + 2) * (kW * kW) + k];
-    s3 += p.parts[(size_t)(q + 3) * (kW * kW) + k];
+  const int q0 = blockIdx.y * group, q1 = min(n_in, q0 + group);
+  float s[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[u] = 0.f;
+  int q = q0;
+  for (; q + 7 < q1; q += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] += in[(size_t)(q + u) * (kW * kW) + k];
   }
-  for (; q < n_parts; ++q) s0 += p.parts[(size_t)q * (kW * kW) + k];
-  p.d_trans[i * p.N + j] = (s0 + s1) + (s2 + s3);
+  for (; q < q1; ++q) s[0] += in[(size_t)q * (kW * kW) + k];
+  const float tot = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  if (final_N > 0) {
+    const int i = k / kW, j = k % kW;
+    if (i < final_N && j < final_N) out[i * final_N + j] = tot;
+  } else {
+    out[(size_t)blockIdx.y * (kW * kW) + k] = tot;
+  }
 }
 
 __global__ void asg_loss_only_kernel(AsgParams p) {
@@ -1008,36 +958,96 @@ __global__ void asg_loss_only_kernel(AsgParams p) {
   float l = NAN;
   if (p.valid[b]) {
     double v = 0.0;
-    if (p.terms & W2L_TERM_FCC) v += p.fccLogZ[b];
-    if (p.terms & W2L_TERM_FAC) v += ((p.terms & W2L_TERM_FCC) ? -1.0 : 1.0) * p.facLogZ[b];
+    if (p.terms & W2L_TERM_FCC) v += p.fccLogZ[b] + p.msum[b];
+    if (p.terms & W2L_TERM_FAC) v += ((p.terms & W2L_TERM_FCC) ? -1.0 : 1.0) * (p.facLogZ[b] + p.msum[b]);
     l = (float)((double)p.scale[b] * v);
   }
   p.loss[b] = l;
 }
 
-int grad_ctas_per_sample(int T) { return (T + kGradChunk * kGradWarps - 1) / (kGradChunk * kGradWarps); }
+int pick_P(int Le) {  // positions per lane: smallest power of two with 32*P >= Le
+  int P = 1;
+  while (32 * P < Le) P <<= 1;
+  return P;
+}
+int fac_grad_warps(int Lp) {  // warps per FAC grad CTA: as many as ~96 KB of shared memory hold, at most 4
+  for (int w = 4; w > 1; --w)
+    if ((size_t)fac_grad_layout(Lp, w).total * 4 <= 96 * 1024) return w;
+  return 1;
+}
+
+int fcc_grad_ctas(int T) { return (T + kFccGradWarps * kFccGradFrames - 1) / (kFccGradWarps * kFccGradFrames); }
+// CTAs per sample of the FAC grad kernel: one resident wave of the chip over the batch (the CTAs loop over their segments)
+template <int P>
+int fac_grad_slots(int warps, size_t smem) {
+  int per_sm = 0;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(asg_fac_grad_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, asg_fac_grad_kernel<P>, warps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * sms;
+}
+int fac_grad_ctas(const AsgParams& p) {
+  const int most = (p.nC + p.fac_grad_warps - 1) / p.fac_grad_warps;
+  static int slots_cache[6] = {0, 0, 0, 0, 0, 0};
+  const int idx = p.P == 1 ? 0 : p.P == 2 ? 1 : p.P == 4 ? 2 : p.P == 8 ? 3 : p.P == 16 ? 4 : 5;
+  if (slots_cache[idx] == 0) {
+    const size_t smem = (size_t)fac_grad_layout(p.Lp, p.fac_grad_warps).total * 4;
+    switch (p.P) {
+      case 1: slots_cache[idx] = fac_grad_slots<1>(p.fac_grad_warps, smem); break;
+      case 2: slots_cache[idx] = fac_grad_slots<2>(p.fac_grad_warps, smem); break;
+      case 4: slots_cache[idx] = fac_grad_slots<4>(p.fac_grad_warps, smem); break;
+      case 8: slots_cache[idx] = fac_grad_slots<8>(p.fac_grad_warps, smem); break;
+      case 16: slots_cache[idx] = fac_grad_slots<16>(p.fac_grad_warps, smem); break;
+      default: slots_cache[idx] = fac_grad_slots<32>(p.fac_grad_warps, smem); break;
+    }
+  }
+  int want = slots_cache[idx] / p.B;
+  if (want < 1) want = 1;
+  return want < most ? want : most;
+}
 
 void carve(AsgParams& p, void* ws, size_t& total) {
   Carver c(ws);
-  const size_t BT = (size_t)p.B * p.T;
-  p.X = c.take<float>(BT * kW);
+  const size_t BT = (size_t)p.B * p.T, BC = (size_t)p.B * p.nC;
+  p.Z = c.take<float>(BT * kW);
   p.mrow = c.take<float>(BT);
   p.A = c.take<float>(BT * kW);
   p.Bh = c.take<float>(BT * kW);
   p.sA = c.take<float>(BT);
   p.G = c.take<float>(BT * kW);
-  p.facA = c.take<float>((size_t)p.B * (p.h > 0 ? p.h : 1) * p.Lp);
-  p.facB = c.take<float>((size_t)p.B * (p.T - p.h > 0 ? p.T - p.h : 1) * p.Lp);
-  p.cA = c.take<double>(BT);
-  p.cB = c.take<double>(BT);
+  p.ckAa = c.take<float>(BC * p.Lp);
+  p.ckBa = c.take<float>(BC * p.Lp);
+  p.ckCA = c.take<double>(BC);
+  p.ckCB = c.take<double>(BC);
   p.fccLogZ = c.take<double>(p.B);
+  p.facLogZ2 = c.take<double>(p.B);
   p.facLogZ = c.take<double>(p.B);
-  p.parts = c.take<float>((size_t)(grad_ctas_per_sample(p.T) + 1) * p.B * kW * kW);
+  p.msum = c.take<double>(p.B);
+  // sized for the most CTAs the FAC grad kernel can use (the actual count depends on the device's occupancy)
+  const size_t nparts = (size_t)(fcc_grad_ctas(p.T) + (p.nC + p.fac_grad_warps - 1) / p.fac_grad_warps) * p.B;
+  p.parts = c.take<float>(nparts * kW * kW);
+  p.parts2 = c.take<float>((nparts + kRedGroup - 1) / kRedGroup * kW * kW);
+  p.order = c.take<int>((size_t)p.B * p.Lp);
+  p.start = c.take<int>((size_t)p.B * 36);
   p.tsz = c.take<int>(p.B);
   p.valid = c.take<int>(p.B);
   p.scale = c.take<float>(p.B);
   p.coef = c.take<float>(p.B);
   total = c.off;
+}
+
+void shape(AsgParams& p, int B, int T, int N, int L) {
+  p.B = B;
+  p.T = T;
+  p.N = N;
+  p.L = L;
+  int Le = L < T ? L : T;
+  if (Le < 1) Le = 1;
+  p.P = pick_P(Le);
+  p.Lp = 32 * p.P;
+  p.nC = (T + kSeg - 1) / kSeg;
+  p.fac_grad_warps = fac_grad_warps(p.Lp);
 }
 
 }  // namespace
@@ -1048,14 +1058,7 @@ using namespace w2l;
 extern "C" size_t w2l_asg_workspace_size(int B, int T, int N, int L) {
   if (B <= 0 || T <= 0 || N <= 0) return 0;
   AsgParams p{};
-  p.B = B;
-  p.T = T;
-  p.N = N;
-  p.L = L;
-  int Le = L < T ? L : T;
-  if (Le < 1) Le = 1;
-  p.Lp = (int)align_up((size_t)Le, 32);
-  p.h = T / 2;
+  shape(p, B, T, N, L);
   size_t total = 0;
   carve(p, nullptr, total);
   return total;
@@ -1076,14 +1079,13 @@ extern "C" int w2l_asg_forward_backward(void* stream_, int terms, int B, int T, 
   if (scale_mode < 0 || scale_mode > 4) return fail(W2L_ERR_INVALID_ARGUMENT, "asg: bad scale mode");
   if (N > kW) return fail(W2L_ERR_UNSUPPORTED, "asg: N > 32 tokens is not covered by the sm_100a kernels");
   AsgParams p{};
-  p.B = B;
-  p.T = T;
-  p.N = N;
-  p.L = target ? L : 0;
-  int Le = p.L < T ? p.L : T;
-  if (Le < 1) Le = 1;
-  p.Lp = (int)align_up((size_t)Le, 32);
-  p.h = T / 2;
+  shape(p, B, T, N, L);  // the workspace is sized for the declared L whether or not a target is given
+  if (!target) p.L = 0;
+  size_t need = 0;
+  carve(p, workspace, need);
+  if (!workspace || workspace_bytes < need)
+    return fail(W2L_ERR_WORKSPACE, "asg: workspace too small (need " + std::to_string(need) + " bytes)");
+  if ((terms & W2L_TERM_FAC) && p.P > 32) return fail(W2L_ERR_UNSUPPORTED, "asg: target longer than 1024 is not covered");
   p.scale_mode = scale_mode;
   p.terms = terms;
   p.need_grad = d_emis != nullptr;
@@ -1094,62 +1096,68 @@ extern "C" int w2l_asg_forward_backward(void* stream_, int terms, int B, int T, 
   p.loss = loss;
   p.d_emis = d_emis;
   p.d_trans = d_trans;
-  size_t need = 0;
-  carve(p, workspace, need);
-  if (!workspace || workspace_bytes < need)
-    return fail(W2L_ERR_WORKSPACE, "asg: workspace too small (need " + std::to_string(need) + " bytes)");
-  size_t smem = 0;
-  if (terms & W2L_TERM_FAC) {
-    p.oring = fac_smem_bytes(p.Lp, 1) <= 200 * 1024;
-    smem = fac_smem_bytes(p.Lp, p.oring);
-    if (smem > 220 * 1024) return fail(W2L_ERR_UNSUPPORTED, "asg: target too long for the shared-memory rows");
-  }
-  const int n_fac = (terms & W2L_TERM_FAC) ? B : 0;
-  const int n_fcc = (terms & W2L_TERM_FCC) ? B : 0;
-  const int gpc = grad_ctas_per_sample(T);
-  p.n_grad_parts = (terms & W2L_TERM_FCC) ? gpc * B : 0;
-  if (!p.need_grad) p.parts = nullptr;
+  const bool has_fac = terms & W2L_TERM_FAC, has_fcc = terms & W2L_TERM_FCC;
+  // slowest chains first (FAC is MUFU-bound, FCC latency-bound, msum trivial)
+  p.n_roles = 0;
+  if (has_fac) p.roles[p.n_roles++] = kRoleFacAlpha;
+  if (has_fac && p.need_grad) p.roles[p.n_roles++] = kRoleFacBeta;
+  if (has_fcc) p.roles[p.n_roles++] = kRoleFccAlpha;
+  if (has_fcc && p.need_grad) p.roles[p.n_roles++] = kRoleFccBeta;
+  p.roles[p.n_roles++] = kRoleMsum;
+  const int gF = fcc_grad_ctas(T), gA = fac_grad_ctas(p);
+  p.n_fcc_parts = (has_fcc && p.need_grad) ? gF * B : 0;
+  p.n_fac_parts = (has_fac && p.need_grad) ? gA * B : 0;
 
   const long long nframes = (long long)B * T;
-  int frame_blocks = (int)std::min<long long>((nframes + 7) / 8, 148 * 8);
-  int meta_blocks = (B + 255) / 256;
+  const int frame_blocks = (int)std::min<long long>((nframes + 7) / 8, 148 * 8);
+  const int meta_blocks = (B + 7) / 8;
   asg_prep_kernel<<<frame_blocks + meta_blocks, 256, 0, stream>>>(p, frame_blocks);
   W2L_LAUNCH_CHECK("asg_prep_kernel");
 
-  const int kmax = p.Lp <= 2 * kGroup ? 2 : p.Lp <= 4 * kGroup ? 4 : p.Lp <= 8 * kGroup ? 8 : 32;
-  if ((terms & W2L_TERM_FAC) && p.Lp > 32 * kGroup)
-    return fail(W2L_ERR_UNSUPPORTED, "asg: target longer than 4096 is not covered");
-#define W2L_LAUNCH_CHAINS(GRAD, K)                                                                            \
-  do {                                                                                                        \
-    if (smem > 48 * 1024)                                                                                     \
-      W2L_CUDA_CHECK(cudaFuncSetAttribute(asg_chains_kernel<GRAD, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                                        \
-    profile_kind(2);                                                                                          \
-    profile_start(stream);                                                                                    \
-    asg_chains_kernel<GRAD, K><<<n_fac + n_fcc, kChainThreads, smem, stream>>>(p, n_fac);                      \
-    profile_stop(stream);                                                                                     \
-  } while (0)
-#define W2L_DISPATCH_CHAINS(GRAD)              \
-  do {                                         \
-    if (kmax == 2) W2L_LAUNCH_CHAINS(GRAD, 2); \
-    else if (kmax == 4) W2L_LAUNCH_CHAINS(GRAD, 4); \
-    else if (kmax == 8) W2L_LAUNCH_CHAINS(GRAD, 8); \
-    else W2L_LAUNCH_CHAINS(GRAD, 32);          \
-  } while (0)
-  if (p.need_grad) {
-    W2L_DISPATCH_CHAINS(true);
-    W2L_LAUNCH_CHECK("asg_chains_kernel<grad>");
-    dim3 grid(gpc, B);
-    asg_grad_kernel<<<grid, kGradWarps * 32, 0, stream>>>(p);
-    W2L_LAUNCH_CHECK("asg_grad_kernel");
-    // partial rows: [0, n_grad_parts) from the FCC grad CTAs, then n_fac rows from the FAC CTAs
-    asg_dtrans_reduce_kernel<<<(kW * kW + 255) / 256, 256, 0, stream>>>(p, p.n_grad_parts + n_fac);
-    W2L_LAUNCH_CHECK("asg_dtrans_reduce_kernel");
-  } else {
-    W2L_DISPATCH_CHAINS(false);
-    W2L_LAUNCH_CHECK("asg_chains_kernel<fwd>");
+#define W2L_FOR_P(MACRO)        \
+  switch (p.P) {                \
+    case 1: MACRO(1); break;    \
+    case 2: MACRO(2); break;    \
+    case 4: MACRO(4); break;    \
+    case 8: MACRO(8); break;    \
+    case 16: MACRO(16); break;  \
+    default: MACRO(32); break;  \
+  }
+#define W2L_LAUNCH_CHAINS(PP) asg_chains_kernel<PP><<<p.n_roles * B, 32, 0, stream>>>(p)
+  profile_kind(2);
+  profile_start(stream);
+  W2L_FOR_P(W2L_LAUNCH_CHAINS)
+  profile_stop(stream);
+  W2L_LAUNCH_CHECK("asg_chains_kernel");
+
+  if (!p.need_grad) {
     asg_loss_only_kernel<<<(B + 127) / 128, 128, 0, stream>>>(p);
     W2L_LAUNCH_CHECK("asg_loss_only_kernel");
+    return W2L_OK;
+  }
+  if (has_fac) {
+    const size_t smem = (size_t)fac_grad_layout(p.Lp, p.fac_grad_warps).total * 4;
+    const dim3 grid(gA, B);
+#define W2L_LAUNCH_FAC_GRAD(PP)                                                                                          \
+  do {                                                                                                                   \
+    if (smem > 48 * 1024)                                                                                                \
+      W2L_CUDA_CHECK(cudaFuncSetAttribute(asg_fac_grad_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    asg_fac_grad_kernel<PP><<<grid, p.fac_grad_warps * 32, smem, stream>>>(p);                                           \
+  } while (0)
+    W2L_FOR_P(W2L_LAUNCH_FAC_GRAD)
+    W2L_LAUNCH_CHECK("asg_fac_grad_kernel");
+  }
+  {
+    const dim3 grid(gF, B);
+    asg_fcc_grad_kernel<<<grid, kFccGradWarps * 32, 0, stream>>>(p);
+    W2L_LAUNCH_CHECK("asg_fcc_grad_kernel");
+  }
+  {
+    const int n_parts = p.n_fcc_parts + p.n_fac_parts, n2 = (n_parts + kRedGroup - 1) / kRedGroup;
+    asg_parts_reduce_kernel<<<dim3((kW * kW + 255) / 256, n2), 256, 0, stream>>>(p.parts, n_parts, kRedGroup, p.parts2, 0);
+    W2L_LAUNCH_CHECK("asg_parts_reduce_kernel");
+    asg_parts_reduce_kernel<<<dim3((kW * kW + 255) / 256, 1), 256, 0, stream>>>(p.parts2, n2, n2, p.d_trans, N);
+    W2L_LAUNCH_CHECK("asg_parts_reduce_kernel");
   }
   return W2L_OK;
 }
