@@ -24,7 +24,7 @@
 //                    the P = Lp/32 CONSECUTIVE target positions P*j .. P*j+P-1 in registers, so the
 //                    l-1 neighbour is a register except for one SHFL per step; 2 MUFU per state
 //                    (ex2 + lg2), the adds packed two states per instruction (FADD2/FFMA2);
-//                    emissions gathered from an 8-frame shared-memory tile; re-centred every 4
+//                    emissions gathered from an 8-frame shared-memory tile; re-centred every 2
 //                    frames (offset carried in double); the row is stored only every 8 frames (a
 //                    checkpoint: a full FAC lattice would be Lp/32 times the size of the emissions).
 //   3. asg_fac_grad_kernel parallel over (sample, 8-frame segment): recomputes the FAC beta rows
@@ -44,10 +44,19 @@ namespace {
 constexpr int kW = 32;            // padded FCC state width (one lane per state)
 constexpr int kBlk = 16;          // frames per register-prefetch block of the FCC chains
 constexpr int kSeg = 8;           // frames per FAC checkpoint segment (= shared-memory tile of the FAC chains)
-constexpr int kRc = 4;            // FAC chains re-centre every kRc frames
+constexpr int kRc = 2;            // FAC chains re-centre every kRc frames
 constexpr float kNeg = -1.0e30f;  // "log zero": finite, absorbing under fp32 addition of ordinary scores
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr double kLn2 = 0.6931471805599453;
+// MUFU.LG2 has a one-signed error: +1.0e-7 (absolute) just above a mantissa of 1, falling to +2e-8 towards 2, and it is
+// exact at 1.0 (scripts/mufu_bias.cu, profiles/mufu_bias_r2.txt).  log2(1 + r) for the small r of a weakly contested
+// state therefore came out 1e-7 too large at every step while an uncontested state (r = 0) got nothing: a differential
+// that grows linearly along the chain (1.4e-4 of the posteriors after 1500 frames).  The recursion evaluates
+// lg2(1.25 * (1 + r)) instead — same instruction count (an FFMA for the FADD): mantissas 1.25 .. 2 for r < 0.6, where
+// the error is small and flat, and the same for r = 0 as for small r — and subtracts the constant log2(1.25) for free by
+// folding it into the transition scores (lse(a - c, b - c) = lse(a, b) - c).
+constexpr float kLgScale = 1.25f;
+constexpr float kLgShift = 0.32192809488736235f;  // log2(1.25)
 constexpr int kFccGradWarps = 8;  // warps per CTA in the FCC grad kernel
 constexpr int kFccGradFrames = 16;  // frames per warp in the FCC grad kernel
 constexpr int kFlushRegs = 16;    // positions per label kept in registers by the label-sum
@@ -101,10 +110,10 @@ __device__ __forceinline__ float lg2f(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// log2(2^a + 2^b) for finite a, b (kNeg stands for log zero): 2 MUFU, no branches
+// log2(2^a + 2^b) + log2(1.25) for finite a, b (kNeg stands for log zero): 2 MUFU, no branches (see kLgScale)
 __device__ __forceinline__ float lse2_log2(float a, float b) {
   const float mx = fmaxf(a, b), mn = fminf(a, b);
-  return mx + lg2f(1.0f + ex2f(mn - mx));
+  return mx + lg2f(fmaf(ex2f(mn - mx), kLgScale, kLgScale));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -186,26 +195,38 @@ __global__ void __launch_bounds__(256) asg_prep_kernel(AsgParams p, int frame_bl
 // register quad for successive loads, which serialises them into dependent ~30-cycle rounds.
 __device__ __forceinline__ float matvec32(const float (&M)[kW], const float* vsm) {
   const unsigned base = (unsigned)__cvta_generic_to_shared(vsm);
-  float4 v[kW / 4];
-#pragma unroll
-  for (int q = 0; q < kW / 4; ++q)
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
-                 : "r"(base + 16u * q));
-  float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  float v[kW];
+  // Eight VOLATILE loads (ptxas keeps their order) whose LAST one feeds the FIRST arithmetic instruction: all eight are
+  // in flight, in 32 distinct registers, before any product issues.  Left to itself ptxas recycles one or two register
+  // quads and sinks each load behind the consumer of the previous one — two loads in flight, four to eight dependent
+  // ~30-cycle rounds per step (profiles/asg_r2.md).
+  asm volatile(
+      "ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%32];\n\t"
+      "ld.volatile.shared.v4.f32 {%4, %5, %6, %7}, [%32+16];\n\t"
+      "ld.volatile.shared.v4.f32 {%8, %9, %10, %11}, [%32+32];\n\t"
+      "ld.volatile.shared.v4.f32 {%12, %13, %14, %15}, [%32+48];\n\t"
+      "ld.volatile.shared.v4.f32 {%16, %17, %18, %19}, [%32+64];\n\t"
+      "ld.volatile.shared.v4.f32 {%20, %21, %22, %23}, [%32+80];\n\t"
+      "ld.volatile.shared.v4.f32 {%24, %25, %26, %27}, [%32+96];\n\t"
+      "ld.volatile.shared.v4.f32 {%28, %29, %30, %31}, [%32+112];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+        "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+        "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+        "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(base));
+  // eight independent two-deep products (one per load) and a tree.  Every product starts from z = 0 * (a value of the
+  // LAST load): a true dependence, so no consumer can issue — and no register quad can be recycled — before all eight
+  // loads have left (the vector entries are finite, 0 * v is an exact zero).
+  float z;
+  asm volatile("mul.f32 %0, %1, 0f00000000;" : "=f"(z) : "f"(v[kW - 1]));
+  const float2 z2 = make_float2(z, z);
+  float2 r[kW / 4];
 #pragma unroll
   for (int q = 0; q < kW / 4; ++q) {
-    float2 lo = make_float2(v[q].x, v[q].y), hi = make_float2(v[q].z, v[q].w);
-    float2 mlo = make_float2(M[4 * q], M[4 * q + 1]), mhi = make_float2(M[4 * q + 2], M[4 * q + 3]);
-    if (q & 1) {
-      a2 = __ffma2_rn(mlo, lo, a2);
-      a3 = __ffma2_rn(mhi, hi, a3);
-    } else {
-      a0 = __ffma2_rn(mlo, lo, a0);
-      a1 = __ffma2_rn(mhi, hi, a1);
-    }
+    const float2 pq = __ffma2_rn(make_float2(M[4 * q], M[4 * q + 1]), make_float2(v[4 * q], v[4 * q + 1]), z2);
+    r[q] = __ffma2_rn(make_float2(M[4 * q + 2], M[4 * q + 3]), make_float2(v[4 * q + 2], v[4 * q + 3]), pq);
   }
-  float2 s = __fadd2_rn(__fadd2_rn(a0, a1), __fadd2_rn(a2, a3));
+  const float2 s = __fadd2_rn(__fadd2_rn(__fadd2_rn(r[0], r[1]), __fadd2_rn(r[2], r[3])), __fadd2_rn(__fadd2_rn(r[4], r[5]), __fadd2_rn(r[6], r[7])));
   return s.x + s.y;
 }
 
@@ -252,6 +273,8 @@ __device__ void fcc_alpha_chain(const AsgParams& p, int b, float* vec /* [2][32]
   for (int k = 0; k < kBlk; ++k) zn[k] = k < T ? __ldg(Zl + (size_t)k * kW) : 0.f;
   float a = 0.f, s = 1.0f;
   int ksum = 0, kcur = 0;
+  float* Ap = Al;
+  float* sp = sAb;
   for (int c = 0; c < nblk; ++c) {
     float zc[kBlk];
     const int tb = c * kBlk;
@@ -282,8 +305,10 @@ __device__ void fcc_alpha_chain(const AsgParams& p, int b, float* vec /* [2][32]
       a = xs * matvec32(M, vb);
       ksum += kcur;
       if (store) {
-        Al[(size_t)t * kW] = a;
-        if (lane == 0) sAb[t] = s;
+        Ap += kW;  // (running pointers: frame t)
+        sp += 1;
+        *Ap = a;
+        if (lane == 0) *sp = s;
       }
       s = pow2_rescale<1>(mx, kcur);  // applied at t+1 from |a_{t-1}| (lag two): damped
     }
@@ -315,6 +340,7 @@ __device__ void fcc_beta_chain(const AsgParams& p, int b, float* vec) {
   }
   float s = 1.0f;
   int kdummy;
+  float* Bp = Bl + (size_t)(T - 1) * kW;
   for (int c = ctop; c >= 0; --c) {
     float zc[kBlk];
     const int tb = c * kBlk;
@@ -334,7 +360,8 @@ __device__ void fcc_beta_chain(const AsgParams& p, int b, float* vec) {
       const float mx = warp_max(u);
       __syncwarp();
       bh = matvec32(M, vb);
-      Bl[(size_t)t * kW] = bh;
+      Bp -= kW;  // (running pointer: frame t)
+      *Bp = bh;
       s = pow2_rescale<0>(mx, kdummy);
     }
   }
@@ -345,7 +372,7 @@ __device__ void fcc_beta_chain(const AsgParams& p, int b, float* vec) {
 //
 // Scores are normalised so that nothing drifts: emissions by the frame maximum (Z <= 0) and transitions by the
 // global transition maximum (s1, s2 <= 0); the recursion then computes alpha_t - t * tmax2 (beta: - (T-1-t) * tmax2),
-// which only moves by the log-count of merging paths, and is re-centred every kRc frames (offset in double).
+// which only moves by the log-count of merging paths, and is re-centred every kRc frames (two-float offset).
 // ------------------------------------------------------------------------------------------
 template <int P>
 struct FacState {
@@ -364,17 +391,25 @@ __device__ __forceinline__ void fac_load_target(FacState<P>& st, const AsgParams
     const int l = lane * P + k;
     const int yl = l < L ? __ldg(yg + l) : 0;
     st.y4[k] = 4 * yl;
-    st.s1[k] = l < L ? (__ldg(p.trans + yl * N + yl) - tmax) * kLog2e : 0.f;
+    st.s1[k] = l < L ? (__ldg(p.trans + yl * N + yl) - tmax) * kLog2e - kLgShift : 0.f;
     float s2 = kNeg;
     if (!beta) {
-      if (l < L && l > 0) s2 = (__ldg(p.trans + yl * N + __ldg(yg + l - 1)) - tmax) * kLog2e;
+      if (l < L && l > 0) s2 = (__ldg(p.trans + yl * N + __ldg(yg + l - 1)) - tmax) * kLog2e - kLgShift;
     } else {
-      if (l + 1 < L) s2 = (__ldg(p.trans + __ldg(yg + l + 1) * N + yl) - tmax) * kLog2e;
+      if (l + 1 < L) s2 = (__ldg(p.trans + __ldg(yg + l + 1) * N + yl) - tmax) * kLog2e - kLgShift;
     }
     st.s2[k] = s2;
     st.v[k] = kNeg;
   }
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float lds_f(uint32_t a) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -389,7 +424,7 @@ __device__ __forceinline__ float2 fac_pair(float va, float na, float s1a, float 
   const float2 mx = make_float2(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
   const float2 mn = make_float2(fminf(a.x, a.y), fminf(b.x, b.y));
   const float2 d = __ffma2_rn(mx, make_float2(-1.f, -1.f), mn);  // mn - mx (exact)
-  const float2 q = __fadd2_rn(make_float2(ex2f(d.x), ex2f(d.y)), make_float2(1.f, 1.f));
+  const float2 q = __ffma2_rn(make_float2(ex2f(d.x), ex2f(d.y)), make_float2(kLgScale, kLgScale), make_float2(kLgScale, kLgScale));
   const float2 base = __fadd2_rn(make_float2(za, zb), mx);
   return __fadd2_rn(base, make_float2(lg2f(q.x), lg2f(q.y)));
 }
@@ -428,19 +463,6 @@ __device__ __forceinline__ void fac_beta_step(FacState<P>& st, const float (&s2)
     }
   }
 }
-// subtract the row maximum (exact bookkeeping in C); rows that are entirely "zero" stay put
-template <int P>
-__device__ __forceinline__ void fac_recentre(FacState<P>& st, double& C) {
-  float m = kNeg;
-#pragma unroll
-  for (int k = 0; k < P; ++k) m = fmaxf(m, st.v[k]);
-  m = warp_max(m);
-  if (m > -1.0e29f) {
-#pragma unroll
-    for (int k = 0; k < P; ++k) st.v[k] -= m;
-    C += (double)m;
-  }
-}
 template <int P>
 __device__ __forceinline__ void fac_store_row(const FacState<P>& st, float* row, int lane) {
   if constexpr (P >= 4) {
@@ -469,118 +491,141 @@ __device__ __forceinline__ void fac_load_row(FacState<P>& st, const float* row, 
   }
 }
 
-template <int P>
-__device__ void fac_alpha_chain(const AsgParams& p, int b, float* ztile /* [kSeg][32] shared */) {
+// C += m in two-float arithmetic (exact two-sum of the high part; the low part collects the rounding errors): the
+// re-centring offset needs more than fp32 (it reaches 1e4..1e5 while differences of 1e-5 matter) but a DADD behind an
+// F2F sits ~40 cycles on the in-order issue path of a lone warp
+__device__ __forceinline__ void twofloat_add(float& hi, float& lo, float m) {
+  const float s = hi + m;
+  const float bb = s - hi;
+  const float e = (hi - (s - bb)) + (m - bb);
+  hi = s;
+  lo += e;
+}
+
+// One warp walks one FAC recursion, P positions per lane.  (A variant that spread a recursion over four warps, two
+// positions per lane, with the boundary value handed from warp to warp through a shared-memory message ring, was built
+// and measured in this round: 186 ns per step against 167 ns for this one — the per-step dependent chain
+// SHFL -> FADD2 -> FMNMX -> FFMA2 -> EX2 -> FADD2 -> LG2 -> FADD2 is ~160 cycles whatever the width, and the ring's
+// bookkeeping cost what the narrower rows saved.  profiles/asg_r2.md.)
+template <int P, bool kBeta>
+__device__ void fac_chain(const AsgParams& p, int b, float* ztile /* [kSeg][32] shared */) {
   const int lane = threadIdx.x & 31;
   const int T = p.T, L = p.tsz[b];
   const float tmax = trans_max(p.trans, p.N, lane);
   FacState<P> st;
-  fac_load_target<P>(st, p, b, L, lane, false, tmax);
+  fac_load_target<P>(st, p, b, L, lane, kBeta, tmax);
   const float* Zl = p.Z + (size_t)b * T * kW + lane;
   const uint32_t zt = (uint32_t)__cvta_generic_to_shared(ztile);
   const bool store = p.need_grad != 0;
-  float zn[kSeg];
+  float Chi = 0.f, Clo = 0.f, pend = kNeg, off = 0.f;
+
+  auto step = [&](int t, int krow) {
+    if (!kBeta)
+      fac_alpha_step<P>(st, zt + krow * (4 * kW), lane);
+    else
+      fac_beta_step<P>(st, st.s2, zt + krow * (4 * kW), lane);
+    // lagged, branch-free re-centring: the maximum taken at one step is subtracted after the next one, so the
+    // CREDUX round trip never sits on the dependent chain
+    if ((t & (kRc - 1)) == (kBeta ? kRc - 1 : 0)) {
+      // the row maximum is put at +off, half of what it lost over the last period, so that the live states straddle
+      // zero until the next re-centring instead of sinking from it: half the magnitude, half the rounding error per
+      // step (the bookkeeping in C is exact whatever is subtracted)
+      const bool live = pend > -1.0e29f;
+      const float off_new = fminf(fmaxf(0.5f * (off - pend), 0.f), 48.f);
+      const float m = live ? pend - off_new : 0.f;
+      off = live ? off_new : off;
 #pragma unroll
-  for (int k = 0; k < kSeg; ++k) zn[k] = k < T ? __ldg(Zl + (size_t)k * kW) : 0.f;
-  double C = 0.0;
-  for (int c = 0; c < p.nC; ++c) {
-    const int tb = c * kSeg;
-    __syncwarp();
+      for (int k = 0; k < P; ++k) st.v[k] -= m;
+      twofloat_add(Chi, Clo, m);
+    }
+    if ((t & (kRc - 1)) == (kBeta ? 0 : kRc - 1)) {
+      float m = st.v[0];
 #pragma unroll
-    for (int k = 0; k < kSeg; ++k) {
-      ztile[k * kW + lane] = zn[k];
-      const int tn = tb + kSeg + k;
-      zn[k] = tn < T ? __ldg(Zl + (size_t)tn * kW) : 0.f;
+      for (int k = 1; k < P; ++k) m = fmaxf(m, st.v[k]);
+      pend = warp_max(m);
     }
-    __syncwarp();
-    int k0 = 0;
-    if (c == 0) {  // alpha_0: position 0 carries the first frame's score
-      if (lane == 0) st.v[0] = ztile[st.y4[0] >> 2];
-      k0 = 1;
-    }
-    const int kend = min(kSeg, T - tb);
-    if (k0 == 0 && kend == kSeg) {  // the common case, fully unrolled
+  };
+
+  if (!kBeta) {
+    // ---- alpha: frames 0 .. T-1; checkpoint c+1 = row of frame (c+1)*kSeg - 1 ----------------------------------------
+    float zn[kSeg];
+#pragma unroll
+    for (int k = 0; k < kSeg; ++k) zn[k] = k < T ? __ldg(Zl + (size_t)k * kW) : 0.f;
+    for (int c = 0; c < p.nC; ++c) {
+      const int tb = c * kSeg;
+      __syncwarp();
 #pragma unroll
       for (int k = 0; k < kSeg; ++k) {
-        fac_alpha_step<P>(st, zt + k * (4 * kW), lane);
-        if ((k + 1) % kRc == 0) fac_recentre<P>(st, C);
+        ztile[k * kW + lane] = zn[k];
+        const int tn = tb + kSeg + k;
+        zn[k] = tn < T ? __ldg(Zl + (size_t)tn * kW) : 0.f;
       }
-    } else {
-      for (int h = 0; h < kSeg; h += kRc) {
-        const int lo = max(k0, h), hi = min(kend, h + kRc);
-        for (int k = lo; k < hi; ++k) fac_alpha_step<P>(st, zt + k * (4 * kW), lane);
-        if (hi > lo) fac_recentre<P>(st, C);
+      __syncwarp();
+      int k0 = 0;
+      if (c == 0) {  // alpha_0: position 0 carries the first frame's score
+        if (lane == 0) st.v[0] = ztile[st.y4[0] >> 2];
+        k0 = 1;
+      }
+      const int kend = min(kSeg, T - tb);
+      if (k0 == 0 && kend == kSeg) {
+#pragma unroll
+        for (int k = 0; k < kSeg; ++k) step(tb + k, k);
+      } else {
+        for (int k = k0; k < kend; ++k) step(tb + k, k);
+      }
+      if (store && c + 1 < p.nC) {
+        fac_store_row<P>(st, p.ckAa + ((size_t)b * p.nC + c + 1) * p.Lp, lane);
+        if (lane == 0) p.ckCA[(size_t)b * p.nC + c + 1] = (double)Chi + (double)Clo;
       }
     }
-    if (store && c + 1 < p.nC) {  // (a full segment: the row was re-centred right above)
-      fac_store_row<P>(st, p.ckAa + ((size_t)b * p.nC + c + 1) * p.Lp, lane);
-      if (lane == 0) p.ckCA[(size_t)b * p.nC + c + 1] = C;
+    // log2 partition function: the last position at the last frame
+    float last = kNeg;
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      if (lane * P + k == L - 1) last = st.v[k];
+    last = warp_max(last);
+    if (lane == 0) {
+      const double z2 = (double)last + (double)Chi + (double)Clo;
+      p.facLogZ2[b] = z2;
+      p.facLogZ[b] = z2 * kLn2 + (double)(T - 1) * (double)tmax;
     }
-  }
-  // log2 partition function: the last position at the last frame
-  float last = kNeg;
-#pragma unroll
-  for (int k = 0; k < P; ++k)
-    if (lane * P + k == L - 1) last = st.v[k];
-  last = warp_max(last);
-  if (lane == 0) {
-    p.facLogZ2[b] = (double)last + C;
-    p.facLogZ[b] = ((double)last + C) * kLn2 + (double)(T - 1) * (double)tmax;
-  }
-}
-
-template <int P>
-__device__ void fac_beta_chain(const AsgParams& p, int b, float* ztile) {
-  const int lane = threadIdx.x & 31;
-  const int T = p.T, L = p.tsz[b];
-  const float tmax = trans_max(p.trans, p.N, lane);
-  FacState<P> st;
-  fac_load_target<P>(st, p, b, L, lane, true, tmax);
-  const float* Zl = p.Z + (size_t)b * T * kW + lane;
-  const uint32_t zt = (uint32_t)__cvta_generic_to_shared(ztile);
-  // segment c covers frames [c*kSeg, c*kSeg + kSeg), walked downwards; the first one holds frame T-1 (initial row)
-  const int ctop = (T - 1) / kSeg;
-  float zn[kSeg];
-#pragma unroll
-  for (int k = 0; k < kSeg; ++k) {
-    const int f = ctop * kSeg + k;
-    zn[k] = f < T ? __ldg(Zl + (size_t)f * kW) : 0.f;
-  }
-  double C = 0.0;
-  for (int c = ctop; c >= 0; --c) {
-    const int tb = c * kSeg;
-    __syncwarp();
+  } else {
+    // ---- beta: frames T-1 .. 0; checkpoint c-1 = row of frame c*kSeg -------------------------------------------------
+    const int ctop = (T - 1) / kSeg;
+    float zn[kSeg];
 #pragma unroll
     for (int k = 0; k < kSeg; ++k) {
-      ztile[k * kW + lane] = zn[k];
-      const int f = tb - kSeg + k;
-      zn[k] = f >= 0 ? __ldg(Zl + (size_t)f * kW) : 0.f;
+      const int f = ctop * kSeg + k;
+      zn[k] = f < T ? __ldg(Zl + (size_t)f * kW) : 0.f;
     }
-    __syncwarp();
-    int khi = kSeg - 1;
-    if (c == ctop) {  // beta_{T-1}: the last position carries the last frame's score
-      const int kl = T - 1 - tb;
+    for (int c = ctop; c >= 0; --c) {
+      const int tb = c * kSeg;
+      __syncwarp();
 #pragma unroll
-      for (int k = 0; k < P; ++k)
-        if (lane * P + k == L - 1) st.v[k] = ztile[kl * kW + (st.y4[k] >> 2)];
-      khi = kl - 1;
-    }
-    if (khi == kSeg - 1) {  // the common case, fully unrolled
+      for (int k = 0; k < kSeg; ++k) {
+        ztile[k * kW + lane] = zn[k];
+        const int f = tb - kSeg + k;
+        zn[k] = f >= 0 ? __ldg(Zl + (size_t)f * kW) : 0.f;
+      }
+      __syncwarp();
+      int khi = kSeg - 1;
+      if (c == ctop) {  // beta_{T-1}: the last position carries the last frame's score
+        const int kl = T - 1 - tb;
 #pragma unroll
-      for (int k = kSeg - 1; k >= 0; --k) {
-        fac_beta_step<P>(st, st.s2, zt + k * (4 * kW), lane);
-        if (k % kRc == 0) fac_recentre<P>(st, C);
+        for (int k = 0; k < P; ++k)
+          if (lane * P + k == L - 1) st.v[k] = ztile[kl * kW + (st.y4[k] >> 2)];
+        khi = kl - 1;
       }
-    } else {
-      for (int h = kSeg - kRc; h >= 0; h -= kRc) {
-        const int hi = min(khi, h + kRc - 1);
-        for (int k = hi; k >= h; --k) fac_beta_step<P>(st, st.s2, zt + k * (4 * kW), lane);
-        if (hi >= h || h == 0) fac_recentre<P>(st, C);
+      if (khi == kSeg - 1) {
+#pragma unroll
+        for (int k = kSeg - 1; k >= 0; --k) step(tb + k, k);
+      } else {
+        for (int k = khi; k >= 0; --k) step(tb + k, k);
       }
-    }
-    if (c >= 1) {  // row of frame c*kSeg = checkpoint c-1 (re-centred right above)
-      fac_store_row<P>(st, p.ckBa + ((size_t)b * p.nC + c - 1) * p.Lp, lane);
-      if (lane == 0) p.ckCB[(size_t)b * p.nC + c - 1] = C;
+      if (c >= 1) {
+        fac_store_row<P>(st, p.ckBa + ((size_t)b * p.nC + c - 1) * p.Lp, lane);
+        if (lane == 0) p.ckCB[(size_t)b * p.nC + c - 1] = (double)Chi + (double)Clo;
+      }
     }
   }
 }
@@ -600,9 +645,9 @@ __global__ void __launch_bounds__(32) asg_chains_kernel(AsgParams p) {
   }
   if (!p.valid[b]) return;
   if (role == kRoleFacAlpha)
-    fac_alpha_chain<P>(p, b, sm);
+    fac_chain<P, false>(p, b, sm);
   else if (role == kRoleFacBeta)
-    fac_beta_chain<P>(p, b, sm);
+    fac_chain<P, true>(p, b, sm);
   else if (role == kRoleFccAlpha)
     fcc_alpha_chain(p, b, sm);
   else
@@ -643,7 +688,7 @@ __device__ __forceinline__ float label_sum(uint32_t row_sa, const float* row, co
 
 // dynamic shared memory of the FAC grad kernel (4-byte words)
 struct FacGradLayout {
-  int order, start, y, ztile, brow, grow, dsum, dtr, per_warp, total;
+  int order, start, y, ztile, bnext, brow, grow, dsum, dtr, per_warp, total;
 };
 __host__ __device__ inline FacGradLayout fac_grad_layout(int Lp, int warps) {
   FacGradLayout f;
@@ -654,9 +699,10 @@ __host__ __device__ inline FacGradLayout fac_grad_layout(int Lp, int warps) {
   f.dsum = o;   o += 2 * Lp;
   f.dtr = o;    o += kW * (kW + 1);
   o = (o + 3) & ~3;
-  f.per_warp = kSeg * kW + kSeg * Lp + Lp + 4;  // Z tile, beta rows, gamma row (+ a zero slot behind it)
+  f.per_warp = 2 * kSeg * kW + Lp + kSeg * Lp + Lp + 4;  // two Z tiles, next beta row, beta rows, gamma row (+ a zero slot)
   f.ztile = o;
-  f.brow = o + kSeg * kW;
+  f.bnext = o + 2 * kSeg * kW;
+  f.brow = f.bnext + Lp;
   f.grow = f.brow + kSeg * Lp;
   f.total = o + warps * f.per_warp;
   return f;
@@ -675,7 +721,7 @@ __device__ __forceinline__ float2 fac_grad_pair(float va, float na, float s1a, f
   const float2 mx = make_float2(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
   const float2 mn = make_float2(fminf(a.x, a.y), fminf(b.x, b.y));
   const float2 d = __ffma2_rn(mx, make_float2(-1.f, -1.f), mn);
-  const float2 q = __fadd2_rn(make_float2(ex2f(d.x), ex2f(d.y)), make_float2(1.f, 1.f));
+  const float2 q = __ffma2_rn(make_float2(ex2f(d.x), ex2f(d.y)), make_float2(kLgScale, kLgScale), make_float2(kLgScale, kLgScale));
   const float2 base = __fadd2_rn(make_float2(za, zb), mx);
   return __fadd2_rn(base, make_float2(lg2f(q.x), lg2f(q.y)));
 }
@@ -708,14 +754,16 @@ __global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
   for (int k = threadIdx.x; k < kW * (kW + 1); k += blockDim.x) dtr_s[k] = 0.f;
   __syncthreads();
 
-  float ds1[P], ds2[P];
+  float2 ds[P];  // (stay, advance) transition statistics of the owned positions
 #pragma unroll
-  for (int k = 0; k < P; ++k) ds1[k] = ds2[k] = 0.f;
+  for (int k = 0; k < P; ++k) ds[k] = make_float2(0.f, 0.f);
   {
-    float* ztile = smem + lay.ztile + warp * lay.per_warp;
+    float* ztile2 = smem + lay.ztile + warp * lay.per_warp;  // [2][kSeg][32]: this segment's Z rows / the next one's
+    float* bnext = smem + lay.bnext + warp * lay.per_warp;   // the next segment's beta checkpoint row
     float* brow = smem + lay.brow + warp * lay.per_warp;
     float* grow = smem + lay.grow + warp * lay.per_warp;
-    const uint32_t zt = (uint32_t)__cvta_generic_to_shared(ztile);
+    const uint32_t zt2 = (uint32_t)__cvta_generic_to_shared(ztile2);
+    const uint32_t bnext_sa = (uint32_t)__cvta_generic_to_shared(bnext);
     const uint32_t grow_sa = (uint32_t)__cvta_generic_to_shared(grow);
     const float tmax = trans_max(p.trans, p.N, lane);
     const float* Zb = p.Z + (size_t)b * T * kW;
@@ -730,11 +778,37 @@ __global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
     FlushIndex fx;
     fx.load(order_s, start_s, lane, Lp);
     if (lane == 0) grow[Lp] = 0.f;
+    // asynchronous copies (no registers) of a segment's inputs: its Z rows and, unless it ends the utterance, the beta
+    // checkpoint row behind it — issued one segment ahead
+    auto prefetch = [&](int c, int buf) {
+      const int t0 = c * kSeg;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int chunk = lane + 32 * h;  // 16-byte chunk of the [kSeg][32] tile
+        const int t = t0 + (chunk >> 3);
+        if (t < T) cp_async16(zt2 + (buf * kSeg * kW) * 4 + chunk * 16, Zb + (size_t)t * kW + (chunk & 7) * 4);
+      }
+      if (t0 + kSeg < T) {
+        const float* src = p.ckBa + ((size_t)b * p.nC + c) * Lp + lane * P;
+        if constexpr (P >= 4) {
+#pragma unroll
+          for (int k = 0; k < P; k += 4) cp_async16(bnext_sa + (lane * P + k) * 4, src + k);
+        } else {
+#pragma unroll
+          for (int k = 0; k < P; ++k) cp_async4(bnext_sa + (lane * P + k) * 4, src + k);
+        }
+      }
+      cp_async_commit();
+    };
     // segments are dealt round-robin to the warps of the sample's CTAs
-    for (int c = blockIdx.x * nw + warp; c < p.nC; c += gridDim.x * nw) {
+    const int cstride = gridDim.x * nw;
+    int c = blockIdx.x * nw + warp, buf = 0;
+    if (c < p.nC) prefetch(c, 0);
+    for (; c < p.nC; c += cstride, buf ^= 1) {
       const int t0 = c * kSeg, t1 = min(T, t0 + kSeg);
-      __syncwarp();
-      for (int k = 0; k < t1 - t0; ++k) ztile[k * kW + lane] = __ldg(Zb + (size_t)(t0 + k) * kW + lane);
+      const uint32_t zt = zt2 + (buf * kSeg * kW) * 4;
+      const float* ztile = ztile2 + buf * kSeg * kW;
+      cp_async_wait_all();
       __syncwarp();
       // ---- backwards: beta-tilde rows of frames t1-1 .. t0 into shared memory --------------------
       double CB = 0.0;
@@ -745,16 +819,37 @@ __global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
         fac_store_row<P>(st, brow + (size_t)(T - 1 - t0) * Lp, lane);
         tstart = T - 2;
       } else {
-        fac_load_row<P>(st, p.ckBa + ((size_t)b * p.nC + c) * Lp, lane);
+        fac_load_row<P>(st, bnext, lane);
         CB = p.ckCB[(size_t)b * p.nC + c];
         tstart = t1 - 1;
+      }
+      __syncwarp();
+      if (c + cstride < p.nC) prefetch(c + cstride, buf ^ 1);
+      // this segment's alpha checkpoint: requested now, used after the backward pass
+      float arow[P];
+      double CA = 0.0;
+      if (t0 > 0) {
+        const float* src = p.ckAa + ((size_t)b * p.nC + c) * Lp + lane * P;
+        if constexpr (P >= 4) {
+#pragma unroll
+          for (int k = 0; k < P; k += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src + k));
+            arow[k] = q.x;
+            arow[k + 1] = q.y;
+            arow[k + 2] = q.z;
+            arow[k + 3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < P; ++k) arow[k] = __ldg(src + k);
+        }
+        CA = p.ckCA[(size_t)b * p.nC + c];
       }
       for (int t = tstart; t >= t0; --t) {
         fac_beta_step<P>(st, s2b, zt + (t - t0) * (4 * kW), lane);
         fac_store_row<P>(st, brow + (size_t)(t - t0) * Lp, lane);
       }
       // ---- forwards: alpha-tilde, occupancies, transition statistics -----------------------------
-      double CA = 0.0;
       int tfirst = t0;
       if (t0 == 0) {
 #pragma unroll
@@ -763,65 +858,59 @@ __global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
         Gb[lane] = (lane == y_s[0]) ? 1.0f : 0.0f;  // frame 0 sits at position 0 with probability one
         tfirst = 1;
       } else {
-        fac_load_row<P>(st, p.ckAa + ((size_t)b * p.nC + c) * Lp, lane);
-        CA = p.ckCA[(size_t)b * p.nC + c];
+#pragma unroll
+        for (int k = 0; k < P; ++k) st.v[k] = arow[k];
       }
       // alpha_{t-1}[l] + s + beta_t[l] - log2 Z  =  tilde values + (CA + CB - facLogZ2): the t * tmax terms cancel
-      const float K = (float)(CA + CB - logZ2);
+      // (+ kLgShift: the transition scores in s1 / s2 carry the folded -log2(1.25))
+      const float K = (float)(CA + CB - logZ2) + kLgShift;
+      const float2 K2 = make_float2(K, K);
       __syncwarp();
       for (int t = tfirst; t < t1; ++t) {
         const uint32_t zrow = zt + (t - t0) * (4 * kW);
         const float* br = brow + (size_t)(t - t0) * Lp + lane * P;
         float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1);
         if (lane == 0) up = kNeg;
-        float xs[P], xa[P];
-        float gs;
+        float2 xv[P];  // (stay, advance) posteriors of the owned positions, unnormalised
         if constexpr (P == 1) {
           const float a0 = st.v[0] + st.s1[0], a1 = up + st.s2[0];
           const float o = br[0] + K;
-          xs[0] = ex2f(a0 + o);
-          xa[0] = ex2f(a1 + o);
-          gs = xs[0] + xa[0];
+          xv[0] = make_float2(ex2f(a0 + o), ex2f(a1 + o));
+          grow[lane] = xv[0].x + xv[0].y;
           st.v[0] = lds_f(zrow + st.y4[0]) + lse2_log2(a0, a1);
         } else {
-          float2 g2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int k = P - 2; k >= 0; k -= 2) {  // pairs, descending: v[k-1], v[k] are still alpha_{t-1}
-            float2 xsa, xsb;
-            const float2 brk = *reinterpret_cast<const float2*>(br + k);
-            const float2 nv = fac_grad_pair(st.v[k], k ? st.v[k - 1] : up, st.s1[k], st.s2[k], lds_f(zrow + st.y4[k]), brk.x + K,  //
-                                            st.v[k + 1], st.v[k], st.s1[k + 1], st.s2[k + 1], lds_f(zrow + st.y4[k + 1]), brk.y + K, xsa, xsb);
-            xs[k] = xsa.x;
-            xa[k] = xsa.y;
-            xs[k + 1] = xsb.x;
-            xa[k + 1] = xsb.y;
-            g2 = __fadd2_rn(g2, __fadd2_rn(xsa, xsb));
+            const float2 brk = __fadd2_rn(*reinterpret_cast<const float2*>(br + k), K2);
+            const float2 nv = fac_grad_pair(st.v[k], k ? st.v[k - 1] : up, st.s1[k], st.s2[k], lds_f(zrow + st.y4[k]), brk.x,  //
+                                            st.v[k + 1], st.v[k], st.s1[k + 1], st.s2[k + 1], lds_f(zrow + st.y4[k + 1]), brk.y, xv[k], xv[k + 1]);
+            *reinterpret_cast<float2*>(grow + lane * P + k) = make_float2(xv[k].x + xv[k].y, xv[k + 1].x + xv[k + 1].y);
             st.v[k] = nv.x;
             st.v[k + 1] = nv.y;
           }
-          gs = g2.x + g2.y;
-        }
-        const float tot = warp_sum(gs);
-        const float inv = tot > 0.f ? __fdividef(1.0f, tot) : 0.f;
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-          ds1[k] = fmaf(xs[k], inv, ds1[k]);
-          ds2[k] = fmaf(xa[k], inv, ds2[k]);
-          grow[lane * P + k] = (xs[k] + xa[k]) * inv;
         }
         __syncwarp();
-        Gb[(size_t)t * kW + lane] = label_sum(grow_sa, grow, order_s, fx);
+        // occupancy per label = sum over its positions / frame total (true division): a frame's occupancies add up
+        // to one exactly as the FCC posteriors do (N = 1: 1 - 1 = 0), and the same total normalises the statistics
+        const float gl = label_sum(grow_sa, grow, order_s, fx);
+        const float gt = warp_sum(gl);
+        Gb[(size_t)t * kW + lane] = gt > 0.f ? gl / gt : 0.f;
+        const float inv = gt > 0.f ? __fdividef(1.0f, gt) : 0.f;
+        const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+        for (int k = 0; k < P; ++k) ds[k] = __ffma2_rn(xv[k], inv2, ds[k]);
         __syncwarp();
       }
     }
+    cp_async_wait_all();
   }
   // ---- CTA partial of the transition gradient (fixed order: deterministic) ----------------------
   for (int w = 0; w < nw; ++w) {
     if (warp == w) {
 #pragma unroll
       for (int k = 0; k < P; ++k) {
-        dsum_s[lane * P + k] += ds1[k];
-        dsum_s[Lp + lane * P + k] += ds2[k];
+        dsum_s[lane * P + k] += ds[k].x;
+        dsum_s[Lp + lane * P + k] += ds[k].y;
       }
     }
     __syncthreads();
@@ -843,14 +932,17 @@ __global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
 // ------------------------------------------------------------------------------------------
 // 4. FCC gradient + emission gradient, from the stored a-hat / b-hat vectors: no dependence between frames
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFccGradWarps * 32) asg_fcc_grad_kernel(AsgParams p) {
+__global__ void __launch_bounds__(kFccGradWarps * 32, 2) asg_fcc_grad_kernel(AsgParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int chunk = blockIdx.x * kFccGradWarps + warp;
   const int T = p.T, N = p.N;
   const bool has_fcc = p.terms & W2L_TERM_FCC, has_fac = p.terms & W2L_TERM_FAC;
   const int ok = p.valid[b];
-  __shared__ float red_s[kW][kW + 1];
+  // shared memory: first the warps' a-hat tiles ((kFccGradFrames + 1) x 32 each), later re-used as the warps'
+  // accumulator slabs (32 x 33 each) of the CTA reduction
+  __shared__ __align__(16) float sm[kFccGradWarps * kW * (kW + 1)];
+  static_assert((kFccGradFrames + 1) * kW <= kW * (kW + 1), "tile must fit in a slab");
   if (chunk == 0 && lane == 0) {
     float l = NAN;
     if (ok) {
@@ -877,26 +969,45 @@ __global__ void __launch_bounds__(kFccGradWarps * 32) asg_fcc_grad_kernel(AsgPar
         if (lane < N) de[(size_t)t * N + lane] = coef * Gb[(size_t)t * kW + lane];
     } else {
       const float coef = p.coef[b];
-      const float* Ab = p.A + (size_t)b * T * kW;
-      const float* Bb = p.Bh + (size_t)b * T * kW;
-      const float* Zb = p.Z + (size_t)b * T * kW;
-      const float* sAb = p.sA + (size_t)b * T;
-#pragma unroll 4
-      for (int t = t0; t < t1; ++t) {
-        const float a = __ldg(Ab + (size_t)t * kW + lane);
-        const float bh = __ldg(Bb + (size_t)t * kW + lane);
-        const float gf = has_fac ? __ldg(Gb + (size_t)t * kW + lane) : 0.f;
-        const float g = a * bh;
-        const float inv = __fdividef(1.0f, warp_sum(g));
-        if (lane < N) de[(size_t)t * N + lane] = coef * (g * inv - gf);
+      const float* Ab = p.A + (size_t)b * T * kW + lane;
+      const float* Bb = p.Bh + (size_t)b * T * kW + lane;
+      const float* Zb = p.Z + (size_t)b * T * kW + lane;
+      const float* Gl = Gb + lane;
+      float* tile = sm + warp * (kW * (kW + 1));
+      const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(tile);
+      // every global read of the chunk is issued before anything is consumed (the frames are independent)
+      float a[kFccGradFrames], bh[kFccGradFrames], z[kFccGradFrames], gf[kFccGradFrames];
+#pragma unroll
+      for (int k = 0; k < kFccGradFrames; ++k) {
+        const int t = t0 + k;
+        const bool in = t < t1;
+        a[k] = in ? __ldg(Ab + (size_t)t * kW) : 0.f;
+        bh[k] = in ? __ldg(Bb + (size_t)t * kW) : 0.f;
+        z[k] = in ? __ldg(Zb + (size_t)t * kW) : 0.f;
+        gf[k] = (in && has_fac) ? __ldg(Gl + (size_t)t * kW) : 0.f;
+      }
+      const float aprev = t0 > 0 ? __ldg(Ab + (size_t)(t0 - 1) * kW) : 0.f;
+      const float sv = (lane < kFccGradFrames && t0 + lane < t1) ? __ldg(p.sA + (size_t)b * T + t0 + lane) : 0.f;  // lane k: s_{t0+k}
+      tile[lane] = aprev;
+#pragma unroll
+      for (int k = 0; k < kFccGradFrames; ++k) tile[(k + 1) * kW + lane] = a[k];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < kFccGradFrames; ++k) {
+        const int t = t0 + k;
+        if (t >= t1) break;
+        const float g = a[k] * bh[k];
+        const float gsum = warp_sum(g);
+        if (lane < N) de[(size_t)t * N + lane] = coef * (g / gsum - gf[k]);  // (true division: N = 1 must give exactly 1 - 1)
         if (t >= 1) {
           // xi_t(i, j) = w_i * a_{t-1}[j] * M'[i][j],  w_i = X_t[i] * s_t * b_t[i] / sum_i a_t[i] b_t[i]
-          const float w = ex2f(__ldg(Zb + (size_t)t * kW + lane)) * bh * (__ldg(sAb + t) * inv);
-          const float4* ap = reinterpret_cast<const float4*>(Ab + (size_t)(t - 1) * kW);
+          const float st = __shfl_sync(0xffffffffu, sv, k);
+          const float w = ex2f(z[k]) * bh[k] * (st * __fdividef(1.0f, gsum));
           const float2 w2 = make_float2(w, w);
 #pragma unroll
           for (int q = 0; q < kW / 4; ++q) {
-            const float4 v = __ldg(ap + q);  // every lane reads the same 16 bytes: one broadcast transaction
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(tile_sa + (k * kW + 4 * q) * 4));
             acc[2 * q] = __ffma2_rn(w2, make_float2(v.x, v.y), acc[2 * q]);
             acc[2 * q + 1] = __ffma2_rn(w2, make_float2(v.z, v.w), acc[2 * q + 1]);
           }
@@ -905,26 +1016,28 @@ __global__ void __launch_bounds__(kFccGradWarps * 32) asg_fcc_grad_kernel(AsgPar
     }
   }
   if (!has_fcc) return;
-  // CTA partial of the FCC transition gradient: sum the warps' accumulators in a fixed order, apply coef * M'
-  for (int k = threadIdx.x; k < kW * (kW + 1); k += blockDim.x) (&red_s[0][0])[k] = 0.f;
+  // CTA partial of the FCC transition gradient: the warps' accumulators go to their slabs, one pass sums them in a
+  // fixed order and applies coef * M'
   __syncthreads();
-  for (int w = 0; w < kFccGradWarps; ++w) {
-    if (warp == w) {
+  {
+    float* slab = sm + warp * (kW * (kW + 1)) + lane * (kW + 1);
 #pragma unroll
-      for (int j = 0; j < kW / 2; ++j) {
-        red_s[lane][2 * j] += acc[j].x;
-        red_s[lane][2 * j + 1] += acc[j].y;
-      }
+    for (int j = 0; j < kW / 2; ++j) {
+      slab[2 * j] = acc[j].x;
+      slab[2 * j + 1] = acc[j].y;
     }
-    __syncthreads();
   }
+  __syncthreads();
   const float tmax = trans_max(p.trans, N, lane);
   const float coef = ok ? p.coef[b] : 0.f;
   float* part = p.parts + ((size_t)b * gridDim.x + blockIdx.x) * (kW * kW);
   for (int k = threadIdx.x; k < kW * kW; k += blockDim.x) {
     const int i = k / kW, j = k % kW;
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < kFccGradWarps; ++w) r += sm[w * (kW * (kW + 1)) + i * (kW + 1) + j];
     const float m = (i < N && j < N) ? __expf(__ldg(p.trans + i * N + j) - tmax) : 0.f;
-    part[k] = coef * red_s[i][j] * m;
+    part[k] = coef * r * m;
   }
 }
 
@@ -1046,6 +1159,7 @@ void shape(AsgParams& p, int B, int T, int N, int L) {
   if (Le < 1) Le = 1;
   p.P = pick_P(Le);
   p.Lp = 32 * p.P;
+
   p.nC = (T + kSeg - 1) / kSeg;
   p.fac_grad_warps = fac_grad_warps(p.Lp);
 }
@@ -1123,9 +1237,9 @@ extern "C" int w2l_asg_forward_backward(void* stream_, int terms, int B, int T, 
     case 16: MACRO(16); break;  \
     default: MACRO(32); break;  \
   }
-#define W2L_LAUNCH_CHAINS(PP) asg_chains_kernel<PP><<<p.n_roles * B, 32, 0, stream>>>(p)
   profile_kind(2);
   profile_start(stream);
+#define W2L_LAUNCH_CHAINS(PP) asg_chains_kernel<PP><<<p.n_roles * B, 32, 0, stream>>>(p)
   W2L_FOR_P(W2L_LAUNCH_CHAINS)
   profile_stop(stream);
   W2L_LAUNCH_CHECK("asg_chains_kernel");
