@@ -688,14 +688,12 @@ __device__ __forceinline__ float label_sum(uint32_t row_sa, const float* row, co
 
 // dynamic shared memory of the FAC grad kernel (4-byte words)
 struct FacGradLayout {
-  int order, start, y, ztile, bnext, brow, grow, dsum, dtr, per_warp, total;
+  int start, ztile, bnext, brow, grow, dsum, dtr, per_warp, total;
 };
 __host__ __device__ inline FacGradLayout fac_grad_layout(int Lp, int warps) {
   FacGradLayout f;
   int o = 0;
-  f.order = o;  o += Lp;
   f.start = o;  o += 36;
-  f.y = o;      o += Lp;
   f.dsum = o;   o += 2 * Lp;
   f.dtr = o;    o += kW * (kW + 1);
   o = (o + 3) & ~3;
@@ -727,7 +725,7 @@ __device__ __forceinline__ float2 fac_grad_pair(float va, float na, float s1a, f
 }
 
 template <int P>
-__global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
+__global__ void __launch_bounds__(128, P <= 8 ? 4 : 2) asg_fac_grad_kernel(AsgParams p) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int b = blockIdx.y;
@@ -739,14 +737,14 @@ __global__ void __launch_bounds__(128) asg_fac_grad_kernel(AsgParams p) {
     return;  // the FCC grad kernel writes the zero gradient rows
   }
   const int L = p.tsz[b];
-  int* order_s = reinterpret_cast<int*>(smem + lay.order);
+  // the label-sorted index and the target stay in global memory (read once per CTA into registers / by the epilogue):
+  // at 55.6 KB per CTA four CTAs fit an SM
+  const int* order_s = p.order + (size_t)b * Lp;
+  const int32_t* y_s = p.target + (size_t)b * p.L;
   int* start_s = reinterpret_cast<int*>(smem + lay.start);
-  int* y_s = reinterpret_cast<int*>(smem + lay.y);
   float* dsum_s = smem + lay.dsum;
   float* dtr_s = smem + lay.dtr;
   for (int l = threadIdx.x; l < Lp; l += blockDim.x) {
-    order_s[l] = l < L ? p.order[(size_t)b * Lp + l] : 0;
-    y_s[l] = l < L ? __ldg(p.target + (size_t)b * p.L + l) : 0;
     dsum_s[l] = 0.f;
     dsum_s[Lp + l] = 0.f;
   }

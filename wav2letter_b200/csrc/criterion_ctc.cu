@@ -8,12 +8,16 @@
 // Pipeline:
 //   1. ctc_prep_kernel   HBM-bound: lz[b][t] = logsumexp_k e[b][t][k] (one pass over the
 //                        activations); per-sample target size / scale.
-//   2. ctc_chains_kernel one CTA per sample, thread per extended-target state, log domain with
-//                        per-step re-centring (fp32 stays accurate for long T): alpha walk
-//                        storing the lattice, then beta walk emitting per-state posteriors.
-//   3. ctc_grad_kernel   HBM-bound: d_emis = coef * (softmax - occupancy), one pass: reads the
-//                        activations once more, writes the gradient once; the <= 2L+1 occupied
-//                        labels of a frame are subtracted afterwards.
+//   2. ctc_chains_kernel latency-bound.  ONE WARP PER RECURSION (alpha and beta of an utterance run concurrently in two
+//                        32-thread CTAs), no barrier anywhere: lane j owns the P = Sp/32 consecutive extended-target
+//                        states P*j .. P*j+P-1 in registers, the s-1 / s-2 neighbours are registers except for two SHFL
+//                        per step; log2 domain, three-way log-sum-exp with 4 MUFU per state; the gathered activations
+//                        e_t[z_s] are requested D frames ahead with plain loads into a register ring; lagged,
+//                        branch-free re-centring with a two-float offset; every alpha / beta row is stored with its
+//                        offset (T' is a few hundred frames and 2L+1 a few hundred states: a few MB).
+//   3. ctc_grad_kernel   HBM-bound, one CTA per frame: posteriors from the two stored rows, occupancy normalised by
+//                        its frame sum, d_emis = coef * (softmax - occupancy): reads the activations once, writes the
+//                        gradient once; the <= 2L+1 occupied labels of a frame are subtracted afterwards.
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -21,40 +25,53 @@
 namespace w2l {
 namespace {
 
-constexpr int kCtcThreads = 256;
-constexpr int kCtcWarps = kCtcThreads / 32;
-// Every per-step global read of the chains (the gathered activations e_t[z_s], the stored alpha row in the beta walk) is
-// requested kCtcDepth steps ahead with cp.async into shared-memory rings; the per-frame scalars live in shared memory.
-// With one-step-ahead register prefetch the step time was one DRAM latency (~0.9 us): 0.28 ms for T' = 150.
-// The depth is a template parameter (8 / 4 / 2 / 1, ring = 2 x depth slots): long targets shrink the rings to fit.
-
-__device__ __forceinline__ void ctc_cp_async4(void* smem_dst, const void* gsrc) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void ctc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void ctc_cp_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
-}
+constexpr float kNeg = -1.0e30f;  // "log zero": finite, absorbing under fp32 addition of ordinary scores
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr double kLn2 = 0.6931471805599453;
+constexpr int kRc = 2;  // frames between re-centrings
+// MUFU.LG2 is one-signed (+1e-7 just above a mantissa of 1, exact at 1.0): the recursion takes lg2(1.25 * sum) and folds
+// the constant log2(1.25) into the emission term (criterion_asg.cu, profiles/mufu_bias_r2.txt)
+constexpr float kLgScale = 1.25f;
+constexpr float kLgShift = 0.32192809488736235f;
 
 struct CtcParams {
-  int B, T, N, L, Sp, scale_mode, need_grad;
-  int t_smem;     // per-frame scalars (lz, alpha offsets) of a sample fit in shared memory
+  int B, T, N, L, Sp, P, scale_mode, need_grad;
   const float* emis;
   const int32_t* target;
   const float* dloss;
   float* loss;
   float* d_emis;
-  float* lz;      // [B][T]
-  float* lat;     // [B][T][Sp] alpha-tilde, overwritten by posteriors
-  double* cA;     // [B][T]
-  float* psum;    // [B][T]
+  float* lz;      // [B][T] natural-log partition of every frame
+  float* lpc;     // [B][T][Sp] the frame's log2-probabilities of the extended-target labels, minus log2 1.25 (compact, coalesced)
+  float* latA;    // [B][T][Sp] alpha-tilde rows (log2 units)
+  float* latB;    // [B][T][Sp] beta-tilde rows (log2 units, include frame t's emission)
+  double* cA;     // [B][T] offset of the stored alpha row (true = tilde + c)
+  double* cB;     // [B][T]
+  double* ll2;    // [B] log2-likelihood
   int* tsz;       // [B] feasible target size
   int* valid;     // [B]
   float* coef;    // [B]
   float* scale;   // [B]
 };
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// C += m in two-float arithmetic (exact two-sum of the high part; the low part collects the rounding errors)
+__device__ __forceinline__ void twofloat_add(float& hi, float& lo, float m) {
+  const float s = hi + m;
+  const float bb = s - hi;
+  const float e = (hi - (s - bb)) + (m - bb);
+  hi = s;
+  lo += e;
+}
 
 __global__ void __launch_bounds__(256) ctc_prep_kernel(CtcParams p, int frame_blocks) {
   const int lane = threadIdx.x & 31;
@@ -76,7 +93,23 @@ __global__ void __launch_bounds__(256) ctc_prep_kernel(CtcParams p, int frame_bl
       const float gm = warp_max(m);
       s = (m == kNegInf) ? 0.f : s * __expf(m - gm);
       s = warp_sum(s);
-      if (lane == 0) p.lz[f] = gm + __logf(s);
+      const float lzf = gm + __logf(s);
+      if (lane == 0) p.lz[f] = lzf;
+      // the frame's scores of the extended-target labels, while its row is hot: lp' = (e[z_s] - lz) * log2e - log2 1.25.
+      // (All declared positions: the feasibility clamp of the target is computed elsewhere in this launch; states past
+      // it are never live.  Out-of-range labels read the blank: such samples are flagged invalid.)
+      const int b = (int)(f / p.T);
+      const int32_t* yg = p.target ? p.target + (size_t)b * p.L : nullptr;
+      float* dst = p.lpc + f * p.Sp;
+      const float c = -fmaf(lzf, kLog2e, kLgShift);
+      for (int st = lane; st < p.Sp; st += 32) {
+        int zs = p.N - 1;
+        if ((st & 1) && (st >> 1) < p.L && yg != nullptr) {
+          const int y = __ldg(yg + (st >> 1));
+          if (y >= 0 && y < p.N - 1) zs = y;
+        }
+        dst[st] = fmaxf(fmaf(__ldg(e + zs), kLog2e, c), kNeg);
+      }
     }
     return;
   }
@@ -101,254 +134,235 @@ __global__ void __launch_bounds__(256) ctc_prep_kernel(CtcParams p, int frame_bl
   p.coef[b] = ok ? sc * (p.dloss ? p.dloss[b] : 1.0f) : 0.f;
 }
 
-__device__ __forceinline__ float lse3f(float a, float b, float c) {
+// log2(2^a + 2^b + 2^c) + log2(1.25) for finite operands (kNeg = log zero): 4 MUFU, no branches
+__device__ __forceinline__ float lse3_log2(float a, float b, float c) {
   const float m = fmaxf(fmaxf(a, b), c);
-  if (m == kNegInf) return kNegInf;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+  const float s = (ex2f(a - m) + ex2f(b - m)) + ex2f(c - m);
+  return m + lg2f(s * kLgScale);
 }
 
-// block-wide max of per-thread values through per-warp slots (caller supplies the barrier)
-template <bool kGrad, int kCtcDepth>
-__global__ void __launch_bounds__(kCtcThreads) ctc_chains_kernel(CtcParams p) {
-  constexpr int kCtcRing = 2 * kCtcDepth;  // slots, power of two > depth
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // the block is sized to the state count (32 .. 256 threads): idle warps would still spend issue slots on every step
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nw = blockDim.x >> 5;
-  const int T = p.T, N = p.N, Sp = p.Sp, blank = N - 1;
-  float* row0 = reinterpret_cast<float*>(smem_raw) + 4;  // index -2..Sp+1 valid
-  float* row1 = row0 + Sp + 8;
-  int32_t* z = reinterpret_cast<int32_t*>(row1 + Sp + 4);
-  float* ering = reinterpret_cast<float*>(z + Sp);              // [kCtcRing][Sp] gathered activations
-  float* lring = ering + (size_t)kCtcRing * Sp;                  // [kCtcRing][Sp] stored alpha rows (beta walk)
-  double* cA_s = reinterpret_cast<double*>(lring + (size_t)kCtcRing * Sp);  // [T] when p.t_smem
-  float* lz_s = reinterpret_cast<float*>(cA_s + (p.t_smem ? p.T : 0));     // [T] when p.t_smem
-  uint8_t* skip = reinterpret_cast<uint8_t*>(lz_s + (p.t_smem ? p.T : 0));  // skip[s]: s-2 -> s allowed
-  __shared__ float wmax[2][kCtcWarps];
-  __shared__ float wsum[2][kCtcWarps];
-  __shared__ double ll_s;
-  if (!p.valid[b]) {
-    if (tid == 0) p.loss[b] = NAN;
-    return;
-  }
-  const int Lb = p.tsz[b];
-  const int S = 2 * Lb + 1;
+// One warp walks one recursion of one utterance; lane j owns the extended-target states P*j .. P*j+P-1.
+//   alpha_t[s] = lp_t[z_s] + lse(alpha_{t-1}[s], alpha_{t-1}[s-1], skip_s ? alpha_{t-1}[s-2] : -inf)
+//   beta_t[s]  = lp_t[z_s] + lse(beta_{t+1}[s],  beta_{t+1}[s+1],  skip_{s+2} ? beta_{t+1}[s+2] : -inf)
+// lp_t[k] = (e_t[k] - lz_t) * log2e.  D = frames of gathered activations in flight (a register ring of D x P values).
+template <int P, int D, bool kBeta>
+__device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * P] shared */) {
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, Sp = p.Sp;
+  const int Lb = p.tsz[b], S = 2 * Lb + 1;
   const int32_t* yg = p.target ? p.target + (size_t)b * p.L : nullptr;
-  const float* eb = p.emis + (size_t)b * T * N;
-  const float* lzb = p.lz + (size_t)b * T;
-  float* lat = p.lat + (size_t)b * T * Sp;
-  for (int s = tid; s < Sp; s += nthr) {
-    int zs = blank;
-    if (s < S && (s & 1)) zs = yg[s >> 1];
-    z[s] = zs;
-  }
-  for (int s = tid; s < Sp + 8; s += nthr) {
-    row0[s - 4] = kNegInf;
-    row1[s - 4] = kNegInf;
-  }
-  const bool ts = p.t_smem != 0;
-  if (ts)
-    for (int t = tid; t < T; t += nthr) lz_s[t] = lzb[t];
-  __syncthreads();
-  for (int s = tid; s < Sp; s += nthr) skip[s] = (s >= 2 && s < S && z[s] != blank && z[s] != z[s - 2]) ? 1 : 0;
-  // t = 0
-  if (tid < 2 && tid < S) row0[tid] = eb[z[tid]] - lzb[0];
-  __syncthreads();
-  {
-    float lm = kNegInf;
-    for (int s = tid; s < S; s += nthr) {
-      lm = fmaxf(lm, row0[s]);
-      if (kGrad) lat[s] = row0[s];
-    }
-    lm = warp_max(lm);
-    if (lane == 0) wmax[0][warp] = lm;
-    if (kGrad && tid == 0) {
-      p.cA[(size_t)b * T] = 0.0;
-      if (p.t_smem) cA_s[0] = 0.0;
-    }
-  }
-  __syncthreads();
-  float* rp = row0;
-  float* rn = row1;
-  double C = 0.0;
-  int par = 0;
-  // one commit group per frame: the activations e_f[z_s] of this thread's states
-  auto issue_a = [&](int f) {
-    if (f < T) {
-      float* dst = ering + (size_t)(f & (kCtcRing - 1)) * Sp;
-      const float* src = eb + (size_t)f * N;
-      for (int s = tid; s < S; s += nthr) ctc_cp_async4(dst + s, src + z[s]);
-    }
-    ctc_cp_commit();
-  };
-  for (int q = 1; q <= kCtcDepth; ++q) issue_a(q);
-  for (int t = 1; t < T; ++t) {
-    ctc_cp_wait<kCtcDepth - 1>();  // frame t has landed (own copies: no barrier needed)
-    issue_a(t + kCtcDepth);
-    float d = wmax[par][0];
+  float* lat = (kBeta ? p.latB : p.latA) + (size_t)b * T * Sp + lane * P;
+  double* coff = (kBeta ? p.cB : p.cA) + (size_t)b * T;
+  const bool store = p.need_grad != 0;
+  float pen[P];  // 0 where the skip transition into (alpha) / out of (beta) this state exists, kNeg where it does not
+  float v[P];
 #pragma unroll
-    for (int w = 1; w < nw; ++w) d = fmaxf(d, wmax[par][w]);
-    if (!(d > -1e30f)) d = 0.f;
-    C += (double)d;
-    const float lzt = (ts ? lz_s[t] : lzb[t]) + d;
-    float lm = kNegInf;
-    const float* er = ering + (size_t)(t & (kCtcRing - 1)) * Sp;
-    for (int s = tid; s < S; s += nthr) {
-      const float a2 = skip[s] ? rp[s - 2] : kNegInf;
-      const float v = lse3f(rp[s], rp[s - 1], a2);
-      const float val = (v == kNegInf) ? kNegInf : v + (er[s] - lzt);
-      rn[s] = val;
-      lm = fmaxf(lm, val);
-      if (kGrad) lat[(size_t)t * Sp + s] = val;
-    }
-    lm = warp_max(lm);
-    if (lane == 0) wmax[par ^ 1][warp] = lm;
-    if (kGrad && tid == 0) {
-      p.cA[(size_t)b * T + t] = C;
-      if (ts) cA_s[t] = C;
-    }
-    __syncthreads();
-    float* tmp = rp;
-    rp = rn;
-    rn = tmp;
-    par ^= 1;
+  for (int k = 0; k < P; ++k) {
+    const int s = lane * P + k;
+    bool sk;
+    if (!kBeta)
+      sk = s >= 2 && s < S && (s & 1) && __ldg(yg + (s >> 1)) != __ldg(yg + (s >> 1) - 1);
+    else
+      sk = s + 2 < S && (s & 1) && __ldg(yg + (s >> 1) + 1) != __ldg(yg + (s >> 1));
+    pen[k] = sk ? 0.f : kNeg;
+    v[k] = kNeg;
   }
-  ctc_cp_wait<0>();
-  if (tid == 0) {
-    const float a = rp[S - 1], a2 = S > 1 ? rp[S - 2] : kNegInf;
-    const double ll = (double)lse2f(a, a2) + C;
-    ll_s = ll;
-    p.loss[b] = (float)(-(double)p.scale[b] * ll);
-  }
-  if (!kGrad) return;
-  __syncthreads();
-  const double ll = ll_s;
-  if (!(ll > -1e30)) {  // infeasible (loss = +inf, e.g. -inf activations on every path): zero gradient —
-    // ctc_grad_kernel zeroes the rows of samples whose `valid` flag is clear (it runs after this kernel)
-    if (tid == 0) p.valid[b] = 0;
-    return;
-  }
-  // ---- beta walk; posteriors overwrite the alpha lattice ------------------------------------------
-  for (int s = tid; s < Sp + 8; s += nthr) {
-    row0[s - 4] = kNegInf;
-    row1[s - 4] = kNegInf;
-  }
-  __syncthreads();
-  rp = row0;
-  rn = row1;
-  if (tid == 0) {
-    row0[S - 1] = eb[(size_t)(T - 1) * N + z[S - 1]] - lzb[T - 1];
-    if (S > 1) row0[S - 2] = eb[(size_t)(T - 1) * N + z[S - 2]] - lzb[T - 1];
-  }
-  __syncthreads();
-  double CB = 0.0;
-  par = 0;
-  {
-    const float K = (float)(p.cA[(size_t)b * T + T - 1] + 0.0 - ll);
-    float lm = kNegInf, ps = 0.f;
-    for (int s = tid; s < S; s += nthr) {
-      const float bt = rp[s];
-      lm = fmaxf(lm, bt);
-      const float lp = eb[(size_t)(T - 1) * N + z[s]] - lzb[T - 1];
-      const float q = lat[(size_t)(T - 1) * Sp + s] + bt - lp + K;
-      const float post = (bt == kNegInf) ? 0.f : __expf(q);
-      lat[(size_t)(T - 1) * Sp + s] = post;
-      ps += post;
-    }
-    lm = warp_max(lm);
-    ps = warp_sum(ps);
-    if (lane == 0) {
-      wmax[0][warp] = lm;
-      wsum[0][warp] = ps;
-    }
-  }
-  __syncthreads();
-  // one commit group per frame: activations and the stored alpha row of this thread's states
-  auto issue_b = [&](int f) {
-    if (f >= 0) {
-      const size_t slot = (size_t)(f & (kCtcRing - 1)) * Sp;
-      const float* src = eb + (size_t)f * N;
-      const float* lsrc = lat + (size_t)f * Sp;
-      for (int s = tid; s < S; s += nthr) {
-        ctc_cp_async4(ering + slot + s, src + z[s]);
-        ctc_cp_async4(lring + slot + s, lsrc + s);
+  // The frame scores come from the compact [T][Sp] array the prep kernel gathered (coalesced: 4 P bytes per lane and
+  // frame), in blocks of D frames copied asynchronously into a double-buffered shared-memory tile one block ahead — no
+  // registers, one wait per block.  (Gathering e_t[z_s] from the 10 000-wide rows inside the walk cost a DRAM round trip
+  // per block whatever the depth: 570-690 ns per step.)
+  const float* lpb = p.lpc + (size_t)b * T * Sp + lane * P;
+  const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(tile) + lane * P * 4;
+  auto request = [&](int base, int buf) {  // walk indices base .. base + D - 1
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const int n = base + i;
+      if (n < T) {
+        const int t = kBeta ? T - 1 - n : n;
+        const float* src = lpb + (size_t)t * Sp;
+        const uint32_t dst = tile_sa + ((buf * D + i) * Sp) * 4;
+        if constexpr (P >= 4) {
+#pragma unroll
+          for (int k = 0; k < P; k += 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 4), "l"(src + k) : "memory");
+        } else if constexpr (P == 2) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        } else {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        }
       }
     }
-    ctc_cp_commit();
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  for (int q = 0; q < kCtcDepth; ++q) issue_b(T - 2 - q);
-  for (int t = T - 2; t >= 0; --t) {
-    ctc_cp_wait<kCtcDepth - 1>();
-    issue_b(t - kCtcDepth);
-    float d = wmax[par][0], psm = wsum[par][0];
+  float Chi = 0.f, Clo = 0.f, pend = kNeg, off = 0.f;
+  request(0, 0);
+  auto step = [&](int t, const float (&lp)[P]) {
+    if (!kBeta) {
+      float up1 = __shfl_up_sync(0xffffffffu, v[P - 1], 1);
+      float up2 = P >= 2 ? __shfl_up_sync(0xffffffffu, v[P >= 2 ? P - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, v[0], 2);
+      if (lane == 0) up1 = up2 = kNeg;
+      if (P == 1 && lane == 1) up2 = kNeg;
 #pragma unroll
-    for (int w = 1; w < nw; ++w) {
-      d = fmaxf(d, wmax[par][w]);
-      psm += wsum[par][w];
+      for (int k = P - 1; k >= 0; --k) {  // descending: v[k-1], v[k-2] are still the previous frame's values
+        const float n1 = k >= 1 ? v[k - 1] : up1;
+        const float n2 = k >= 2 ? v[k - 2] : (k == 1 ? up1 : up2);
+        v[k] = lp[k] + lse3_log2(v[k], n1, n2 + pen[k]);
+      }
+    } else {
+      float dn1 = __shfl_down_sync(0xffffffffu, v[0], 1);
+      float dn2 = P >= 2 ? __shfl_down_sync(0xffffffffu, v[P >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, v[0], 2);
+      if (lane == 31) dn1 = dn2 = kNeg;
+      if (P == 1 && lane == 30) dn2 = kNeg;
+#pragma unroll
+      for (int k = 0; k < P; ++k) {  // ascending: v[k+1], v[k+2] are still the next frame's values
+        const float n1 = k + 1 < P ? v[k + 1] : dn1;
+        const float n2 = k + 2 < P ? v[k + 2] : (k + 1 < P ? dn1 : dn2);
+        v[k] = lp[k] + lse3_log2(v[k], n1, n2 + pen[k]);
+      }
     }
-    if (tid == 0) p.psum[(size_t)b * T + t + 1] = psm;
-    if (!(d > -1e30f)) d = 0.f;
-    CB += (double)d;
-    const float lz_t = ts ? lz_s[t] : lzb[t];
-    const float K = (float)((ts ? cA_s[t] : p.cA[(size_t)b * T + t]) + CB - ll);
-    float lm = kNegInf, ps = 0.f;
-    const size_t slot = (size_t)(t & (kCtcRing - 1)) * Sp;
-    for (int s = tid; s < S; s += nthr) {
-      const float b2 = (s + 2 < S && skip[s + 2]) ? rp[s + 2] : kNegInf;
-      const float v = lse3f(rp[s], rp[s + 1], b2);
-      const float lp = ering[slot + s] - lz_t;
-      const float val = (v == kNegInf) ? kNegInf : v + (lp - d);
-      rn[s] = val;
-      lm = fmaxf(lm, val);
-      const float q = lring[slot + s] + val - lp + K;
-      const float post = (val == kNegInf) ? 0.f : __expf(q);
-      lat[(size_t)t * Sp + s] = post;
-      ps += post;
+    // lagged, branch-free re-centring (criterion_asg.cu): the maximum taken at one step is subtracted after the next
+    if ((t & (kRc - 1)) == (kBeta ? kRc - 1 : 0)) {
+      const bool live = pend > -1.0e29f;
+      const float off_new = fminf(fmaxf(0.5f * (off - pend), 0.f), 48.f);
+      const float m = live ? pend - off_new : 0.f;
+      off = live ? off_new : off;
+#pragma unroll
+      for (int k = 0; k < P; ++k) v[k] -= m;
+      twofloat_add(Chi, Clo, m);
     }
-    lm = warp_max(lm);
-    ps = warp_sum(ps);
-    if (lane == 0) {
-      wmax[par ^ 1][warp] = lm;
-      wsum[par ^ 1][warp] = ps;
+    if ((t & (kRc - 1)) == (kBeta ? 0 : kRc - 1)) {
+      float m = v[0];
+#pragma unroll
+      for (int k = 1; k < P; ++k) m = fmaxf(m, v[k]);
+      pend = warp_max(m);
     }
-    __syncthreads();
-    float* tmp = rp;
-    rp = rn;
-    rn = tmp;
-    par ^= 1;
+    if (store) {
+      if constexpr (P >= 4) {
+#pragma unroll
+        for (int k = 0; k < P; k += 4) *reinterpret_cast<float4*>(lat + (size_t)t * Sp + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < P; ++k) lat[(size_t)t * Sp + k] = v[k];
+      }
+      if (lane == 0) coff[t] = (double)Chi + (double)Clo;
+    }
+  };
+  int buf = 0;
+  for (int base = 0; base < T; base += D, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // this block has landed
+    __syncwarp();
+    request(base + D, buf ^ 1);
+    const float* my = tile + (size_t)buf * D * Sp + lane * P;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const int n = base + i;  // walk index
+      if (n < T) {
+        const int t = kBeta ? T - 1 - n : n;
+        float lp[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) lp[k] = my[i * Sp + k];
+        if (n == 0) {
+          // first frame: (the folded -log2(1.25) belongs to the recursion's lg2(1.25 x); the first row has none)
+#pragma unroll
+          for (int k = 0; k < P; ++k) {
+            const int s = lane * P + k;
+            const bool on = kBeta ? (s == S - 1 || s == S - 2) : (s < 2 && s < S);
+            if (on) v[k] = lp[k] + kLgShift;
+          }
+          if (store) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) lat[(size_t)t * Sp + k] = v[k];
+            if (lane == 0) coff[t] = 0.0;
+          }
+        } else {
+          step(t, lp);
+        }
+      }
+    }
   }
-  ctc_cp_wait<0>();
-  if (tid == 0) {
-    float psm = 0.f;
-    for (int w = 0; w < nw; ++w) psm += wsum[par][w];
-    p.psum[(size_t)b * T] = psm;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (!kBeta) {
+    // log2-likelihood = lse of the last two states at the last frame
+    float a = kNeg;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int s = lane * P + k;
+      if (s == S - 1 || s == S - 2) a = fmaxf(a, v[k]);
+    }
+    const float m = warp_max(a);
+    float e = 0.f;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int s = lane * P + k;
+      if (s == S - 1 || s == S - 2) e += ex2f(v[k] - m);
+    }
+    e = warp_sum(e);
+    if (lane == 0) {
+      const bool feasible = m > -1.0e29f;
+      const double l2 = (double)m + (double)log2f(e) + (double)Chi + (double)Clo;
+      p.ll2[b] = l2;
+      p.loss[b] = feasible ? (float)(-(double)p.scale[b] * l2 * kLn2) : INFINITY;
+      if (!feasible) p.valid[b] = 0;  // infeasible (e.g. -inf activations on every path): the grad kernel writes zero rows
+    }
   }
 }
 
-// one CTA per frame: gradient = coef * (softmax - occupancy)
+template <int P, int D>
+__global__ void __launch_bounds__(32) ctc_chains_kernel(CtcParams p) {
+  const int b = blockIdx.x % p.B;
+  const bool beta = blockIdx.x >= p.B;
+  if (!p.valid[b]) {
+    if (!beta && threadIdx.x == 0) p.loss[b] = NAN;
+    return;
+  }
+  __shared__ __align__(16) float tile[2 * D * 32 * P];
+  if (beta)
+    ctc_chain<P, D, true>(p, b, tile);
+  else
+    ctc_chain<P, D, false>(p, b, tile);
+}
+
+// one CTA per frame: posteriors from the stored alpha / beta rows, gradient = coef * (softmax - occupancy / frame sum)
+constexpr int kCtcMaxStates = 2048;
 __global__ void __launch_bounds__(256) ctc_grad_kernel(CtcParams p) {
   const long long f = blockIdx.x;  // frame index b*T + t
   const int b = (int)(f / p.T);
   const int N = p.N, Sp = p.Sp;
   const float* e = p.emis + f * N;
   float* de = p.d_emis + f * N;
+  __shared__ float post_s[kCtcMaxStates];
+  __shared__ float wsum_s[8];
   if (!p.valid[b]) {
     for (int k = threadIdx.x; k < N; k += blockDim.x) de[k] = 0.f;
     return;
   }
   const float coef = p.coef[b];
   const float lz = p.lz[f];
+  const int S = 2 * p.tsz[b] + 1;
+  const int32_t* yg = p.target ? p.target + (size_t)b * p.L : nullptr;
+  // posteriors of the frame's states: alpha-tilde + beta-tilde - lp + (cA + cB - ll2); beta includes the frame's emission
+  const float K = (float)(p.cA[f] + p.cB[f] - p.ll2[b]);
+  const float* A = p.latA + f * Sp;
+  const float* Bt = p.latB + f * Sp;
+  float ps = 0.f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float lp = p.lpc[f * Sp + s] + kLgShift;
+    const float q = ex2f(A[s] + Bt[s] - lp + K);
+    post_s[s] = q;
+    ps += q;
+  }
+  ps = warp_sum(ps);
+  if ((threadIdx.x & 31) == 0) wsum_s[threadIdx.x >> 5] = ps;
   for (int k = threadIdx.x; k < N; k += blockDim.x) de[k] = coef * __expf(__ldg(e + k) - lz);
   __syncthreads();
-  const int S = 2 * p.tsz[b] + 1;
-  const float ps = p.psum[f];
-  const float inv = ps > 0.f ? coef / ps : 0.f;
-  const float* post = p.lat + f * Sp;
-  const int32_t* yg = p.target ? p.target + (size_t)b * p.L : nullptr;
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += wsum_s[w];
+  const float inv = tot > 0.f ? coef / tot : 0.f;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    const float v = post[s];
-    if (v != 0.f) {
+    const float q = post_s[s];
+    if (q != 0.f) {
       const int zs = (s & 1) ? yg[s >> 1] : N - 1;
-      atomicAdd(de + zs, -v * inv);
+      atomicAdd(de + zs, -q * inv);
     }
   }
 }
@@ -357,9 +371,12 @@ void carve(CtcParams& p, void* ws, size_t& total) {
   Carver c(ws);
   const size_t BT = (size_t)p.B * p.T;
   p.lz = c.take<float>(BT);
-  p.lat = c.take<float>(BT * p.Sp);
+  p.lpc = c.take<float>(BT * p.Sp);
+  p.latA = c.take<float>(BT * p.Sp);
+  p.latB = c.take<float>(BT * p.Sp);
   p.cA = c.take<double>(BT);
-  p.psum = c.take<float>(BT);
+  p.cB = c.take<double>(BT);
+  p.ll2 = c.take<double>(p.B);
   p.tsz = c.take<int>(p.B);
   p.valid = c.take<int>(p.B);
   p.coef = c.take<float>(p.B);
@@ -367,10 +384,13 @@ void carve(CtcParams& p, void* ws, size_t& total) {
   total = c.off;
 }
 
-int ctc_sp(int T, int L) {
+// states per lane: the smallest power of two with 32*P >= 2*min(L,T)+1
+int ctc_p(int T, int L) {
   int Le = L < T ? L : T;
   if (Le < 0) Le = 0;
-  return (int)align_up((size_t)(2 * Le + 1), 32);
+  int P = 1;
+  while (32 * P < 2 * Le + 1) P <<= 1;
+  return P;
 }
 
 }  // namespace
@@ -384,7 +404,8 @@ extern "C" size_t w2l_ctc_workspace_size(int B, int T, int N, int L) {
   p.B = B;
   p.T = T;
   p.N = N;
-  p.Sp = ctc_sp(T, L);
+  p.P = ctc_p(T, L);
+  p.Sp = 32 * p.P;
   size_t total = 0;
   carve(p, nullptr, total);
   return total;
@@ -403,7 +424,9 @@ extern "C" int w2l_ctc_forward_backward(void* stream_, int B, int T, int N, int 
   p.T = T;
   p.N = N;
   p.L = target ? L : 0;
-  p.Sp = ctc_sp(T, p.L);
+  p.P = ctc_p(T, L);  // (the workspace is sized for the declared L whether or not a target is given)
+  p.Sp = 32 * p.P;
+  if (p.Sp > kCtcMaxStates) return fail(W2L_ERR_UNSUPPORTED, "ctc: target longer than 1023 is not covered");
   p.scale_mode = scale_mode;
   p.need_grad = d_emis != nullptr;
   p.emis = emis;
@@ -415,41 +438,27 @@ extern "C" int w2l_ctc_forward_backward(void* stream_, int B, int T, int N, int 
   carve(p, workspace, need);
   if (!workspace || workspace_bytes < need)
     return fail(W2L_ERR_WORKSPACE, "ctc: workspace too small (need " + std::to_string(need) + " bytes)");
-  const size_t smem_base = (size_t)(2 * (p.Sp + 8) + p.Sp) * 4 + p.Sp + 64;
-  int depth = 8;
-  while (depth > 1 && smem_base + (size_t)4 * depth * p.Sp * 4 > 200 * 1024) depth >>= 1;
-  size_t smem = smem_base + (size_t)4 * depth * p.Sp * 4;  // two rings of 2*depth slots
-  if (smem > 200 * 1024) return fail(W2L_ERR_UNSUPPORTED, "ctc: target too long for the shared-memory rows");
-  p.t_smem = smem + (size_t)T * 12 <= 200 * 1024 ? 1 : 0;
-  if (p.t_smem) smem += (size_t)T * 12;
   const long long nframes = (long long)B * T;
   const int frame_blocks = (int)std::min<long long>((nframes + 7) / 8, 148 * 8);
   ctc_prep_kernel<<<frame_blocks + (B + 255) / 256, 256, 0, stream>>>(p, frame_blocks);
   W2L_LAUNCH_CHECK("ctc_prep_kernel");
+  const int grid = p.need_grad ? 2 * B : B;  // alpha chains, then beta chains
+  profile_kind(2);
+  profile_start(stream);
+  switch (p.P) {  // (states per lane, frames of gathered activations in flight)
+    case 1: ctc_chains_kernel<1, 8><<<grid, 32, 0, stream>>>(p); break;
+    case 2: ctc_chains_kernel<2, 8><<<grid, 32, 0, stream>>>(p); break;
+    case 4: ctc_chains_kernel<4, 8><<<grid, 32, 0, stream>>>(p); break;
+    case 8: ctc_chains_kernel<8, 4><<<grid, 32, 0, stream>>>(p); break;
+    case 16: ctc_chains_kernel<16, 2><<<grid, 32, 0, stream>>>(p); break;
+    case 32: ctc_chains_kernel<32, 1><<<grid, 32, 0, stream>>>(p); break;
+    default: ctc_chains_kernel<64, 1><<<grid, 32, 0, stream>>>(p); break;
+  }
+  profile_stop(stream);
+  W2L_LAUNCH_CHECK("ctc_chains_kernel");
   if (p.need_grad) {
-#define W2L_CTC_LAUNCH(GRAD, D)                                                                                               \
-  do {                                                                                                                         \
-    if (smem > 48 * 1024)                                                                                                      \
-      W2L_CUDA_CHECK(cudaFuncSetAttribute(ctc_chains_kernel<GRAD, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ctc_chains_kernel<GRAD, D><<<B, std::min(kCtcThreads, p.Sp), smem, stream>>>(p);                                                          \
-  } while (0)
-#define W2L_CTC_DISPATCH(GRAD)                \
-  do {                                        \
-    if (depth == 8) W2L_CTC_LAUNCH(GRAD, 8);  \
-    else if (depth == 4) W2L_CTC_LAUNCH(GRAD, 4); \
-    else if (depth == 2) W2L_CTC_LAUNCH(GRAD, 2); \
-    else W2L_CTC_LAUNCH(GRAD, 1);             \
-  } while (0)
-    profile_kind(2);
-    profile_start(stream);
-    W2L_CTC_DISPATCH(true);
-    profile_stop(stream);
-    W2L_LAUNCH_CHECK("ctc_chains_kernel<grad>");
     ctc_grad_kernel<<<(unsigned)nframes, 256, 0, stream>>>(p);
     W2L_LAUNCH_CHECK("ctc_grad_kernel");
-  } else {
-    W2L_CTC_DISPATCH(false);
-    W2L_LAUNCH_CHECK("ctc_chains_kernel<fwd>");
   }
   return W2L_OK;
 }

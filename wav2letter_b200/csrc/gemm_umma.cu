@@ -520,12 +520,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 //   * the exposed epilogue: TWO accumulators live in TMEM (2 x BN columns); while warps 0..3 drain accumulator i
 //     (tcgen05.ld -> bias / ReLU / dropout -> transposition -> coalesced stores), the MMA thread already accumulates the
 //     next tile into accumulator i ^ 1 and the TMA warp keeps the operand ring full across the tile boundary.
-// Roles: warps 0..3 epilogue, warp 4 TMA producer, warp 5 MMA issuer + TMEM owner, (F32X3 only) warps 6..9 operand split.
+// Roles: warps 0..3 epilogue, warp 4 TMA producer, warp 5 MMA issuer + TMEM owner, (F32X3 only) warps 6..13 operand split.
 // Barriers: full / empty (/ ready) per ring stage with a k-block counter that runs across tiles; acc_full / acc_empty per
 // accumulator with the tile counter's parity.
 // ================================================================================================
 __host__ __device__ constexpr int pstages_for(int mode, int bn) { return mode == kF32x3 ? 3 : (bn <= 160 ? 5 : 4); }
-__host__ __device__ constexpr int pthreads_for(int mode) { return mode == kF32x3 ? 320 : 192; }
+constexpr int kSplitThreads = 256;  // F32X3: eight split warps (two per scheduler): the split of a stage takes ~300 cycles, well inside its three MMAs
+__host__ __device__ constexpr int pthreads_for(int mode) { return mode == kF32x3 ? 192 + kSplitThreads : 192; }
 __host__ __device__ constexpr int acc_stride_for(int bn) { return bn <= 128 ? 128 : 256; }
 constexpr int kTbufBytes = 4 * 32 * 36 * 4;  // per warp [32][36] floats: 128-bit conflict-free both ways (the scalar path uses a 33 pitch)
 __host__ __device__ constexpr size_t psmem_for(int mode, int bn) {
@@ -574,7 +575,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&ready[s], 128);
+      mbar_init(&ready[s], kSplitThreads);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -703,11 +704,11 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       mbar_arrive(&acc_empty[acc]);  // this thread's TMEM reads of the accumulator are complete
     }
   } else if (kSplit) {
-    // ===== F32X3 operand split (warps 6..9): x = hi + lo, hi = tf32(x) written back in place, lo = tf32(x - hi) in the
+    // ===== F32X3 operand split (warps 6..13): x = hi + lo, hi = tf32(x) written back in place, lo = tf32(x - hi) in the
     // second tile of the stage; round-to-nearest by integer arithmetic (add half an ulp of the 13 dropped bits, clear them):
     // full-rate ALU ops instead of quarter-rate cvt.rna
     const int tid = threadIdx.x - 192;
-    constexpr int kVecA = kTileBytes / 16 / 128, kVecB = kTileBytesB / 16 / 128;
+    constexpr int kVecA = kTileBytes / 16 / kSplitThreads, kVecB = kTileBytesB / 16 / kSplitThreads;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int m0, n0, kb_begin, num_kb;
@@ -744,9 +745,9 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           lo[i] = l;
         };
 #pragma unroll
-        for (int i = 0; i < kVecA; ++i) split(ta, la, i * 128 + tid);
+        for (int i = 0; i < kVecA; ++i) split(ta, la, i * kSplitThreads + tid);
 #pragma unroll
-        for (int i = 0; i < kVecB; ++i) split(tb, lb, i * 128 + tid);
+        for (int i = 0; i < kVecB; ++i) split(tb, lb, i * kSplitThreads + tid);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&ready[s]);
       }
