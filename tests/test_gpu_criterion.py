@@ -69,6 +69,7 @@ def check_asg(e, tr, y, mode="none", dloss=None, terms=None, tol=TOL):
     (1, 1, 5, 1, "none"), (2, 2, 3, 2, "none"), (3, 3, 4, 3, "input_sz"), (3, 17, 30, 5, "target_sz"),
     (4, 100, 30, 20, "target_sz_sqrt"), (2, 101, 32, 33, "input_sz_sqrt"), (5, 64, 1, 7, "none"),
     (8, 500, 30, 80, "target_sz_sqrt"), (2, 257, 30, 257, "none"), (3, 40, 30, 100, "none"),
+    (3, 700, 30, 666, "target_sz_sqrt"), (2, 1100, 28, 1000, "none"),  # long targets: the sliced (halo) FAC gradient path
 ])
 def test_asg_parity(B, T, N, L, mode):
     e, tr, y = make_asg(B, T, N, L, seed=B * 1000 + T)

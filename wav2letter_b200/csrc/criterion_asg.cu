@@ -68,6 +68,7 @@ struct AsgParams {
   int B, T, N, L, Lp, P, nC, scale_mode, terms, need_grad;
   int n_roles, roles[5];
   int n_fcc_parts, n_fac_parts, fac_grad_warps;
+  int Wg;  // row slices of the FAC grad kernel (1: a warp holds the whole row; > 1: the halo path, one warp per slice)
   const float* emis;
   const int32_t* target;
   const float* trans;
@@ -83,8 +84,8 @@ struct AsgParams {
   float* sA;        // [B][T] power-of-two scale applied at step t of the alpha chain
   float* ckAa;      // [B][nC][Lp] FAC alpha-tilde row of frame c*kSeg-1 (c >= 1), log2 units
   float* ckBa;      // [B][nC][Lp] FAC beta-tilde  row of frame (c+1)*kSeg (when < T)
-  double* ckCA;     // [B][nC] offset of the stored alpha row (true = tilde + C + t * tmax2)
-  double* ckCB;     // [B][nC]
+  double* ckCA;     // [B][nC][32] per-lane offsets of the stored alpha row (true = tilde + C[lane] + t * tmax2)
+  double* ckCB;     // [B][nC][32]
   float* G;         // [B][T][32] FAC occupancy per label, normalised per frame
   double* fccLogZ;  // [B] natural log, without sum_t m_t
   double* facLogZ2; // [B] log2 units, without sum_t m_t and without (T-1) * tmax * log2e (what the grad kernel subtracts)
@@ -383,20 +384,21 @@ struct FacState {
 };
 
 template <int P>
-__device__ __forceinline__ void fac_load_target(FacState<P>& st, const AsgParams& p, int b, int L, int lane, bool beta, float tmax) {
+__device__ __forceinline__ void fac_load_target(FacState<P>& st, const AsgParams& p, int b, int L, int lane, bool beta, float tmax,
+                                                int base = 0) {
   const int32_t* yg = p.target + (size_t)b * p.L;
   const int N = p.N;
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    const int l = lane * P + k;
-    const int yl = l < L ? __ldg(yg + l) : 0;
+    const int l = base + lane * P + k;  // (base < 0: the left halo of a row slice; positions outside [0, L) are dead)
+    const int yl = (l >= 0 && l < L) ? __ldg(yg + l) : 0;
     st.y4[k] = 4 * yl;
-    st.s1[k] = l < L ? (__ldg(p.trans + yl * N + yl) - tmax) * kLog2e - kLgShift : 0.f;
+    st.s1[k] = (l >= 0 && l < L) ? (__ldg(p.trans + yl * N + yl) - tmax) * kLog2e - kLgShift : 0.f;
     float s2 = kNeg;
     if (!beta) {
       if (l < L && l > 0) s2 = (__ldg(p.trans + yl * N + __ldg(yg + l - 1)) - tmax) * kLog2e - kLgShift;
     } else {
-      if (l + 1 < L) s2 = (__ldg(p.trans + __ldg(yg + l + 1) * N + yl) - tmax) * kLog2e - kLgShift;
+      if (l >= 0 && l + 1 < L) s2 = (__ldg(p.trans + __ldg(yg + l + 1) * N + yl) - tmax) * kLog2e - kLgShift;
     }
     st.s2[k] = s2;
     st.v[k] = kNeg;
@@ -430,9 +432,10 @@ __device__ __forceinline__ float2 fac_pair(float va, float na, float s1a, float 
 }
 // one alpha step: row_t[l] = z_t[y_l] + lse(row[l] + s1, row[l-1] + s2); zrow = shared byte address of frame t's Z row
 template <int P>
-__device__ __forceinline__ void fac_alpha_step(FacState<P>& st, uint32_t zrow, int lane) {
+__device__ __forceinline__ void fac_alpha_step(FacState<P>& st, uint32_t zrow, int lane, float D) {
   const float (&s2)[P] = st.s2;
-  float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1);
+  // D = (offset of lane-1) - (offset of this lane): every lane keeps its values relative to its OWN offset
+  float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1) + D;
   if (lane == 0) up = kNeg;
   if constexpr (P == 1) {
     st.v[0] = lds_f(zrow + st.y4[0]) + lse2_log2(st.v[0] + st.s1[0], up + s2[0]);
@@ -448,8 +451,8 @@ __device__ __forceinline__ void fac_alpha_step(FacState<P>& st, uint32_t zrow, i
 }
 // one beta step: row_t[l] = z_t[y_l] + lse(row[l] + s1, row[l+1] + s2)
 template <int P>
-__device__ __forceinline__ void fac_beta_step(FacState<P>& st, const float (&s2)[P], uint32_t zrow, int lane) {
-  float dn = __shfl_down_sync(0xffffffffu, st.v[0], 1);
+__device__ __forceinline__ void fac_beta_step(FacState<P>& st, const float (&s2)[P], uint32_t zrow, int lane, float D) {
+  float dn = __shfl_down_sync(0xffffffffu, st.v[0], 1) + D;  // D = (offset of lane+1) - (offset of this lane)
   if (lane == 31) dn = kNeg;
   if constexpr (P == 1) {
     st.v[0] = lds_f(zrow + st.y4[0]) + lse2_log2(st.v[0] + st.s1[0], dn + s2[0]);
@@ -517,32 +520,48 @@ __device__ void fac_chain(const AsgParams& p, int b, float* ztile /* [kSeg][32] 
   const float* Zl = p.Z + (size_t)b * T * kW + lane;
   const uint32_t zt = (uint32_t)__cvta_generic_to_shared(ztile);
   const bool store = p.need_grad != 0;
-  float Chi = 0.f, Clo = 0.f, pend = kNeg, off = 0.f;
+  // Every LANE keeps its P positions relative to its own offset (two-float Chi + Clo): values stay within a few tens of
+  // their lane's maximum wherever the row's global maximum is.  With one offset per row the states far below the row
+  // maximum — which carry the posterior mass when the alignment band is tight (L close to T, the TDS-output regime) —
+  // lost absolute precision: 1.8e-4 on the posteriors at T = 700, L = 540 against 4.5e-6 with per-lane offsets in a
+  // float32 emulation (profiles/asg_r2.md).  D is the neighbour's offset minus this lane's, added to the value that crosses
+  // the lane boundary.
+  float Chi = 0.f, Clo = 0.f, pend = kNeg, off = 0.f, D = 0.f;
 
   auto step = [&](int t, int krow) {
     if (!kBeta)
-      fac_alpha_step<P>(st, zt + krow * (4 * kW), lane);
+      fac_alpha_step<P>(st, zt + krow * (4 * kW), lane, D);
     else
-      fac_beta_step<P>(st, st.s2, zt + krow * (4 * kW), lane);
-    // lagged, branch-free re-centring: the maximum taken at one step is subtracted after the next one, so the
-    // CREDUX round trip never sits on the dependent chain
+      fac_beta_step<P>(st, st.s2, zt + krow * (4 * kW), lane, D);
+    // lagged, branch-free re-centring: the lane maximum taken at one step is subtracted after the next one
     if ((t & (kRc - 1)) == (kBeta ? kRc - 1 : 0)) {
-      // the row maximum is put at +off, half of what it lost over the last period, so that the live states straddle
-      // zero until the next re-centring instead of sinking from it: half the magnitude, half the rounding error per
-      // step (the bookkeeping in C is exact whatever is subtracted)
+      // the lane maximum is put at +off, half of what it lost over the last period, so that the live states straddle
+      // zero until the next re-centring instead of sinking from it (the bookkeeping is exact whatever is subtracted)
       const bool live = pend > -1.0e29f;
       const float off_new = fminf(fmaxf(0.5f * (off - pend), 0.f), 48.f);
       const float m = live ? pend - off_new : 0.f;
       off = live ? off_new : off;
-#pragma unroll
-      for (int k = 0; k < P; ++k) st.v[k] -= m;
       twofloat_add(Chi, Clo, m);
+      // the neighbour's offset after ITS update; a lane that holds nothing yet follows its neighbour, so that the first
+      // value to cross into it arrives at the right magnitude (a lane still at offset 0 next to one at -5000 would take
+      // the crossing value at 5000: ulp 5e-4)
+      float nhi = kBeta ? __shfl_down_sync(0xffffffffu, Chi, 1) : __shfl_up_sync(0xffffffffu, Chi, 1);
+      float nlo = kBeta ? __shfl_down_sync(0xffffffffu, Clo, 1) : __shfl_up_sync(0xffffffffu, Clo, 1);
+      const float sub = live ? m : (nhi - Chi) + (nlo - Clo);  // what leaves the values: the re-centring, or the move to the neighbour's offset
+      Chi = live ? Chi : nhi;
+      Clo = live ? Clo : nlo;
+#pragma unroll
+      for (int k = 0; k < P; ++k) st.v[k] -= sub;
+      // D against the neighbour's FINAL offset of this round (it may itself just have moved to its neighbour's)
+      nhi = kBeta ? __shfl_down_sync(0xffffffffu, Chi, 1) : __shfl_up_sync(0xffffffffu, Chi, 1);
+      nlo = kBeta ? __shfl_down_sync(0xffffffffu, Clo, 1) : __shfl_up_sync(0xffffffffu, Clo, 1);
+      D = (nhi - Chi) + (nlo - Clo);
     }
     if ((t & (kRc - 1)) == (kBeta ? 0 : kRc - 1)) {
       float m = st.v[0];
 #pragma unroll
       for (int k = 1; k < P; ++k) m = fmaxf(m, st.v[k]);
-      pend = warp_max(m);
+      pend = m;
     }
   };
 
@@ -575,20 +594,17 @@ __device__ void fac_chain(const AsgParams& p, int b, float* ztile /* [kSeg][32] 
       }
       if (store && c + 1 < p.nC) {
         fac_store_row<P>(st, p.ckAa + ((size_t)b * p.nC + c + 1) * p.Lp, lane);
-        if (lane == 0) p.ckCA[(size_t)b * p.nC + c + 1] = (double)Chi + (double)Clo;
+        p.ckCA[((size_t)b * p.nC + c + 1) * kW + lane] = (double)Chi + (double)Clo;
       }
     }
-    // log2 partition function: the last position at the last frame
-    float last = kNeg;
+    // log2 partition function: the last position at the last frame (its lane writes it)
 #pragma unroll
     for (int k = 0; k < P; ++k)
-      if (lane * P + k == L - 1) last = st.v[k];
-    last = warp_max(last);
-    if (lane == 0) {
-      const double z2 = (double)last + (double)Chi + (double)Clo;
-      p.facLogZ2[b] = z2;
-      p.facLogZ[b] = z2 * kLn2 + (double)(T - 1) * (double)tmax;
-    }
+      if (lane * P + k == L - 1) {
+        const double z2 = (double)st.v[k] + (double)Chi + (double)Clo;
+        p.facLogZ2[b] = z2;
+        p.facLogZ[b] = z2 * kLn2 + (double)(T - 1) * (double)tmax;
+      }
   } else {
     // ---- beta: frames T-1 .. 0; checkpoint c-1 = row of frame c*kSeg -------------------------------------------------
     const int ctop = (T - 1) / kSeg;
@@ -624,7 +640,7 @@ __device__ void fac_chain(const AsgParams& p, int b, float* ztile /* [kSeg][32] 
       }
       if (c >= 1) {
         fac_store_row<P>(st, p.ckBa + ((size_t)b * p.nC + c - 1) * p.Lp, lane);
-        if (lane == 0) p.ckCB[(size_t)b * p.nC + c - 1] = (double)Chi + (double)Clo;
+        p.ckCB[((size_t)b * p.nC + c - 1) * kW + lane] = (double)Chi + (double)Clo;
       }
     }
   }
@@ -809,7 +825,9 @@ __global__ void __launch_bounds__(128, P <= 8 ? 4 : 2) asg_fac_grad_kernel(AsgPa
       cp_async_wait_all();
       __syncwarp();
       // ---- backwards: beta-tilde rows of frames t1-1 .. t0 into shared memory --------------------
+      // (checkpoint rows come with one offset per lane; DA / DB re-base the value that crosses a lane boundary)
       double CB = 0.0;
+      float DB = 0.f, DA = 0.f;
       int tstart;
       if (t1 >= T) {
 #pragma unroll
@@ -818,7 +836,9 @@ __global__ void __launch_bounds__(128, P <= 8 ? 4 : 2) asg_fac_grad_kernel(AsgPa
         tstart = T - 2;
       } else {
         fac_load_row<P>(st, bnext, lane);
-        CB = p.ckCB[(size_t)b * p.nC + c];
+        const double* cb = p.ckCB + ((size_t)b * p.nC + c) * kW;
+        CB = cb[lane];
+        DB = lane < 31 ? (float)(cb[lane + 1] - CB) : 0.f;
         tstart = t1 - 1;
       }
       __syncwarp();
@@ -841,10 +861,12 @@ __global__ void __launch_bounds__(128, P <= 8 ? 4 : 2) asg_fac_grad_kernel(AsgPa
 #pragma unroll
           for (int k = 0; k < P; ++k) arow[k] = __ldg(src + k);
         }
-        CA = p.ckCA[(size_t)b * p.nC + c];
+        const double* ca = p.ckCA + ((size_t)b * p.nC + c) * kW;
+        CA = ca[lane];
+        DA = lane > 0 ? (float)(ca[lane - 1] - CA) : 0.f;
       }
       for (int t = tstart; t >= t0; --t) {
-        fac_beta_step<P>(st, s2b, zt + (t - t0) * (4 * kW), lane);
+        fac_beta_step<P>(st, s2b, zt + (t - t0) * (4 * kW), lane, DB);
         fac_store_row<P>(st, brow + (size_t)(t - t0) * Lp, lane);
       }
       // ---- forwards: alpha-tilde, occupancies, transition statistics -----------------------------
@@ -867,7 +889,7 @@ __global__ void __launch_bounds__(128, P <= 8 ? 4 : 2) asg_fac_grad_kernel(AsgPa
       for (int t = tfirst; t < t1; ++t) {
         const uint32_t zrow = zt + (t - t0) * (4 * kW);
         const float* br = brow + (size_t)(t - t0) * Lp + lane * P;
-        float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1);
+        float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1) + DA;
         if (lane == 0) up = kNeg;
         float2 xv[P];  // (stay, advance) posteriors of the owned positions, unnormalised
         if constexpr (P == 1) {
@@ -923,6 +945,262 @@ __global__ void __launch_bounds__(128, P <= 8 ? 4 : 2) asg_fac_grad_kernel(AsgPa
   }
   __syncthreads();
   const float sgn = (p.terms & W2L_TERM_FCC) ? -1.0f : 1.0f;  // FAC enters ASG with a minus sign
+  const float cf = sgn * p.coef[b];
+  for (int k = threadIdx.x; k < kW * kW; k += blockDim.x) part[k] = cf * dtr_s[(k / kW) * (kW + 1) + (k % kW)];
+}
+
+// ---- long targets (Lp > 256): the halo path ---------------------------------------------------------------------
+// A warp cannot hold more than 8 positions per lane without spilling (and a 16- or 32-position lane serialises 200-400
+// instructions per step).  Within an 8-frame segment the recursion reaches only 8 positions sideways, so a row is cut into
+// W slices of 240 useful positions (lanes 1..30) plus one halo lane on either side: the W warps of a CTA take the W
+// slices of one segment with the 8-per-lane code above and exchange nothing about the recursion — the 6 % of redundant
+// halo arithmetic buys it.  They meet once per frame (one CTA barrier) to add their per-label occupancy sums, so the
+// frame is normalised by its true total exactly as on the single-warp path.
+constexpr int kHaloUse = 240;
+constexpr int kHaloRow = 256;
+constexpr int kHaloMaxW = 5;  // 1024 positions
+struct HaloLayout {
+  int gsh, dtr, order, start, y, dsum, ztile, bnext, brow, grow, per_warp, total;
+};
+__host__ __device__ inline HaloLayout halo_layout(int warps) {
+  HaloLayout f;
+  int o = 0;
+  f.gsh = o;    o += 2 * kHaloMaxW * kW;  // [2 frame parities][W][32] per-label partial sums
+  f.dtr = o;    o += kW * (kW + 1);
+  o = (o + 3) & ~3;
+  const int w0 = o;
+  f.order = 0;                        // offsets inside a warp's block
+  f.start = kHaloRow;
+  f.y = f.start + 36;
+  f.dsum = f.y + kHaloRow + 16;
+  f.ztile = (f.dsum + 2 * kHaloRow + 3) & ~3;
+  f.bnext = f.ztile + 2 * kSeg * kW;
+  f.brow = f.bnext + kHaloRow;
+  f.grow = f.brow + kSeg * kHaloRow;
+  f.per_warp = (f.grow + kHaloRow + 4 + 3) & ~3;
+  f.total = w0 + warps * f.per_warp;
+  f.order += w0;  // absolute offsets of warp 0's block
+  f.start += w0;
+  f.y += w0;
+  f.dsum += w0;
+  f.ztile += w0;
+  f.bnext += w0;
+  f.brow += w0;
+  f.grow += w0;
+  return f;
+}
+
+__global__ void __launch_bounds__(32 * kHaloMaxW) asg_fac_grad_halo_kernel(AsgParams p) {
+  constexpr int P = 8;
+  extern __shared__ __align__(16) float smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;  // warp = slice
+  const int b = blockIdx.y;
+  const int T = p.T;
+  const HaloLayout lay = halo_layout(W);
+  float* part = p.parts + ((size_t)p.n_fcc_parts + (size_t)b * gridDim.x + blockIdx.x) * (kW * kW);
+  if (!p.valid[b]) {
+    for (int k = threadIdx.x; k < kW * kW; k += blockDim.x) part[k] = 0.f;
+    return;
+  }
+  const int L = p.tsz[b];
+  const int base = kHaloUse * w - P;                              // position of lane 0, k = 0 (the left halo lane)
+  const int lo_use = kHaloUse * w, hi_use = min(L, lo_use + kHaloUse);  // the useful positions of this slice
+  float* gsh = smem + lay.gsh;
+  float* dtr_s = smem + lay.dtr;
+  const int wo = w * lay.per_warp;
+  int* order_s = reinterpret_cast<int*>(smem + lay.order + wo);  // useful positions (slice-local index l - base), sorted by label
+  int* start_s = reinterpret_cast<int*>(smem + lay.start + wo);
+  int* y_s = reinterpret_cast<int*>(smem + lay.y + wo);          // label of position base + i
+  float* dsum_s = smem + lay.dsum + wo;
+  const int32_t* yg = p.target + (size_t)b * p.L;
+  for (int k = threadIdx.x; k < kW * (kW + 1); k += blockDim.x) dtr_s[k] = 0.f;
+  for (int i = lane; i < kHaloRow + 16; i += 32) {
+    const int l = base + i;
+    y_s[i] = (l >= 0 && l < L) ? __ldg(yg + l) : 0;
+  }
+  __syncwarp();
+  {  // label-sorted index of the slice's useful positions (stable)
+    int cnt = 0;
+    for (int l = lo_use; l < hi_use; ++l) cnt += (y_s[l - base] == lane);
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    int w0 = pre - cnt;
+    start_s[lane] = w0;
+    if (lane == 31) start_s[32] = pre;
+    for (int l = lo_use; l < hi_use; ++l)
+      if (y_s[l - base] == lane) order_s[w0++] = l - base;
+  }
+  __syncthreads();
+
+  float2 ds[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) ds[k] = make_float2(0.f, 0.f);
+  {
+    float* ztile2 = smem + lay.ztile + wo;
+    float* bnext = smem + lay.bnext + wo;
+    float* brow = smem + lay.brow + wo;
+    float* grow = smem + lay.grow + wo;
+    const uint32_t zt2 = (uint32_t)__cvta_generic_to_shared(ztile2);
+    const uint32_t bnext_sa = (uint32_t)__cvta_generic_to_shared(bnext);
+    const uint32_t grow_sa = (uint32_t)__cvta_generic_to_shared(grow);
+    const float tmax = trans_max(p.trans, p.N, lane);
+    const float* Zb = p.Z + (size_t)b * T * kW;
+    float* Gb = p.G + (size_t)b * T * kW;
+    const double logZ2 = p.facLogZ2[b];
+    const bool useful = lane >= 1 && lane <= 30;
+    FacState<P> st;
+    float s2b[P];
+    fac_load_target<P>(st, p, b, L, lane, true, tmax, base);
+#pragma unroll
+    for (int k = 0; k < P; ++k) s2b[k] = st.s2[k];
+    fac_load_target<P>(st, p, b, L, lane, false, tmax, base);
+    FlushIndex fx;
+    fx.load(order_s, start_s, lane, kHaloRow);
+    if (lane == 0) grow[kHaloRow] = 0.f;
+    const int l0 = base + lane * P;  // first position of this lane
+    // the chain lane (p.P positions each) whose offset this lane's positions carry, and its neighbours' across the lane edges
+    auto chain_lane = [&](int l) { return min(max(l, 0), p.Lp - 1) / p.P; };
+    const int cl = chain_lane(l0), cl_prev = chain_lane(l0 - P), cl_next = chain_lane(l0 + P);
+    auto prefetch = [&](int c, int buf) {
+      const int t0 = c * kSeg;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int chunk = lane + 32 * h;
+        const int t = t0 + (chunk >> 3);
+        if (t < T) cp_async16(zt2 + (buf * kSeg * kW) * 4 + chunk * 16, Zb + (size_t)t * kW + (chunk & 7) * 4);
+      }
+      if (t0 + kSeg < T) {
+        const float* src = p.ckBa + ((size_t)b * p.nC + c) * p.Lp;
+#pragma unroll
+        for (int k = 0; k < P; k += 4) {
+          const int l = l0 + k;
+          if (l >= 0 && l < p.Lp)
+            cp_async16(bnext_sa + (lane * P + k) * 4, src + l);
+          else
+            *reinterpret_cast<float4*>(bnext + lane * P + k) = make_float4(kNeg, kNeg, kNeg, kNeg);
+        }
+      }
+      cp_async_commit();
+    };
+    // every warp of the CTA walks the same segments (one barrier per frame pairs them up)
+    int buf = 0;
+    if ((int)blockIdx.x < p.nC) prefetch(blockIdx.x, 0);
+    for (int c = blockIdx.x; c < p.nC; c += gridDim.x, buf ^= 1) {
+      const int t0 = c * kSeg, t1 = min(T, t0 + kSeg);
+      const uint32_t zt = zt2 + (buf * kSeg * kW) * 4;
+      const float* ztile = ztile2 + buf * kSeg * kW;
+      cp_async_wait_all();
+      __syncwarp();
+      // ---- backwards: beta-tilde rows of frames t1-1 .. t0 (exact on the useful lanes: the right halo absorbs the edge) ----
+      double CB = 0.0;
+      float DB = 0.f, DA = 0.f;
+      int tstart;
+      if (t1 >= T) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) st.v[k] = (l0 + k == L - 1) ? ztile[(T - 1 - t0) * kW + (st.y4[k] >> 2)] : kNeg;
+        fac_store_row<P>(st, brow + (size_t)(T - 1 - t0) * kHaloRow, lane);
+        tstart = T - 2;
+      } else {
+        fac_load_row<P>(st, bnext, lane);
+        const double* cb = p.ckCB + ((size_t)b * p.nC + c) * kW;
+        CB = cb[cl];
+        DB = (float)(cb[cl_next] - CB);
+        tstart = t1 - 1;
+      }
+      __syncwarp();
+      if (c + (int)gridDim.x < p.nC) prefetch(c + gridDim.x, buf ^ 1);
+      float arow[P];
+      double CA = 0.0;
+      if (t0 > 0) {
+        const float* src = p.ckAa + ((size_t)b * p.nC + c) * p.Lp;
+#pragma unroll
+        for (int k = 0; k < P; k += 4) {
+          const int l = l0 + k;
+          float4 q = make_float4(kNeg, kNeg, kNeg, kNeg);
+          if (l >= 0 && l < p.Lp) q = __ldg(reinterpret_cast<const float4*>(src + l));
+          arow[k] = q.x;
+          arow[k + 1] = q.y;
+          arow[k + 2] = q.z;
+          arow[k + 3] = q.w;
+        }
+        const double* ca = p.ckCA + ((size_t)b * p.nC + c) * kW;
+        CA = ca[cl];
+        DA = (float)(ca[cl_prev] - CA);
+      }
+      for (int t = tstart; t >= t0; --t) {
+        fac_beta_step<P>(st, s2b, zt + (t - t0) * (4 * kW), lane, DB);
+        fac_store_row<P>(st, brow + (size_t)(t - t0) * kHaloRow, lane);
+      }
+      // ---- forwards (exact on the useful lanes: the left halo absorbs the edge) --------------------------------------
+      int tfirst = t0;
+      if (t0 == 0) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) st.v[k] = (l0 + k == 0) ? ztile[st.y4[k] >> 2] : kNeg;
+        if (w == 0) Gb[lane] = (lane == y_s[P]) ? 1.0f : 0.0f;  // frame 0 sits at position 0 (slice 0, local index P)
+        tfirst = 1;
+      } else {
+#pragma unroll
+        for (int k = 0; k < P; ++k) st.v[k] = arow[k];
+      }
+      // halo lanes contribute nothing: their posteriors are switched off through the exponent
+      const float K = useful ? (float)(CA + CB - logZ2) + kLgShift : kNeg;
+      const float2 K2 = make_float2(K, K);
+      __syncwarp();
+      for (int t = tfirst; t < t1; ++t) {
+        const uint32_t zrow = zt + (t - t0) * (4 * kW);
+        const float* br = brow + (size_t)(t - t0) * kHaloRow + lane * P;
+        float up = __shfl_up_sync(0xffffffffu, st.v[P - 1], 1) + DA;
+        if (lane == 0) up = kNeg;
+        float2 xv[P];
+#pragma unroll
+        for (int k = P - 2; k >= 0; k -= 2) {
+          const float2 brk = __fadd2_rn(*reinterpret_cast<const float2*>(br + k), K2);
+          const float2 nv = fac_grad_pair(st.v[k], k ? st.v[k - 1] : up, st.s1[k], st.s2[k], lds_f(zrow + st.y4[k]), brk.x,  //
+                                          st.v[k + 1], st.v[k], st.s1[k + 1], st.s2[k + 1], lds_f(zrow + st.y4[k + 1]), brk.y, xv[k], xv[k + 1]);
+          *reinterpret_cast<float2*>(grow + lane * P + k) = make_float2(xv[k].x + xv[k].y, xv[k + 1].x + xv[k + 1].y);
+          st.v[k] = nv.x;
+          st.v[k + 1] = nv.y;
+        }
+        __syncwarp();
+        // this slice's per-label sums meet the other slices' (one CTA barrier per frame, buffers alternate by parity)
+        float* gbuf = gsh + (t & 1) * (kHaloMaxW * kW);
+        gbuf[w * kW + lane] = label_sum(grow_sa, grow, order_s, fx);
+        __syncthreads();
+        float gl = 0.f;
+        for (int ww = 0; ww < W; ++ww) gl += gbuf[ww * kW + lane];
+        const float gt = warp_sum(gl);
+        if (w == 0) Gb[(size_t)t * kW + lane] = gt > 0.f ? gl / gt : 0.f;
+        const float inv = gt > 0.f ? __fdividef(1.0f, gt) : 0.f;
+        const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+        for (int k = 0; k < P; ++k) ds[k] = __ffma2_rn(xv[k], inv2, ds[k]);
+      }
+    }
+    cp_async_wait_all();
+  }
+  // ---- CTA partial of the transition gradient: slice by slice (fixed order: deterministic) ------------------------
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    dsum_s[lane * P + k] = ds[k].x;
+    dsum_s[kHaloRow + lane * P + k] = ds[k].y;
+  }
+  __syncwarp();
+  for (int ww = 0; ww < W; ++ww) {
+    if (w == ww) {  // lane n adds this slice's useful positions with label n to row n
+      float* row = dtr_s + lane * (kW + 1);
+      for (int i = start_s[lane]; i < start_s[lane + 1]; ++i) {
+        const int li = order_s[i];
+        row[lane] += dsum_s[li];
+        if (base + li > 0) row[y_s[li - 1]] += dsum_s[kHaloRow + li];
+      }
+    }
+    __syncthreads();
+  }
+  const float sgn = (p.terms & W2L_TERM_FCC) ? -1.0f : 1.0f;
   const float cf = sgn * p.coef[b];
   for (int k = threadIdx.x; k < kW * kW; k += blockDim.x) part[k] = cf * dtr_s[(k / kW) * (kW + 1) + (k % kW)];
 }
@@ -1099,6 +1377,17 @@ int fac_grad_slots(int warps, size_t smem) {
   return per_sm * sms;
 }
 int fac_grad_ctas(const AsgParams& p) {
+  if (p.Wg > 1) {  // the halo kernel: one CTA of Wg warps per segment, CTAs loop over their sample's segments
+    const size_t smem = (size_t)halo_layout(p.Wg).total * 4;
+    int per_sm = 0;
+    cudaFuncSetAttribute(asg_fac_grad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, asg_fac_grad_halo_kernel, 32 * p.Wg, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int want = per_sm * sms / p.B;
+    if (want < 1) want = 1;
+    return want < p.nC ? want : p.nC;
+  }
   const int most = (p.nC + p.fac_grad_warps - 1) / p.fac_grad_warps;
   static int slots_cache[6] = {0, 0, 0, 0, 0, 0};
   const int idx = p.P == 1 ? 0 : p.P == 2 ? 1 : p.P == 4 ? 2 : p.P == 8 ? 3 : p.P == 16 ? 4 : 5;
@@ -1129,14 +1418,14 @@ void carve(AsgParams& p, void* ws, size_t& total) {
   p.G = c.take<float>(BT * kW);
   p.ckAa = c.take<float>(BC * p.Lp);
   p.ckBa = c.take<float>(BC * p.Lp);
-  p.ckCA = c.take<double>(BC);
-  p.ckCB = c.take<double>(BC);
+  p.ckCA = c.take<double>(BC * kW);
+  p.ckCB = c.take<double>(BC * kW);
   p.fccLogZ = c.take<double>(p.B);
   p.facLogZ2 = c.take<double>(p.B);
   p.facLogZ = c.take<double>(p.B);
   p.msum = c.take<double>(p.B);
   // sized for the most CTAs the FAC grad kernel can use (the actual count depends on the device's occupancy)
-  const size_t nparts = (size_t)(fcc_grad_ctas(p.T) + (p.nC + p.fac_grad_warps - 1) / p.fac_grad_warps) * p.B;
+  const size_t nparts = (size_t)(fcc_grad_ctas(p.T) + (p.Wg > 1 ? p.nC : (p.nC + p.fac_grad_warps - 1) / p.fac_grad_warps)) * p.B;
   p.parts = c.take<float>(nparts * kW * kW);
   p.parts2 = c.take<float>((nparts + kRedGroup - 1) / kRedGroup * kW * kW);
   p.order = c.take<int>((size_t)p.B * p.Lp);
@@ -1159,7 +1448,9 @@ void shape(AsgParams& p, int B, int T, int N, int L) {
   p.Lp = 32 * p.P;
 
   p.nC = (T + kSeg - 1) / kSeg;
-  p.fac_grad_warps = fac_grad_warps(p.Lp);
+  // long targets: the FAC grad kernel cuts the row into slices of 240 useful positions (the halo path), 4 warps per CTA
+  p.Wg = p.P >= 16 ? (Le + kHaloUse - 1) / kHaloUse : 1;
+  p.fac_grad_warps = p.Wg > 1 ? p.Wg : fac_grad_warps(p.Lp);
 }
 
 }  // namespace
@@ -1247,7 +1538,12 @@ extern "C" int w2l_asg_forward_backward(void* stream_, int terms, int B, int T, 
     W2L_LAUNCH_CHECK("asg_loss_only_kernel");
     return W2L_OK;
   }
-  if (has_fac) {
+  if (has_fac && p.Wg > 1) {
+    const size_t smem = (size_t)halo_layout(p.Wg).total * 4;
+    W2L_CUDA_CHECK(cudaFuncSetAttribute(asg_fac_grad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    asg_fac_grad_halo_kernel<<<dim3(gA, B), 32 * p.Wg, smem, stream>>>(p);
+    W2L_LAUNCH_CHECK("asg_fac_grad_halo_kernel");
+  } else if (has_fac) {
     const size_t smem = (size_t)fac_grad_layout(p.Lp, p.fac_grad_warps).total * 4;
     const dim3 grid(gA, B);
 #define W2L_LAUNCH_FAC_GRAD(PP)                                                                                          \
