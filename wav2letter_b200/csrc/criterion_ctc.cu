@@ -45,8 +45,8 @@ struct CtcParams {
   float* lpc;     // [B][T][Sp] the frame's log2-probabilities of the extended-target labels, minus log2 1.25 (compact, coalesced)
   float* latA;    // [B][T][Sp] alpha-tilde rows (log2 units)
   float* latB;    // [B][T][Sp] beta-tilde rows (log2 units, include frame t's emission)
-  double* cA;     // [B][T] offset of the stored alpha row (true = tilde + c)
-  double* cB;     // [B][T]
+  double* cA;     // [B][T][32] per-lane offsets of the stored alpha row (true = tilde + c[lane])
+  double* cB;     // [B][T][32]
   double* ll2;    // [B] log2-likelihood
   int* tsz;       // [B] feasible target size
   int* valid;     // [B]
@@ -152,7 +152,7 @@ __device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * 
   const int Lb = p.tsz[b], S = 2 * Lb + 1;
   const int32_t* yg = p.target ? p.target + (size_t)b * p.L : nullptr;
   float* lat = (kBeta ? p.latB : p.latA) + (size_t)b * T * Sp + lane * P;
-  double* coff = (kBeta ? p.cB : p.cA) + (size_t)b * T;
+  double* coff = (kBeta ? p.cB : p.cA) + (size_t)b * T * 32;
   const bool store = p.need_grad != 0;
   float pen[P];  // 0 where the skip transition into (alpha) / out of (beta) this state exists, kNeg where it does not
   float v[P];
@@ -193,12 +193,14 @@ __device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  float Chi = 0.f, Clo = 0.f, pend = kNeg, off = 0.f;
+  float Chi = 0.f, Clo = 0.f, pend = kNeg, off = 0.f, Dn = 0.f, Dn2 = 0.f;  // Dn: neighbour lane's offset minus this lane's
   request(0, 0);
   auto step = [&](int t, const float (&lp)[P]) {
     if (!kBeta) {
       float up1 = __shfl_up_sync(0xffffffffu, v[P - 1], 1);
       float up2 = P >= 2 ? __shfl_up_sync(0xffffffffu, v[P >= 2 ? P - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, v[0], 2);
+      up1 += Dn;  // the previous lane's values are relative to ITS offset: D = its offset - this lane's
+      up2 += (P == 1) ? Dn2 : Dn;
       if (lane == 0) up1 = up2 = kNeg;
       if (P == 1 && lane == 1) up2 = kNeg;
 #pragma unroll
@@ -210,6 +212,8 @@ __device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * 
     } else {
       float dn1 = __shfl_down_sync(0xffffffffu, v[0], 1);
       float dn2 = P >= 2 ? __shfl_down_sync(0xffffffffu, v[P >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, v[0], 2);
+      dn1 += Dn;
+      dn2 += (P == 1) ? Dn2 : Dn;
       if (lane == 31) dn1 = dn2 = kNeg;
       if (P == 1 && lane == 30) dn2 = kNeg;
 #pragma unroll
@@ -219,21 +223,35 @@ __device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * 
         v[k] = lp[k] + lse3_log2(v[k], n1, n2 + pen[k]);
       }
     }
-    // lagged, branch-free re-centring (criterion_asg.cu): the maximum taken at one step is subtracted after the next
+    // lagged, branch-free re-centring with one offset PER LANE (criterion_asg.cu: with a single offset per row the states far
+    // below the row maximum lose absolute precision, and in CTC's tight bands those carry the posterior mass)
     if ((t & (kRc - 1)) == (kBeta ? kRc - 1 : 0)) {
       const bool live = pend > -1.0e29f;
       const float off_new = fminf(fmaxf(0.5f * (off - pend), 0.f), 48.f);
       const float m = live ? pend - off_new : 0.f;
       off = live ? off_new : off;
-#pragma unroll
-      for (int k = 0; k < P; ++k) v[k] -= m;
       twofloat_add(Chi, Clo, m);
+      float nhi = kBeta ? __shfl_down_sync(0xffffffffu, Chi, 1) : __shfl_up_sync(0xffffffffu, Chi, 1);
+      float nlo = kBeta ? __shfl_down_sync(0xffffffffu, Clo, 1) : __shfl_up_sync(0xffffffffu, Clo, 1);
+      const float sub = live ? m : (nhi - Chi) + (nlo - Clo);  // a lane that holds nothing yet follows its neighbour's offset
+      Chi = live ? Chi : nhi;
+      Clo = live ? Clo : nlo;
+#pragma unroll
+      for (int k = 0; k < P; ++k) v[k] -= sub;
+      nhi = kBeta ? __shfl_down_sync(0xffffffffu, Chi, 1) : __shfl_up_sync(0xffffffffu, Chi, 1);
+      nlo = kBeta ? __shfl_down_sync(0xffffffffu, Clo, 1) : __shfl_up_sync(0xffffffffu, Clo, 1);
+      Dn = (nhi - Chi) + (nlo - Clo);
+      if (P == 1) {  // one state per lane: the s-2 neighbour lives two lanes away
+        nhi = kBeta ? __shfl_down_sync(0xffffffffu, Chi, 2) : __shfl_up_sync(0xffffffffu, Chi, 2);
+        nlo = kBeta ? __shfl_down_sync(0xffffffffu, Clo, 2) : __shfl_up_sync(0xffffffffu, Clo, 2);
+        Dn2 = (nhi - Chi) + (nlo - Clo);
+      }
     }
     if ((t & (kRc - 1)) == (kBeta ? 0 : kRc - 1)) {
       float m = v[0];
 #pragma unroll
       for (int k = 1; k < P; ++k) m = fmaxf(m, v[k]);
-      pend = warp_max(m);
+      pend = m;
     }
     if (store) {
       if constexpr (P >= 4) {
@@ -243,7 +261,7 @@ __device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * 
 #pragma unroll
         for (int k = 0; k < P; ++k) lat[(size_t)t * Sp + k] = v[k];
       }
-      if (lane == 0) coff[t] = (double)Chi + (double)Clo;
+      coff[(size_t)t * 32 + lane] = (double)Chi + (double)Clo;
     }
   };
   int buf = 0;
@@ -271,7 +289,7 @@ __device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * 
           if (store) {
 #pragma unroll
             for (int k = 0; k < P; ++k) lat[(size_t)t * Sp + k] = v[k];
-            if (lane == 0) coff[t] = 0.0;
+            coff[(size_t)t * 32 + lane] = 0.0;
           }
         } else {
           step(t, lp);
@@ -281,24 +299,24 @@ __device__ void ctc_chain(const CtcParams& p, int b, float* tile /* [2][D][32 * 
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (!kBeta) {
-    // log2-likelihood = lse of the last two states at the last frame
-    float a = kNeg;
+    // log2-likelihood = lse of the last two states at the last frame (absolute values: the two may sit in different lanes)
+    double a0 = -1.0e300, a1 = -1.0e300;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       const int s = lane * P + k;
-      if (s == S - 1 || s == S - 2) a = fmaxf(a, v[k]);
+      const double av = (double)v[k] + (double)Chi + (double)Clo;
+      if (s == S - 1) a0 = av;
+      if (s == S - 2) a1 = av;
     }
-    const float m = warp_max(a);
-    float e = 0.f;
 #pragma unroll
-    for (int k = 0; k < P; ++k) {
-      const int s = lane * P + k;
-      if (s == S - 1 || s == S - 2) e += ex2f(v[k] - m);
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 = fmax(a0, __shfl_xor_sync(0xffffffffu, a0, o));
+      a1 = fmax(a1, __shfl_xor_sync(0xffffffffu, a1, o));
     }
-    e = warp_sum(e);
     if (lane == 0) {
-      const bool feasible = m > -1.0e29f;
-      const double l2 = (double)m + (double)log2f(e) + (double)Chi + (double)Clo;
+      const double m = fmax(a0, a1);
+      const bool feasible = m > -1.0e29;
+      const double l2 = m + log2(exp2(a0 - m) + exp2(a1 - m));
       p.ll2[b] = l2;
       p.loss[b] = feasible ? (float)(-(double)p.scale[b] * l2 * kLn2) : INFINITY;
       if (!feasible) p.valid[b] = 0;  // infeasible (e.g. -inf activations on every path): the grad kernel writes zero rows
@@ -340,12 +358,16 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(CtcParams p) {
   const int S = 2 * p.tsz[b] + 1;
   const int32_t* yg = p.target ? p.target + (size_t)b * p.L : nullptr;
   // posteriors of the frame's states: alpha-tilde + beta-tilde - lp + (cA + cB - ll2); beta includes the frame's emission
-  const float K = (float)(p.cA[f] + p.cB[f] - p.ll2[b]);
+  const double* cA = p.cA + f * 32;
+  const double* cB = p.cB + f * 32;
+  const double ll2 = p.ll2[b];
+  const int P = p.P;
   const float* A = p.latA + f * Sp;
   const float* Bt = p.latB + f * Sp;
   float ps = 0.f;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     const float lp = p.lpc[f * Sp + s] + kLgShift;
+    const float K = (float)(cA[s / P] + cB[s / P] - ll2);  // the offsets of the lane that owns state s
     const float q = ex2f(A[s] + Bt[s] - lp + K);
     post_s[s] = q;
     ps += q;
@@ -374,8 +396,8 @@ void carve(CtcParams& p, void* ws, size_t& total) {
   p.lpc = c.take<float>(BT * p.Sp);
   p.latA = c.take<float>(BT * p.Sp);
   p.latB = c.take<float>(BT * p.Sp);
-  p.cA = c.take<double>(BT);
-  p.cB = c.take<double>(BT);
+  p.cA = c.take<double>(BT * 32);
+  p.cB = c.take<double>(BT * 32);
   p.ll2 = c.take<double>(p.B);
   p.tsz = c.take<int>(p.B);
   p.valid = c.take<int>(p.B);
