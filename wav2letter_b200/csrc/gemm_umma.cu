@@ -43,6 +43,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma_ptx.cuh"
@@ -525,7 +526,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // accumulator with the tile counter's parity.
 // ================================================================================================
 __host__ __device__ constexpr int pstages_for(int mode, int bn) { return mode == kF32x3 ? 3 : (bn <= 160 ? 5 : 4); }
-constexpr int kSplitThreads = 256;  // F32X3: eight split warps (two per scheduler): the split of a stage takes ~300 cycles, well inside its three MMAs
+constexpr int kSplitThreads = 256;  // F32X3: split warps of the comparison variant (the default launches 384 threads = twelve warps, see launch_persistent_bn)
 __host__ __device__ constexpr int pthreads_for(int mode) { return mode == kF32x3 ? 192 + kSplitThreads : 192; }
 __host__ __device__ constexpr int acc_stride_for(int bn) { return bn <= 128 ? 128 : 256; }
 constexpr int kTbufBytes = 4 * 32 * 36 * 4;  // per warp [32][36] floats: 128-bit conflict-free both ways (the scalar path uses a 33 pitch)
@@ -533,8 +534,8 @@ __host__ __device__ constexpr size_t psmem_for(int mode, int bn) {
   return pstages_for(mode, bn) * stage_bytes(mode, bn) + kTbufBytes + 256 + 2 * 1024 + 1024;  // ring + transposition + barriers + 2 bias rows + slack
 }
 
-template <int kMode, bool kAMn, bool kBMn, int BN>
-__global__ void __launch_bounds__(pthreads_for(kMode), 1)
+template <int kMode, bool kAMn, bool kBMn, int BN, int kST = kSplitThreads>
+__global__ void __launch_bounds__(kMode == kF32x3 ? 192 + kST : 192, 1)
 gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p, int tiles_m,
                             int tiles_n) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -575,7 +576,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&ready[s], kSplitThreads);
+      mbar_init(&ready[s], kST);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -708,7 +709,7 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     // second tile of the stage; round-to-nearest by integer arithmetic (add half an ulp of the 13 dropped bits, clear them):
     // full-rate ALU ops instead of quarter-rate cvt.rna
     const int tid = threadIdx.x - 192;
-    constexpr int kVecA = kTileBytes / 16 / kSplitThreads, kVecB = kTileBytesB / 16 / kSplitThreads;
+    constexpr int kNVecA = kTileBytes / 16, kNVecB = kTileBytesB / 16;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int m0, n0, kb_begin, num_kb;
@@ -745,9 +746,9 @@ gemm_umma_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           lo[i] = l;
         };
 #pragma unroll
-        for (int i = 0; i < kVecA; ++i) split(ta, la, i * kSplitThreads + tid);
+        for (int i = tid; i < kNVecA; i += kST) split(ta, la, i);
 #pragma unroll
-        for (int i = 0; i < kVecB; ++i) split(tb, lb, i * kSplitThreads + tid);
+        for (int i = tid; i < kNVecB; i += kST) split(tb, lb, i);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&ready[s]);
       }
@@ -841,7 +842,26 @@ int launch_persistent_bn(cudaStream_t stream, const CUtensorMap& ma, const CUten
   const int total = tiles_m * tiles_n * p.k_splits;
   profile_kind(1);
   profile_start(stream);
-  gemm_umma_persistent_kernel<kMode, kAMn, kBMn, BN><<<std::min(total, sm_count()), pthreads_for(kMode), smem, stream>>>(ma, mb, p, tiles_m, tiles_n);
+  if constexpr (kMode == kF32x3) {
+    // twelve split warps by default (measured: GEMM time per TDS+CTC step 10.15 ms with four, 8.56 with eight, 8.13 with
+    // twelve); W2L_F32X3_SPLIT_THREADS=256 selects the eight-warp variant for comparison
+    static const int st = [] {
+      const char* e = getenv("W2L_F32X3_SPLIT_THREADS");
+      return (e && atoi(e) == 256) ? 256 : 384;
+    }();
+    if (st == 384) {
+      static bool configured384 = false;
+      if (!configured384) {
+        W2L_CUDA_CHECK(cudaFuncSetAttribute(gemm_umma_persistent_kernel<kMode, kAMn, kBMn, BN, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured384 = true;
+      }
+      gemm_umma_persistent_kernel<kMode, kAMn, kBMn, BN, 384><<<std::min(total, sm_count()), 192 + 384, smem, stream>>>(ma, mb, p, tiles_m, tiles_n);
+    } else {
+      gemm_umma_persistent_kernel<kMode, kAMn, kBMn, BN><<<std::min(total, sm_count()), pthreads_for(kMode), smem, stream>>>(ma, mb, p, tiles_m, tiles_n);
+    }
+  } else {
+    gemm_umma_persistent_kernel<kMode, kAMn, kBMn, BN><<<std::min(total, sm_count()), pthreads_for(kMode), smem, stream>>>(ma, mb, p, tiles_m, tiles_n);
+  }
   profile_stop(stream);
   W2L_LAUNCH_CHECK(kernel_name(kMode));
   return W2L_OK;
