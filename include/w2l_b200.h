@@ -100,8 +100,9 @@ W2L_API long long w2l_trace_list(char* out, long long out_bytes);
  * L is the padded target width; the per-sample size is the index of the last non-negative
  * entry + 1, clamped to T (upstream getTargetSizeArray).  Samples whose target is empty or
  * holds a label outside [0,N) get loss = NaN and zero gradient.
- * Supported: N <= 32 (token sets of the ASG recipes are ~30: conv_glu/.../train.cfg),
- * L such that the per-CTA shared-memory rows fit (L <= ~6000).
+ * Supported: N <= 32 (token sets of the ASG recipes are ~30: conv_glu/.../train.cfg) and
+ * targets of at most 1024 positions after the clamp to T (min(L, T) <= 1024: a warp walks a
+ * recursion with up to 32 positions per lane); W2L_ERR_UNSUPPORTED beyond.
  * ---------------------------------------------------------------------------------------- */
 W2L_API size_t w2l_asg_workspace_size(int B, int T, int N, int L);
 W2L_API int w2l_asg_forward_backward(void* stream, int terms, int B, int T, int N, int L, int scale_mode,
@@ -129,7 +130,8 @@ W2L_API int w2l_fac_viterbi(void* stream, int B, int T, int N, int L, const floa
  * N-1 appended last: Train.cpp:248-251).  Replaces ConnectionistTemporalClassification
  * Criterion::forward (CTCLoss, Train.cpp:406-407; CUDA backend upstream = warp-ctc).
  * Every sample runs over the full padded T (the loop passes no input sizes to CTC/ASG:
- * Train.cpp:1473-1477).  d_emis may be NULL (forward only).
+ * Train.cpp:1473-1477).  d_emis may be NULL (forward only).  Targets of at most 1023 labels
+ * after the clamp to T (2 * min(L, T) + 1 <= 2048 extended states); W2L_ERR_UNSUPPORTED beyond.
  * w2l_argmax_path = CTCLoss::viterbiPath (per-frame argmax, first maximum wins).
  * ---------------------------------------------------------------------------------------- */
 W2L_API size_t w2l_ctc_workspace_size(int B, int T, int N, int L);
