@@ -75,7 +75,8 @@ def lse2(a, b):
 
 
 def fac_emulate(e, y, tr):
-    """log-domain FAC, alpha from t=0 and beta from t=T-1 meeting at h=T//2, per-step
+    """ROUND-1 formulation (kept as an independent fp32 cross-check of the oracle; the kernels no longer use it):
+    log-domain FAC, alpha from t=0 and beta from t=T-1 meeting at h=T//2, per-step
     re-centring by the band max, gamma = xi_stay + xi_adv, renormalised per frame.  returns logZ, G[T,N], dtrans[N,N]"""
     T, N = e.shape
     L = len(y)
@@ -191,3 +192,127 @@ def fac_emulate(e, y, tr):
     np.add.at(dtr, (y, y), ds1)
     np.add.at(dtr, (y[1:], y[:-1]), ds2[1:])
     return logZ, G, dtr
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Round-2 formulation of the FAC recursions (criterion_asg.cu: fac_chain / asg_fac_grad_kernel): log2 domain, scores
+# normalised by the frame maximum and the global transition maximum, lg2(1.25 * (1 + r)) with the constant folded into the
+# transition scores, P consecutive positions per lane, re-centring every kRc frames either with ONE offset per row (the
+# first version) or with one offset PER LANE (what the kernels do).  exp2 / log2 are exact here (float64, rounded to
+# float32): the MUFU table error is a separate, measured effect (profiles/mufu_bias_r2.txt).
+# ------------------------------------------------------------------------------------------------------------------
+LOG2E = 1.4426950408889634
+NEG = F(-1.0e30)
+LG_SCALE = F(1.25)
+LG_SHIFT = F(0.32192809488736235)
+
+
+def _lse2_log2(a, b):
+    mx = np.maximum(a, b)
+    mn = np.minimum(a, b)
+    d = (mn - mx).astype(F)
+    r = np.exp2(d.astype(np.float64)).astype(F)
+    q = (r * LG_SCALE + LG_SCALE).astype(F)
+    return (mx + np.log2(q.astype(np.float64)).astype(F)).astype(F)
+
+
+def fac_chain_emulate(e, y, tr, offsets="lane", P=8, kRc=2):
+    """posteriors gamma[T][L] and log-partition (natural log) of the forced alignment, float32 arithmetic of the round-2
+    kernels.  offsets: 'lane' (one re-centring offset per lane of P positions) or 'row' (one per row)."""
+    T, N = e.shape
+    L = len(y)
+    e64 = e.astype(np.float64)
+    m = e64.max(1, keepdims=True)
+    z = ((e64 - m) * LOG2E).astype(F)
+    tmax = float(tr.max())
+    s1 = ((tr[y, y].astype(np.float64) - tmax) * LOG2E).astype(F) - LG_SHIFT
+    s2a = np.full(L, NEG, F)
+    s2a[1:] = ((tr[y[1:], y[:-1]].astype(np.float64) - tmax) * LOG2E).astype(F) - LG_SHIFT
+    s2b = np.full(L, NEG, F)
+    s2b[:-1] = s2a[1:]
+    nl = (L + P - 1) // P
+    lane = np.arange(L) // P
+
+    def walk(beta):
+        v = np.full(L, NEG, F)
+        C = np.zeros(nl if offsets == "lane" else 1, np.float64)
+        off = np.zeros_like(C)
+        pend = np.full(C.shape, float(NEG))
+        rows = np.zeros((T, L), np.float64)
+        if not beta:
+            v[0] = z[0, y[0]]
+        else:
+            v[L - 1] = z[T - 1, y[L - 1]]
+
+        def total():
+            return v.astype(np.float64) + (C[lane] if offsets == "lane" else C[0])
+
+        rows[T - 1 if beta else 0] = total()
+        for t in (range(T - 2, -1, -1) if beta else range(1, T)):
+            if not beta:
+                nb = np.concatenate(([NEG], v[:-1]))
+                if offsets == "lane":  # the value crossing a lane boundary is re-based by the offset difference
+                    nb = (nb + np.concatenate(([0.0], C[lane[:-1]] - C[lane[1:]])).astype(F)).astype(F)
+                v = (z[t, y] + _lse2_log2((v + s1).astype(F), (nb + s2a).astype(F))).astype(F)
+            else:
+                nb = np.concatenate((v[1:], [NEG]))
+                if offsets == "lane":
+                    nb = (nb + np.concatenate((C[lane[1:]] - C[lane[:-1]], [0.0])).astype(F)).astype(F)
+                v = (z[t, y] + _lse2_log2((v + s1).astype(F), (nb + s2b).astype(F))).astype(F)
+            # lagged re-centring: the maximum taken at one frame is subtracted after the next one; the maximum is put at
+            # +off, half of what it lost over the last period
+            apply_phase = (t % kRc) == (kRc - 1 if beta else 0)
+            measure_phase = (t % kRc) == (0 if beta else kRc - 1)
+            if apply_phase:
+                for j in range(len(C)):
+                    sl = slice(j * P, (j + 1) * P) if offsets == "lane" else slice(0, L)
+                    if pend[j] > -1e29:
+                        off_new = min(max(0.5 * (off[j] - pend[j]), 0.0), 48.0)
+                        mm = F(pend[j] - off_new)
+                        off[j] = off_new
+                        v[sl] = (v[sl] - mm).astype(F)
+                        C[j] += float(mm)
+                    elif offsets == "lane":  # a lane that holds nothing yet follows its neighbour's offset
+                        jn = j + 1 if beta else j - 1
+                        if 0 <= jn < len(C):
+                            v[sl] = (v[sl] - F(C[jn] - C[j])).astype(F)
+                            C[j] = C[jn]
+            if measure_phase:
+                for j in range(len(C)):
+                    sl = slice(j * P, (j + 1) * P) if offsets == "lane" else slice(0, L)
+                    pend[j] = float(v[sl].max())
+            rows[t] = total()
+        return rows
+
+    A = walk(False)
+    Bt = walk(True)
+    logz2 = A[T - 1, L - 1]
+    g = np.exp2(A + Bt - z[:, y].astype(np.float64) - logz2)
+    g /= g.sum(1, keepdims=True)  # the grad kernel normalises every frame by its total
+    logz = logz2 / LOG2E + (T - 1) * tmax + float(m.sum())
+    return g, logz
+
+
+def fac_posteriors_float64(e, y, tr):
+    """float64 reference of the same posteriors"""
+    T, N = e.shape
+    L = len(y)
+    e = e.astype(np.float64)
+    tr = tr.astype(np.float64)
+    s1 = tr[y, y]
+    s2 = np.full(L, -np.inf)
+    s2[1:] = tr[y[1:], y[:-1]]
+    A = np.full((T, L), -np.inf)
+    Bt = np.full((T, L), -np.inf)
+    A[0, 0] = e[0, y[0]]
+    for t in range(1, T):
+        nb = np.concatenate(([-np.inf], A[t - 1, :-1]))
+        A[t] = e[t, y] + np.logaddexp(A[t - 1] + s1, nb + s2)
+    Bt[T - 1, L - 1] = e[T - 1, y[L - 1]]
+    s2b = np.full(L, -np.inf)
+    s2b[:-1] = s2[1:]
+    for t in range(T - 2, -1, -1):
+        nb = np.concatenate((Bt[t + 1, 1:], [-np.inf]))
+        Bt[t] = e[t, y] + np.logaddexp(Bt[t + 1] + s1, nb + s2b)
+    g = np.exp(A + Bt - e[:, y] - A[T - 1, L - 1])
+    return g / g.sum(1, keepdims=True), A[T - 1, L - 1]
