@@ -316,3 +316,96 @@ def fac_posteriors_float64(e, y, tr):
         Bt[t] = e[t, y] + np.logaddexp(Bt[t + 1] + s1, nb + s2b)
     g = np.exp(A + Bt - e[:, y] - A[T - 1, L - 1])
     return g / g.sum(1, keepdims=True), A[T - 1, L - 1]
+
+
+def ctc_chain_emulate(e, y, P=4, kRc=2):
+    """float32 arithmetic of the round-2 CTC kernels (criterion_ctc.cu): log-softmax scores of the extended-target labels
+    gathered per frame (lp' = (e - lz) * log2e - log2 1.25), three-way log2-sum-exp with lg2(1.25 * sum), P consecutive
+    states per lane with one re-centring offset per lane (lagged), alpha and beta stored, posteriors normalised per
+    frame.  Returns (loss (natural log, unscaled), d_emis [T][N] = softmax - occupancy)."""
+    T, N = e.shape
+    L = len(y)
+    S = 2 * L + 1
+    blank = N - 1
+    zlab = np.full(S, blank, np.int64)
+    zlab[1::2] = y
+    e64 = e.astype(np.float64)
+    lz = np.log(np.exp(e64 - e64.max(1, keepdims=True)).sum(1)) + e64.max(1)
+    lp = np.maximum(((e64[:, zlab] - lz[:, None]) * LOG2E).astype(F) - LG_SHIFT, NEG).astype(F)  # [T][S], shift folded
+    skip_in = np.zeros(S, bool)   # s-2 -> s allowed
+    skip_in[3::2] = y[1:] != y[:-1]
+    pen_a = np.where(skip_in, F(0), NEG).astype(F)
+    pen_b = np.full(S, NEG, F)    # s -> s+2 allowed
+    pen_b[:-2] = pen_a[2:]
+    nl = (S + P - 1) // P
+    lane = np.arange(S) // P
+
+    def lse3(a, b, c):
+        mx = np.maximum(np.maximum(a, b), c)
+        ssum = (np.exp2((a - mx).astype(F).astype(np.float64)).astype(F) + np.exp2((b - mx).astype(F).astype(np.float64)).astype(F)).astype(F)
+        ssum = (ssum + np.exp2((c - mx).astype(F).astype(np.float64)).astype(F)).astype(F)
+        return (mx + np.log2((ssum * LG_SCALE).astype(F).astype(np.float64)).astype(F)).astype(F)
+
+    def walk(beta):
+        v = np.full(S, NEG, F)
+        C = np.zeros(nl, np.float64)
+        off = np.zeros(nl)
+        pend = np.full(nl, float(NEG))
+        rows = np.zeros((T, S), np.float64)
+        t0 = T - 1 if beta else 0
+        if not beta:
+            v[:min(2, S)] = lp[0, :min(2, S)] + LG_SHIFT
+        else:
+            v[S - 1] = lp[T - 1, S - 1] + LG_SHIFT
+            if S > 1:
+                v[S - 2] = lp[T - 1, S - 2] + LG_SHIFT
+        rows[t0] = v.astype(np.float64) + C[lane]
+        for t in (range(T - 2, -1, -1) if beta else range(1, T)):
+            Cl = C[lane]
+            if not beta:
+                n1 = np.concatenate(([NEG], v[:-1]))
+                n2 = np.concatenate(([NEG, NEG], v[:-2]))
+                d1 = np.concatenate(([0.0], Cl[:-1] - Cl[1:]))
+                d2 = np.concatenate(([0.0, 0.0], Cl[:-2] - Cl[2:]))
+                pen = pen_a
+            else:
+                n1 = np.concatenate((v[1:], [NEG]))
+                n2 = np.concatenate((v[2:], [NEG, NEG]))
+                d1 = np.concatenate((Cl[1:] - Cl[:-1], [0.0]))
+                d2 = np.concatenate((Cl[2:] - Cl[:-2], [0.0, 0.0]))
+                pen = pen_b
+            n1 = (n1 + d1.astype(F)).astype(F)
+            n2 = ((n2 + d2.astype(F)).astype(F) + pen).astype(F)
+            v = (lp[t] + lse3(v, n1, n2)).astype(F)
+            if (t % kRc) == (kRc - 1 if beta else 0):
+                for j in range(nl):
+                    sl = slice(j * P, (j + 1) * P)
+                    if pend[j] > -1e29:
+                        off_new = min(max(0.5 * (off[j] - pend[j]), 0.0), 48.0)
+                        mm = F(pend[j] - off_new)
+                        off[j] = off_new
+                        v[sl] = (v[sl] - mm).astype(F)
+                        C[j] += float(mm)
+                    else:
+                        jn = j + 1 if beta else j - 1
+                        if 0 <= jn < nl:
+                            v[sl] = (v[sl] - F(C[jn] - C[j])).astype(F)
+                            C[j] = C[jn]
+            if (t % kRc) == (0 if beta else kRc - 1):
+                for j in range(nl):
+                    pend[j] = float(v[j * P:(j + 1) * P].max())
+            rows[t] = v.astype(np.float64) + C[lane]
+        return rows
+
+    A = walk(False)
+    Bt = walk(True)
+    last = [A[T - 1, S - 1]] + ([A[T - 1, S - 2]] if S > 1 else [])
+    ll2 = max(last) + np.log2(sum(2.0 ** (x - max(last)) for x in last))
+    lp_true = lp.astype(np.float64) + float(LG_SHIFT)
+    post = np.exp2(A + Bt - lp_true - ll2)
+    post /= post.sum(1, keepdims=True)
+    occ = np.zeros((T, N))
+    for s_ in range(S):
+        occ[:, zlab[s_]] += post[:, s_]
+    soft = np.exp(e64 - lz[:, None])
+    return -ll2 / LOG2E, soft - occ

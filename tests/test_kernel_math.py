@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
-from kernel_math_emulation import fac_chain_emulate, fac_emulate, fac_posteriors_float64, fcc_emulate
+from kernel_math_emulation import ctc_chain_emulate, fac_chain_emulate, fac_emulate, fac_posteriors_float64, fcc_emulate
 
 
 def rel(a, b):
@@ -86,3 +86,20 @@ def test_fac_per_lane_offsets_keep_tight_bands_accurate():
     err_row = np.abs(fac_chain_emulate(e, y, tr, "row")[0] - g64).max()
     assert err_lane < 2e-5
     assert err_row > 3 * err_lane  # documents why the offsets are per lane
+
+
+@pytest.mark.parametrize("T,N,L,seed", [(1, 5, 0, 0), (3, 6, 1, 1), (30, 12, 9, 2), (150, 200, 60, 3), (90, 40, 44, 4)])
+def test_ctc_round2_chain_formulation(T, N, L, seed):
+    """the log2-domain three-way recursion of the round-2 CTC kernels (per-lane offsets, lagged re-centring, lg2(1.25 x))
+    against the oracle, repeated labels and a tight band (2L+1 close to T) included"""
+    rng = np.random.default_rng(90 + seed)
+    e = (rng.normal(0, 1, (T, N)) * 3).astype(np.float32)
+    y = rng.integers(0, N - 1, L).astype(np.int32)
+    if L > 4:
+        y[3] = y[2]  # an adjacent repeat: no skip transition there
+    if T < 2 * L + 1 - L:  # keep the target feasible
+        return
+    loss, grad = ctc_chain_emulate(e, y)
+    ol, og = oracle.ctc(e[None], y[None] if L else np.full((1, 1), -1, np.int32), "none")
+    assert abs(loss - ol[0]) <= 1e-5 * abs(ol[0]) + 1e-5
+    assert rel(grad, og[0]) < 2e-5
