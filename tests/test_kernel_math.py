@@ -103,3 +103,47 @@ def test_ctc_round2_chain_formulation(T, N, L, seed):
     ol, og = oracle.ctc(e[None], y[None] if L else np.full((1, 1), -1, np.int32), "none")
     assert abs(loss - ol[0]) <= 1e-5 * abs(ol[0]) + 1e-5
     assert rel(grad, og[0]) < 2e-5
+
+
+def test_halo_slices_reproduce_the_full_row():
+    """The sliced FAC gradient path (asg_fac_grad_halo_kernel): within an 8-frame segment the recursion reaches only 8
+    positions sideways, so a slice of 240 useful positions with an 8-position halo on either side, started from the full
+    row's checkpoint and cut off from its neighbours, reproduces the full row on its useful positions exactly."""
+    rng = np.random.default_rng(11)
+    L, N, steps = 700, 30, 8
+    y = rng.integers(0, N, L)
+    tr = 4 * np.eye(N) + rng.normal(0, 0.1, (N, N))
+    s1 = tr[y, y]
+    s2a = np.full(L, -np.inf)
+    s2a[1:] = tr[y[1:], y[:-1]]
+    s2b = np.full(L, -np.inf)
+    s2b[:-1] = s2a[1:]
+    e = rng.normal(0, 3, (steps, N))
+
+    def alpha_steps(row, sa1, sa2, lab):
+        for t in range(steps):
+            nb = np.concatenate(([-np.inf], row[:-1]))
+            row = e[t, lab] + np.logaddexp(row + sa1, nb + sa2)
+        return row
+
+    def beta_steps(row, sb1, sb2, lab):
+        for t in range(steps - 1, -1, -1):
+            nb = np.concatenate((row[1:], [-np.inf]))
+            row = e[t, lab] + np.logaddexp(row + sb1, nb + sb2)
+        return row
+
+    a0 = rng.normal(-20, 10, L)
+    b0 = rng.normal(-20, 10, L)
+    full_a, full_b = alpha_steps(a0, s1, s2a, y), beta_steps(b0, s1, s2b, y)
+    for w in range((L + 239) // 240):
+        base = 240 * w - 8
+        idx = np.arange(base, base + 256)
+        ok = (idx >= 0) & (idx < L)
+        ii = np.clip(idx, 0, L - 1)
+        pick = lambda x, dead: np.where(ok, x[ii], dead)  # noqa: E731
+        lab = np.where(ok, y[ii], 0)
+        sl_a = alpha_steps(pick(a0, -np.inf), pick(s1, 0.0), pick(s2a, -np.inf), lab)
+        sl_b = beta_steps(pick(b0, -np.inf), pick(s1, 0.0), pick(s2b, -np.inf), lab)
+        use = ok & (np.arange(256) >= 8) & (np.arange(256) < 248)
+        np.testing.assert_array_equal(sl_a[use], full_a[idx[use]])
+        np.testing.assert_array_equal(sl_b[use], full_b[idx[use]])
