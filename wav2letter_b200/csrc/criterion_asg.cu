@@ -24,13 +24,16 @@
 //                    the P = Lp/32 CONSECUTIVE target positions P*j .. P*j+P-1 in registers, so the
 //                    l-1 neighbour is a register except for one SHFL per step; 2 MUFU per state
 //                    (ex2 + lg2), the adds packed two states per instruction (FADD2/FFMA2);
-//                    emissions gathered from an 8-frame shared-memory tile; re-centred every 2
-//                    frames (offset carried in double); the row is stored only every 8 frames (a
-//                    checkpoint: a full FAC lattice would be Lp/32 times the size of the emissions).
+//                    emissions gathered from an 8-frame shared-memory tile; every lane re-centres its
+//                    own positions every 2 frames (two-float offset per lane, lagged, branch-free);
+//                    the row is stored only every 8 frames (a checkpoint: a full FAC lattice would
+//                    be Lp/32 times the size of the emissions).
 //   3. asg_fac_grad_kernel parallel over (sample, 8-frame segment): recomputes the FAC beta rows
 //                          of the segment backwards from the checkpoint into shared memory, then
 //                          the alpha rows forwards, emitting per-frame normalised occupancies per
 //                          label (through the label-sorted index) and transition statistics.
+//                          Targets longer than 256: asg_fac_grad_halo_kernel, the row cut into
+//                          slices of 240 positions + halo lanes, one warp per slice.
 //   4. asg_fcc_grad_kernel parallel over frames, from the stored FCC vectors:
 //                          d_emis = coef*(gamma_fcc - gamma_fac), d_trans partials.
 //   5. asg_parts_reduce_kernel (x2)  deterministic tree sum of the d_trans partials (no atomics).
@@ -507,7 +510,7 @@ __device__ __forceinline__ void twofloat_add(float& hi, float& lo, float m) {
 
 // One warp walks one FAC recursion, P positions per lane.  (A variant that spread a recursion over four warps, two
 // positions per lane, with the boundary value handed from warp to warp through a shared-memory message ring, was built
-// and measured in this round: 186 ns per step against 167 ns for this one — the per-step dependent chain
+// and measured in this round: 186 ns per step against 162 ns for this one — the per-step dependent chain
 // SHFL -> FADD2 -> FMNMX -> FFMA2 -> EX2 -> FADD2 -> LG2 -> FADD2 is ~160 cycles whatever the width, and the ring's
 // bookkeeping cost what the narrower rows saved.  profiles/asg_r2.md.)
 template <int P, bool kBeta>
