@@ -6,15 +6,16 @@
 // L <- min(L+R,T)-R with R adjacent repeats.
 //
 // Pipeline:
-//   1. ctc_prep_kernel   HBM-bound: lz[b][t] = logsumexp_k e[b][t][k] (one pass over the
-//                        activations); per-sample target size / scale.
+//   1. ctc_prep_kernel   HBM-bound: lz[b][t] = logsumexp_k e[b][t][k] (one pass over the activations) and, while the row is
+//                        hot, the frame's scores of the extended-target labels gathered into a compact [T][Sp] array;
+//                        per-sample target size / scale.
 //   2. ctc_chains_kernel latency-bound.  ONE WARP PER RECURSION (alpha and beta of an utterance run concurrently in two
 //                        32-thread CTAs), no barrier anywhere: lane j owns the P = Sp/32 consecutive extended-target
 //                        states P*j .. P*j+P-1 in registers, the s-1 / s-2 neighbours are registers except for two SHFL
-//                        per step; log2 domain, three-way log-sum-exp with 4 MUFU per state; the gathered activations
-//                        e_t[z_s] are requested D frames ahead with plain loads into a register ring; lagged,
-//                        branch-free re-centring with a two-float offset; every alpha / beta row is stored with its
-//                        offset (T' is a few hundred frames and 2L+1 a few hundred states: a few MB).
+//                        per step; log2 domain, three-way log-sum-exp with 4 MUFU per state; the compact scores arrive
+//                        by cp.async in a double-buffered shared-memory tile, one block of D frames ahead; lagged,
+//                        branch-free re-centring with a two-float offset PER LANE; every alpha / beta row is stored with
+//                        its 32 offsets (T' is a few hundred frames and 2L+1 a few hundred states: a few MB).
 //   3. ctc_grad_kernel   HBM-bound, one CTA per frame: posteriors from the two stored rows, occupancy normalised by
 //                        its frame sum, d_emis = coef * (softmax - occupancy): reads the activations once, writes the
 //                        gradient once; the <= 2L+1 occupied labels of a frame are subtracted afterwards.
